@@ -1,0 +1,145 @@
+/*
+ * neurovit_b200 — C ABI of the B200 (sm_100a) ViT3D / NeuroEncoder hot path.
+ *
+ * The reference (gillet-thomas/NeuroViT) is pure PyTorch and has no FFI of its own; every entry point
+ * below therefore cites the reference *Python* call site it replaces (file:line under the reference
+ * root). Host code (neurovit_b200/*.py, the drop-in nn.Modules) binds these symbols with ctypes; see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates; the library never
+ *     frees or retains memory past the call);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden syncs;
+ *   - leading dimensions / strides are in ELEMENTS; sizes are plain ints;
+ *   - return value: 0 = NV_OK, 1 = bad argument, 2 = unsupported shape, 3 = CUDA error,
+ *     4 = not initialised; nv_last_error() returns the thread-local message of the last failure;
+ *   - there is NO CPU fallback: on a device that is not sm_100 nv_device_check() fails.
+ */
+#ifndef NEUROVIT_B200_H
+#define NEUROVIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NV_ABI_VERSION 1
+
+int nv_version(void);
+const char* nv_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x (B200) */
+int nv_device_check(void);
+
+/* ---- linear layers: nn.Linear fwd / dgrad / wgrad ------------------------------------------------
+ * replaces: vit_3d.py:94 (patch embedding), :41,50 (to_qkv), :43-45,60 (to_out), :19-22 (FeedForward)
+ * and their autograd backward.  C = epilogue(alpha * A * B^T), bf16 operands, fp32 accumulation on
+ * tcgen05 tensor cores (TMEM accumulators, TMA-fed 128B-swizzled tiles).
+ *   a_mn = 0: A is [M,K] row-major (lda);  a_mn = 1: A is stored [K,M] row-major (lda)
+ *   b_mn = 0: B is [N,K] row-major (ldb);  b_mn = 1: B is stored [K,N] row-major (ldb)
+ * epilogue, in order: *alpha, +bias[N], *gelu'(gelu_u[M,N]) (dgrad through GELU), out_pre = value and
+ * value = gelu(value) when apply_gelu, +residual[M,N] (fp32), then store: out_f32 (or red.add into it
+ * when accumulate=1 — required for k_splits > 1) and/or the bf16 copy out_bf16.
+ * block_n: 0 = auto, or 128 / 256 (CTA tile 128 x block_n). */
+int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
+                 const void* A, int64_t lda, const void* B, int64_t ldb,
+                 const float* bias, const float* residual, int64_t ld_res,
+                 const void* gelu_u, int64_t ld_u,
+                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
+                 void* out_pre, int64_t ld_pre,
+                 int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, void* stream);
+
+/* fp32 verification GEMM (CUDA-core FMA, arbitrary strides, batch index z = z1*Z2 + z2):
+ * C[z][m][n] = epilogue(alpha * sum_k A[z][m,k] * B[z][n,k]); same epilogue order as nv_gemm_bf16, all
+ * fp32; residual/gelu_u/out_pre share C's batch offsets. Also serves the [B,1024]x[1024,num_classes]
+ * head (vit_3d.py:107-110). */
+int nv_gemm_f32(int M, int N, int K, int Z1, int Z2,
+                const float* A, int64_t sa_m, int64_t sa_k, int64_t sa_z1, int64_t sa_z2,
+                const float* B, int64_t sb_n, int64_t sb_k, int64_t sb_z1, int64_t sb_z2,
+                float* C, int64_t sc_m, int64_t sc_z1, int64_t sc_z2,
+                const float* bias, const float* residual, int64_t ld_res,
+                const float* gelu_u, int64_t ld_u, float* out_pre, int64_t ld_pre,
+                int apply_gelu, int accumulate, float alpha, void* stream);
+
+/* ---- LayerNorm ------------------------------------------------------------------------------------
+ * replaces: nn.LayerNorm at vit_3d.py:18,37,93,95,108 (eps 1e-5 default, biased variance).
+ * Rows may be addressed through a grouped map r -> (r / group) * gstride + goff + r % group
+ * (group = 0: identity) so the [B, n+1, D] token tensor can be walked without its cls rows.
+ * add (optional): y += add[(r % add_mod) + add_off, :]  — the positional embedding (vit_3d.py:118). */
+int nv_layernorm_fwd(const float* x, int64_t ld_x, int x_group, int x_gstride, int x_goff,
+                     const float* gamma, const float* beta,
+                     const float* add, int64_t ld_add, int add_mod, int add_off,
+                     void* y, int y_is_bf16, int64_t ld_y, int y_group, int y_gstride, int y_goff,
+                     float* mean, float* rstd, int M, int D, float eps, void* stream);
+/* dx = LNbwd(dy) (+ dres); dgamma/dbeta/colsum are ACCUMULATED (atomicAdd) — zero or pre-load them.
+ * colsum (optional) += sum_rows dx_out: the bias gradient of the linear feeding the residual stream. */
+int nv_layernorm_bwd(const float* dy, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff,
+                     const float* x, int64_t ld_x, int x_group, int x_gstride, int x_goff,
+                     const float* mean, const float* rstd, const float* gamma,
+                     const float* dres, int64_t ld_dres,
+                     float* dx, int64_t ld_dx, int dx_group, int dx_gstride, int dx_goff,
+                     void* dx_bf16, int64_t ld_dxb,
+                     float* dgamma, float* dbeta, float* colsum, int M, int D, void* stream);
+/* x[b, 0, :] = cls + pos[0]  (vit_3d.py:116-118) */
+int nv_cls_row(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D, void* stream);
+
+/* ---- 3D patch gather + LayerNorm(patch_dim) -------------------------------------------------------
+ * replaces: Rearrange('b c (f pf) (h p1) (w p2) -> b (f h w) (p1 p2 pf c)') + nn.LayerNorm(patch_dim)
+ * at vit_3d.py:92-93, on the strided view built by ViT3DEncoder.forward (NeuroEncoder.py:200-202).
+ * dims[5] = {B,C,F,H,W}, strides[5] = element strides of the view, patch[3] = {pf,p1,p2}.
+ * out [B*n, ld_out] (bf16 or fp32; columns >= patch_dim are zero), raw (optional, fp32 [B*n,patch_dim])
+ * receives the un-normalised gathered patches — the bit-exact patch-index contract. */
+int nv_patch_gather_ln(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
+                       const float* gamma, const float* beta, void* out, int out_is_bf16, int64_t ld_out,
+                       float* raw, float* mean, float* rstd, float eps, void* stream);
+/* dgamma/dbeta of that LayerNorm from dP = d(loss)/d(LN output) [B*n, ld_dp] (accumulated) */
+int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
+                           const float* dP, int64_t ld_dp, const float* mean, const float* rstd,
+                           float* dgamma, float* dbeta, void* stream);
+
+/* ---- attention --------------------------------------------------------------------------------------
+ * replaces: vit_3d.py:51-59. q/k/v are read in place from the QKV projection output
+ * [B, N, 3*H*64] (pointers to the q, k, v column blocks; shared batch/row strides), O is written as
+ * [B, N, H*64]; lse [B,H,N] fp32 is saved for backward. head_dim must be 64 (bf16 flash kernels). */
+int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                     void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse,
+                     int B, int N, int H, int head_dim, float scale, void* stream);
+/* delta_ws: fp32 workspace of B*H*N elements */
+int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                     const void* o, const void* dO, int64_t o_batch_stride, int64_t o_row_stride,
+                     const float* lse, float* delta_ws,
+                     void* dq, void* dk, void* dv, int64_t dqkv_batch_stride, int64_t dqkv_row_stride,
+                     int B, int N, int H, int head_dim, float scale, void* stream);
+/* fp32 verification path: materialised softmax (vit_3d.py:55) and its backward, in place */
+int nv_softmax_fwd(float* s, int64_t rows, int n, void* stream);
+int nv_softmax_bwd(const float* P, float* dP, int64_t rows, int n, void* stream);
+
+/* ---- helpers around the GEMMs ---------------------------------------------------------------------- */
+int nv_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* out[r,c] (optional) and outT[c,r] = bf16(in[r,c]): bf16 weight caches for fwd and dgrad */
+int nv_cast_transpose_f32_bf16(const float* in, void* out, void* outT, int R, int C, void* stream);
+/* out[c] += sum_r in[r,c]  (bias gradients) */
+int nv_colsum(const void* in, int in_is_bf16, int64_t ld, float* out, int M, int N, void* stream);
+/* out[j] += sum_b in[b*batch_stride + j], j < L  (pos_embedding / cls_token gradients) */
+int nv_batch_sum(const float* in, int64_t batch_stride, float* out, int B, int64_t L, void* stream);
+/* pool='mean' (vit_3d.py:123) */
+int nv_mean_pool_fwd(const float* x, float* pooled, int B, int N, int D, void* stream);
+int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int N, int D, void* stream);
+
+/* ---- 4D temporal head -------------------------------------------------------------------------------
+ * replaces: TemporalTransformer (nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True),
+ * post-norm, ReLU, dim_ff = F) + mean over T + ProjectionHead Linear(2,2); NeuroEncoder.py:63-66,207-230.
+ * params: packed fp32 vector, layout documented in neurovit_b200/functional.py (TEMPORAL_LAYOUT).
+ * x [B,T,2] -> out [B,2] (optional) and/or seq_out [B,T,2] = the encoder layer's per-timepoint output
+ * (TemporalTransformer.forward called on its own); saved [B, T*4] keeps the LN1 output and LN2 input.
+ * bwd takes dout [B,2] and/or dseq [B,T,2] (either may be null), writes per-sequence parameter
+ * gradients to dparams_ws [B, P] (reduce with nv_batch_sum) and dx [B,T,2] (optional). */
+int nv_temporal_fwd(const float* x, const float* params, float* out, float* seq_out, float* saved,
+                    int B, int T, int F, float eps, void* stream);
+int nv_temporal_bwd(const float* x, const float* params, const float* saved, const float* dout, const float* dseq,
+                    float* dparams_ws, float* dx, int B, int T, int F, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUROVIT_B200_H */

@@ -1,0 +1,176 @@
+// extern "C" surface of libneurovit_b200.so — thin argument checks + launches. See include/neurovit_b200.h.
+#include "nv_common.cuh"
+#include "../../include/neurovit_b200.h"
+
+const char* nv_last_error_impl();
+
+// launchers implemented in the kernel translation units
+int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, int64_t lda, const bf16* B, int64_t ldb,
+                      const float* bias, const float* residual, int64_t ld_res, const bf16* gelu_u, int64_t ld_u,
+                      float* out_f32, int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
+                      int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, cudaStream_t stream);
+int nv_simt_gemm_launch(int M, int N, int K, int Z1, int Z2, const float* A, int64_t sa_m, int64_t sa_k, int64_t sa_z1,
+                        int64_t sa_z2, const float* B, int64_t sb_n, int64_t sb_k, int64_t sb_z1, int64_t sb_z2,
+                        float* C, int64_t sc_m, int64_t sc_z1, int64_t sc_z2, const float* bias, const float* residual,
+                        int64_t ld_res, const float* gelu_u, int64_t ld_u, float* out_pre, int64_t ld_pre,
+                        int apply_gelu, int accumulate, float alpha, cudaStream_t stream);
+int nv_softmax_fwd_launch(float* s, int64_t rows, int n, cudaStream_t stream);
+int nv_softmax_bwd_launch(const float* P, float* dP, int64_t rows, int n, cudaStream_t stream);
+int nv_ln_fwd_launch(const float* x, int64_t ld_x, int xg, int xs, int xo, const float* gamma, const float* beta,
+                     const float* add, int64_t ld_add, int add_mod, int add_off, void* y, int y_is_bf16, int64_t ld_y,
+                     int yg, int ys, int yo, float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream);
+int nv_ln_bwd_launch(const float* dy, int64_t ld_dy, int dyg, int dys, int dyo, const float* x, int64_t ld_x, int xg,
+                     int xs, int xo, const float* mean, const float* rstd, const float* gamma, const float* dres,
+                     int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo, bf16* dx_bf16,
+                     int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D, cudaStream_t stream);
+int nv_cls_row_launch(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D,
+                      cudaStream_t stream);
+int nv_patch_gather_ln_launch(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
+                              const float* gamma, const float* beta, void* out, int out_is_bf16, int64_t ld_out,
+                              float* raw, float* mean, float* rstd, float eps, cudaStream_t stream);
+int nv_patch_ln_param_grad_launch(const float* video, const int64_t* dims, const int64_t* strides,
+                                  const int64_t* patch, const float* dP, int64_t ld_dp, const float* mean,
+                                  const float* rstd, float* dgamma, float* dbeta, cudaStream_t stream);
+int nv_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                       bf16* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse, int B, int N, int H,
+                       int head_dim, float scale, cudaStream_t stream);
+int nv_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                       const bf16* o, const bf16* dO, int64_t o_batch_stride, int64_t o_row_stride, const float* lse,
+                       float* delta_ws, bf16* dq, bf16* dk, bf16* dv, int64_t dqkv_batch_stride,
+                       int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
+int nv_cast_f32_bf16_launch(const float* in, bf16* out, int64_t n, cudaStream_t stream);
+int nv_cast_transpose_launch(const float* in, bf16* out, bf16* outT, int R, int C, cudaStream_t stream);
+int nv_colsum_launch(const void* in, int in_is_bf16, int64_t ld, float* out, int M, int N, cudaStream_t stream);
+int nv_batch_sum_launch(const float* in, int64_t batch_stride, float* out, int B, int64_t L, cudaStream_t stream);
+int nv_mean_pool_fwd_launch(const float* x, float* pooled, int B, int N, int D, cudaStream_t stream);
+int nv_mean_pool_bwd_launch(const float* dpooled, float* dx, bf16* dx_bf16, int B, int N, int D, cudaStream_t stream);
+int nv_temporal_fwd_launch(const float* x, const float* params, float* out, float* seq_out, float* saved, int B,
+                           int T, int F, float eps, cudaStream_t stream);
+int nv_temporal_bwd_launch(const float* x, const float* params, const float* saved, const float* dout,
+                           const float* dseq, float* dparams_ws, float* dx, int B, int T, int F, float eps,
+                           cudaStream_t stream);
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int nv_version(void) { return NV_ABI_VERSION; }
+const char* nv_last_error(void) { return nv_last_error_impl(); }
+
+int nv_device_check(void) {
+  int dev = 0;
+  NV_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  NV_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    nv_set_error("neurovit_b200 kernels are built for sm_100a only; current device has compute capability %d.x", major);
+    return NV_ERR_UNSUPPORTED;
+  }
+  return NV_OK;
+}
+
+int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb,
+                 const float* bias, const float* residual, int64_t ld_res, const void* gelu_u, int64_t ld_u,
+                 float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, void* out_pre, int64_t ld_pre,
+                 int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, void* stream) {
+  return nv_gemm_tc_launch(a_mn, b_mn, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, bias, residual, ld_res,
+                           (const bf16*)gelu_u, ld_u, out_f32, ld_f32, (bf16*)out_bf16, ld_bf16, (bf16*)out_pre,
+                           ld_pre, apply_gelu, accumulate, alpha, k_splits, block_n, ST(stream));
+}
+
+int nv_gemm_f32(int M, int N, int K, int Z1, int Z2, const float* A, int64_t sa_m, int64_t sa_k, int64_t sa_z1,
+                int64_t sa_z2, const float* B, int64_t sb_n, int64_t sb_k, int64_t sb_z1, int64_t sb_z2, float* C,
+                int64_t sc_m, int64_t sc_z1, int64_t sc_z2, const float* bias, const float* residual, int64_t ld_res,
+                const float* gelu_u, int64_t ld_u, float* out_pre, int64_t ld_pre, int apply_gelu, int accumulate,
+                float alpha, void* stream) {
+  return nv_simt_gemm_launch(M, N, K, Z1, Z2, A, sa_m, sa_k, sa_z1, sa_z2, B, sb_n, sb_k, sb_z1, sb_z2, C, sc_m,
+                             sc_z1, sc_z2, bias, residual, ld_res, gelu_u, ld_u, out_pre, ld_pre, apply_gelu,
+                             accumulate, alpha, ST(stream));
+}
+
+int nv_layernorm_fwd(const float* x, int64_t ld_x, int x_group, int x_gstride, int x_goff, const float* gamma,
+                     const float* beta, const float* add, int64_t ld_add, int add_mod, int add_off, void* y,
+                     int y_is_bf16, int64_t ld_y, int y_group, int y_gstride, int y_goff, float* mean, float* rstd,
+                     int M, int D, float eps, void* stream) {
+  return nv_ln_fwd_launch(x, ld_x, x_group, x_gstride, x_goff, gamma, beta, add, ld_add, add_mod, add_off, y,
+                          y_is_bf16, ld_y, y_group, y_gstride, y_goff, mean, rstd, M, D, eps, ST(stream));
+}
+
+int nv_layernorm_bwd(const float* dy, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff, const float* x,
+                     int64_t ld_x, int x_group, int x_gstride, int x_goff, const float* mean, const float* rstd,
+                     const float* gamma, const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dx_group,
+                     int dx_gstride, int dx_goff, void* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
+                     float* colsum, int M, int D, void* stream) {
+  return nv_ln_bwd_launch(dy, ld_dy, dy_group, dy_gstride, dy_goff, x, ld_x, x_group, x_gstride, x_goff, mean, rstd,
+                          gamma, dres, ld_dres, dx, ld_dx, dx_group, dx_gstride, dx_goff, (bf16*)dx_bf16, ld_dxb,
+                          dgamma, dbeta, colsum, M, D, ST(stream));
+}
+
+int nv_cls_row(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D, void* stream) {
+  return nv_cls_row_launch(cls, pos, x, batch_stride, B, D, ST(stream));
+}
+
+int nv_patch_gather_ln(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
+                       const float* gamma, const float* beta, void* out, int out_is_bf16, int64_t ld_out, float* raw,
+                       float* mean, float* rstd, float eps, void* stream) {
+  return nv_patch_gather_ln_launch(video, dims, strides, patch, gamma, beta, out, out_is_bf16, ld_out, raw, mean,
+                                   rstd, eps, ST(stream));
+}
+
+int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
+                           const float* dP, int64_t ld_dp, const float* mean, const float* rstd, float* dgamma,
+                           float* dbeta, void* stream) {
+  return nv_patch_ln_param_grad_launch(video, dims, strides, patch, dP, ld_dp, mean, rstd, dgamma, dbeta, ST(stream));
+}
+
+int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                     void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse, int B, int N, int H,
+                     int head_dim, float scale, void* stream) {
+  return nv_attn_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
+                            (bf16*)o, o_batch_stride, o_row_stride, lse, B, N, H, head_dim, scale, ST(stream));
+}
+
+int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                     const void* o, const void* dO, int64_t o_batch_stride, int64_t o_row_stride, const float* lse,
+                     float* delta_ws, void* dq, void* dk, void* dv, int64_t dqkv_batch_stride,
+                     int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, void* stream) {
+  return nv_attn_bwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
+                            (const bf16*)o, (const bf16*)dO, o_batch_stride, o_row_stride, lse, delta_ws, (bf16*)dq,
+                            (bf16*)dk, (bf16*)dv, dqkv_batch_stride, dqkv_row_stride, B, N, H, head_dim, scale,
+                            ST(stream));
+}
+
+int nv_softmax_fwd(float* s, int64_t rows, int n, void* stream) { return nv_softmax_fwd_launch(s, rows, n, ST(stream)); }
+int nv_softmax_bwd(const float* P, float* dP, int64_t rows, int n, void* stream) {
+  return nv_softmax_bwd_launch(P, dP, rows, n, ST(stream));
+}
+
+int nv_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
+  return nv_cast_f32_bf16_launch(in, (bf16*)out, n, ST(stream));
+}
+int nv_cast_transpose_f32_bf16(const float* in, void* out, void* outT, int R, int C, void* stream) {
+  return nv_cast_transpose_launch(in, (bf16*)out, (bf16*)outT, R, C, ST(stream));
+}
+int nv_colsum(const void* in, int in_is_bf16, int64_t ld, float* out, int M, int N, void* stream) {
+  return nv_colsum_launch(in, in_is_bf16, ld, out, M, N, ST(stream));
+}
+int nv_batch_sum(const float* in, int64_t batch_stride, float* out, int B, int64_t L, void* stream) {
+  return nv_batch_sum_launch(in, batch_stride, out, B, L, ST(stream));
+}
+int nv_mean_pool_fwd(const float* x, float* pooled, int B, int N, int D, void* stream) {
+  return nv_mean_pool_fwd_launch(x, pooled, B, N, D, ST(stream));
+}
+int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int N, int D, void* stream) {
+  return nv_mean_pool_bwd_launch(dpooled, dx, (bf16*)dx_bf16, B, N, D, ST(stream));
+}
+
+int nv_temporal_fwd(const float* x, const float* params, float* out, float* seq_out, float* saved, int B, int T,
+                    int F, float eps, void* stream) {
+  return nv_temporal_fwd_launch(x, params, out, seq_out, saved, B, T, F, eps, ST(stream));
+}
+int nv_temporal_bwd(const float* x, const float* params, const float* saved, const float* dout, const float* dseq,
+                    float* dparams_ws, float* dx, int B, int T, int F, float eps, void* stream) {
+  return nv_temporal_bwd_launch(x, params, saved, dout, dseq, dparams_ws, dx, B, T, F, eps, ST(stream));
+}
+
+}  // extern "C"

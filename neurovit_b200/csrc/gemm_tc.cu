@@ -1,0 +1,380 @@
+// tcgen05 GEMM for the ViT3D linear layers (reference: src/models/vit_3d.py:18-22,41-45,50,60,94 —
+// every nn.Linear on the hot path, forward, dgrad and wgrad).
+//
+//   C[M,N] = epilogue( alpha * sum_k A[m,k] * B[n,k] )      bf16 operands, fp32 accumulate in TMEM
+//
+// Operand storage (row-major, leading dimension in elements):
+//   A K-major : A[M, K]          A MN-major : A stored as [K, M]   (wgrad: dY^T without a transpose pass)
+//   B K-major : B[N, K]          B MN-major : B stored as [K, N]   (wgrad: X, dgrad: W)
+//
+// Structure (one persistent CTA per SM, 320 threads):
+//   warps 0-7  epilogue: tcgen05.ld -> regs -> swizzled smem transpose -> coalesced global I/O
+//   warp  8    TMA producer (one lane): 128B-swizzled tiles into a STAGES-deep mbarrier ring
+//   warp  9    TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16
+// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i
+// overlaps the main loop of tile i+1. Split-K work units accumulate with red.global.add.f32
+// straight into the fp32 gradient buffer (wgrad).
+#include "nv_common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int TMA_WARP = 8;
+constexpr int MMA_WARP = 9;
+constexpr int NUM_THREADS = 320;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;          // per epilogue warp
+
+enum : int { EPI_GELU = 1, EPI_ATOMIC = 2 };
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, k_splits, k_blocks_total, k_blocks_per_split;
+  const float* bias;      // [N] or null
+  const float* residual;  // [M, ld_res] fp32 or null (added after activation)
+  const bf16* gelu_u;     // [M, ld_u] or null: acc *= gelu'(u)  (dgrad through GELU)
+  float* out_f32;         // [M, ld_f32] or null
+  bf16* out_bf16;         // [M, ld_bf16] or null (final value, bf16 copy)
+  bf16* out_pre;          // [M, ld_pre] or null (pre-activation, only with EPI_GELU)
+  int64_t ld_res, ld_u, ld_f32, ld_bf16, ld_pre;
+  int flags;
+  float alpha;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = A_OFF + STAGES * A_STAGE_BYTES;
+  static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
+};
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem + L::A_OFF;
+  uint8_t* sB = smem + L::B_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+  constexpr uint32_t STAGE_TX = A_STAGE_BYTES + L::B_STAGE_BYTES;
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.k_splits;
+        const int tile = unit / p.k_splits;
+        const int n_blk = tile % p.num_n_tiles;
+        const int m_blk = tile / p.num_n_tiles;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_TX);
+          uint8_t* a_dst = sA + s * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + s * L::B_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(a_dst + i * (BLOCK_K * 128), &tmap_a, &full_bar[s],
+                          m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_2d(b_dst + i * (BLOCK_K * 128), &tmap_b, &full_bar[s],
+                          n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // K-major: 8-row groups are 1024 B apart (SBO), LBO unused (1).
+      // MN-major: 64-element column slabs are BLOCK_K*128 B apart (LBO), 8-k groups 1024 B (SBO).
+      constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;  // bytes per UMMA_K
+      constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.k_splits;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * L::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -----------------------------------------
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int half = warp >> 2;   // which column chunks (even/odd) this warp owns
+    float* stage = reinterpret_cast<float*>(smem + L::EPI_OFF + warp * EPI_STAGE_BYTES);
+    const int sub_r = lane >> 3;  // row within a group of 4 in the coalesced phase
+    const int sub_c = lane & 7;   // 16-byte column chunk
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit / p.k_splits;
+      const int n_blk = tile % p.num_n_tiles;
+      const int m_blk = tile / p.num_n_tiles;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < BLOCK_N / 32; c += 2) {
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        const int gn = col0 + sub_c * 4;
+        const bool col_ok = gn < p.N;
+        // prefetch the epilogue's global operands before touching TMEM (hides L2/HBM latency)
+        float4 res[8];
+        uint2 uu[8];
+        if (p.residual != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int gm = row0 + i * 4 + sub_r;
+            res[i] = (col_ok && gm < p.M)
+                         ? *reinterpret_cast<const float4*>(p.residual + (int64_t)gm * p.ld_res + gn)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (p.gelu_u != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int gm = row0 + i * 4 + sub_r;
+            uu[i] = (col_ok && gm < p.M)
+                        ? *reinterpret_cast<const uint2*>(p.gelu_u + (int64_t)gm * p.ld_u + gn)
+                        : make_uint2(0u, 0u);
+          }
+        }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
+
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
+        tmem_ld_wait();
+        // row-per-thread -> swizzled staging (16B chunk j of row `lane` lands at chunk j^(lane&7))
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + sub_r;
+          const int gm = row0 + r;
+          float4 a = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_c ^ (r & 7)) << 2));
+          if (!(col_ok && gm < p.M)) continue;
+          a.x = a.x * p.alpha + bias4.x;
+          a.y = a.y * p.alpha + bias4.y;
+          a.z = a.z * p.alpha + bias4.z;
+          a.w = a.w * p.alpha + bias4.w;
+          if (p.gelu_u != nullptr) {
+            const float2 u01 = unpack_bf16x2(uu[i].x);
+            const float2 u23 = unpack_bf16x2(uu[i].y);
+            a.x *= gelu_erf_grad(u01.x);
+            a.y *= gelu_erf_grad(u01.y);
+            a.z *= gelu_erf_grad(u23.x);
+            a.w *= gelu_erf_grad(u23.y);
+          }
+          if (p.flags & EPI_GELU) {
+            if (p.out_pre != nullptr)
+              *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
+                  make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            a.x = gelu_erf(a.x);
+            a.y = gelu_erf(a.y);
+            a.z = gelu_erf(a.z);
+            a.w = gelu_erf(a.w);
+          }
+          if (p.residual != nullptr) {
+            a.x += res[i].x;
+            a.y += res[i].y;
+            a.z += res[i].z;
+            a.w += res[i].w;
+          }
+          if (p.flags & EPI_ATOMIC) {
+            float* dst = p.out_f32 + (int64_t)gm * p.ld_f32 + gn;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x),
+                         "f"(a.y), "f"(a.z), "f"(a.w)
+                         : "memory");
+          } else if (p.out_f32 != nullptr) {
+            *reinterpret_cast<float4*>(p.out_f32 + (int64_t)gm * p.ld_f32 + gn) = a;
+          }
+          if (p.out_bf16 != nullptr)
+            *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
+                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                   cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation; idempotent, races are benign
+  if (!attr_set) {
+    NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p);
+  NV_LAUNCH_CHECK("gemm_tc_kernel");
+  return NV_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+                 const GemmParams& p, int grid, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, false, false>(ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_variant<BLOCK_N, STAGES, false, true>(ta, tb, p, grid, stream);
+  if (a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, true, false>(ta, tb, p, grid, stream);
+  return launch_variant<BLOCK_N, STAGES, true, true>(ta, tb, p, grid, stream);
+}
+
+}  // namespace
+
+// Host entry used by the C ABI (api.cu). All pointers are device pointers; lds in elements.
+int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, int64_t lda,
+                      const bf16* B, int64_t ldb, const float* bias, const float* residual,
+                      int64_t ld_res, const bf16* gelu_u, int64_t ld_u, float* out_f32,
+                      int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
+                      int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
+                      cudaStream_t stream) {
+  NV_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  NV_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+  NV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16B strides)");
+  NV_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             "gemm: operands must be 16-byte aligned");
+  NV_REQUIRE(out_f32 != nullptr || out_bf16 != nullptr, "gemm: no output buffer");
+  NV_REQUIRE(!accumulate || out_f32 != nullptr, "gemm: accumulate needs an fp32 output");
+  NV_REQUIRE(block_n == 128 || block_n == 256 || block_n == 0, "gemm: block_n must be 0, 128 or 256");
+
+  if (block_n == 0) block_n = (N >= 256) ? 256 : 128;
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!a_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)M; box[0] = BLOCK_K; box[1] = BLOCK_M; }
+    else       { dims[0] = (uint64_t)M; dims[1] = (uint64_t)K; box[0] = 64;      box[1] = BLOCK_K; }
+    strides[0] = (uint64_t)lda * 2;
+    int s = nv_encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dims, strides, box,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+    if (s != NV_OK) return s;
+    if (!b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BLOCK_K; box[1] = (uint32_t)block_n; }
+    else       { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64;      box[1] = BLOCK_K; }
+    strides[0] = (uint64_t)ldb * 2;
+    s = nv_encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dims, strides, box,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+    if (s != NV_OK) return s;
+  }
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (N + block_n - 1) / block_n;
+  p.k_blocks_total = (K + BLOCK_K - 1) / BLOCK_K;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > p.k_blocks_total) k_splits = p.k_blocks_total;
+  p.k_blocks_per_split = (p.k_blocks_total + k_splits - 1) / k_splits;
+  p.k_splits = (p.k_blocks_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  NV_REQUIRE(p.k_splits == 1 || accumulate, "gemm: split-K needs accumulate=1 (red.add epilogue)");
+  p.bias = bias; p.residual = residual; p.gelu_u = gelu_u;
+  p.out_f32 = out_f32; p.out_bf16 = out_bf16; p.out_pre = out_pre;
+  p.ld_res = ld_res; p.ld_u = ld_u; p.ld_f32 = ld_f32; p.ld_bf16 = ld_bf16; p.ld_pre = ld_pre;
+  p.flags = (apply_gelu ? EPI_GELU : 0) | (accumulate ? EPI_ATOMIC : 0);
+  p.alpha = alpha;
+
+  const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+  const int grid = total_units < nv_num_sms() ? total_units : nv_num_sms();
+  if (block_n == 256) return launch_major<256, 4>(a_mn, b_mn, ta, tb, p, grid, stream);
+  return launch_major<128, 6>(a_mn, b_mn, ta, tb, p, grid, stream);
+}

@@ -1,0 +1,76 @@
+// Host-side plumbing shared by all kernels: error text, device query, TMA descriptor encoding.
+#include "nv_common.cuh"
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+
+namespace {
+thread_local char g_err[1024] = "";
+std::mutex g_mu;
+int g_num_sms = 0;
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+}  // namespace
+
+void nv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* nv_last_error_impl() { return g_err; }
+
+int nv_check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return NV_OK;
+  nv_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return NV_ERR_CUDA;
+}
+
+int nv_num_sms() {
+  if (g_num_sms > 0) return g_num_sms;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    return 148;
+  g_num_sms = n;
+  return n;
+}
+
+int nv_encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base,
+                   const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                   CUtensorMapSwizzle swizzle) {
+  if (g_encode == nullptr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_encode == nullptr) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        nv_set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+        return NV_ERR_CUDA;
+      }
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+  }
+  cuuint64_t gdims[5], gstr[4];
+  cuuint32_t gbox[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = g_encode(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    nv_set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank=%d dims=[%llu,%llu,..] box=[%u,%u,..] "
+                 "stride0=%llu base=%p",
+                 (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                 box[0], rank > 1 ? box[1] : 0,
+                 (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), base);
+    return NV_ERR_CUDA;
+  }
+  return NV_OK;
+}

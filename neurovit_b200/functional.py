@@ -1,0 +1,615 @@
+"""Autograd boundary of the hot path: one torch.autograd.Function per fusion group, each a fixed
+sequence of C-ABI kernel launches (neurovit_b200.ops). Reference semantics: src/models/vit_3d.py
+(FeedForward :14-26, Attention :28-60, ViT.forward :112-126) and src/models/NeuroEncoder.py:49-68,207-230.
+
+Precision modes
+  "bf16"  (default) bf16 tensor-core operands (tcgen05 GEMMs, flash attention), fp32 accumulation, fp32
+          residual stream, fp32 LayerNorm/softmax statistics  -> 2e-2 relative parity bar;
+  "fp32"  verification mode: CUDA-core fp32 GEMMs and materialised softmax -> 1e-5 parity bar.
+No path here falls back to torch math or to the CPU oracle.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+NUM_SMS = 148
+
+_VALID_MODES = ("bf16", "fp32")
+
+
+def check_mode(mode: str) -> str:
+    if mode not in _VALID_MODES:
+        raise ValueError(f"precision mode must be one of {_VALID_MODES}, got {mode!r}")
+    return mode
+
+
+# ------------------------------------------------------------------------------------ weight cache
+class WeightCache:
+    """bf16 copies of fp32 master weights, refreshed when the parameter's version counter moves
+    (optimizer steps and load_state_dict are in-place and bump it). Derived buffers only: never part of
+    state_dict (SURVEY §5 checkpoint contract)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def bf16(self, w: torch.Tensor, pad_k: int = 0) -> torch.Tensor:
+        key = (w.data_ptr(), tuple(w.shape), pad_k)
+        hit = self._c.get(key)
+        ver = w._version
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        if pad_k and pad_k != wd.shape[1]:
+            buf = hit[1] if hit is not None else torch.zeros(wd.shape[0], pad_k, device=wd.device, dtype=BF16)
+            tmp = ops.cast_bf16(wd)
+            buf[:, : wd.shape[1]].copy_(tmp)  # layout glue for K not a multiple of 8 (e.g. patch 9: 729 -> 736)
+            out = buf
+        else:
+            out = ops.cast_bf16(wd, out=hit[1] if hit is not None else None)
+        self._c[key] = (ver, out)
+        return out
+
+    def clear(self):
+        self._c.clear()
+
+
+# ------------------------------------------------------------------------------- bf16 grad side-car
+class GradStash:
+    """The residual-stream gradient is fp32 (autograd tensors), but the next dgrad/wgrad GEMM wants it
+    as a bf16 MMA operand. The LayerNorm-backward kernel that produces it writes both; the bf16 copy and
+    the column sum (bias gradient) ride along here, keyed by the fp32 tensor's storage."""
+
+    def __init__(self):
+        self._e = None
+
+    def put(self, t: torch.Tensor, bf=None, colsum=None):
+        # keep only the latest entry; holding `t` itself pins its storage so the address cannot be reused
+        self._e = (t, t._version, bf, colsum)
+
+    def take(self, t: torch.Tensor):
+        e, self._e = self._e, None
+        if e is None:
+            return None, None
+        src, ver, bf, colsum = e
+        if src.data_ptr() == t.data_ptr() and src.shape == t.shape and src.stride() == t.stride() \
+                and src._version == ver and t._version == ver:
+            return bf, colsum
+        return None, None
+
+
+_STASH = GradStash()
+
+
+def _splitk(tiles: int, k_blocks: int) -> int:
+    """Pick split-K so tiles*splits fills whole waves of NUM_SMS persistent CTAs."""
+    best, best_eff = 1, 0.0
+    for s in range(1, 33):
+        if k_blocks // s < 4 and s > 1:
+            break
+        units = tiles * s
+        eff = units / (math.ceil(units / NUM_SMS) * NUM_SMS)
+        if eff > best_eff + 0.03:
+            best, best_eff = s, eff
+    return best
+
+
+# ---------------------------------------------------------------------------------------- engine
+class Engine:
+    """Kernel sequences shared by the autograd Functions. `mode` picks the operand dtype."""
+
+    def __init__(self, mode: str):
+        self.mode = check_mode(mode)
+        self.act = BF16 if mode == "bf16" else F32
+        self.wc = WeightCache()
+
+    # -- primitives ------------------------------------------------------------------------------
+    def w(self, weight, pad_k=0):
+        return self.wc.bf16(weight, pad_k) if self.mode == "bf16" else weight.detach()
+
+    def linear(self, a, weight, *, bias=None, residual=None, gelu=False, out_dtype=None, pad_k=0):
+        """out = epilogue(a @ W^T). Returns (out, pre_activation or None)."""
+        M, N = a.shape[0], weight.shape[0]
+        out_dtype = out_dtype or self.act
+        dev = a.device
+        bias = None if bias is None else bias.detach()
+        pre = torch.empty(M, N, device=dev, dtype=self.act) if gelu else None
+        out = torch.empty(M, N, device=dev, dtype=out_dtype)
+        if self.mode == "bf16":
+            ops.gemm_bf16(a, self.w(weight, pad_k), bias=bias, residual=residual,
+                          out_f32=out if out_dtype == F32 else None, out_bf16=out if out_dtype == BF16 else None,
+                          out_pre=pre, apply_gelu=gelu)
+        else:
+            ops.linear_f32(a, weight.detach(), bias=bias, residual=residual, out=out, out_pre=pre, apply_gelu=gelu)
+        return out, pre
+
+    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, n_cols=None):
+        """dx[M, K_in] = dy[M, N_out] @ W[N_out, K_in]  (optionally * gelu'(u))."""
+        M, K_in = dy.shape[0], weight.shape[1]
+        out_dtype = out_dtype or self.act
+        out = torch.empty(M, K_in, device=dy.device, dtype=out_dtype)
+        if self.mode == "bf16":
+            ops.gemm_bf16(dy, self.w(weight), b_mn=True, gelu_u=gelu_u,
+                          out_f32=out if out_dtype == F32 else None, out_bf16=out if out_dtype == BF16 else None)
+        else:
+            ops.linear_f32(dy, weight.detach(), w_kn=True, gelu_u=gelu_u, out=out)
+        return out
+
+    def wgrad(self, dy, x, k_in=None):
+        """dW[N_out, K_in] = dy[M, N_out]^T @ x[M, K_in], fp32 (split-K red.add on the tensor-core path)."""
+        M, N_out = dy.shape
+        K_in = x.shape[1]
+        dW = torch.zeros(N_out, K_in, device=dy.device, dtype=F32)
+        if self.mode == "bf16":
+            bn = 256 if K_in >= 256 else 128
+            tiles = math.ceil(N_out / 128) * math.ceil(K_in / bn)
+            ops.gemm_bf16(dy, x, a_mn=True, b_mn=True, out_f32=dW, accumulate=True,
+                          k_splits=_splitk(tiles, math.ceil(M / 64)), block_n=bn)
+        else:
+            ops.linear_f32(dy, x, x_km=True, w_kn=True, out=dW)
+        if k_in is not None and k_in != K_in:
+            dW = dW[:, :k_in].contiguous()
+        return dW
+
+    def bias_grad(self, dy, colsum=None):
+        if colsum is not None:
+            return colsum
+        out = torch.zeros(dy.shape[1], device=dy.device, dtype=F32)
+        ops.colsum(dy, out)
+        return out
+
+    def ln_fwd(self, x, weight, bias, eps, out_dtype=None):
+        M, D = x.shape
+        y = torch.empty(M, D, device=x.device, dtype=out_dtype or self.act)
+        mean = torch.empty(M, device=x.device, dtype=F32)
+        rstd = torch.empty(M, device=x.device, dtype=F32)
+        ops.layernorm_fwd(x, weight.detach(), bias.detach(), y, M=M, D=D, mean=mean, rstd=rstd, eps=eps)
+        return y, mean, rstd
+
+    def ln_bwd(self, dy, x, mean, rstd, weight, dres=None, want_colsum=False):
+        """Returns dx (fp32), dx in the activation dtype (bf16 copy or the same fp32 tensor), dgamma, dbeta,
+        colsum(dx) or None."""
+        M, D = x.shape
+        dev = x.device
+        dx = torch.empty(M, D, device=dev, dtype=F32)
+        dxb = torch.empty(M, D, device=dev, dtype=BF16) if self.mode == "bf16" else None
+        dg = torch.zeros(D, device=dev, dtype=F32)
+        db = torch.zeros(D, device=dev, dtype=F32)
+        cs = torch.zeros(D, device=dev, dtype=F32) if want_colsum else None
+        ops.layernorm_bwd(dy, x, mean, rstd, weight.detach(), M=M, D=D, dres=dres, dx=dx, dx_bf16=dxb, dgamma=dg,
+                          dbeta=db, colsum=cs)
+        return dx, (dxb if dxb is not None else dx), dg, db, cs
+
+    def as_act(self, g):
+        """fp32 gradient -> MMA operand dtype, preferring the stashed bf16 copy from the producing kernel."""
+        bf, cs = _STASH.take(g)
+        if self.mode == "fp32":
+            return g, cs
+        if bf is None:
+            bf = ops.cast_bf16(g)
+        return bf, cs
+
+    # -- attention core (after the pre-norm) ------------------------------------------------------
+    def attn_core_fwd(self, a, x_res, w_qkv, w_out, b_out, B, N, heads, dim_head):
+        """a = LN(x) [M,D] in act dtype; returns x_res + to_out(attention(a)) (fp32) and the saved tensors.
+        vit_3d.py:50-60,73."""
+        M = a.shape[0]
+        inner = heads * dim_head
+        scale = dim_head ** -0.5
+        dev = a.device
+        qkv, _ = self.linear(a, w_qkv)
+        o = torch.empty(M, inner, device=dev, dtype=self.act)
+        if self.mode == "bf16":
+            lse = torch.empty(B, heads, N, device=dev, dtype=F32)
+            ops.attention_fwd(qkv, o, lse, B=B, N=N, H=heads, head_dim=dim_head, scale=scale)
+            aux = lse
+        else:
+            P = torch.empty(B, heads, N, N, device=dev, dtype=F32)
+            rs = qkv.stride(0)
+            # dots = q k^T * scale
+            ops.gemm_f32(N, N, dim_head, (qkv, 0), (rs, 1, N * rs, dim_head), (qkv, inner),
+                         (rs, 1, N * rs, dim_head), P, (N, heads * N * N, N * N), Z1=B, Z2=heads, alpha=scale)
+            ops.softmax_fwd(P, B * heads * N, N)
+            # out = attn v, written as 'b n (h d)'
+            ops.gemm_f32(N, dim_head, N, P, (N, 1, heads * N * N, N * N), (qkv, 2 * inner),
+                         (1, rs, N * rs, dim_head), o, (inner, N * inner, dim_head), Z1=B, Z2=heads)
+            aux = P
+        if w_out is None:  # project_out == False (heads == 1 and dim_head == dim): to_out is Identity
+            y = torch.empty(M, inner, device=dev, dtype=F32)
+            raise NotImplementedError("project_out=False (heads=1, dim_head=dim) is not on the NeuroViT hot path")
+        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32)
+        return y, (qkv, o, aux)
+
+    def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head):
+        """Returns da (fp32 grad wrt the LN output), dWqkv, dWout, dbout. dy is the fp32 grad of the block
+        output; its residual branch is handled by the caller."""
+        qkv, o, aux = saved
+        M = a.shape[0]
+        inner = heads * dim_head
+        scale = dim_head ** -0.5
+        dev = a.device
+        dO = self.dgrad(dy_act, w_out)
+        dWo = self.wgrad(dy_act, o)
+        dbo = self.bias_grad(dy, dy_colsum)
+        dqkv = torch.empty(M, 3 * inner, device=dev, dtype=self.act)
+        if self.mode == "bf16":
+            ws = torch.empty(B * heads * N, device=dev, dtype=F32)
+            ops.attention_bwd(qkv, o, dO, aux, ws, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=scale)
+        else:
+            P = aux
+            rs, drs = qkv.stride(0), dqkv.stride(0)
+            zP = (heads * N * N, N * N)
+            # dV[key,d] = sum_q P[q,key] dO[q,d]
+            ops.gemm_f32(N, dim_head, N, P, (1, N, *zP), dO, (1, inner, N * inner, dim_head), (dqkv, 2 * inner),
+                         (drs, N * drs, dim_head), Z1=B, Z2=heads)
+            dP = torch.empty_like(P)
+            # dP = dO V^T
+            ops.gemm_f32(N, N, dim_head, dO, (inner, 1, N * inner, dim_head), (qkv, 2 * inner),
+                         (rs, 1, N * rs, dim_head), dP, (N, *zP), Z1=B, Z2=heads)
+            ops.softmax_bwd(P, dP, B * heads * N, N)  # dP <- dS
+            # dQ = dS K * scale ; dK = dS^T Q * scale
+            ops.gemm_f32(N, dim_head, N, dP, (N, 1, *zP), (qkv, inner), (1, rs, N * rs, dim_head), (dqkv, 0),
+                         (drs, N * drs, dim_head), Z1=B, Z2=heads, alpha=scale)
+            ops.gemm_f32(N, dim_head, N, dP, (1, N, *zP), (qkv, 0), (1, rs, N * rs, dim_head), (dqkv, inner),
+                         (drs, N * drs, dim_head), Z1=B, Z2=heads, alpha=scale)
+        da = self.dgrad(dqkv, w_qkv, out_dtype=F32)
+        dWqkv = self.wgrad(dqkv, a)
+        return da, dWqkv, dWo, dbo
+
+    # -- feed-forward core -------------------------------------------------------------------------
+    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2):
+        g, u = self.linear(a, w1, bias=b1, gelu=True)
+        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32)
+        return y, (u, g)
+
+    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, w2):
+        u, g = saved
+        dU = self.dgrad(dy_act, w2, gelu_u=u)
+        dW2 = self.wgrad(dy_act, g)
+        db2 = self.bias_grad(dy, dy_colsum)
+        da = self.dgrad(dU, w1, out_dtype=F32)
+        dW1 = self.wgrad(dU, a)
+        db1 = self.bias_grad(dU)
+        return da, dW1, db1, dW2, db2
+
+
+_ENGINES = {}
+
+
+def engine(mode: str) -> Engine:
+    e = _ENGINES.get(mode)
+    if e is None:
+        e = _ENGINES[mode] = Engine(mode)
+    return e
+
+
+def _flat(x):
+    """[B, N, D] -> ([B*N, D] contiguous fp32, B, N)."""
+    B, N, D = x.shape
+    if x.dtype != F32:
+        x = x.float()
+    return x.contiguous().view(B * N, D), B, N
+
+
+# --------------------------------------------------------------------------- autograd: LayerNorm
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim; fp32 in, fp32 out (used where module hooks must observe the
+    output: the Grad-CAM target Attention.norm, NeuroEncoder.py:70-82)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, mode):
+        eng = engine(mode)
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).float().contiguous()
+        y, mean, rstd = eng.ln_fwd(x2, weight, bias, eps, out_dtype=F32)
+        ctx.save_for_backward(x2, mean, rstd, weight)
+        ctx.mode = mode
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, weight = ctx.saved_tensors
+        eng = engine(ctx.mode)
+        dy2 = dy.reshape(x2.shape).float().contiguous()
+        dx, dxa, dg, db, _ = eng.ln_bwd(dy2, x2, mean, rstd, weight)
+        dx = dx.view(ctx.shape)
+        _STASH.put(dx, dxa.view(ctx.shape) if ctx.mode == "bf16" else None)
+        return dx, dg, db, None, None
+
+
+# ----------------------------------------------------------------- autograd: attention sub-block
+class AttnBlockFn(torch.autograd.Function):
+    """x + to_out(attention(LN(x)))  — vit_3d.py:48-60 with the residual of :73 fused in."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w_qkv, w_out, b_out, heads, dim_head, eps, mode):
+        eng = engine(mode)
+        x2, B, N = _flat(x)
+        a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
+        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head)
+        ctx.save_for_backward(x2, mean, rstd, a, ln_w, w_qkv, w_out, *saved)
+        ctx.cfg = (B, N, heads, dim_head, mode)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, a, ln_w, w_qkv, w_out, *saved = ctx.saved_tensors
+        B, N, heads, dim_head, mode = ctx.cfg
+        eng = engine(mode)
+        dy = dy.contiguous()
+        dy_act, cs = eng.as_act(dy)
+        dy2 = dy.view(B * N, -1)
+        da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w_qkv, w_out, B, N, heads,
+                                                dim_head)
+        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True)
+        dx = dx.view(B, N, -1)
+        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
+        return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None
+
+
+class AttnCoreFn(torch.autograd.Function):
+    """x_res + to_out(attention(a)) where a = Attention.norm(x) was produced by the real nn.LayerNorm
+    module call (so forward/backward hooks on it fire)."""
+
+    @staticmethod
+    def forward(ctx, a, x_res, w_qkv, w_out, b_out, heads, dim_head, mode):
+        eng = engine(mode)
+        a2, B, N = _flat(a)
+        x2, _, _ = _flat(x_res)
+        a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
+        y, saved = eng.attn_core_fwd(a_act, x2, w_qkv, w_out, b_out, B, N, heads, dim_head)
+        ctx.save_for_backward(a_act, w_qkv, w_out, *saved)
+        ctx.cfg = (B, N, heads, dim_head, mode)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a_act, w_qkv, w_out, *saved = ctx.saved_tensors
+        B, N, heads, dim_head, mode = ctx.cfg
+        eng = engine(mode)
+        dy = dy.contiguous()
+        dy_act, cs = eng.as_act(dy)
+        da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy.view(B * N, -1), dy_act.view(B * N, -1), cs, a_act, saved, w_qkv,
+                                                w_out, B, N, heads, dim_head)
+        return da.view(B, N, -1), dy, dWqkv, dWo, dbo, None, None, None
+
+
+# ------------------------------------------------------------------- autograd: feed-forward block
+class FFBlockFn(torch.autograd.Function):
+    """x + W2 gelu(W1 LN(x) + b1) + b2  — vit_3d.py:14-26 with the residual of :74 fused in."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode):
+        eng = engine(mode)
+        x2, B, N = _flat(x)
+        a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
+        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2)
+        ctx.save_for_backward(x2, mean, rstd, a, ln_w, w1, w2, *saved)
+        ctx.cfg = (B, N, mode)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, a, ln_w, w1, w2, *saved = ctx.saved_tensors
+        B, N, mode = ctx.cfg
+        eng = engine(mode)
+        dy = dy.contiguous()
+        dy_act, cs = eng.as_act(dy)
+        dy2 = dy.view(B * N, -1)
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w1, w2)
+        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True)
+        dx = dx.view(B, N, -1)
+        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
+        return dx, dg, db, dW1, db1, dW2, db2, None, None
+
+
+class FFCoreFn(torch.autograd.Function):
+    """x_res + W2 gelu(W1 a + b1) + b2 where a = FeedForward.net[0](x) came from the real LayerNorm module
+    call (hooks on net[0] fire)."""
+
+    @staticmethod
+    def forward(ctx, a, x_res, w1, b1, w2, b2, mode):
+        eng = engine(mode)
+        a2, B, N = _flat(a)
+        x2, _, _ = _flat(x_res)
+        a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
+        y, saved = eng.ff_core_fwd(a_act, x2, w1, b1, w2, b2)
+        ctx.save_for_backward(a_act, w1, w2, *saved)
+        ctx.cfg = (B, N, mode)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a_act, w1, w2, *saved = ctx.saved_tensors
+        B, N, mode = ctx.cfg
+        eng = engine(mode)
+        dy = dy.contiguous()
+        dy_act, cs = eng.as_act(dy)
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy.view(B * N, -1), dy_act.view(B * N, -1), cs, a_act, saved, w1, w2)
+        return da.view(B, N, -1), dy, dW1, db1, dW2, db2, None
+
+
+# ---------------------------------------------------------------------- autograd: patch embedding
+class PatchEmbedFn(torch.autograd.Function):
+    """to_patch_embedding + cls token + positional embedding — vit_3d.py:91-96,113-118.
+    Rearrange -> LN(patch_dim) -> Linear(patch_dim, dim) -> LN(dim); x = cat(cls, .) + pos[:, :n+1]."""
+
+    @staticmethod
+    def forward(ctx, video, ln1_w, ln1_b, lin_w, lin_b, ln2_w, ln2_b, cls_token, pos_embedding, patch, eps, mode):
+        eng = engine(mode)
+        if video.dtype != F32:
+            video = video.float()
+        B = video.shape[0]
+        pf, p1, p2 = patch
+        n = (video.shape[2] // pf) * (video.shape[3] // p1) * (video.shape[4] // p2)
+        P = video.shape[1] * pf * p1 * p2
+        D = lin_w.shape[0]
+        if n + 1 > pos_embedding.shape[1]:
+            raise RuntimeError(f"The size of tensor a ({n + 1}) must match the size of tensor b "
+                               f"({pos_embedding.shape[1]}) at non-singleton dimension 1")
+        dev = video.device
+        Kp = (P + 7) // 8 * 8
+        patches = torch.empty(B * n, Kp, device=dev, dtype=eng.act)
+        mean1 = torch.empty(B * n, device=dev, dtype=F32)
+        rstd1 = torch.empty(B * n, device=dev, dtype=F32)
+        ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
+        if mode == "bf16":
+            e, _ = eng.linear(patches, lin_w, bias=lin_b, out_dtype=F32, pad_k=Kp)
+        else:
+            e, _ = eng.linear(patches[:, :P], lin_w, bias=lin_b, out_dtype=F32)
+        x = torch.empty(B, n + 1, D, device=dev, dtype=F32)
+        mean2 = torch.empty(B * n, device=dev, dtype=F32)
+        rstd2 = torch.empty(B * n, device=dev, dtype=F32)
+        pos = pos_embedding.detach().view(-1, D)
+        ops.layernorm_fwd(e, ln2_w.detach(), ln2_b.detach(), x, M=B * n, D=D, ymap=(n, n + 1, 1), add=pos, ld_add=D,
+                          add_mod=n, add_off=1, mean=mean2, rstd=rstd2, eps=eps)
+        ops.cls_row(cls_token.detach().view(-1), pos, x, (n + 1) * D, B, D)
+        ctx.save_for_backward(video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, lin_w)
+        ctx.cfg = (B, n, P, D, patch, mode, pos_embedding.shape, cls_token.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, lin_w = ctx.saved_tensors
+        B, n, P, D, patch, mode, pos_shape, cls_shape = ctx.cfg
+        eng = engine(mode)
+        dev = dx.device
+        dx = dx.contiguous()
+        _STASH.take(dx)
+        # d_pos[:n+1] = sum_b dx ; d_cls = sum_b dx[:, 0]
+        dpos = torch.zeros(pos_shape, device=dev, dtype=F32)
+        ops.batch_sum(dx, (n + 1) * D, dpos, B, (n + 1) * D)
+        dcls = dpos.view(-1, D)[0].clone().view(cls_shape)
+        # LN(dim) backward on the patch rows only (token offset 1)
+        de = torch.empty(B * n, D, device=dev, dtype=F32)
+        deb = torch.empty(B * n, D, device=dev, dtype=BF16) if mode == "bf16" else None
+        dg2 = torch.zeros(D, device=dev, dtype=F32)
+        db2 = torch.zeros(D, device=dev, dtype=F32)
+        dlin_b = torch.zeros(D, device=dev, dtype=F32)
+        ops.layernorm_bwd(dx, e, mean2, rstd2, ln2_w.detach(), M=B * n, D=D, dymap=(n, n + 1, 1), dx=de, dx_bf16=deb,
+                          dgamma=dg2, dbeta=db2, colsum=dlin_b)
+        de_act = deb if mode == "bf16" else de
+        Kp = patches.shape[1]
+        if mode == "bf16":
+            dlin_w = eng.wgrad(de_act, patches, k_in=P)
+            # dP = de @ W (fp32), only needed for the patch LayerNorm's gamma/beta
+            dP = torch.empty(B * n, Kp, device=dev, dtype=F32)
+            ops.gemm_bf16(de_act, eng.w(lin_w, Kp), b_mn=True, out_f32=dP)
+        else:
+            dlin_w = eng.wgrad(de_act, patches[:, :P])
+            dP = torch.empty(B * n, Kp, device=dev, dtype=F32)
+            ops.linear_f32(de, lin_w.detach(), w_kn=True, out=dP[:, :P])
+        dg1 = torch.zeros(P, device=dev, dtype=F32)
+        db1 = torch.zeros(P, device=dev, dtype=F32)
+        ops.patch_ln_param_grad(video, patch, dP, mean1, rstd1, dg1, db1)
+        return None, dg1, db1, dlin_w, dlin_b, dg2, db2, dcls, dpos, None, None, None
+
+
+# --------------------------------------------------------------------- autograd: pool + mlp_head
+class HeadFn(torch.autograd.Function):
+    """cls/mean pool -> LayerNorm(dim) -> Linear(dim, num_classes) — vit_3d.py:123-126."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, b, pool, eps, mode):
+        B, N, D = x.shape
+        dev = x.device
+        x = x.contiguous()
+        C = w.shape[0]
+        y = torch.empty(B, D, device=dev, dtype=F32)
+        mean = torch.empty(B, device=dev, dtype=F32)
+        rstd = torch.empty(B, device=dev, dtype=F32)
+        if pool == "mean":
+            pooled = torch.empty(B, D, device=dev, dtype=F32)
+            ops.mean_pool_fwd(x, pooled, B, N, D)
+            ops.layernorm_fwd(pooled, ln_w.detach(), ln_b.detach(), y, M=B, D=D, mean=mean, rstd=rstd, eps=eps)
+        else:
+            pooled = None
+            ops.layernorm_fwd(x, ln_w.detach(), ln_b.detach(), y, M=B, D=D, ld_x=N * D, mean=mean, rstd=rstd, eps=eps)
+        logits = ops.linear_f32(y, w.detach(), bias=b.detach())
+        ctx.save_for_backward(x, pooled, y, mean, rstd, ln_w, w)
+        ctx.cfg = (B, N, D, C, pool, mode)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, pooled, y, mean, rstd, ln_w, w = ctx.saved_tensors
+        B, N, D, C, pool, mode = ctx.cfg
+        dev = x.device
+        dl = dlogits.float().contiguous()
+        dw = ops.linear_f32(dl, y, x_km=True, w_kn=True)            # [C, D] = dl^T y
+        db = torch.zeros(C, device=dev, dtype=F32)
+        ops.colsum(dl, db)
+        dy = ops.linear_f32(dl, w.detach(), w_kn=True)              # [B, D]
+        dg = torch.zeros(D, device=dev, dtype=F32)
+        dbeta = torch.zeros(D, device=dev, dtype=F32)
+        dx = torch.zeros(B, N, D, device=dev, dtype=F32)            # cls pool: only token 0 gets gradient
+        dxb = torch.zeros(B, N, D, device=dev, dtype=BF16) if mode == "bf16" else None
+        if pool == "mean":
+            dpooled = torch.empty(B, D, device=dev, dtype=F32)
+            ops.layernorm_bwd(dy, pooled, mean, rstd, ln_w.detach(), M=B, D=D, dx=dpooled, dgamma=dg, dbeta=dbeta)
+            ops.mean_pool_bwd(dpooled, dx, dxb, B, N, D)
+        else:
+            ops.layernorm_bwd(dy, x, mean, rstd, ln_w.detach(), M=B, D=D, ld_x=N * D, dx=dx, ld_dx=N * D,
+                              dx_bf16=dxb, ld_dxb=N * D, dgamma=dg, dbeta=dbeta)
+        _STASH.put(dx, dxb)
+        return dx, dg, dbeta, dw, db, None, None, None
+
+
+# ------------------------------------------------------------------------- 4D temporal head (K10)
+TEMPORAL_KEYS = (
+    "temporal.self_attn.in_proj_weight", "temporal.self_attn.in_proj_bias",
+    "temporal.self_attn.out_proj.weight", "temporal.self_attn.out_proj.bias",
+    "temporal.linear1.weight", "temporal.linear1.bias", "temporal.linear2.weight", "temporal.linear2.bias",
+    "temporal.norm1.weight", "temporal.norm1.bias", "temporal.norm2.weight", "temporal.norm2.bias",
+    "head.weight", "head.bias",
+)
+
+
+def pack_temporal_params(tensors):
+    """Concatenate the 14 parameter tensors (order = TEMPORAL_KEYS) into the packed fp32 vector the kernel
+    reads (layout in csrc/temporal.cu). Pure data movement."""
+    return torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
+
+
+class TemporalHeadFn(torch.autograd.Function):
+    """TemporalTransformer -> mean over T -> ProjectionHead, NeuroEncoder.py:63-66."""
+
+    @staticmethod
+    def forward(ctx, x, eps, *params):
+        B, T, E = x.shape
+        if E != 2:
+            raise ValueError("the temporal kernel implements d_model=2 (NeuroEncoder.py:211)")
+        F = params[4].shape[0]
+        x = x.float().contiguous()
+        packed = pack_temporal_params(params)
+        out = torch.empty(B, 2, device=x.device, dtype=F32)
+        saved = torch.empty(B, T * 4, device=x.device, dtype=F32)
+        ops.temporal_fwd(x, packed, out, saved, B, T, F, eps)
+        ctx.save_for_backward(x, packed, saved)
+        ctx.cfg = (B, T, F, eps, [p.shape for p in params], x.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, packed, saved = ctx.saved_tensors
+        B, T, F, eps, shapes, need_dx = ctx.cfg
+        dev = x.device
+        ws = torch.empty(B, packed.numel(), device=dev, dtype=F32)
+        dx = torch.empty(B, T, 2, device=dev, dtype=F32) if ctx.needs_input_grad[0] else None
+        ops.temporal_bwd(x, packed, saved, dout.float().contiguous(), ws, dx, B, T, F, eps)
+        flat = torch.zeros(packed.numel(), device=dev, dtype=F32)
+        ops.batch_sum(ws, packed.numel(), flat, B, packed.numel())
+        grads, off = [], 0
+        for s in shapes:
+            n = math.prod(s)
+            grads.append(flat[off:off + n].view(s))
+            off += n
+        return (dx, None, *grads)

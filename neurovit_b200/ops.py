@@ -1,0 +1,239 @@
+"""Tensor-level wrappers over the C ABI: PyTorch supplies device memory and the current stream, the
+library does all arithmetic. No torch math ops are used on the data path here."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise _lib.NeuroViTLibraryError(
+            "neurovit_b200 runs on CUDA (sm_100a) only; got a CPU tensor and there is no CPU fallback")
+    _lib.require_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _rowmajor(t: torch.Tensor, name: str) -> int:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} "
+                         f"strides {t.stride()}")
+    return t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------- GEMMs
+def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=None, out_f32=None,
+              out_bf16=None, out_pre=None, apply_gelu=False, accumulate=False, alpha=1.0, k_splits=1,
+              block_n=0):
+    """C[M,N] = epilogue(alpha * A @ B^T) on tcgen05. a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N])."""
+    _dev(a)
+    assert a.dtype == BF16 and b.dtype == BF16, "gemm_bf16 operands must be bfloat16"
+    lda, ldb = _rowmajor(a, "a"), _rowmajor(b, "b")
+    (K, M) = a.shape if a_mn else (a.shape[1], a.shape[0])
+    (Kb, N) = b.shape if b_mn else (b.shape[1], b.shape[0])
+    if K != Kb:
+        raise ValueError(f"gemm_bf16: reduction dims differ ({K} vs {Kb})")
+    for t, nm, dt in ((out_f32, "out_f32", F32), (out_bf16, "out_bf16", BF16), (out_pre, "out_pre", BF16),
+                      (residual, "residual", F32), (gelu_u, "gelu_u", BF16)):
+        if t is not None:
+            assert t.dtype == dt and tuple(t.shape) == (M, N), f"{nm}: expected {dt} [{M},{N}], got {t.dtype} {tuple(t.shape)}"
+            _rowmajor(t, nm)
+    if bias is not None:
+        assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
+    ld = lambda t: 0 if t is None else t.stride(0)
+    _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
+              _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
+              _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), int(apply_gelu), int(accumulate),
+              float(alpha), int(k_splits), int(block_n), _stream())
+
+
+def gemm_f32(M, N, K, a, sa, b, sb, c, sc, *, Z1=1, Z2=1, bias=None, residual=None, gelu_u=None, out_pre=None,
+             ld_aux=0, apply_gelu=False, accumulate=False, alpha=1.0):
+    """fp32 verification GEMM. sa=(m,k,z1,z2) sb=(n,k,z1,z2) sc=(m,z1,z2) element strides; a/b/c may be
+    tensors or (tensor, element_offset) pairs. residual/gelu_u/out_pre share C's batch offsets and use
+    row stride ld_aux."""
+    def base(t):
+        if isinstance(t, tuple):
+            t, off = t
+            _dev(t)
+            assert t.dtype == F32
+            return ctypes.c_void_p(t.data_ptr() + 4 * off)
+        _dev(t)
+        assert t.dtype == F32
+        return _ptr(t)
+
+    _lib.call("nv_gemm_f32", M, N, K, Z1, Z2, base(a), sa[0], sa[1], sa[2], sa[3], base(b), sb[0], sb[1], sb[2],
+              sb[3], base(c), sc[0], sc[1], sc[2], _ptr(bias), _ptr(residual), ld_aux, _ptr(gelu_u), ld_aux,
+              _ptr(out_pre), ld_aux, int(apply_gelu), int(accumulate), float(alpha), _stream())
+
+
+def linear_f32(x, w, *, bias=None, residual=None, gelu_u=None, out=None, out_pre=None, apply_gelu=False,
+               accumulate=False, alpha=1.0, w_kn=False, x_km=False):
+    """fp32 helper on top of gemm_f32: out[M,N] = x[M,K] @ w[N,K]^T (w_kn: w is [K,N]; x_km: x is [K,M])."""
+    (K, M) = x.shape if x_km else (x.shape[1], x.shape[0])
+    (Kw, N) = w.shape if w_kn else (w.shape[1], w.shape[0])
+    assert K == Kw, f"linear_f32: {K} vs {Kw}"
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=F32)
+    sa = (x.stride(1), x.stride(0), 0, 0) if x_km else (x.stride(0), x.stride(1), 0, 0)
+    sb = (w.stride(1), w.stride(0), 0, 0) if w_kn else (w.stride(0), w.stride(1), 0, 0)
+    assert out.stride(1) == 1
+    for t in (residual, gelu_u, out_pre):
+        if t is not None:
+            assert t.stride(1) == 1 and t.stride(0) == out.stride(0) and t.dtype == F32
+    gemm_f32(M, N, K, x, sa, w, sb, out, (out.stride(0), 0, 0), bias=bias, residual=residual, gelu_u=gelu_u,
+             out_pre=out_pre, ld_aux=out.stride(0), apply_gelu=apply_gelu, accumulate=accumulate, alpha=alpha)
+    return out
+
+
+# --------------------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x, gamma, beta, y, *, M, D, ld_x=None, ld_y=None, xmap=(0, 0, 0), ymap=(0, 0, 0), add=None,
+                  ld_add=0, add_mod=1, add_off=0, mean=None, rstd=None, eps=1e-5):
+    _dev(x)
+    assert x.dtype == F32 and y.dtype in (F32, BF16)
+    _lib.call("nv_layernorm_fwd", _ptr(x), D if ld_x is None else ld_x, *xmap, _ptr(gamma), _ptr(beta), _ptr(add),
+              ld_add, add_mod, add_off, _ptr(y), int(y.dtype == BF16), D if ld_y is None else ld_y, *ymap,
+              _ptr(mean), _ptr(rstd), M, D, float(eps), _stream())
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, M, D, ld_dy=None, ld_x=None, dymap=(0, 0, 0), xmap=(0, 0, 0),
+                  dres=None, ld_dres=None, dx=None, ld_dx=None, dxmap=(0, 0, 0), dx_bf16=None, ld_dxb=None,
+                  dgamma=None, dbeta=None, colsum=None):
+    _dev(x)
+    assert dy.dtype == F32 and x.dtype == F32
+    _lib.call("nv_layernorm_bwd", _ptr(dy), D if ld_dy is None else ld_dy, *dymap, _ptr(x),
+              D if ld_x is None else ld_x, *xmap, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
+              D if ld_dres is None else ld_dres, _ptr(dx), D if ld_dx is None else ld_dx, *dxmap, _ptr(dx_bf16),
+              D if ld_dxb is None else ld_dxb, _ptr(dgamma), _ptr(dbeta), _ptr(colsum), M, D, _stream())
+
+
+def cls_row(cls, pos, x, batch_stride, B, D):
+    _dev(x)
+    _lib.call("nv_cls_row", _ptr(cls), _ptr(pos), _ptr(x), batch_stride, B, D, _stream())
+
+
+# ------------------------------------------------------------------------------------ patch gather
+def _i64x(vals):
+    return (ctypes.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def patch_gather_ln(video, patch, gamma, beta, out, *, raw=None, mean=None, rstd=None, eps=1e-5):
+    """video: 5-D fp32 view [B,C,F,H,W] (any strides); patch=(pf,p1,p2); out [B*n, ld] bf16/fp32 or None."""
+    _dev(video)
+    assert video.dtype == F32 and video.dim() == 5
+    dims, strides, p = _i64x(video.shape), _i64x(video.stride()), _i64x(patch)
+    _lib.call("nv_patch_gather_ln", _ptr(video), dims, strides, p, _ptr(gamma), _ptr(beta), _ptr(out),
+              int(out is not None and out.dtype == BF16), 0 if out is None else out.stride(0), _ptr(raw),
+              _ptr(mean), _ptr(rstd), float(eps), _stream())
+
+
+def patch_ln_param_grad(video, patch, dP, mean, rstd, dgamma, dbeta):
+    _dev(video)
+    assert dP.dtype == F32 and dP.stride(1) == 1
+    dims, strides, p = _i64x(video.shape), _i64x(video.stride()), _i64x(patch)
+    _lib.call("nv_patch_ln_param_grad", _ptr(video), dims, strides, p, _ptr(dP), dP.stride(0), _ptr(mean),
+              _ptr(rstd), _ptr(dgamma), _ptr(dbeta), _stream())
+
+
+# --------------------------------------------------------------------------------------- attention
+def _off(t, elems):
+    return ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
+
+
+def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale):
+    """qkv [B*N, 3*H*hd] bf16 (q|k|v column blocks), o [B*N, H*hd] bf16, lse [B,H,N] fp32."""
+    _dev(qkv)
+    assert qkv.dtype == BF16 and o.dtype == BF16 and lse.dtype == F32
+    inner = H * head_dim
+    rs = qkv.stride(0)
+    _lib.call("nv_attention_fwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
+              N * o.stride(0), o.stride(0), _ptr(lse), B, N, H, head_dim, float(scale), _stream())
+
+
+def attention_bwd(qkv, o, dO, lse, delta_ws, dqkv, *, B, N, H, head_dim, scale):
+    _dev(qkv)
+    inner = H * head_dim
+    rs, drs = qkv.stride(0), dqkv.stride(0)
+    assert o.stride(0) == dO.stride(0)
+    _lib.call("nv_attention_bwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
+              _ptr(dO), N * o.stride(0), o.stride(0), _ptr(lse), _ptr(delta_ws), _off(dqkv, 0), _off(dqkv, inner),
+              _off(dqkv, 2 * inner), N * drs, drs, B, N, H, head_dim, float(scale), _stream())
+
+
+def softmax_fwd(s, rows, n):
+    _dev(s)
+    _lib.call("nv_softmax_fwd", _ptr(s), rows, n, _stream())
+
+
+def softmax_bwd(P, dP, rows, n):
+    _dev(P)
+    _lib.call("nv_softmax_bwd", _ptr(P), _ptr(dP), rows, n, _stream())
+
+
+# ----------------------------------------------------------------------------------------- helpers
+def cast_bf16(x, out=None):
+    _dev(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.call("nv_cast_f32_bf16", _ptr(x), _ptr(out), x.numel(), _stream())
+    return out
+
+
+def cast_transpose_bf16(w, out=None, outT=None):
+    """w [R,C] fp32 -> (bf16 [R,C] or None, bf16 [C,R])."""
+    _dev(w)
+    assert w.dtype == F32 and w.dim() == 2 and w.is_contiguous()
+    R, C = w.shape
+    if outT is None:
+        outT = torch.empty(C, R, device=w.device, dtype=BF16)
+    _lib.call("nv_cast_transpose_f32_bf16", _ptr(w), _ptr(out), _ptr(outT), R, C, _stream())
+    return out, outT
+
+
+def colsum(x, out, *, M=None, N=None):
+    _dev(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == F32
+    M = x.shape[0] if M is None else M
+    N = x.shape[1] if N is None else N
+    _lib.call("nv_colsum", _ptr(x), int(x.dtype == BF16), x.stride(0), _ptr(out), M, N, _stream())
+
+
+def batch_sum(x, batch_stride, out, B, L):
+    _dev(x)
+    _lib.call("nv_batch_sum", _ptr(x), batch_stride, _ptr(out), B, L, _stream())
+
+
+def mean_pool_fwd(x, pooled, B, N, D):
+    _dev(x)
+    _lib.call("nv_mean_pool_fwd", _ptr(x), _ptr(pooled), B, N, D, _stream())
+
+
+def mean_pool_bwd(dpooled, dx, dx_bf16, B, N, D):
+    _dev(dx)
+    _lib.call("nv_mean_pool_bwd", _ptr(dpooled), _ptr(dx), _ptr(dx_bf16), B, N, D, _stream())
+
+
+def temporal_fwd(x, params, out, saved, B, T, F, eps=1e-5, seq_out=None):
+    _dev(x)
+    _lib.call("nv_temporal_fwd", _ptr(x), _ptr(params), _ptr(out), _ptr(seq_out), _ptr(saved), B, T, F, float(eps),
+              _stream())
+
+
+def temporal_bwd(x, params, saved, dout, dparams_ws, dx, B, T, F, eps=1e-5, dseq=None):
+    _dev(x)
+    _lib.call("nv_temporal_bwd", _ptr(x), _ptr(params), _ptr(saved), _ptr(dout), _ptr(dseq), _ptr(dparams_ws),
+              _ptr(dx), B, T, F, float(eps), _stream())

@@ -1,0 +1,279 @@
+"""Per-kernel parity on the GPU, each C-ABI kernel against the matching torch sub-graph (fp32/fp64 on the
+same device). Tolerances: bf16 kernels 2e-2 relative (north_star), fp32 kernels 1e-5, index work bit-exact."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on CPU boxes too; every test here is gpu-marked
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from einops import rearrange  # noqa: E402
+
+from neurovit_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("shape", [(256, 256, 128), (385, 1536, 1024), (130, 72, 200)])
+def test_gemm_bf16_plain(a_mn, b_mn, block_n, shape):
+    M, N, K = shape
+    torch.manual_seed(1)
+    a = torch.randn((K, M) if a_mn else (M, K), device=DEV).to(torch.bfloat16)
+    b = torch.randn((K, N) if b_mn else (N, K), device=DEV).to(torch.bfloat16)
+    if (a_mn and M % 8) or (b_mn and N % 8) or ((not a_mn or not b_mn) and K % 8):
+        pytest.skip("TMA needs 16-byte row strides")
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm_bf16(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, block_n=block_n)
+    af = a.double().t() if a_mn else a.double()
+    bf = b.double().t() if b_mn else b.double()
+    assert rel_err(out, af @ bf.t()) < 1e-3
+
+
+def test_gemm_bf16_epilogues():
+    torch.manual_seed(2)
+    M, N, K = 770, 1024, 512
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    ref = a.double() @ w.double().t() + bias.double()
+    # bias + residual, fp32 out + bf16 copy
+    out = torch.empty(M, N, device=DEV)
+    outb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, bias=bias, residual=res, out_f32=out, out_bf16=outb)
+    assert rel_err(out, ref + res.double()) < 1e-3
+    assert rel_err(outb, ref + res.double()) < 1e-2
+    # bias + GELU: pre-activation and activation in bf16
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    act = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, bias=bias, out_pre=pre, out_bf16=act, apply_gelu=True)
+    assert rel_err(pre, ref) < 1e-2
+    assert rel_err(act, torch.nn.functional.gelu(ref)) < 1e-2
+    # dgrad through GELU: acc * gelu'(u)
+    u = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    ud = u.double().requires_grad_(True)
+    g, = torch.autograd.grad(torch.nn.functional.gelu(ud).sum(), ud)
+    ops.gemm_bf16(a, w, gelu_u=u, out_f32=out)
+    assert rel_err(out, (a.double() @ w.double().t()) * g) < 1e-3
+    # split-K accumulate into a pre-loaded fp32 buffer (wgrad): dW[N_out,K_in] = dY^T X
+    dy = torch.randn(M, 256, device=DEV).to(torch.bfloat16)
+    x = torch.randn(M, 384, device=DEV).to(torch.bfloat16)
+    dw = torch.full((256, 384), 0.5, device=DEV)
+    ops.gemm_bf16(dy, x, a_mn=True, b_mn=True, out_f32=dw, accumulate=True, k_splits=5)
+    assert rel_err(dw, dy.double().t() @ x.double() + 0.5) < 1e-3
+
+
+def test_gemm_f32_matches_torch():
+    torch.manual_seed(3)
+    M, N, K = 200, 136, 300
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    out = ops.linear_f32(x, w, bias=bias, residual=res)
+    assert rel_err(out, x.double() @ w.double().t() + bias.double() + res.double()) < 1e-5
+    out2 = ops.linear_f32(x.t().contiguous(), w.t().contiguous(), x_km=True, w_kn=True)
+    assert rel_err(out2, x.double() @ w.double().t()) < 1e-5
+    pre = torch.empty(M, N, device=DEV)
+    out3 = ops.linear_f32(x, w, bias=bias, out_pre=pre, apply_gelu=True)
+    assert rel_err(pre, x.double() @ w.double().t() + bias.double()) < 1e-5
+    assert rel_err(out3, torch.nn.functional.gelu(x.double() @ w.double().t() + bias.double())) < 1e-5
+
+
+# -------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("D", [64, 512, 1024])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(D, out_dtype):
+    torch.manual_seed(4)
+    M = 777
+    x = (torch.randn(M, D, device=DEV) * 2 + 0.5).requires_grad_(True)
+    g = (torch.randn(D, device=DEV) * 0.5 + 1).requires_grad_(True)
+    b = torch.randn(D, device=DEV).requires_grad_(True)
+    y = torch.empty(M, D, device=DEV, dtype=out_dtype)
+    mean = torch.empty(M, device=DEV)
+    rstd = torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x.detach(), g.detach(), b.detach(), y, M=M, D=D, mean=mean, rstd=rstd)
+    ref = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5)
+    assert rel_err(y, ref) < (1e-5 if out_dtype == torch.float32 else 1e-2)
+    dy = torch.randn(M, D, device=DEV)
+    dres = torch.randn(M, D, device=DEV)
+    gx, gg, gb = torch.autograd.grad(ref, (x, g, b), dy.double())
+    dx = torch.empty(M, D, device=DEV)
+    dxb = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    dg = torch.zeros(D, device=DEV)
+    db = torch.zeros(D, device=DEV)
+    cs = torch.zeros(D, device=DEV)
+    ops.layernorm_bwd(dy, x.detach(), mean, rstd, g.detach(), M=M, D=D, dres=dres, dx=dx, dx_bf16=dxb, dgamma=dg,
+                      dbeta=db, colsum=cs)
+    assert rel_err(dx, gx.double() + dres.double()) < 1e-5
+    assert rel_err(dxb, gx.double() + dres.double()) < 1e-2
+    assert rel_err(dg, gg) < 1e-4
+    assert rel_err(db, gb) < 1e-4
+    assert rel_err(cs, (gx.double() + dres.double()).sum(0)) < 1e-4
+
+
+def test_layernorm_row_maps_and_pos_add():
+    """LN over the patch rows written into x[B, n+1, D] at token offset 1 with the pos-embedding add."""
+    torch.manual_seed(5)
+    B, n, D = 3, 10, 128
+    e = torch.randn(B * n, D, device=DEV)
+    g = torch.randn(D, device=DEV)
+    b = torch.randn(D, device=DEV)
+    pos = torch.randn(n + 1, D, device=DEV)
+    cls = torch.randn(D, device=DEV)
+    x = torch.zeros(B, n + 1, D, device=DEV)
+    ops.layernorm_fwd(e, g, b, x, M=B * n, D=D, ymap=(n, n + 1, 1), add=pos, ld_add=D, add_mod=n, add_off=1)
+    ops.cls_row(cls, pos, x, (n + 1) * D, B, D)
+    ref = torch.nn.functional.layer_norm(e, (D,), g, b).view(B, n, D) + pos[1:]
+    ref = torch.cat([(cls + pos[0]).expand(B, 1, D), ref], 1)
+    assert rel_err(x, ref) < 1e-5
+
+
+# ----------------------------------------------------------------------------------- patch gather
+@pytest.mark.parametrize("layout", ["neuro_view", "contiguous"])
+@pytest.mark.parametrize("geom", [(2, 1, 16, 16, 8, 8), (2, 1, 18, 18, 18, 9), (1, 2, 8, 12, 4, 4)])
+def test_patch_gather_bit_exact(layout, geom):
+    B, C, H, W, D_, p = geom
+    torch.manual_seed(6)
+    if layout == "neuro_view":
+        if C != 1:
+            pytest.skip("ViT3DEncoder view has one channel")
+        x = torch.randn(B, H, W, D_, device=DEV)
+        video = x.permute(0, 3, 1, 2).unsqueeze(1)  # [B,1,D,H,W] view, NeuroEncoder.py:201-202
+    else:
+        video = torch.randn(B, C, D_, H, W, device=DEV)
+    ref = rearrange(video, 'b c (f pf) (h p1) (w p2) -> b (f h w) (p1 p2 pf c)', p1=p, p2=p, pf=p)
+    n, P = ref.shape[1], ref.shape[2]
+    raw = torch.empty(B * n, P, device=DEV)
+    ld = (P + 7) // 8 * 8
+    out = torch.empty(B * n, ld, device=DEV)
+    g = torch.randn(P, device=DEV)
+    b = torch.randn(P, device=DEV)
+    mean = torch.empty(B * n, device=DEV)
+    rstd = torch.empty(B * n, device=DEV)
+    ops.patch_gather_ln(video, (p, p, p), g, b, out, raw=raw, mean=mean, rstd=rstd)
+    assert torch.equal(raw.view(B, n, P), ref), "patch index mapping must be bit-exact"
+    lnref = torch.nn.functional.layer_norm(ref.double(), (P,), g.double(), b.double())
+    assert rel_err(out[:, :P], lnref.view(B * n, P)) < 1e-5
+    assert (out[:, P:] == 0).all()
+    # parameter gradients of that LayerNorm
+    dP = torch.randn(B * n, ld, device=DEV)
+    dg = torch.zeros(P, device=DEV)
+    db = torch.zeros(P, device=DEV)
+    ops.patch_ln_param_grad(video, (p, p, p), dP, mean, rstd, dg, db)
+    xh = torch.nn.functional.layer_norm(ref.double(), (P,)).view(B * n, P)
+    assert rel_err(dg, (dP[:, :P].double() * xh).sum(0)) < 1e-4
+    assert rel_err(db, dP[:, :P].double().sum(0)) < 1e-4
+
+
+# -------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, B, N, H, hd):
+    q, k, v = qkv.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    p = s.softmax(-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * hd)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 385, 8), (1, 64, 2), (3, 9, 2), (1, 1729, 1)])
+def test_attention_fwd_bwd(B, N, H):
+    hd = 64
+    torch.manual_seed(7)
+    qkv = torch.randn(B * N, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    o = torch.empty(B * N, H * hd, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=DEV)
+    ops.attention_fwd(qkv, o, lse, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5)
+    qd = qkv.double().requires_grad_(True)
+    oref, lref = _attn_ref(qd, B, N, H, hd)
+    assert rel_err(o, oref) < 1e-2
+    assert rel_err(lse, lref) < 1e-3
+    dO = torch.randn(B * N, H * hd, device=DEV).to(torch.bfloat16)
+    gref, = torch.autograd.grad(oref, qd, dO.double())
+    dqkv = torch.zeros_like(qkv)
+    ws = torch.empty(B * H * N, device=DEV)
+    ops.attention_bwd(qkv, o, dO, lse, ws, dqkv, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5)
+    inner = H * hd
+    for nm, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
+        assert rel_err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
+
+
+def test_softmax_fwd_bwd():
+    torch.manual_seed(8)
+    rows, n = 333, 385
+    s = torch.randn(rows, n, device=DEV) * 3
+    ref = s.double().requires_grad_(True)
+    p = ref.softmax(-1)
+    P = s.clone()
+    ops.softmax_fwd(P, rows, n)
+    assert rel_err(P, p) < 1e-5
+    dP = torch.randn(rows, n, device=DEV)
+    g, = torch.autograd.grad(p, ref, dP.double())
+    ops.softmax_bwd(P, dP, rows, n)
+    assert rel_err(dP, g) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------- helpers
+def test_cast_colsum_batchsum_pool():
+    torch.manual_seed(9)
+    w = torch.randn(300, 136, device=DEV)
+    wb, wt = ops.cast_transpose_bf16(w, out=torch.empty(300, 136, device=DEV, dtype=torch.bfloat16))
+    assert torch.equal(wb, w.to(torch.bfloat16)) and torch.equal(wt, w.t().contiguous().to(torch.bfloat16))
+    v = torch.randn(1027, device=DEV)
+    assert torch.equal(ops.cast_bf16(v), v.to(torch.bfloat16))
+    x = torch.randn(1000, 200, device=DEV)
+    out = torch.ones(200, device=DEV)
+    ops.colsum(x, out)
+    assert rel_err(out, x.double().sum(0) + 1) < 1e-5
+    xb = x.to(torch.bfloat16)
+    out.zero_()
+    ops.colsum(xb, out)
+    assert rel_err(out, xb.double().sum(0)) < 1e-5
+    y = torch.randn(7, 50, 32, device=DEV)
+    acc = torch.zeros(50 * 32, device=DEV)
+    ops.batch_sum(y, 50 * 32, acc, 7, 50 * 32)
+    assert rel_err(acc, y.double().sum(0).flatten()) < 1e-5
+    pooled = torch.empty(7, 32, device=DEV)
+    ops.mean_pool_fwd(y, pooled, 7, 50, 32)
+    assert rel_err(pooled, y.double().mean(1)) < 1e-5
+    dx = torch.empty_like(y)
+    ops.mean_pool_bwd(pooled, dx, None, 7, 50, 32)
+    assert rel_err(dx, (pooled / 50).unsqueeze(1).expand_as(y)) < 1e-6
+
+
+# --------------------------------------------------------------------------------------- temporal
+def test_temporal_head_matches_torch():
+    from neurovit_b200.functional import pack_temporal_params, TEMPORAL_KEYS
+    torch.manual_seed(10)
+    B, T, F = 5, 140, 2048
+    layer = torch.nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True, dropout=0.0).to(DEV).double()
+    enc = torch.nn.TransformerEncoder(layer, num_layers=1, enable_nested_tensor=False)
+    head = torch.nn.Linear(2, 2).to(DEV).double()
+    x = torch.randn(B, T, 2, device=DEV).double().requires_grad_(True)
+    ref = head(enc(x).mean(1))
+    dout = torch.randn(B, 2, device=DEV).double()
+    named = {"temporal." + k: v for k, v in enc.layers[0].named_parameters()}
+    named.update({"head.weight": head.weight, "head.bias": head.bias})
+    tensors = [named[k] for k in TEMPORAL_KEYS]
+    grads = torch.autograd.grad(ref, [x] + tensors, dout)
+    params = pack_temporal_params([t.detach().float() for t in tensors])
+    out = torch.empty(B, 2, device=DEV)
+    saved = torch.empty(B, T * 4, device=DEV)
+    ops.temporal_fwd(x.detach().float(), params, out, saved, B, T, F)
+    assert rel_err(out, ref) < 1e-4
+    ws = torch.empty(B, params.numel(), device=DEV)
+    dx = torch.empty(B, T, 2, device=DEV)
+    ops.temporal_bwd(x.detach().float(), params, saved, dout.float(), ws, dx, B, T, F)
+    gflat = torch.cat([g.flatten() for g in grads[1:]])
+    assert rel_err(ws.double().sum(0), gflat) < 1e-3
+    assert rel_err(dx, grads[0]) < 1e-3
