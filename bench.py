@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: ViT3D training-step throughput (volumes/sec) on synthetic 1x64x64x48 volumes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference] [--config cfgA|cfgB]
+
+A "step" = forward + CrossEntropy + backward (+ bucketed gradient all-reduce for N>1) + AdamW step on one
+batch of `--batch` volumes per GPU (BASELINE.json configs[1]: batch 64, patch 8, 385 tokens, model dims of
+NeuroEncoder.py:181-195). N>1 is launched by torchrun, one rank per GPU (weak scaling: per-GPU batch fixed).
+Rank 0 prints ONE JSON line (see the driver contract in the task statement).
+
+--impl reference times the reference's CPU path (the oracle port of src/models/vit_3d.py + the step of
+src/Trainer.py:65-76, fp32, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---- workload definitions (BASELINE.json configs) ------------------------------------------------------
+CONFIGS = {
+    # volume [H, W, D] as delivered by the datasets (Trainer.py:66), model dims hard-coded in NeuroEncoder.py:181-195
+    "cfgA": dict(vol=(64, 64, 48), patch=8, tokens=385, gflop_fwd_bwd=93.469),
+    "cfgB": dict(vol=(96, 96, 96), patch=8, tokens=1729, gflop_fwd_bwd=505.432),
+}
+MODEL = dict(dim=1024, depth=6, heads=8, dim_head=64, mlp_dim=2048, num_classes=2)
+DROPOUT = 0.0  # the fused path implements p=0 this round; the reference arm runs the same p
+
+
+def vit_ctor(cfg):
+    H, W, D = cfg["vol"]
+    return dict(channels=1, image_size=(H, W), image_patch_size=cfg["patch"], frames=D,
+                frame_patch_size=cfg["patch"], num_classes=MODEL["num_classes"], dim=MODEL["dim"],
+                depth=MODEL["depth"], heads=MODEL["heads"], mlp_dim=MODEL["mlp_dim"], dim_head=MODEL["dim_head"],
+                dropout=DROPOUT, emb_dropout=DROPOUT, pool="cls")
+
+
+def gemm_flops_per_volume(cfg):
+    """Algorithmic FLOPs of the linear-layer GEMMs only (2*M*N*K; bwd = 2x fwd, patch embed 1x), per volume —
+    the work the dominant kernel (gemm_tc_kernel) does. SURVEY §8d / BASELINE.md §2."""
+    N = cfg["tokens"]
+    n = N - 1
+    p3 = cfg["patch"] ** 3
+    D, inner, mlp = MODEL["dim"], MODEL["heads"] * MODEL["dim_head"], MODEL["mlp_dim"]
+    per_layer = 2 * N * (D * 3 * inner + inner * D + 2 * D * mlp)
+    fwd = MODEL["depth"] * per_layer
+    patch = 2 * n * p3 * D
+    return 3 * fwd + 2 * patch  # patch: fwd + wgrad + the dgrad used for the patch-LN parameter grads is extra work
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured")
+    except Exception:
+        return dict(tflops=1400.0, hbm=6650.0, src="fallback")  # B200_PROFILING.md fallback (sustained)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference arm / cpu_baseline: oracle port on the host cores ------------------------------------
+def cpu_reference_step_fn(cfg, batch, seed=42):
+    """Returns (step_fn, n_volumes): one fp32 CPU training step of the oracle port (forward, CE, backward, AdamW)."""
+    from oracle import vit3d_oracle as O
+    from neurovit_b200.vit_3d import ViT  # parameter container only (same init as the reference under the seed)
+    torch.manual_seed(seed)
+    m = ViT(**vit_ctor(cfg))
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01)
+    H, W, D = cfg["vol"]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, H, W, D, generator=g)
+    y = torch.randint(0, 2, (batch,), generator=g)
+    p = cfg["patch"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logits = O.vit3d_forward(params, O.neuro_view(x), patch=(p, p, p), heads=MODEL["heads"],
+                                 dim_head=MODEL["dim_head"])
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step, batch
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = args.ref_batch
+    step, nvol = cpu_reference_step_fn(cfg, batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = nvol * args.steps / dt
+    sample = f"{nvol} volume(s)/step x {args.steps} steps, fp32, dropout {DROPOUT}, oracle port of vit_3d.py + Trainer.py:65-76"
+    line = {"impl": "reference", "metric": "ViT3D training volumes/sec (fwd+bwd+AdamW)", "value": v,
+            "unit": "volumes/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, cfg, batch), "batch_per_step": batch, "dropout": DROPOUT},
+            "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, cfg, batch):
+    H, W, D = cfg["vol"]
+    return (f"ViT3D training step, batch {batch} synthetic 1x{H}x{W}x{D} volumes, patch {cfg['patch']} "
+            f"({cfg['tokens'] - 1} patches + cls), dim 1024 depth 6 heads 8 mlp 2048")
+
+
+# ---- our arm ------------------------------------------------------------------------------------------
+def run_ours(args, cfg):
+    import torch.distributed as dist
+    from neurovit_b200 import _lib, ops
+    from neurovit_b200.NeuroEncoder import ViT3DEncoder
+    from neurovit_b200.trainer import DataParallelTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; neurovit_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device(local)
+
+    H, W, D = cfg["vol"]
+    B = args.batch
+    torch.manual_seed(42)
+    enc = ViT3DEncoder({"DEVICE": dev, "TRAINING_DROPOUT": DROPOUT, "TRAINING_VIT_INPUT_SIZE": H,
+                        "GRADCAM_CUBE_SIZE": 8, "TRAINING_VIT_PATCH_SIZE": cfg["patch"], "DATASET_NAME": "adni"}) \
+        if H == W == D else None
+    if enc is None:  # non-cubic volume (64x64x48): ViT3DEncoder hard-codes frames=image_size, so build ViT directly
+        from neurovit_b200.vit_3d import ViT
+
+        class Enc(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.vit3d = ViT(**vit_ctor(cfg))
+
+            def forward(self, x):  # same layout adapter as ViT3DEncoder.forward (NeuroEncoder.py:200-204)
+                return self.vit3d(x.permute(0, 3, 1, 2).unsqueeze(1))
+
+        enc = Enc().to(dev)
+    enc.train()
+    trainer = DataParallelTrainer(enc, lr=1e-4, weight_decay=0.01)
+
+    g = torch.Generator().manual_seed(42 + rank)
+    n_buf = 3  # rotate host/device input buffers; one batch (50 MB) + activations (GBs) far exceed the 126 MB L2
+    host_x = [torch.randn(B, H, W, D, generator=g).pin_memory() for _ in range(n_buf)]
+    host_y = [torch.randint(0, 2, (B,), generator=g).pin_memory() for _ in range(n_buf)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(loop_fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop_fn(steps)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident_loop(steps):
+        for i in range(steps):
+            trainer.step(dev_x[i % n_buf], dev_y[i % n_buf])
+
+    losses = []
+
+    def e2e_loop(steps):
+        for i in range(steps):
+            x = host_x[i % n_buf].to(dev, non_blocking=True)
+            y = host_y[i % n_buf].to(dev, non_blocking=True)
+            loss = trainer.step(x, y)
+            losses.append(loss.item())  # device -> host read of the step's result
+
+    resident_loop(args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ops.PROFILE.reset()
+    ops.PROFILE.enabled = not args.no_kernel_events
+    _lib.LAUNCHES.reset()
+    ms = timed(resident_loop, args.steps)
+    launches = _lib.LAUNCHES.count
+    ops.PROFILE.enabled = False
+    clocks = sampler.stop() if sampler else None
+    gemm_ms, gemm_flops, gemm_calls = ops.PROFILE.summary()
+    e2e_loop(min(2, args.warmup))
+    ms_e2e = timed(e2e_loop, args.steps)
+
+    if rank == 0:
+        peaks = load_peaks()
+        vps = world * B * args.steps / (ms * 1e-3)
+        vps_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        model_tflops = vps / world * cfg["gflop_fwd_bwd"] / 1e3
+        line = {
+            "metric": "ViT3D training volumes/sec (fwd+bwd+AdamW)", "value": vps, "unit": "volumes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args, cfg, B), "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "dropout": DROPOUT, "optimizer": "AdamW(fused)",
+                       "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2; 3 rotating input buffers",
+                       "model_tflops_per_gpu": model_tflops,
+                       "model_frac_of_peak": model_tflops / peaks["tflops"]},
+            "clocks": clocks,
+            "e2e": {"value": vps_e2e, "unit": "volumes/s", "h2d_bytes_per_step": B * H * W * D * 4 + B * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 linear fwd/dgrad/wgrad)",
+                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                         "peak_source": f"{peaks['src']} bf16_tflops_sustained",
+                         "launches_timed": gemm_calls, "avg_launch_ms": gemm_ms / max(gemm_calls, 1),
+                         "share_of_step": gemm_ms / ms if ms > 0 else None},
+        }
+        if not args.skip_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            step, nvol = cpu_reference_step_fn(cfg, 1)
+            step()
+            t0 = time.perf_counter()
+            n = 0
+            while n < 3 or (time.perf_counter() - t0 < 10 and n < 40):
+                step()
+                n += 1
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nvol * n / dt, "unit": "volumes/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} steps of 1 volume (fwd+CE+bwd+AdamW), fp32, torch CPU, oracle port"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="volumes per GPU per step")
+    ap.add_argument("--config", default="cfgA", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=2, help="volumes per CPU reference step (bounded sample)")
+    ap.add_argument("--no-kernel-events", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        if args.steps > 6:
+            args.steps = 6  # bounded sample: the whole run must end within minutes on the host cores
+        if args.warmup > 2:
+            args.warmup = 2
+        run_reference(args, cfg)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

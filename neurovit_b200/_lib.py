@@ -104,5 +104,20 @@ def require_device(device_index: int) -> None:
     _device_ok.add(device_index)
 
 
+class _LaunchCounter:
+    """Counts the CUDA kernels launched through the C ABI (bench.py reports it as `gpu_launches`)."""
+    KERNELS_PER_CALL = {"nv_attention_bwd": 3, "nv_version": 0, "nv_device_check": 0}
+
+    def __init__(self):
+        self.count = 0
+
+    def reset(self):
+        self.count = 0
+
+
+LAUNCHES = _LaunchCounter()
+
+
 def call(name: str, *args) -> None:
     check(getattr(load(), name)(*args), name)
+    LAUNCHES.count += _LaunchCounter.KERNELS_PER_CALL.get(name, 1)

@@ -613,3 +613,67 @@ class TemporalHeadFn(torch.autograd.Function):
             grads.append(flat[off:off + n].view(s))
             off += n
         return (dx, None, *grads)
+
+
+class TemporalSeqFn(torch.autograd.Function):
+    """TemporalTransformer.forward on its own: [B, T, 2] -> [B, T, 2] (NeuroEncoder.py:213-216)."""
+
+    @staticmethod
+    def forward(ctx, x, eps, *params):
+        B, T, E = x.shape
+        if E != 2:
+            raise ValueError("the temporal kernel implements d_model=2 (NeuroEncoder.py:211)")
+        F = params[4].shape[0]
+        x = x.float().contiguous()
+        dev = x.device
+        ident = [torch.eye(2, device=dev, dtype=F32), torch.zeros(2, device=dev, dtype=F32)]  # unused head slot
+        packed = pack_temporal_params(list(params) + ident)
+        seq = torch.empty(B, T, 2, device=dev, dtype=F32)
+        saved = torch.empty(B, T * 4, device=dev, dtype=F32)
+        ops.temporal_fwd(x, packed, None, saved, B, T, F, eps, seq_out=seq)
+        ctx.save_for_backward(x, packed, saved)
+        ctx.cfg = (B, T, F, eps, [p.shape for p in params])
+        return seq
+
+    @staticmethod
+    def backward(ctx, dseq):
+        x, packed, saved = ctx.saved_tensors
+        B, T, F, eps, shapes = ctx.cfg
+        dev = x.device
+        ws = torch.empty(B, packed.numel(), device=dev, dtype=F32)
+        dx = torch.empty(B, T, 2, device=dev, dtype=F32) if ctx.needs_input_grad[0] else None
+        ops.temporal_bwd(x, packed, saved, None, ws, dx, B, T, F, eps, dseq=dseq.float().contiguous())
+        flat = torch.zeros(packed.numel(), device=dev, dtype=F32)
+        ops.batch_sum(ws, packed.numel(), flat, B, packed.numel())
+        grads, off = [], 0
+        for s in shapes:
+            n = math.prod(s)
+            grads.append(flat[off:off + n].view(s))
+            off += n
+        return (dx, None, *grads)
+
+
+class SmallLinearFn(torch.autograd.Function):
+    """fp32 nn.Linear on the CUDA-core GEMM (ProjectionHead called on its own, NeuroEncoder.py:226-228)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).float().contiguous()
+        out = ops.linear_f32(x2, w.detach(), bias=None if b is None else b.detach())
+        ctx.save_for_backward(x2, w)
+        ctx.shape = shape
+        ctx.has_bias = b is not None
+        return out.view(*shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, w.shape[0]).float().contiguous()
+        dx = ops.linear_f32(dy2, w.detach(), w_kn=True).view(ctx.shape)
+        dw = ops.linear_f32(dy2, x2, x_km=True, w_kn=True)
+        db = None
+        if ctx.has_bias:
+            db = torch.zeros(w.shape[0], device=dy.device, dtype=F32)
+            ops.colsum(dy2, db)
+        return dx, dw, db

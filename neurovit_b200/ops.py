@@ -12,6 +12,42 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+class _KernelProfile:
+    """CUDA-event timing of the dominant kernel (the tcgen05 GEMM) on the launching stream, used by bench.py
+    for the roofline object. Off by default; events are only recorded while `enabled`."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = []
+
+    def reset(self):
+        self.events = []
+
+    def region(self, flops):
+        prof = self
+
+        class _R:
+            def __enter__(self_r):
+                self_r.e0 = torch.cuda.Event(enable_timing=True)
+                self_r.e1 = torch.cuda.Event(enable_timing=True)
+                self_r.e0.record()
+
+            def __exit__(self_r, *exc):
+                self_r.e1.record()
+                prof.events.append((self_r.e0, self_r.e1, flops))
+                return False
+
+        return _R()
+
+    def summary(self):
+        """(total ms, total flops, launches) — call after torch.cuda.synchronize()."""
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.events)
+        return ms, sum(f for _, _, f in self.events), len(self.events)
+
+
+PROFILE = _KernelProfile()
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -54,6 +90,13 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     if bias is not None:
         assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
     ld = lambda t: 0 if t is None else t.stride(0)
+    if PROFILE.enabled:
+        with PROFILE.region(2.0 * M * N * K):
+            _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
+                      _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
+                      _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), int(apply_gelu), int(accumulate),
+                      float(alpha), int(k_splits), int(block_n), _stream())
+        return
     _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
               _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
               _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), int(apply_gelu), int(accumulate),

@@ -214,6 +214,8 @@ class ViT(nn.Module, _PrecisionMixin):
             raise ValueError(f"Shape mismatch: volume {tuple(video.shape[2:])} is not divisible by the patch size "
                              f"{(pf, p1, p2)}")
         _check_dropout(self, self.dropout.p)
+        if video.shape[0] == 0:  # empty batch: nothing to launch
+            return video.new_zeros((0, self.mlp_head[1].out_features), dtype=torch.float32)
         pe = self.to_patch_embedding
         if pe[1].weight.numel() != video.shape[1] * pf * p1 * p2:
             raise ValueError(f"Shape mismatch: patch_dim {video.shape[1] * pf * p1 * p2} != LayerNorm dim "

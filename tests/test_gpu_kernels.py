@@ -259,7 +259,12 @@ def test_temporal_head_matches_torch():
     layer = torch.nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True, dropout=0.0).to(DEV).double()
     enc = torch.nn.TransformerEncoder(layer, num_layers=1, enable_nested_tensor=False)
     head = torch.nn.Linear(2, 2).to(DEV).double()
-    x = torch.randn(B, T, 2, device=DEV).double().requires_grad_(True)
+    # keep both 2-element LayerNorms out of saturation (|x0 - x1| ~ sqrt(eps)), otherwise every gradient is
+    # the round-off residue of an exact cancellation and nothing meaningful is compared
+    with torch.no_grad():
+        layer.norm1.weight.mul_(0.003)
+        layer.norm1.bias.zero_()
+    x = (0.005 * torch.randn(B, T, 2, device=DEV)).double().requires_grad_(True)
     ref = head(enc(x).mean(1))
     dout = torch.randn(B, 2, device=DEV).double()
     named = {"temporal." + k: v for k, v in enc.layers[0].named_parameters()}

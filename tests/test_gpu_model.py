@@ -1,0 +1,172 @@
+"""Module-level parity on the GPU: the drop-in ViT / NeuroEncoder (CUDA kernels through the C ABI) against
+the CPU oracle on the same seeded inputs and weights, and against the committed golden fixtures produced
+by the unmodified reference. Tolerances from BASELINE.json north_star: 2e-2 relative (bf16 operands, fp32
+accumulation), 1e-5 for the fp32 verification mode (logits; gradients 1e-4: they pass through fp32 atomics
+and long reductions), measured as max|a-b| / max|b| per tensor."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("CUDA device required", allow_module_level=True)
+
+from neurovit_b200.vit_3d import ViT  # noqa: E402
+from neurovit_b200.NeuroEncoder import NeuroEncoder  # noqa: E402
+from oracle import vit3d_oracle as O  # noqa: E402  (checker only)
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda"
+TOL = {"bf16": dict(logits=2e-2, grad=2e-2), "fp32": dict(logits=1e-5, grad=1e-4)}
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def _golden_vit(name, ctor):
+    g = np.load(os.path.join(GOLD, name))
+    m = ViT(**ctor)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    m.load_state_dict(sd, strict=True)  # keys must match the reference 1:1
+    return g, m.to(DEV).eval()
+
+
+SMALL = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=2, dim=64, depth=2,
+             heads=2, mlp_dim=128, channels=1, dim_head=64)
+P4 = dict(image_size=(8, 12), image_patch_size=4, frames=4, frame_patch_size=4, num_classes=3, dim=64, depth=1,
+          heads=2, mlp_dim=64, channels=2, dim_head=64, pool="mean")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,ctor", [("vit3d_small.npz", SMALL), ("vit3d_p4.npz", P4)])
+def test_vit_matches_reference_golden(name, ctor, mode):
+    g, m = _golden_vit(name, ctor)
+    m.set_precision(mode)
+    video = torch.from_numpy(g["video"]).to(DEV)
+    labels = torch.from_numpy(g["labels"]).to(DEV)
+    logits = m(video)
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    tol = TOL[mode]
+    assert rel(logits, g["logits"]) < tol["logits"]
+    worst = {}
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        worst[k] = rel(p.grad, g["grad." + k])
+    bad = {k: v for k, v in worst.items() if v >= tol["grad"]}
+    assert not bad, f"gradient mismatch ({mode}): {bad}"
+
+
+def _cfg(dim, tmp, grid=16, patch=8, precision="bf16"):
+    return {"DEVICE": DEV, "TRAINING_DIM": dim, "TRAINING_DROPOUT": 0.0, "TRAINING_VIT_INPUT_SIZE": grid,
+            "GRADCAM_CUBE_SIZE": 8, "TRAINING_VIT_PATCH_SIZE": patch, "DATASET_NAME": "adni",
+            "GLOBAL_BASE_PATH": tmp, "BEST_MODEL_PATH": "best.pth", "GRADCAM_THRESHOLD": 10, "GRADCAM_SLICE_DIM": 0,
+            "GRADCAM_SLICE_IDX": 3, "PRECISION": precision}
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_neuroencoder_3d_golden_with_gradcam_hooks(tmp_path, mode):
+    """Full-size model dims (1024/6/8/2048) through ViT3DEncoder's permuted view, with the Grad-CAM hooks of
+    NeuroEncoder.py:70-82 live on layers[-1][0].norm."""
+    g = np.load(os.path.join(GOLD, "neuro3d.npz"))
+    torch.manual_seed(1234)  # same seed as oracle/gen_golden.py: identical initial weights (checksum pinned)
+    m = NeuroEncoder(_cfg(3, str(tmp_path), precision=mode)).eval()
+    checksum = float(sum(v.double().sum() for v in m.state_dict().values()))
+    assert abs(checksum - float(g["sd_checksum"][0])) < 1e-4
+    x = torch.from_numpy(g["x"]).to(DEV)
+    logits = m(x)
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(g["labels"]).to(DEV))
+    loss.backward()
+    tol = TOL[mode]
+    assert rel(logits, g["logits"]) < tol["logits"]
+    params = dict(m.named_parameters())
+    for k in [f[5:] for f in g.files if f.startswith("grad.")]:
+        assert rel(params[k].grad, g["grad." + k]) < tol["grad"] * 2, k
+    gn = float(sum((p.grad.double() ** 2).sum() for p in m.parameters()) ** 0.5)
+    assert abs(gn - float(g["gradnorm"][0])) / float(g["gradnorm"][0]) < tol["grad"]
+    # hooks observed the LayerNorm output and its gradient, on the host, like the reference
+    assert m.activations.device.type == "cpu" and tuple(m.activations.shape) == (2, 9, 1024)
+    assert rel(m.activations[:, :3, :8], g["act_hook"]) < tol["logits"] * 5
+    assert rel(m.gradients[:, :3, :8], g["grad_hook"]) < tol["grad"] * 2
+
+
+def test_neuroencoder_gradcam_map(tmp_path):
+    torch.manual_seed(1234)
+    m = NeuroEncoder(_cfg(3, str(tmp_path), precision="fp32")).eval()
+    x = torch.randn(1, 16, 16, 16, device=DEV)
+    cam, cls = m.get_attention_map(x)
+    assert tuple(cam.shape) == (16, 16, 16) and cls.shape == (1,)
+    assert torch.isfinite(cam).all() and cam.min() >= 0 and cam.max() <= 1 + 1e-6
+    img, attn = m.visualize_slice(cam, x)
+    assert img.shape == (16, 16) and tuple(attn.shape) == (16, 16)
+    assert m.activations.shape[1] == 9 and m.gradients.shape == m.activations.shape
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_neuroencoder_4d_golden(tmp_path, mode):
+    g = np.load(os.path.join(GOLD, "neuro4d.npz"))
+    torch.manual_seed(1234)
+    m3 = NeuroEncoder(_cfg(3, str(tmp_path)))
+    torch.save(m3.state_dict(), os.path.join(str(tmp_path), "best.pth"))
+    torch.manual_seed(4321)
+    m = NeuroEncoder(_cfg(4, str(tmp_path), precision=mode)).eval()
+    for k, v in m.state_dict().items():
+        if not k.startswith("volume_encoder."):
+            assert np.array_equal(v.cpu().numpy(), g["sd." + k]), k
+    assert not any(p.requires_grad for p in m.volume_encoder.parameters())
+    out = m(torch.from_numpy(g["x"]).to(DEV))
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(g["labels"]).to(DEV))
+    loss.backward()
+    # the frozen ViT's 2 logits feed LayerNorms over 2 elements; the bf16 ViT perturbs its inputs by ~1e-2
+    assert rel(out, g["out"]) < (5e-2 if mode == "bf16" else 1e-4)
+    params = dict(m.named_parameters())
+    for k in [f[5:] for f in g.files if f.startswith("grad.")]:
+        assert params[k].grad is not None, k
+        if "norm2" in k or "projection_head" in k:  # the well-conditioned gradients (see tests/test_oracle.py)
+            assert rel(params[k].grad, g["grad." + k]) < (5e-2 if mode == "bf16" else 1e-3), k
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vit_vs_oracle_ragged_tokens(mode):
+    """cfgA geometry (64x64x48 / patch 8 -> 385 tokens, not a multiple of any tile) at reduced width, against
+    the CPU oracle run on the same weights; direct ViT call with a contiguous [B,1,F,H,W] tensor."""
+    torch.manual_seed(11)
+    ctor = dict(image_size=64, image_patch_size=8, frames=48, frame_patch_size=8, num_classes=2, dim=128, depth=2,
+                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    m = ViT(**ctor)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    video = torch.randn(2, 1, 48, 64, 64)
+    labels = torch.tensor([1, 0])
+    ref_logits, ref_loss, ref_grads = O.vit3d_loss_and_grads(sd, video, labels, patch=(8, 8, 8), heads=2)
+    m = m.to(DEV).eval().set_precision(mode)
+    logits = m(video.to(DEV))
+    torch.nn.functional.cross_entropy(logits, labels.to(DEV)).backward()
+    tol = TOL[mode]
+    assert rel(logits, ref_logits) < tol["logits"]
+    bad = {k: rel(p.grad, ref_grads[k]) for k, p in m.named_parameters() if rel(p.grad, ref_grads[k]) >= tol["grad"]}
+    assert not bad, bad
+
+
+def test_errors_and_contract():
+    m = ViT(**SMALL).to(DEV)
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 1, 16, 16, 12, device=DEV))          # not divisible by the patch size
+    with pytest.raises(Exception):
+        m(torch.randn(1, 1, 16, 16, 16))                       # CPU tensor: no CPU fallback
+    with pytest.raises(AssertionError):
+        ViT(**{**SMALL, "pool": "max"})
+    # smaller volume than configured: pos_embedding is sliced to n+1 (vit_3d.py:118)
+    out = m.eval()(torch.randn(1, 1, 8, 16, 16, device=DEV))
+    assert out.shape == (1, 2)
+    # B = 0 (empty batch) is a no-op that keeps shapes
+    assert m(torch.randn(0, 1, 16, 16, 16, device=DEV)).shape == (0, 2)

@@ -1,0 +1,114 @@
+"""Pin the oracle (oracle/vit3d_oracle.py) against golden vectors produced by the unmodified reference
+(oracle/gen_golden.py, run in the build container). CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit3d_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def _sd(g, prefix="sd."):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+@pytest.mark.parametrize("tag", ["c1_p8", "c2_p4", "c1_p9"])
+def test_patch_index_closed_form_is_bit_exact(tag):
+    g = _load("patch_index.npz")
+    B, C, Fr, H, W, p = g[tag + "_shape"].tolist()
+    v = np.arange(B * C * Fr * H * W, dtype=np.int64).reshape(B, C, Fr, H, W)
+    assert np.array_equal(O.patchify_np(v, p, p, p), g[tag + "_contig"])
+    if C == 1:
+        x = torch.arange(B * H * W * Fr, dtype=torch.int64).reshape(B, H, W, Fr)
+        view = O.neuro_view(x)
+        got = O.patchify_np(view.numpy(), p, p, p)
+        assert np.array_equal(got, g[tag + "_view"])
+        # through the ViT3DEncoder view a patch is a row-major p^3 box of x[b, h, w, d]
+        n_h = H // p
+        t = 1 * (n_h * (W // p)) + 0 * (W // p) + 1 if Fr // p > 1 and W // p > 1 else 0
+        di, rem = divmod(t, n_h * (W // p))
+        hi, wi = divmod(rem, W // p)
+        box = x[0, hi * p:(hi + 1) * p, wi * p:(wi + 1) * p, di * p:(di + 1) * p].reshape(-1).numpy()
+        assert np.array_equal(got[0, t], box)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("vit3d_small.npz", dict(patch=(8, 8, 8), heads=2, dim_head=64, pool="cls")),
+    ("vit3d_p4.npz", dict(patch=(4, 4, 4), heads=2, dim_head=64, pool="mean")),
+])
+def test_vit3d_oracle_matches_reference(name, kw):
+    g = _load(name)
+    sd = _sd(g)
+    video = torch.from_numpy(g["video"])
+    labels = torch.from_numpy(g["labels"])
+    logits, loss, grads = O.vit3d_loss_and_grads(sd, video, labels, **kw)
+    assert rel(logits, g["logits"]) < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    for k in sd:
+        assert rel(grads[k], g["grad." + k]) < 2e-4, k
+
+
+def _neuro_sd(seed, dim, tmp):
+    from neurovit_b200.NeuroEncoder import NeuroEncoder
+    cfg = {"DEVICE": "cpu", "TRAINING_DIM": dim, "TRAINING_DROPOUT": 0.0, "TRAINING_VIT_INPUT_SIZE": 16,
+           "GRADCAM_CUBE_SIZE": 8, "TRAINING_VIT_PATCH_SIZE": 8, "DATASET_NAME": "adni", "GLOBAL_BASE_PATH": tmp,
+           "BEST_MODEL_PATH": "best.pth", "GRADCAM_THRESHOLD": 10, "GRADCAM_SLICE_DIM": 0, "GRADCAM_SLICE_IDX": 0}
+    torch.manual_seed(seed)
+    return NeuroEncoder(cfg)
+
+
+def test_neuroencoder_3d_oracle_and_seeded_weights(tmp_path):
+    g = _load("neuro3d.npz")
+    m = _neuro_sd(1234, 3, str(tmp_path))
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    # the drop-in module tree initialises exactly like the reference under the same seed
+    assert len(sd) == 78
+    checksum = float(sum(v.double().sum() for v in sd.values()))
+    assert abs(checksum - float(g["sd_checksum"][0])) < 1e-6
+    x = torch.from_numpy(g["x"])
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits = O.neuroencoder_forward(leaf, x, patch=8)
+    assert rel(logits.detach(), g["logits"]) < 1e-5
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(g["labels"]))
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    keys = [k[5:] for k in g.files if k.startswith("grad.")]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys])
+    for k, gr in zip(keys, grads):
+        assert rel(gr, g["grad." + k]) < 5e-4, k
+
+
+def test_neuroencoder_4d_oracle(tmp_path):
+    g3 = _neuro_sd(1234, 3, str(tmp_path))
+    torch.save(g3.state_dict(), os.path.join(str(tmp_path), "best.pth"))
+    g = _load("neuro4d.npz")
+    m4 = _neuro_sd(4321, 4, str(tmp_path))
+    sd = {k: v.detach() for k, v in m4.state_dict().items()}
+    for k in g.files:  # temporal / projection weights initialise identically to the reference
+        if k.startswith("sd."):
+            assert np.array_equal(sd[k[3:]].numpy(), g[k]), k
+    assert len([k for k in sd if not k.startswith("volume_encoder.")]) == 14
+    leaf = {k: (v.clone().requires_grad_(True) if not k.startswith("volume_encoder.") else v) for k, v in sd.items()}
+    out = O.neuroencoder_forward(leaf, torch.from_numpy(g["x"]), patch=8, training_dim=4)
+    assert rel(out.detach(), g["out"]) < 1e-5
+    loss = torch.nn.functional.cross_entropy(out, torch.from_numpy(g["labels"]))
+    keys = [k[5:] for k in g.files if k.startswith("grad.")]
+    assert len(keys) == 14
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys])
+    for k, gr in zip(keys, grads):
+        # LayerNorm over 2 elements saturates (xhat = +-1), so every gradient upstream of norm2 is the fp32
+        # round-off residue of an exact cancellation (~1e-15 here): those only agree to a few percent between
+        # any two fp32 evaluation orders. Well-conditioned gradients are held to 1e-3.
+        tol = 1e-3 if ("norm2" in k or "projection_head" in k) else 0.2
+        assert rel(gr, g["grad." + k]) < tol, k

@@ -1,0 +1,87 @@
+"""Host-side logic of the data-parallel step (neurovit_b200/trainer.py) on CPU with the gloo backend,
+world_size 2: batch sharding, flat-gradient bucketing, hook-driven bucket all-reduce, and equality of the
+averaged shard gradients with the full-batch gradients. The model here is a plain torch module — the
+trainer is model-agnostic; the CUDA model itself has no CPU path."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neurovit_b200.trainer import DataParallelTrainer, FlatGradBuckets, shard_batch
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(12, 32), torch.nn.GELU(), torch.nn.LayerNorm(32),
+                               torch.nn.Linear(32, 16), torch.nn.GELU(), torch.nn.Linear(16, 2))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(1)
+        X = torch.randn(8, 12)
+        Y = torch.randint(0, 2, (8,))
+        m = _model()
+        tr = DataParallelTrainer(m, optimizer=torch.optim.SGD(m.parameters(), lr=0.0), bucket_mb=0)
+        assert len(tr.buckets.buckets) == len(list(m.parameters()))  # bucket_mb=0: one bucket per parameter
+        loss = tr.step(shard_batch(X, rank, world), shard_batch(Y, rank, world))
+        grads = [p.grad.clone() for p in m.parameters()]
+        # every grad is still a view into the flat buffer, laid out in reverse parameter order
+        flat = tr.buckets.flat
+        off = 0
+        for p in reversed(list(m.parameters())):
+            assert p.grad.data_ptr() == flat.data_ptr() + 4 * off
+            off += p.numel()
+        q.put((rank, float(loss), [g.numpy() for g in grads]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_step_world2_gloo_matches_full_batch():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process full batch
+    torch.manual_seed(1)
+    X = torch.randn(8, 12)
+    Y = torch.randint(0, 2, (8,))
+    m = _model()
+    torch.nn.functional.cross_entropy(m(X), Y).backward()
+    full = [p.grad.numpy() for p in m.parameters()]
+    for rank, loss, grads in res:
+        for g, f in zip(grads, full):
+            assert abs(g - f).max() < 1e-6, "averaged shard gradients must equal the full-batch gradients"
+    assert abs(sum(r[1] for r in res) / world - float(torch.nn.functional.cross_entropy(_model()(X), Y))) < 1e-6
+
+
+def test_shard_batch_and_buckets_single_process():
+    x = torch.arange(12).view(6, 2)
+    assert torch.equal(shard_batch(x, 1, 3), x[2:4])
+    with pytest.raises(ValueError):
+        shard_batch(x, 0, 4)
+    m = _model()
+    b = FlatGradBuckets(list(m.parameters()), bucket_bytes=1 << 30)
+    assert len(b.buckets) == 1 and b.buckets[0][1] == sum(p.numel() for p in m.parameters())
+    m(torch.randn(3, 12)).sum().backward()
+    assert b.flat.abs().sum() > 0
+    b.zero()
+    assert b.flat.abs().sum() == 0 and all(p.grad.abs().sum() == 0 for p in m.parameters())
