@@ -39,14 +39,15 @@ int nv_device_check(void);
  *   b_mn = 0: B is [N,K] row-major (ldb);  b_mn = 1: B is stored [K,N] row-major (ldb)
  * epilogue, in order: *alpha, +bias[N], *gelu'(gelu_u[M,N]) (dgrad through GELU), out_pre = value and
  * value = gelu(value) when apply_gelu, +residual[M,N] (fp32), then store: out_f32 (or red.add into it
- * when accumulate=1 — required for k_splits > 1) and/or the bf16 copy out_bf16.
+ * when accumulate=1 — required for k_splits > 1) and/or the bf16 copy out_bf16; colsum[N] (optional)
+ * += sum over rows of the stored value (the bias gradient of the layer below, fused into the dgrad).
  * block_n: 0 = auto, or 128 / 256 (CTA tile 128 x block_n). */
 int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  const void* A, int64_t lda, const void* B, int64_t ldb,
                  const float* bias, const float* residual, int64_t ld_res,
                  const void* gelu_u, int64_t ld_u,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
-                 void* out_pre, int64_t ld_pre,
+                 void* out_pre, int64_t ld_pre, float* colsum,
                  int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, void* stream);
 
 /* fp32 verification GEMM (CUDA-core FMA, arbitrary strides, batch index z = z1*Z2 + z2):

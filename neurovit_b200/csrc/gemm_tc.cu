@@ -39,6 +39,7 @@ struct GemmParams {
   float* out_f32;         // [M, ld_f32] or null
   bf16* out_bf16;         // [M, ld_bf16] or null (final value, bf16 copy)
   bf16* out_pre;          // [M, ld_pre] or null (pre-activation, only with EPI_GELU)
+  float* colsum;          // [N] or null: += sum over rows of the final value (bias gradient, red.add)
   int64_t ld_res, ld_u, ld_f32, ld_bf16, ld_pre;
   int flags;
   float alpha;
@@ -232,6 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = t;
         }
         __syncwarp();
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + sub_r;
@@ -276,6 +278,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (p.out_bf16 != nullptr)
             *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
                 make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+          csum.x += a.x; csum.y += a.y; csum.z += a.z; csum.w += a.w;
+        }
+        if (p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups, one vector red per column chunk
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+            csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+            csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+            csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+          }
+          if (sub_r == 0 && col_ok)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + gn), "f"(csum.x),
+                         "f"(csum.y), "f"(csum.z), "f"(csum.w) : "memory");
         }
         __syncwarp();
       }
@@ -326,7 +341,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       const bf16* B, int64_t ldb, const float* bias, const float* residual,
                       int64_t ld_res, const bf16* gelu_u, int64_t ld_u, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
-                      int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
+                      float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
                       cudaStream_t stream) {
   NV_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   NV_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
@@ -368,7 +383,8 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   p.k_splits = (p.k_blocks_total + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
   NV_REQUIRE(p.k_splits == 1 || accumulate, "gemm: split-K needs accumulate=1 (red.add epilogue)");
   p.bias = bias; p.residual = residual; p.gelu_u = gelu_u;
-  p.out_f32 = out_f32; p.out_bf16 = out_bf16; p.out_pre = out_pre;
+  p.out_f32 = out_f32; p.out_bf16 = out_bf16; p.out_pre = out_pre; p.colsum = colsum;
+  NV_REQUIRE(colsum == nullptr || p.k_splits == 1, "gemm: colsum needs k_splits == 1");
   p.ld_res = ld_res; p.ld_u = ld_u; p.ld_f32 = ld_f32; p.ld_bf16 = ld_bf16; p.ld_pre = ld_pre;
   p.flags = (apply_gelu ? EPI_GELU : 0) | (accumulate ? EPI_ATOMIC : 0);
   p.alpha = alpha;

@@ -93,97 +93,101 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, RowMap xmap, const floa
 }
 
 // dx[dxmap(r)] = LNbwd(dy[dymap(r)]; x[xmap(r)]) (+ dres[r]);   dgamma/dbeta (+= via atomics);
-// optional colsum_out[D] += sum_rows dx (bias gradient of the linear that produced x's residual branch)
-template <int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// optional colsum_out[D] += sum_rows dx (bias gradient of the linear that produced x's residual branch).
+// Column-owner layout: thread t owns the float4 column chunk t (blockDim = D/4 rounded up to a warp), the
+// CTA walks the rows four at a time (12 independent 16-byte loads in flight per thread, ~60 registers, so
+// several CTAs stay resident per SM), the two per-row reductions go warp-shuffle -> shared -> broadcast,
+// and the per-column dgamma/dbeta/colsum partials stay in 12 registers for the whole grid-stride loop.
+constexpr int LNB_ROWS = 4;
+constexpr int LNB_MAX_WARPS = 16;
+
+__global__ void __launch_bounds__(LNB_MAX_WARPS * 32)
 ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, RowMap dymap, const float* __restrict__ x,
               int64_t ld_x, RowMap xmap, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ gamma, const float* __restrict__ dres, int64_t ld_dres,
               float* __restrict__ dx, int64_t ld_dx, RowMap dxmap, bf16* __restrict__ dx_bf16,
               int64_t ld_dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ colsum_out, int M, int D) {
-  extern __shared__ float red[];  // [LN_WARPS][D]
+  __shared__ float red[2][LNB_MAX_WARPS][2 * LNB_ROWS];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int nvec = D >> 2;
-  float4 acc_g[NV], acc_b[NV], acc_c[NV];
+  const int nwarps = blockDim.x >> 5;
+  const int c = threadIdx.x;  // float4 column chunk owned by this thread
+  const bool active = c < (D >> 2);
+  const float inv_d = 1.0f / (float)D;
+  float4 acc_g = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_g, acc_c = acc_g;
+  const float4 g = active ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  int buf = 0;
+  for (int r0 = blockIdx.x * LNB_ROWS; r0 < M; r0 += gridDim.x * LNB_ROWS) {
+    float4 xv[LNB_ROWS], dv[LNB_ROWS], rv[LNB_ROWS];
+    float mean[LNB_ROWS], rstd[LNB_ROWS];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    acc_g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc_b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc_c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float4 g[NV];
-#pragma unroll
-  for (int j = 0; j < NV; ++j)
-    if (lane + 32 * j < nvec) g[j] = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * j));
-
-  for (int r = blockIdx.x * LN_WARPS + warp; r < M; r += gridDim.x * LN_WARPS) {
-    const float* xr = x + xmap(r) * ld_x;
-    const float* dyr = dy + dymap(r) * ld_dy;
-    const float mean = mean_in[r], rstd = rstd_in[r];
-    float4 xh[NV], gh[NV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c = lane + 32 * j;
-      if (c < nvec) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c);
-        const float4 d = *reinterpret_cast<const float4*>(dyr + 4 * c);
-        xh[j].x = (xv.x - mean) * rstd; xh[j].y = (xv.y - mean) * rstd;
-        xh[j].z = (xv.z - mean) * rstd; xh[j].w = (xv.w - mean) * rstd;
-        acc_g[j].x += d.x * xh[j].x; acc_g[j].y += d.y * xh[j].y;
-        acc_g[j].z += d.z * xh[j].z; acc_g[j].w += d.w * xh[j].w;
-        acc_b[j].x += d.x; acc_b[j].y += d.y; acc_b[j].z += d.z; acc_b[j].w += d.w;
-        gh[j].x = d.x * g[j].x; gh[j].y = d.y * g[j].y; gh[j].z = d.z * g[j].z; gh[j].w = d.w * g[j].w;
-        s1 += (gh[j].x + gh[j].y) + (gh[j].z + gh[j].w);
-        s2 += (gh[j].x * xh[j].x + gh[j].y * xh[j].y) + (gh[j].z * xh[j].z + gh[j].w * xh[j].w);
-      }
+    for (int k = 0; k < LNB_ROWS; ++k) {
+      const int r = r0 + k;
+      const bool ok = active && r < M;
+      xv[k] = ok ? *reinterpret_cast<const float4*>(x + xmap(r) * ld_x + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[k] = ok ? *reinterpret_cast<const float4*>(dy + dymap(r) * ld_dy + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rv[k] = (ok && dres) ? *reinterpret_cast<const float4*>(dres + (int64_t)r * ld_dres + 4 * c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      mean[k] = r < M ? mean_in[r] : 0.f;
+      rstd[k] = r < M ? rstd_in[r] : 0.f;
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
-    if (dx != nullptr || dx_bf16 != nullptr) {
-      const int64_t orow = dxmap(r);
+    float4 xh[LNB_ROWS], gh[LNB_ROWS];
+    float part[2 * LNB_ROWS];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int c = lane + 32 * j;
-        if (c < nvec) {
-          float4 o;
-          o.x = rstd * (gh[j].x - s1 - xh[j].x * s2);
-          o.y = rstd * (gh[j].y - s1 - xh[j].y * s2);
-          o.z = rstd * (gh[j].z - s1 - xh[j].z * s2);
-          o.w = rstd * (gh[j].w - s1 - xh[j].w * s2);
-          if (dres) {
-            const float4 a = *reinterpret_cast<const float4*>(dres + (int64_t)r * ld_dres + 4 * c);
-            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-          }
-          acc_c[j].x += o.x; acc_c[j].y += o.y; acc_c[j].z += o.z; acc_c[j].w += o.w;
-          if (dx) *reinterpret_cast<float4*>(dx + orow * ld_dx + 4 * c) = o;
-          if (dx_bf16) OutStore<bf16>::st(dx_bf16 + orow * ld_dxb + 4 * c, o);
-        }
-      }
+    for (int k = 0; k < LNB_ROWS; ++k) {
+      const bool ok = active && (r0 + k) < M;
+      xh[k].x = ok ? (xv[k].x - mean[k]) * rstd[k] : 0.f;
+      xh[k].y = ok ? (xv[k].y - mean[k]) * rstd[k] : 0.f;
+      xh[k].z = ok ? (xv[k].z - mean[k]) * rstd[k] : 0.f;
+      xh[k].w = ok ? (xv[k].w - mean[k]) * rstd[k] : 0.f;
+      acc_g.x += dv[k].x * xh[k].x; acc_g.y += dv[k].y * xh[k].y;
+      acc_g.z += dv[k].z * xh[k].z; acc_g.w += dv[k].w * xh[k].w;
+      acc_b.x += dv[k].x; acc_b.y += dv[k].y; acc_b.z += dv[k].z; acc_b.w += dv[k].w;
+      gh[k].x = dv[k].x * g.x; gh[k].y = dv[k].y * g.y; gh[k].z = dv[k].z * g.z; gh[k].w = dv[k].w * g.w;
+      part[2 * k] = (gh[k].x + gh[k].y) + (gh[k].z + gh[k].w);
+      part[2 * k + 1] = (gh[k].x * xh[k].x + gh[k].y * xh[k].y) + (gh[k].z * xh[k].z + gh[k].w * xh[k].w);
     }
-  }
-  // CTA-level reduction of the per-warp column partials, then one atomic per column per CTA
-  for (int pass = 0; pass < 3; ++pass) {
-    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : colsum_out);
-    if (dst == nullptr) continue;  // uniform across the CTA
-    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c = lane + 32 * j;
-      if (c < nvec) {
-        const float4 a = pass == 0 ? acc_g[j] : (pass == 1 ? acc_b[j] : acc_c[j]);
-        *reinterpret_cast<float4*>(red + warp * D + 4 * c) = a;
-      }
+    for (int i = 0; i < 2 * LNB_ROWS; ++i) part[i] = warp_sum(part[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 2 * LNB_ROWS; ++i) red[buf][warp][i] = part[i];
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+    __syncthreads();  // one barrier per 4 rows; `red` is double-buffered so the next iteration may overwrite
+#pragma unroll
+    for (int i = 0; i < 2 * LNB_ROWS; ++i) {
       float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += red[w * D + c];
-      atomicAdd(dst + c, s);
+      for (int w = 0; w < nwarps; ++w) s += red[buf][w][i];
+      part[i] = s * inv_d;
     }
+    buf ^= 1;
+#pragma unroll
+    for (int k = 0; k < LNB_ROWS; ++k) {
+      const int r = r0 + k;
+      if (!(active && r < M)) continue;
+      const float s1 = part[2 * k], s2 = part[2 * k + 1];
+      float4 o;
+      o.x = rstd[k] * (gh[k].x - s1 - xh[k].x * s2) + rv[k].x;
+      o.y = rstd[k] * (gh[k].y - s1 - xh[k].y * s2) + rv[k].y;
+      o.z = rstd[k] * (gh[k].z - s1 - xh[k].z * s2) + rv[k].z;
+      o.w = rstd[k] * (gh[k].w - s1 - xh[k].w * s2) + rv[k].w;
+      acc_c.x += o.x; acc_c.y += o.y; acc_c.z += o.z; acc_c.w += o.w;
+      const int64_t orow = dxmap(r);
+      if (dx) *reinterpret_cast<float4*>(dx + orow * ld_dx + 4 * c) = o;
+      if (dx_bf16) OutStore<bf16>::st(dx_bf16 + orow * ld_dxb + 4 * c, o);
+    }
+  }
+  if (active) {
+    if (dgamma)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + 4 * c), "f"(acc_g.x), "f"(acc_g.y),
+                   "f"(acc_g.z), "f"(acc_g.w) : "memory");
+    if (dbeta)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + 4 * c), "f"(acc_b.x), "f"(acc_b.y),
+                   "f"(acc_b.z), "f"(acc_b.w) : "memory");
+    if (colsum_out)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum_out + 4 * c), "f"(acc_c.x),
+                   "f"(acc_c.y), "f"(acc_c.z), "f"(acc_c.w) : "memory");
   }
 }
 
@@ -242,18 +246,18 @@ int nv_ln_bwd_launch(const float* dy, int64_t ld_dy, int dyg, int dys, int dyo, 
                      cudaStream_t stream) {
   NV_REQUIRE(M >= 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm bwd: D=%d must be a multiple of 4 and <= 2048", D);
   if (M == 0) return NV_OK;
+  for (const float* p : {dgamma, dbeta, colsum})
+    NV_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "layernorm bwd: dgamma/dbeta/colsum must be 16-byte aligned");
   RowMap dym{dyg, dys, dyo}, xm{xg, xs, xo}, dxm{dxg, dxs, dxo};
-  int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  const int cap = nv_num_sms() * 2;
+  const int threads = ((D / 4 + 31) / 32) * 32;
+  int ctas_per_sm = 1;  // size the persistent grid to exactly one resident wave
+  NV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ln_bwd_kernel, threads, 0));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int grid = (M + LNB_ROWS - 1) / LNB_ROWS;
+  const int cap = nv_num_sms() * ctas_per_sm;
   if (grid > cap) grid = cap;
-  const size_t smem = (size_t)LN_WARPS * D * sizeof(float);
-  if (smem > 48 * 1024) {
-    NV_LN_DISPATCH(D, NV_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)smem)));
-  }
-  NV_LN_DISPATCH(D, ln_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, stream>>>(
-                        dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx, dxm, dx_bf16,
-                        ld_dxb, dgamma, dbeta, colsum, M, D));
+  ln_bwd_kernel<<<grid, threads, 0, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
+                                              dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D);
   NV_LAUNCH_CHECK("ln_bwd_kernel");
   return NV_OK;
 }

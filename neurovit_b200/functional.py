@@ -130,17 +130,21 @@ class Engine:
             ops.linear_f32(a, weight.detach(), bias=bias, residual=residual, out=out, out_pre=pre, apply_gelu=gelu)
         return out, pre
 
-    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, n_cols=None):
-        """dx[M, K_in] = dy[M, N_out] @ W[N_out, K_in]  (optionally * gelu'(u))."""
+    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, want_colsum=False):
+        """dx[M, K_in] = dy[M, N_out] @ W[N_out, K_in]  (optionally * gelu'(u)). With want_colsum the column
+        sums of dx (the bias gradient of the layer below) come out of the same GEMM epilogue."""
         M, K_in = dy.shape[0], weight.shape[1]
         out_dtype = out_dtype or self.act
         out = torch.empty(M, K_in, device=dy.device, dtype=out_dtype)
+        cs = torch.zeros(K_in, device=dy.device, dtype=F32) if want_colsum else None
         if self.mode == "bf16":
-            ops.gemm_bf16(dy, self.w(weight), b_mn=True, gelu_u=gelu_u,
+            ops.gemm_bf16(dy, self.w(weight), b_mn=True, gelu_u=gelu_u, colsum=cs,
                           out_f32=out if out_dtype == F32 else None, out_bf16=out if out_dtype == BF16 else None)
         else:
             ops.linear_f32(dy, weight.detach(), w_kn=True, gelu_u=gelu_u, out=out)
-        return out
+            if want_colsum:
+                ops.colsum(out, cs)
+        return (out, cs) if want_colsum else out
 
     def wgrad(self, dy, x, k_in=None):
         """dW[N_out, K_in] = dy[M, N_out]^T @ x[M, K_in], fp32 (split-K red.add on the tensor-core path)."""
@@ -180,9 +184,9 @@ class Engine:
         dev = x.device
         dx = torch.empty(M, D, device=dev, dtype=F32)
         dxb = torch.empty(M, D, device=dev, dtype=BF16) if self.mode == "bf16" else None
-        dg = torch.zeros(D, device=dev, dtype=F32)
-        db = torch.zeros(D, device=dev, dtype=F32)
-        cs = torch.zeros(D, device=dev, dtype=F32) if want_colsum else None
+        z = torch.zeros(3 if want_colsum else 2, D, device=dev, dtype=F32)  # one fill for all accumulators
+        dg, db = z[0], z[1]
+        cs = z[2] if want_colsum else None
         ops.layernorm_bwd(dy, x, mean, rstd, weight.detach(), M=M, D=D, dres=dres, dx=dx, dx_bf16=dxb, dgamma=dg,
                           dbeta=db, colsum=cs)
         return dx, (dxb if dxb is not None else dx), dg, db, cs
@@ -271,12 +275,11 @@ class Engine:
 
     def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, w2):
         u, g = saved
-        dU = self.dgrad(dy_act, w2, gelu_u=u)
+        dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True)
         dW2 = self.wgrad(dy_act, g)
         db2 = self.bias_grad(dy, dy_colsum)
         da = self.dgrad(dU, w1, out_dtype=F32)
         dW1 = self.wgrad(dU, a)
-        db1 = self.bias_grad(dU)
         return da, dW1, db1, dW2, db2
 
 

@@ -72,7 +72,7 @@ def _rowmajor(t: torch.Tensor, name: str) -> int:
 
 # ------------------------------------------------------------------------------------------- GEMMs
 def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=None, out_f32=None,
-              out_bf16=None, out_pre=None, apply_gelu=False, accumulate=False, alpha=1.0, k_splits=1,
+              out_bf16=None, out_pre=None, colsum=None, apply_gelu=False, accumulate=False, alpha=1.0, k_splits=1,
               block_n=0):
     """C[M,N] = epilogue(alpha * A @ B^T) on tcgen05. a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N])."""
     _dev(a)
@@ -94,13 +94,13 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
         with PROFILE.region(2.0 * M * N * K):
             _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
                       _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
-                      _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), int(apply_gelu), int(accumulate),
-                      float(alpha), int(k_splits), int(block_n), _stream())
+                      _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
+                      int(accumulate), float(alpha), int(k_splits), int(block_n), _stream())
         return
     _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
               _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
-              _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), int(apply_gelu), int(accumulate),
-              float(alpha), int(k_splits), int(block_n), _stream())
+              _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
+              int(accumulate), float(alpha), int(k_splits), int(block_n), _stream())
 
 
 def gemm_f32(M, N, K, a, sa, b, sb, c, sc, *, Z1=1, Z2=1, bias=None, residual=None, gelu_u=None, out_pre=None,

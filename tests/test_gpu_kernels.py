@@ -64,8 +64,10 @@ def test_gemm_bf16_epilogues():
     u = torch.randn(M, N, device=DEV).to(torch.bfloat16)
     ud = u.double().requires_grad_(True)
     g, = torch.autograd.grad(torch.nn.functional.gelu(ud).sum(), ud)
-    ops.gemm_bf16(a, w, gelu_u=u, out_f32=out)
+    cs = torch.ones(N, device=DEV)
+    ops.gemm_bf16(a, w, gelu_u=u, out_f32=out, colsum=cs)
     assert rel_err(out, (a.double() @ w.double().t()) * g) < 1e-3
+    assert rel_err(cs, ((a.double() @ w.double().t()) * g).sum(0) + 1) < 1e-3   # fused bias-gradient column sum
     # split-K accumulate into a pre-loaded fp32 buffer (wgrad): dW[N_out,K_in] = dY^T X
     dy = torch.randn(M, 256, device=DEV).to(torch.bfloat16)
     x = torch.randn(M, 384, device=DEV).to(torch.bfloat16)

@@ -134,11 +134,12 @@ def test_neuroencoder_4d_golden(tmp_path, mode):
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_vit_vs_oracle_ragged_tokens(mode):
-    """cfgA geometry (64x64x48 / patch 8 -> 385 tokens, not a multiple of any tile) at reduced width, against
-    the CPU oracle run on the same weights; direct ViT call with a contiguous [B,1,F,H,W] tensor."""
+    """cfgA (BASELINE configs[1] geometry and model dims: 64x64x48 / patch 8 -> 385 tokens, not a multiple of
+    any tile; dim 1024, depth 6, heads 8, mlp 2048) against the CPU oracle run on the same weights; direct ViT
+    call with a contiguous [B,1,F,H,W] tensor (the permuted-K patch layout)."""
     torch.manual_seed(11)
-    ctor = dict(image_size=64, image_patch_size=8, frames=48, frame_patch_size=8, num_classes=2, dim=128, depth=2,
-                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    ctor = dict(image_size=64, image_patch_size=8, frames=48, frame_patch_size=8, num_classes=2, dim=1024, depth=6,
+                heads=8, mlp_dim=2048, channels=1, dim_head=64)
     m = ViT(**ctor)
     with torch.no_grad():
         for p in m.parameters():
@@ -147,7 +148,7 @@ def test_vit_vs_oracle_ragged_tokens(mode):
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     video = torch.randn(2, 1, 48, 64, 64)
     labels = torch.tensor([1, 0])
-    ref_logits, ref_loss, ref_grads = O.vit3d_loss_and_grads(sd, video, labels, patch=(8, 8, 8), heads=2)
+    ref_logits, ref_loss, ref_grads = O.vit3d_loss_and_grads(sd, video, labels, patch=(8, 8, 8), heads=8)
     m = m.to(DEV).eval().set_precision(mode)
     logits = m(video.to(DEV))
     torch.nn.functional.cross_entropy(logits, labels.to(DEV)).backward()
