@@ -48,7 +48,7 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  const void* gelu_u, int64_t ld_u,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
                  void* out_pre, int64_t ld_pre, float* colsum,
-                 int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, void* stream);
+                 int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group, void* stream);
 
 /* fp32 verification GEMM (CUDA-core FMA, arbitrary strides, batch index z = z1*Z2 + z2):
  * C[z][m][n] = epilogue(alpha * sum_k A[z][m,k] * B[z][n,k]); same epilogue order as nv_gemm_bf16, all

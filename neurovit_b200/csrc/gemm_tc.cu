@@ -7,19 +7,25 @@
 //   A K-major : A[M, K]          A MN-major : A stored as [K, M]   (wgrad: dY^T without a transpose pass)
 //   B K-major : B[N, K]          B MN-major : B stored as [K, N]   (wgrad: X, dgrad: W)
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (persistent, one CTA per SM, 320 threads):
 //   warps 0-7  epilogue: tcgen05.ld -> regs -> swizzled smem transpose -> coalesced global I/O
 //   warp  8    TMA producer (one lane): 128B-swizzled tiles into a STAGES-deep mbarrier ring
-//   warp  9    TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16
-// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i
-// overlaps the main loop of tile i+1. Split-K work units accumulate with red.global.add.f32
-// straight into the fp32 gradient buffer (wgrad).
+//   warp  9    TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, K=16 per instruction
+// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1. Split-K work units accumulate with red.global.add.f32 straight into the fp32
+// gradient buffer (wgrad).
+//
+// CG = 1: one CTA computes a 128 x BLOCK_N tile (tcgen05.mma.cta_group::1, M=128).
+// CG = 2: a CTA pair (cluster of 2, same TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2
+//         (M=256): each CTA stages its own 128 rows of A and HALF of the B tile, the leader CTA issues the
+//         MMA for both, each CTA's TMEM holds its 128 accumulator rows. Per-SM L2->smem traffic drops by a
+//         third (the 1-CTA 128x256 tile is L2-bandwidth bound on B200: 96 B/clk/SM x 148 SMs > L2's ~6.3 KB/clk).
 #include "nv_common.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int BLOCK_M = 128;  // accumulator rows per CTA (TMEM lanes)
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMA_WARP = 8;
@@ -27,6 +33,7 @@ constexpr int MMA_WARP = 9;
 constexpr int NUM_THREADS = 320;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;          // per epilogue warp
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;       // shared::cluster address of the pair's leader CTA
 
 enum : int { EPI_GELU = 1, EPI_ATOMIC = 2 };
 
@@ -45,9 +52,10 @@ struct GemmParams {
   float alpha;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CG>
 struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = BLOCK_N / CG;  // B rows staged by one CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + STAGES * A_STAGE_BYTES;
   static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
@@ -57,12 +65,145 @@ struct SmemLayout {
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
 };
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+// ---- cluster / cta_group::2 PTX --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are signalled on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK),
+      "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at the same smem offset in BOTH CTAs of the pair once the issued MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// ---- epilogue of one 32-row x 32-column chunk (shared by both CTA-group modes) ------------------------
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], float* stage, int lane,
+                                               int row0, int col0, const float4 (&res)[8], const uint2 (&uu)[8],
+                                               const float4 bias4) {
+  const int sub_r = lane >> 3, sub_c = lane & 7;
+  const int gn = col0 + sub_c * 4;
+  const bool col_ok = gn < p.N;
+  // row-per-thread -> swizzled staging (16B chunk j of row `lane` lands at chunk j^(lane&7))
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                           __uint_as_float(v[4 * j + 3]));
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = t;
+  }
+  __syncwarp();
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + sub_r;
+    const int gm = row0 + r;
+    float4 a = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_c ^ (r & 7)) << 2));
+    if (!(col_ok && gm < p.M)) continue;
+    a.x = a.x * p.alpha + bias4.x;
+    a.y = a.y * p.alpha + bias4.y;
+    a.z = a.z * p.alpha + bias4.z;
+    a.w = a.w * p.alpha + bias4.w;
+    if (p.gelu_u != nullptr) {
+      const float2 u01 = unpack_bf16x2(uu[i].x);
+      const float2 u23 = unpack_bf16x2(uu[i].y);
+      a.x *= gelu_erf_grad(u01.x);
+      a.y *= gelu_erf_grad(u01.y);
+      a.z *= gelu_erf_grad(u23.x);
+      a.w *= gelu_erf_grad(u23.y);
+    }
+    if (p.flags & EPI_GELU) {
+      if (p.out_pre != nullptr)
+        *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
+            make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+      a.x = gelu_erf(a.x);
+      a.y = gelu_erf(a.y);
+      a.z = gelu_erf(a.z);
+      a.w = gelu_erf(a.w);
+    }
+    if (p.residual != nullptr) {
+      a.x += res[i].x;
+      a.y += res[i].y;
+      a.z += res[i].z;
+      a.w += res[i].w;
+    }
+    if (p.flags & EPI_ATOMIC) {
+      float* dst = p.out_f32 + (int64_t)gm * p.ld_f32 + gn;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                   : "memory");
+    } else if (p.out_f32 != nullptr) {
+      *reinterpret_cast<float4*>(p.out_f32 + (int64_t)gm * p.ld_f32 + gn) = a;
+    }
+    if (p.out_bf16 != nullptr)
+      *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
+          make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    csum.x += a.x; csum.y += a.y; csum.z += a.z; csum.w += a.w;
+  }
+  if (p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups, one vector red per column chunk
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
+      csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+      csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
+      csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+    }
+    if (sub_r == 0 && col_ok)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + gn), "f"(csum.x), "f"(csum.y),
+                   "f"(csum.z), "f"(csum.w) : "memory");
+  }
+  __syncwarp();
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
+  // the dynamic smem window starts at the same offset in every CTA, so the aligned layout (and therefore
+  // every barrier / tile offset) is identical in both CTAs of a pair
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem + L::A_OFF;
@@ -76,71 +217,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], CG);  // leader's arrive.expect_tx (+ the peer's remote arrive)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS * CG);
     }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
-    tmem_alloc(tmem_slot, 2 * BLOCK_N);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(tmem_slot, 2 * BLOCK_N); tmem_relinquish_pair(); }
+    else         { tmem_alloc(tmem_slot, 2 * BLOCK_N); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
-  constexpr uint32_t STAGE_TX = A_STAGE_BYTES + L::B_STAGE_BYTES;
+  const int worker = blockIdx.x / CG;         // CTA (CG=1) or CTA-pair (CG=2) index
+  const int num_workers = gridDim.x / CG;
+  constexpr uint32_t STAGE_TX = (A_STAGE_BYTES + L::B_STAGE_BYTES) * CG;  // bytes landing per stage, both CTAs
 
   if (warp == TMA_WARP) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = worker; unit < total_units; unit += num_workers) {
         const int split = unit % p.k_splits;
         const int tile = unit / p.k_splits;
         const int n_blk = tile % p.num_n_tiles;
         const int m_blk = tile / p.num_n_tiles;
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
+        const int m0 = (m_blk * CG + (int)cta_rank) * BLOCK_M;
+        const int n0 = n_blk * BLOCK_N + (int)cta_rank * L::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], STAGE_TX);
+          if (CG == 1 || leader) mbar_arrive_expect_tx(&full_bar[s], STAGE_TX);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * L::B_STAGE_BYTES;
           if (!A_MN) {
-            tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * BLOCK_K, m_blk * BLOCK_M);
+            if (CG == 2) tma_load_2d_pair(a_dst, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
+            else         tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * BLOCK_K, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(a_dst + i * (BLOCK_K * 128), &tmap_a, &full_bar[s],
-                          m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < BLOCK_M / 64; ++i) {
+              if (CG == 2) tma_load_2d_pair(a_dst + i * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + i * 64, kb * BLOCK_K);
+              else         tma_load_2d(a_dst + i * (BLOCK_K * 128), &tmap_a, &full_bar[s], m0 + i * 64, kb * BLOCK_K);
+            }
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n_blk * BLOCK_N);
+            if (CG == 2) tma_load_2d_pair(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
+            else         tma_load_2d(b_dst, &tmap_b, &full_bar[s], kb * BLOCK_K, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(b_dst + i * (BLOCK_K * 128), &tmap_b, &full_bar[s],
-                          n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < L::B_ROWS / 64; ++i) {
+              if (CG == 2) tma_load_2d_pair(b_dst + i * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + i * 64, kb * BLOCK_K);
+              else         tma_load_2d(b_dst + i * (BLOCK_K * 128), &tmap_b, &full_bar[s], n0 + i * 64, kb * BLOCK_K);
+            }
           }
+          if (CG == 2 && !leader) mbar_arrive_remote(&full_bar[s], 0);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major: 8-row groups are 1024 B apart (SBO), LBO unused (1).
       // MN-major: 64-element column slabs are BLOCK_K*128 B apart (LBO), 8-k groups 1024 B (SBO).
       constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16;
@@ -151,7 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = worker; unit < total_units; unit += num_workers) {
         const int split = unit % p.k_splits;
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
@@ -167,10 +319,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = umma_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
             const uint64_t db = umma_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else         umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[acc]);
+          // frees the smem stage (in both CTAs) once these MMAs retire
+          if (CG == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+          if (kb == kb1 - 1) {
+            if (CG == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
@@ -185,11 +341,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int sub_c = lane & 7;   // 16-byte column chunk
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = worker; unit < total_units; unit += num_workers) {
       const int tile = unit / p.k_splits;
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = tile / p.num_n_tiles;
-      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
 #pragma unroll 1
@@ -225,113 +381,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
         tmem_ld_wait();
-        // row-per-thread -> swizzled staging (16B chunk j of row `lane` lands at chunk j^(lane&7))
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = t;
-        }
-        __syncwarp();
-        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + sub_r;
-          const int gm = row0 + r;
-          float4 a = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_c ^ (r & 7)) << 2));
-          if (!(col_ok && gm < p.M)) continue;
-          a.x = a.x * p.alpha + bias4.x;
-          a.y = a.y * p.alpha + bias4.y;
-          a.z = a.z * p.alpha + bias4.z;
-          a.w = a.w * p.alpha + bias4.w;
-          if (p.gelu_u != nullptr) {
-            const float2 u01 = unpack_bf16x2(uu[i].x);
-            const float2 u23 = unpack_bf16x2(uu[i].y);
-            a.x *= gelu_erf_grad(u01.x);
-            a.y *= gelu_erf_grad(u01.y);
-            a.z *= gelu_erf_grad(u23.x);
-            a.w *= gelu_erf_grad(u23.y);
-          }
-          if (p.flags & EPI_GELU) {
-            if (p.out_pre != nullptr)
-              *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
-                  make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-            a.x = gelu_erf(a.x);
-            a.y = gelu_erf(a.y);
-            a.z = gelu_erf(a.z);
-            a.w = gelu_erf(a.w);
-          }
-          if (p.residual != nullptr) {
-            a.x += res[i].x;
-            a.y += res[i].y;
-            a.z += res[i].z;
-            a.w += res[i].w;
-          }
-          if (p.flags & EPI_ATOMIC) {
-            float* dst = p.out_f32 + (int64_t)gm * p.ld_f32 + gn;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x),
-                         "f"(a.y), "f"(a.z), "f"(a.w)
-                         : "memory");
-          } else if (p.out_f32 != nullptr) {
-            *reinterpret_cast<float4*>(p.out_f32 + (int64_t)gm * p.ld_f32 + gn) = a;
-          }
-          if (p.out_bf16 != nullptr)
-            *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
-                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-          csum.x += a.x; csum.y += a.y; csum.z += a.z; csum.w += a.w;
-        }
-        if (p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups, one vector red per column chunk
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {
-            csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
-            csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
-            csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o);
-            csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
-          }
-          if (sub_r == 0 && col_ok)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + gn), "f"(csum.x),
-                         "f"(csum.y), "f"(csum.z), "f"(csum.w) : "memory");
-        }
-        __syncwarp();
+        epilogue_chunk(p, v, stage, lane, row0, col0, res, uu, bias4);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[acc], 0);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, 2 * BLOCK_N); else tmem_dealloc(tmem_base, 2 * BLOCK_N);
   }
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                    cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG>;
   static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG>;
   static bool attr_set = false;  // per instantiation; idempotent, races are benign
   if (!attr_set) {
     NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
-  kern<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(ta, tb, p);
-  NV_LAUNCH_CHECK("gemm_tc_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NV_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return NV_OK;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CG>
 int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
                  const GemmParams& p, int grid, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, false, false>(ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return launch_variant<BLOCK_N, STAGES, false, true>(ta, tb, p, grid, stream);
-  if (a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, true, false>(ta, tb, p, grid, stream);
-  return launch_variant<BLOCK_N, STAGES, true, true>(ta, tb, p, grid, stream);
+  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, false, false, CG>(ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_variant<BLOCK_N, STAGES, false, true, CG>(ta, tb, p, grid, stream);
+  if (a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, true, false, CG>(ta, tb, p, grid, stream);
+  return launch_variant<BLOCK_N, STAGES, true, true, CG>(ta, tb, p, grid, stream);
 }
 
 }  // namespace
@@ -342,7 +445,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       int64_t ld_res, const bf16* gelu_u, int64_t ld_u, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
-                      cudaStream_t stream) {
+                      int cta_group, cudaStream_t stream) {
   NV_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   NV_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   NV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16B strides)");
@@ -351,8 +454,12 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   NV_REQUIRE(out_f32 != nullptr || out_bf16 != nullptr, "gemm: no output buffer");
   NV_REQUIRE(!accumulate || out_f32 != nullptr, "gemm: accumulate needs an fp32 output");
   NV_REQUIRE(block_n == 128 || block_n == 256 || block_n == 0, "gemm: block_n must be 0, 128 or 256");
+  NV_REQUIRE(cta_group >= 0 && cta_group <= 2, "gemm: cta_group must be 0 (auto), 1 or 2");
 
   if (block_n == 0) block_n = (N >= 256) ? 256 : 128;
+  const int num_sms = nv_num_sms();
+  if (cta_group == 0) cta_group = (M > BLOCK_M && num_sms % 2 == 0) ? 2 : 1;
+  const int b_rows = block_n / cta_group;  // B rows staged per CTA
 
   CUtensorMap ta, tb;
   {
@@ -364,7 +471,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
     int s = nv_encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dims, strides, box,
                            CU_TENSOR_MAP_SWIZZLE_128B);
     if (s != NV_OK) return s;
-    if (!b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BLOCK_K; box[1] = (uint32_t)block_n; }
+    if (!b_mn) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = BLOCK_K; box[1] = (uint32_t)b_rows; }
     else       { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 64;      box[1] = BLOCK_K; }
     strides[0] = (uint64_t)ldb * 2;
     s = nv_encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, dims, strides, box,
@@ -374,7 +481,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.num_m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_m_tiles = (M + BLOCK_M * cta_group - 1) / (BLOCK_M * cta_group);
   p.num_n_tiles = (N + block_n - 1) / block_n;
   p.k_blocks_total = (K + BLOCK_K - 1) / BLOCK_K;
   if (k_splits < 1) k_splits = 1;
@@ -390,7 +497,12 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   p.alpha = alpha;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
-  const int grid = total_units < nv_num_sms() ? total_units : nv_num_sms();
-  if (block_n == 256) return launch_major<256, 4>(a_mn, b_mn, ta, tb, p, grid, stream);
-  return launch_major<128, 6>(a_mn, b_mn, ta, tb, p, grid, stream);
+  const int max_workers = num_sms / cta_group;
+  const int grid = (total_units < max_workers ? total_units : max_workers) * cta_group;
+  if (cta_group == 2) {
+    if (block_n == 256) return launch_major<256, 6, 2>(a_mn, b_mn, ta, tb, p, grid, stream);
+    return launch_major<128, 8, 2>(a_mn, b_mn, ta, tb, p, grid, stream);
+  }
+  if (block_n == 256) return launch_major<256, 4, 1>(a_mn, b_mn, ta, tb, p, grid, stream);
+  return launch_major<128, 6, 1>(a_mn, b_mn, ta, tb, p, grid, stream);
 }

@@ -10,6 +10,7 @@ No path here falls back to torch math or to the CPU oracle.
 """
 from __future__ import annotations
 
+import collections
 import math
 
 import torch
@@ -35,14 +36,20 @@ class WeightCache:
     (optimizer steps and load_state_dict are in-place and bump it). Derived buffers only: never part of
     state_dict (SURVEY §5 checkpoint contract)."""
 
+    MAX_ENTRIES = 512
+
     def __init__(self):
-        self._c = {}
+        self._c = collections.OrderedDict()
 
     def bf16(self, w: torch.Tensor, pad_k: int = 0) -> torch.Tensor:
+        # Keyed by the storage address. Every entry keeps a reference to (an alias of) the source tensor, so
+        # that address cannot be handed to a different tensor while the entry lives — a freed model's weights
+        # can never be mistaken for a new model's. Entries are dropped LRU.
         key = (w.data_ptr(), tuple(w.shape), pad_k)
         hit = self._c.get(key)
         ver = w._version
         if hit is not None and hit[0] == ver:
+            self._c.move_to_end(key)
             return hit[1]
         wd = w.detach()
         if not wd.is_contiguous():
@@ -54,7 +61,10 @@ class WeightCache:
             out = buf
         else:
             out = ops.cast_bf16(wd, out=hit[1] if hit is not None else None)
-        self._c[key] = (ver, out)
+        self._c[key] = (ver, out, wd)  # wd aliases w's storage: pins the address (see above)
+        self._c.move_to_end(key)
+        while len(self._c) > self.MAX_ENTRIES:
+            self._c.popitem(last=False)
         return out
 
     def clear(self):
@@ -88,14 +98,14 @@ class GradStash:
 _STASH = GradStash()
 
 
-def _splitk(tiles: int, k_blocks: int) -> int:
-    """Pick split-K so tiles*splits fills whole waves of NUM_SMS persistent CTAs."""
+def _splitk(tiles: int, k_blocks: int, workers: int = NUM_SMS) -> int:
+    """Pick split-K so tiles*splits fills whole waves of the persistent workers (CTAs or CTA pairs)."""
     best, best_eff = 1, 0.0
     for s in range(1, 33):
         if k_blocks // s < 4 and s > 1:
             break
         units = tiles * s
-        eff = units / (math.ceil(units / NUM_SMS) * NUM_SMS)
+        eff = units / (math.ceil(units / workers) * workers)
         if eff > best_eff + 0.03:
             best, best_eff = s, eff
     return best
@@ -153,9 +163,10 @@ class Engine:
         dW = torch.zeros(N_out, K_in, device=dy.device, dtype=F32)
         if self.mode == "bf16":
             bn = 256 if K_in >= 256 else 128
-            tiles = math.ceil(N_out / 128) * math.ceil(K_in / bn)
+            cg = 1 if (ops.GEMM_CTA_GROUP == 1 or N_out <= 128) else 2
+            tiles = math.ceil(N_out / (128 * cg)) * math.ceil(K_in / bn)
             ops.gemm_bf16(dy, x, a_mn=True, b_mn=True, out_f32=dW, accumulate=True,
-                          k_splits=_splitk(tiles, math.ceil(M / 64)), block_n=bn)
+                          k_splits=_splitk(tiles, math.ceil(M / 64), NUM_SMS // cg), block_n=bn, cta_group=cg)
         else:
             ops.linear_f32(dy, x, x_km=True, w_kn=True, out=dW)
         if k_in is not None and k_in != K_in:

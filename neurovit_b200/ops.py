@@ -3,6 +3,7 @@ library does all arithmetic. No torch math ops are used on the data path here.""
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -47,6 +48,9 @@ class _KernelProfile:
 
 PROFILE = _KernelProfile()
 
+# tcgen05 CTA-group mode of the GEMM: 0 = auto (CTA pairs, 256-row tiles), 1 = single CTA, 2 = CTA pair
+GEMM_CTA_GROUP = int(os.environ.get("NEUROVIT_GEMM_CG", "0"))
+
 
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -73,7 +77,7 @@ def _rowmajor(t: torch.Tensor, name: str) -> int:
 # ------------------------------------------------------------------------------------------- GEMMs
 def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=None, out_f32=None,
               out_bf16=None, out_pre=None, colsum=None, apply_gelu=False, accumulate=False, alpha=1.0, k_splits=1,
-              block_n=0):
+              block_n=0, cta_group=None):
     """C[M,N] = epilogue(alpha * A @ B^T) on tcgen05. a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N])."""
     _dev(a)
     assert a.dtype == BF16 and b.dtype == BF16, "gemm_bf16 operands must be bfloat16"
@@ -90,17 +94,19 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     if bias is not None:
         assert bias.dtype == F32 and bias.numel() == N and bias.is_contiguous()
     ld = lambda t: 0 if t is None else t.stride(0)
+    if cta_group is None:
+        cta_group = GEMM_CTA_GROUP
     if PROFILE.enabled:
         with PROFILE.region(2.0 * M * N * K):
             _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
                       _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
                       _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
-                      int(accumulate), float(alpha), int(k_splits), int(block_n), _stream())
+                      int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), _stream())
         return
     _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
               _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
               _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
-              int(accumulate), float(alpha), int(k_splits), int(block_n), _stream())
+              int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), _stream())
 
 
 def gemm_f32(M, N, K, a, sa, b, sb, c, sc, *, Z1=1, Z2=1, bias=None, residual=None, gelu_u=None, out_pre=None,

@@ -25,8 +25,9 @@ def rel_err(a, b):
 # ------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("block_n", [128, 256])
-@pytest.mark.parametrize("shape", [(256, 256, 128), (385, 1536, 1024), (130, 72, 200)])
-def test_gemm_bf16_plain(a_mn, b_mn, block_n, shape):
+@pytest.mark.parametrize("shape", [(256, 256, 128), (392, 1536, 1024), (136, 72, 200), (385, 264, 520)])
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_bf16_plain(a_mn, b_mn, block_n, shape, cg):
     M, N, K = shape
     torch.manual_seed(1)
     a = torch.randn((K, M) if a_mn else (M, K), device=DEV).to(torch.bfloat16)
@@ -34,7 +35,7 @@ def test_gemm_bf16_plain(a_mn, b_mn, block_n, shape):
     if (a_mn and M % 8) or (b_mn and N % 8) or ((not a_mn or not b_mn) and K % 8):
         pytest.skip("TMA needs 16-byte row strides")
     out = torch.empty(M, N, device=DEV)
-    ops.gemm_bf16(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, block_n=block_n)
+    ops.gemm_bf16(a, b, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, block_n=block_n, cta_group=cg)
     af = a.double().t() if a_mn else a.double()
     bf = b.double().t() if b_mn else b.double()
     assert rel_err(out, af @ bf.t()) < 1e-3
