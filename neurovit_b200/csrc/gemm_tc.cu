@@ -120,10 +120,69 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
-// ---- epilogue of one 32-row x 32-column chunk (shared by both CTA-group modes) ------------------------
+// ---- epilogue ---------------------------------------------------------------------------------------
+// EPI_MODE: 0 = store (alpha, bias, residual, fp32/bf16 out, split-K red.add, column sums)
+//           1 = bias + exact-erf GELU forward (writes pre-activation and activation, bf16)
+//           2 = dgrad through GELU: acc * gelu'(u) (+ column sums)
+// erf is evaluated with Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one
+// MUFU.RCP + one MUFU.EX2 + 7 FMAs; gelu' reuses the same exponential (exp(-u^2/2) is erf's exp(-x^2)).
+__device__ __forceinline__ void erf_parts(float u, float& erf_v, float& expv) {
+  const float x = u * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  expv = exp2f(-x * x * 1.4426950408889634f);  // exp(-x^2) = exp(-u^2/2)
+  erf_v = copysignf(fmaf(-poly, expv, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_fast(float u) {
+  float e, ex;
+  erf_parts(u, e, ex);
+  return 0.5f * u * (1.0f + e);
+}
+__device__ __forceinline__ float gelu_grad_fast(float u) {
+  float e, ex;
+  erf_parts(u, e, ex);
+  return fmaf(u * 0.39894228040143267794f, ex, 0.5f * (1.0f + e));
+}
+
+struct EpiAux {  // global operands of one 32x32 chunk, prefetched one chunk ahead
+  float4 res[8];
+  uint2 uu[8];
+  float4 bias4;
+};
+
+template <int EPI_MODE>
+__device__ __forceinline__ void epi_prefetch(const GemmParams& p, EpiAux& x, int lane, int row0, int col0) {
+  const int sub_r = lane >> 3, sub_c = lane & 7;
+  const int gn = col0 + sub_c * 4;
+  const bool col_ok = gn < p.N;
+  if (EPI_MODE == 0 && p.residual != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gm = row0 + i * 4 + sub_r;
+      x.res[i] = (col_ok && gm < p.M) ? *reinterpret_cast<const float4*>(p.residual + (int64_t)gm * p.ld_res + gn)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (EPI_MODE == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gm = row0 + i * 4 + sub_r;
+      x.uu[i] = (col_ok && gm < p.M) ? *reinterpret_cast<const uint2*>(p.gelu_u + (int64_t)gm * p.ld_u + gn)
+                                     : make_uint2(0u, 0u);
+    }
+  }
+  x.bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EPI_MODE != 2 && p.bias != nullptr && col_ok) x.bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
+}
+
+template <int EPI_MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], float* stage, int lane,
-                                               int row0, int col0, const float4 (&res)[8], const uint2 (&uu)[8],
-                                               const float4 bias4) {
+                                               int row0, int col0, const EpiAux& x) {
   const int sub_r = lane >> 3, sub_c = lane & 7;
   const int gn = col0 + sub_c * 4;
   const bool col_ok = gn < p.N;
@@ -141,47 +200,42 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     const int r = i * 4 + sub_r;
     const int gm = row0 + r;
     float4 a = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_c ^ (r & 7)) << 2));
-    if (!(col_ok && gm < p.M)) continue;
-    a.x = a.x * p.alpha + bias4.x;
-    a.y = a.y * p.alpha + bias4.y;
-    a.z = a.z * p.alpha + bias4.z;
-    a.w = a.w * p.alpha + bias4.w;
-    if (p.gelu_u != nullptr) {
-      const float2 u01 = unpack_bf16x2(uu[i].x);
-      const float2 u23 = unpack_bf16x2(uu[i].y);
-      a.x *= gelu_erf_grad(u01.x);
-      a.y *= gelu_erf_grad(u01.y);
-      a.z *= gelu_erf_grad(u23.x);
-      a.w *= gelu_erf_grad(u23.y);
-    }
-    if (p.flags & EPI_GELU) {
-      if (p.out_pre != nullptr)
+    const bool ok = col_ok && gm < p.M;
+    if (EPI_MODE == 0) {
+      a.x = fmaf(a.x, p.alpha, x.bias4.x);
+      a.y = fmaf(a.y, p.alpha, x.bias4.y);
+      a.z = fmaf(a.z, p.alpha, x.bias4.z);
+      a.w = fmaf(a.w, p.alpha, x.bias4.w);
+      if (p.residual != nullptr) {
+        a.x += x.res[i].x; a.y += x.res[i].y; a.z += x.res[i].z; a.w += x.res[i].w;
+      }
+    } else if (EPI_MODE == 1) {
+      a.x += x.bias4.x; a.y += x.bias4.y; a.z += x.bias4.z; a.w += x.bias4.w;
+      if (ok && p.out_pre != nullptr)
         *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
             make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-      a.x = gelu_erf(a.x);
-      a.y = gelu_erf(a.y);
-      a.z = gelu_erf(a.z);
-      a.w = gelu_erf(a.w);
+      a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
+    } else {
+      const float2 u01 = unpack_bf16x2(x.uu[i].x);
+      const float2 u23 = unpack_bf16x2(x.uu[i].y);
+      a.x *= gelu_grad_fast(u01.x); a.y *= gelu_grad_fast(u01.y);
+      a.z *= gelu_grad_fast(u23.x); a.w *= gelu_grad_fast(u23.y);
     }
-    if (p.residual != nullptr) {
-      a.x += res[i].x;
-      a.y += res[i].y;
-      a.z += res[i].z;
-      a.w += res[i].w;
+    if (ok) {
+      if (EPI_MODE == 0 && (p.flags & EPI_ATOMIC)) {
+        float* dst = p.out_f32 + (int64_t)gm * p.ld_f32 + gn;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z),
+                     "f"(a.w) : "memory");
+      } else if (p.out_f32 != nullptr) {
+        *reinterpret_cast<float4*>(p.out_f32 + (int64_t)gm * p.ld_f32 + gn) = a;
+      }
+      if (p.out_bf16 != nullptr)
+        *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
+            make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+      csum.x += a.x; csum.y += a.y; csum.z += a.z; csum.w += a.w;
     }
-    if (p.flags & EPI_ATOMIC) {
-      float* dst = p.out_f32 + (int64_t)gm * p.ld_f32 + gn;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
-                   : "memory");
-    } else if (p.out_f32 != nullptr) {
-      *reinterpret_cast<float4*>(p.out_f32 + (int64_t)gm * p.ld_f32 + gn) = a;
-    }
-    if (p.out_bf16 != nullptr)
-      *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
-          make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-    csum.x += a.x; csum.y += a.y; csum.z += a.z; csum.w += a.w;
   }
-  if (p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups, one vector red per column chunk
+  if (EPI_MODE != 1 && p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups, one vector red per chunk
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
       csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o);
@@ -196,7 +250,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   __syncwarp();
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -248,7 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr uint32_t STAGE_TX = (A_STAGE_BYTES + L::B_STAGE_BYTES) * CG;  // bytes landing per stage, both CTAs
 
   if (warp == TMA_WARP) {
-    if (lane == 0) {
+    {  // all 32 lanes walk the loop (warp-uniform control flow keeps the TMA operands in uniform registers);
+       // one elected lane arms the barrier and issues the copies
       int s = 0;
       uint32_t ph = 0;
       for (int unit = worker; unit < total_units; unit += num_workers) {
@@ -262,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n0 = n_blk * BLOCK_N + (int)cta_rank * L::B_ROWS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (elect_one()) {
           if (CG == 1 || leader) mbar_arrive_expect_tx(&full_bar[s], STAGE_TX);
           uint8_t* a_dst = sA + s * A_STAGE_BYTES;
           uint8_t* b_dst = sB + s * L::B_STAGE_BYTES;
@@ -286,12 +342,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           if (CG == 2 && !leader) mbar_arrive_remote(&full_bar[s], 0);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    if (lane == 0 && leader) {
+    if (leader) {  // whole warp walks the loop; the elected lane issues tcgen05.mma / tcgen05.commit
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major: 8-row groups are 1024 B apart (SBO), LBO unused (1).
       // MN-major: 64-element column slabs are BLOCK_K*128 B apart (LBO), 8-k groups 1024 B (SBO).
@@ -299,6 +357,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16;
       constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;  // bytes per UMMA_K
       constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      // descriptors differ between stages / k-steps only in the 14-bit start-address field: build once
+      const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(sA), A_LBO, 1024);
+      const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(sB), B_LBO, 1024);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -313,20 +374,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + s * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + s * L::B_STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t da = a_desc0 + (uint64_t)((s * A_STAGE_BYTES) >> 4);
+            const uint64_t db = b_desc0 + (uint64_t)((s * L::B_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_addr + k * A_KSTEP, A_LBO, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_addr + k * B_KSTEP, B_LBO, 1024);
-            if (CG == 2) umma_f16_ss_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else         umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (CG == 2) umma_f16_ss_pair(d_tmem, da + (uint64_t)((k * A_KSTEP) >> 4), db + (uint64_t)((k * B_KSTEP) >> 4), idesc, accum);
+              else         umma_f16_ss(d_tmem, da + (uint64_t)((k * A_KSTEP) >> 4), db + (uint64_t)((k * B_KSTEP) >> 4), idesc, accum);
+            }
+            // frees the smem stage (in both CTAs) once these MMAs retire
+            if (CG == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+            if (kb == kb1 - 1) {
+              if (CG == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+            }
           }
-          // frees the smem stage (in both CTAs) once these MMAs retire
-          if (CG == 2) umma_commit_pair(&empty_bar[s]); else umma_commit(&empty_bar[s]);
-          if (kb == kb1 - 1) {
-            if (CG == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
-          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
@@ -337,8 +400,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int half = warp >> 2;   // which column chunks (even/odd) this warp owns
     float* stage = reinterpret_cast<float*>(smem + L::EPI_OFF + warp * EPI_STAGE_BYTES);
-    const int sub_r = lane >> 3;  // row within a group of 4 in the coalesced phase
-    const int sub_c = lane & 7;   // 16-byte column chunk
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = worker; unit < total_units; unit += num_workers) {
@@ -346,42 +407,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = tile / p.num_n_tiles;
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
+      constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks owned by this warp (every other one)
+      EpiAux aux[2];
+      const int colbase = n_blk * BLOCK_N + half * 32;
+      epi_prefetch<EPI_MODE>(p, aux[0], lane, row0, colbase);  // overlaps the wait for the accumulator
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = half; c < BLOCK_N / 32; c += 2) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        const int gn = col0 + sub_c * 4;
-        const bool col_ok = gn < p.N;
-        // prefetch the epilogue's global operands before touching TMEM (hides L2/HBM latency)
-        float4 res[8];
-        uint2 uu[8];
-        if (p.residual != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int gm = row0 + i * 4 + sub_r;
-            res[i] = (col_ok && gm < p.M)
-                         ? *reinterpret_cast<const float4*>(p.residual + (int64_t)gm * p.ld_res + gn)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+      for (int ci = 0; ci < CHUNKS; ++ci) {
+        const int col0 = colbase + ci * 64;
+        if (ci + 1 < CHUNKS) epi_prefetch<EPI_MODE>(p, aux[(ci + 1) & 1], lane, row0, col0 + 64);
+        if (col0 < p.N) {  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * 32 + ci * 64, v);
+          tmem_ld_wait();
+          epilogue_chunk<EPI_MODE>(p, v, stage, lane, row0, col0, aux[ci & 1]);
         }
-        if (p.gelu_u != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int gm = row0 + i * 4 + sub_r;
-            uu[i] = (col_ok && gm < p.M)
-                        ? *reinterpret_cast<const uint2*>(p.gelu_u + (int64_t)gm * p.ld_u + gn)
-                        : make_uint2(0u, 0u);
-          }
-        }
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && col_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
-
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
-        tmem_ld_wait();
-        epilogue_chunk(p, v, stage, lane, row0, col0, res, uu, bias4);
       }
       tc_fence_before();
       __syncwarp();
@@ -401,12 +442,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                    cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES, CG>;
   static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG, EPI_MODE>;
   static bool attr_set = false;  // per instantiation; idempotent, races are benign
   if (!attr_set) {
     NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -429,12 +470,20 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
 }
 
 template <int BLOCK_N, int STAGES, int CG>
-int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
+int launch_major(int a_mn, int b_mn, int epi_mode, const CUtensorMap& ta, const CUtensorMap& tb,
                  const GemmParams& p, int grid, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, false, false, CG>(ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return launch_variant<BLOCK_N, STAGES, false, true, CG>(ta, tb, p, grid, stream);
-  if (a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, true, false, CG>(ta, tb, p, grid, stream);
-  return launch_variant<BLOCK_N, STAGES, true, true, CG>(ta, tb, p, grid, stream);
+  if (epi_mode == 1) {  // GELU forward: activations x weights, both K-major
+    NV_REQUIRE(!a_mn && !b_mn, "gemm: apply_gelu is only built for K-major operands (forward linear)");
+    return launch_variant<BLOCK_N, STAGES, false, false, CG, 1>(ta, tb, p, grid, stream);
+  }
+  if (epi_mode == 2) {  // dgrad through GELU: dY [M,K] x W stored [K,N]
+    NV_REQUIRE(!a_mn && b_mn, "gemm: gelu_u is only built for the dgrad layout (A K-major, B MN-major)");
+    return launch_variant<BLOCK_N, STAGES, false, true, CG, 2>(ta, tb, p, grid, stream);
+  }
+  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, false, false, CG, 0>(ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_variant<BLOCK_N, STAGES, false, true, CG, 0>(ta, tb, p, grid, stream);
+  if (a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, true, false, CG, 0>(ta, tb, p, grid, stream);
+  return launch_variant<BLOCK_N, STAGES, true, true, CG, 0>(ta, tb, p, grid, stream);
 }
 
 }  // namespace
@@ -499,10 +548,15 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int max_workers = num_sms / cta_group;
   const int grid = (total_units < max_workers ? total_units : max_workers) * cta_group;
+  NV_REQUIRE(!(apply_gelu && gelu_u != nullptr), "gemm: apply_gelu and gelu_u are mutually exclusive");
+  NV_REQUIRE(!((apply_gelu || gelu_u != nullptr) && (residual != nullptr || accumulate || alpha != 1.0f)),
+             "gemm: the GELU epilogues take no residual / accumulate / alpha");
+  NV_REQUIRE(!(gelu_u != nullptr && bias != nullptr), "gemm: the GELU-grad epilogue takes no bias");
+  const int epi_mode = apply_gelu ? 1 : (gelu_u != nullptr ? 2 : 0);
   if (cta_group == 2) {
-    if (block_n == 256) return launch_major<256, 6, 2>(a_mn, b_mn, ta, tb, p, grid, stream);
-    return launch_major<128, 8, 2>(a_mn, b_mn, ta, tb, p, grid, stream);
+    if (block_n == 256) return launch_major<256, 6, 2>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
+    return launch_major<128, 8, 2>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
   }
-  if (block_n == 256) return launch_major<256, 4, 1>(a_mn, b_mn, ta, tb, p, grid, stream);
-  return launch_major<128, 6, 1>(a_mn, b_mn, ta, tb, p, grid, stream);
+  if (block_n == 256) return launch_major<256, 4, 1>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
+  return launch_major<128, 6, 1>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
 }
