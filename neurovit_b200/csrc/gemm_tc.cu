@@ -27,10 +27,10 @@ namespace {
 constexpr int BLOCK_M = 128;  // accumulator rows per CTA (TMEM lanes)
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int TMA_WARP = 8;
-constexpr int MMA_WARP = 9;
-constexpr int NUM_THREADS = 320;
+// epilogue warps: 8 for the store epilogue (memory-bound: residual prefetch is double-buffered in registers),
+// 16 for the two GELU epilogues (instruction-bound: four warps per SM sub-partition hide the MUFU/FMA chains)
+__host__ __device__ constexpr int epi_warps(int epi_mode) { return epi_mode == 0 ? 8 : 16; }
+__host__ __device__ constexpr int num_threads(int epi_mode) { return (epi_warps(epi_mode) + 2) * 32; }
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;          // per epilogue warp
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;       // shared::cluster address of the pair's leader CTA
@@ -52,7 +52,7 @@ struct GemmParams {
   float alpha;
 };
 
-template <int BLOCK_N, int STAGES, int CG>
+template <int BLOCK_N, int STAGES, int CG, int NUM_EPI_WARPS>
 struct SmemLayout {
   static constexpr int B_ROWS = BLOCK_N / CG;  // B rows staged by one CTA
   static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
@@ -157,27 +157,29 @@ struct EpiAux {  // global operands of one 32x32 chunk, prefetched one chunk ahe
 
 template <int EPI_MODE>
 __device__ __forceinline__ void epi_prefetch(const GemmParams& p, EpiAux& x, int lane, int row0, int col0) {
+  // Out-of-range rows/columns are CLAMPED to a valid address instead of predicated: a "ok ? load : 0"
+  // select makes the warp wait for the load right here and defeats the prefetch; clamped values are
+  // simply never stored.
   const int sub_r = lane >> 3, sub_c = lane & 7;
-  const int gn = col0 + sub_c * 4;
-  const bool col_ok = gn < p.N;
+  const int gn_raw = col0 + sub_c * 4;
+  const bool col_ok = gn_raw < p.N;
+  const int gn = col_ok ? gn_raw : 0;
   if (EPI_MODE == 0 && p.residual != nullptr) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int gm = row0 + i * 4 + sub_r;
-      x.res[i] = (col_ok && gm < p.M) ? *reinterpret_cast<const float4*>(p.residual + (int64_t)gm * p.ld_res + gn)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int gm = min(row0 + i * 4 + sub_r, p.M - 1);
+      x.res[i] = *reinterpret_cast<const float4*>(p.residual + (int64_t)gm * p.ld_res + gn);
     }
   }
   if (EPI_MODE == 2) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int gm = row0 + i * 4 + sub_r;
-      x.uu[i] = (col_ok && gm < p.M) ? *reinterpret_cast<const uint2*>(p.gelu_u + (int64_t)gm * p.ld_u + gn)
-                                     : make_uint2(0u, 0u);
+      const int gm = min(row0 + i * 4 + sub_r, p.M - 1);
+      x.uu[i] = *reinterpret_cast<const uint2*>(p.gelu_u + (int64_t)gm * p.ld_u + gn);
     }
   }
   x.bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI_MODE != 2 && p.bias != nullptr && col_ok) x.bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
+  if (EPI_MODE != 2 && p.bias != nullptr) x.bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
 }
 
 template <int EPI_MODE>
@@ -251,10 +253,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 }
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(EPI_MODE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES, CG>;
+  constexpr int NUM_EPI_WARPS = epi_warps(EPI_MODE);
+  constexpr int TMA_WARP = NUM_EPI_WARPS;
+  constexpr int MMA_WARP = NUM_EPI_WARPS + 1;
+  using L = SmemLayout<BLOCK_N, STAGES, CG, NUM_EPI_WARPS>;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem window starts at the same offset in every CTA, so the aligned layout (and therefore
   // every barrier / tile offset) is identical in both CTAs of a pair
@@ -398,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ------------------------------- epilogue warps -----------------------------------------
     const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int half = warp >> 2;   // which column chunks (even/odd) this warp owns
+    const int part = warp >> 2;   // which 32-column chunks (part, part + W, ...) this warp owns
     float* stage = reinterpret_cast<float*>(smem + L::EPI_OFF + warp * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_ph = 0;
@@ -407,21 +412,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = tile / p.num_n_tiles;
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
-      constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks owned by this warp (every other one)
-      EpiAux aux[2];
-      const int colbase = n_blk * BLOCK_N + half * 32;
-      epi_prefetch<EPI_MODE>(p, aux[0], lane, row0, colbase);  // overlaps the wait for the accumulator
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
+      constexpr int W = NUM_EPI_WARPS / 4;        // warps sharing one TMEM lane quarter split the columns
+      constexpr int CHUNKS = BLOCK_N / (32 * W);  // 32-column chunks owned by this warp
+      const int colbase = n_blk * BLOCK_N + part * 32;
+      const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + part * 32;
+      if constexpr (EPI_MODE == 0) {
+        EpiAux aux[2];
+        epi_prefetch<EPI_MODE>(p, aux[0], lane, row0, colbase);  // overlaps the wait for the accumulator
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
 #pragma unroll
-      for (int ci = 0; ci < CHUNKS; ++ci) {
-        const int col0 = colbase + ci * 64;
-        if (ci + 1 < CHUNKS) epi_prefetch<EPI_MODE>(p, aux[(ci + 1) & 1], lane, row0, col0 + 64);
-        if (col0 < p.N) {  // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * 32 + ci * 64, v);
-          tmem_ld_wait();
-          epilogue_chunk<EPI_MODE>(p, v, stage, lane, row0, col0, aux[ci & 1]);
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          const int col0 = colbase + ci * 32 * W;
+          if (ci + 1 < CHUNKS) epi_prefetch<EPI_MODE>(p, aux[(ci + 1) & 1], lane, row0, col0 + 32 * W);
+          if (col0 < p.N) {  // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(tm_row + ci * 32 * W, v);
+            tmem_ld_wait();
+            epilogue_chunk<EPI_MODE>(p, v, stage, lane, row0, col0, aux[ci & 1]);
+          }
+        }
+      } else {
+        EpiAux aux;
+        epi_prefetch<EPI_MODE>(p, aux, lane, row0, colbase);
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          const int col0 = colbase + ci * 32 * W;
+          if (ci > 0) epi_prefetch<EPI_MODE>(p, aux, lane, row0, col0);
+          if (col0 < p.N) {  // warp-uniform
+            uint32_t v[32];
+            tmem_ld_32x32(tm_row + ci * 32 * W, v);
+            tmem_ld_wait();
+            epilogue_chunk<EPI_MODE>(p, v, stage, lane, row0, col0, aux);
+          }
         }
       }
       tc_fence_before();
@@ -445,7 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                    cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES, CG>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG, epi_warps(EPI_MODE)>;
   static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG, EPI_MODE>;
   static bool attr_set = false;  // per instantiation; idempotent, races are benign
@@ -455,7 +480,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(num_threads(EPI_MODE));
   cfg.dynamicSmemBytes = L::DYN_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -469,21 +494,31 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   return NV_OK;
 }
 
-template <int BLOCK_N, int STAGES, int CG>
+// pipeline depth: what fits in 227 KB next to the epilogue staging (4 KB per epilogue warp)
+template <int BLOCK_N, int CG, int EPI_MODE>
+constexpr int stages_for() {
+  constexpr int stage_bytes = A_STAGE_BYTES + (BLOCK_N / CG) * BLOCK_K * 2;
+  constexpr int budget = 232448 - 1024 - 256 - epi_warps(EPI_MODE) * EPI_STAGE_BYTES;
+  constexpr int n = budget / stage_bytes;
+  return n > 8 ? 8 : n;
+}
+
+template <int BLOCK_N, int CG>
 int launch_major(int a_mn, int b_mn, int epi_mode, const CUtensorMap& ta, const CUtensorMap& tb,
                  const GemmParams& p, int grid, cudaStream_t stream) {
   if (epi_mode == 1) {  // GELU forward: activations x weights, both K-major
     NV_REQUIRE(!a_mn && !b_mn, "gemm: apply_gelu is only built for K-major operands (forward linear)");
-    return launch_variant<BLOCK_N, STAGES, false, false, CG, 1>(ta, tb, p, grid, stream);
+    return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 1>(), false, false, CG, 1>(ta, tb, p, grid, stream);
   }
   if (epi_mode == 2) {  // dgrad through GELU: dY [M,K] x W stored [K,N]
     NV_REQUIRE(!a_mn && b_mn, "gemm: gelu_u is only built for the dgrad layout (A K-major, B MN-major)");
-    return launch_variant<BLOCK_N, STAGES, false, true, CG, 2>(ta, tb, p, grid, stream);
+    return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 2>(), false, true, CG, 2>(ta, tb, p, grid, stream);
   }
-  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, false, false, CG, 0>(ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return launch_variant<BLOCK_N, STAGES, false, true, CG, 0>(ta, tb, p, grid, stream);
-  if (a_mn && !b_mn) return launch_variant<BLOCK_N, STAGES, true, false, CG, 0>(ta, tb, p, grid, stream);
-  return launch_variant<BLOCK_N, STAGES, true, true, CG, 0>(ta, tb, p, grid, stream);
+  constexpr int S = stages_for<BLOCK_N, CG, 0>();
+  if (!a_mn && !b_mn) return launch_variant<BLOCK_N, S, false, false, CG, 0>(ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_variant<BLOCK_N, S, false, true, CG, 0>(ta, tb, p, grid, stream);
+  if (a_mn && !b_mn) return launch_variant<BLOCK_N, S, true, false, CG, 0>(ta, tb, p, grid, stream);
+  return launch_variant<BLOCK_N, S, true, true, CG, 0>(ta, tb, p, grid, stream);
 }
 
 }  // namespace
@@ -554,9 +589,9 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   NV_REQUIRE(!(gelu_u != nullptr && bias != nullptr), "gemm: the GELU-grad epilogue takes no bias");
   const int epi_mode = apply_gelu ? 1 : (gelu_u != nullptr ? 2 : 0);
   if (cta_group == 2) {
-    if (block_n == 256) return launch_major<256, 6, 2>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
-    return launch_major<128, 8, 2>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
+    if (block_n == 256) return launch_major<256, 2>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
+    return launch_major<128, 2>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
   }
-  if (block_n == 256) return launch_major<256, 4, 1>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
-  return launch_major<128, 6, 1>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
+  if (block_n == 256) return launch_major<256, 1>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
+  return launch_major<128, 1>(a_mn, b_mn, epi_mode, ta, tb, p, grid, stream);
 }

@@ -66,7 +66,8 @@ def test_gemm_bf16_epilogues():
     ud = u.double().requires_grad_(True)
     g, = torch.autograd.grad(torch.nn.functional.gelu(ud).sum(), ud)
     cs = torch.ones(N, device=DEV)
-    ops.gemm_bf16(a, w, gelu_u=u, out_f32=out, colsum=cs)
+    wt = w.t().contiguous()  # dgrad layout: B stored [K, N]
+    ops.gemm_bf16(a, wt, b_mn=True, gelu_u=u, out_f32=out, colsum=cs)
     assert rel_err(out, (a.double() @ w.double().t()) * g) < 1e-3
     assert rel_err(cs, ((a.double() @ w.double().t()) * g).sum(0) + 1) < 1e-3   # fused bias-gradient column sum
     # split-K accumulate into a pre-loaded fp32 buffer (wgrad): dW[N_out,K_in] = dY^T X
