@@ -146,8 +146,12 @@ def test_vit_vs_oracle_ragged_tokens(mode):
             if p.dim() == 1:
                 p.add_(0.1 * torch.randn_like(p))
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    # Labels are all the same class on purpose: at random init every sample produces nearly the same logits, so
+    # with opposite labels the per-sample gradients of the batch-summed parameters (pos_embedding, cls_token,
+    # patch-embedding biases) cancel to ~3% of their size and a 0.3% bf16 rounding error on each reads as 5-6%
+    # of the (ill-conditioned) sum. Same-class labels keep the comparison well-conditioned.
     video = torch.randn(2, 1, 48, 64, 64)
-    labels = torch.tensor([1, 0])
+    labels = torch.tensor([1, 1])
     ref_logits, ref_loss, ref_grads = O.vit3d_loss_and_grads(sd, video, labels, patch=(8, 8, 8), heads=8)
     m = m.to(DEV).eval().set_precision(mode)
     logits = m(video.to(DEV))
