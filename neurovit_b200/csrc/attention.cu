@@ -85,14 +85,11 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // C[16 x 64] += A[16 x 64(k)] * Bt where the B tile is stored [n][k]
-// n16: number of 16-column groups of the B tile that hold valid rows (ragged last tile: skip the rest)
-__device__ __forceinline__ void mm_a_bnk(float (&c)[8][4], const uint32_t (&a)[4][4], const uint8_t* btile, int lane,
-                                         int n16 = 4) {
+__device__ __forceinline__ void mm_a_bnk(float (&c)[8][4], const uint32_t (&a)[4][4], const uint8_t* btile, int lane) {
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
-      if (np >= n16) continue;  // warp-uniform
       uint32_t r[4];
       ldsm_b_nk(r, btile, 16 * np, ks, lane);
       mma_bf16(c[2 * np], a[ks], r[0], r[1]);
@@ -100,12 +97,9 @@ __device__ __forceinline__ void mm_a_bnk(float (&c)[8][4], const uint32_t (&a)[4
     }
 }
 // C[16 x 64] += A[16 x 64(k)] * B where the B tile is stored [k][n]
-// k16: number of 16-row groups of the B tile (= k steps) that hold valid rows
-__device__ __forceinline__ void mm_a_bkn(float (&c)[8][4], const uint32_t (&a)[4][4], const uint8_t* btile, int lane,
-                                         int k16 = 4) {
+__device__ __forceinline__ void mm_a_bkn(float (&c)[8][4], const uint32_t (&a)[4][4], const uint8_t* btile, int lane) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    if (kk >= k16) continue;  // warp-uniform
+  for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {
       uint32_t r[4];
@@ -113,7 +107,6 @@ __device__ __forceinline__ void mm_a_bkn(float (&c)[8][4], const uint32_t (&a)[4
       mma_bf16(c[2 * dp], a[kk], r[0], r[1]);
       mma_bf16(c[2 * dp + 1], a[kk], r[2], r[3]);
     }
-  }
 }
 // accumulator tile (16 x 64 fp32, C layout) -> A fragments (bf16) for a following MMA over its columns
 __device__ __forceinline__ void acc_to_afrag(uint32_t (&a)[4][4], const float (&c)[8][4]) {
@@ -160,7 +153,6 @@ attn_fwd_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensorOut o, float
   float m_run[2] = {-INFINITY, -INFINITY};  // running max (log2 domain) for rows g, g+8
   float l_run[2] = {0.f, 0.f};
   const float c = scale * LOG2E;
-  const bool warp_active = q0 + warp * 16 < N;
 
   for (int j = 0; j < nkv; ++j) {
     cp_async_wait<0>();
@@ -174,13 +166,11 @@ attn_fwd_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensorOut o, float
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) ldsm_a(qf[ks], sQ, warp * 16, ks, lane);
     }
-    if (!warp_active) continue;  // this warp's 16 query rows are all padding (ragged last tile): syncs only
-    const int key0 = j * BR;
-    const int g16 = (min(BR, N - key0) + 15) >> 4;  // 16-key groups with valid keys in this block
     float s[8][4];
     zero_acc(s);
-    mm_a_bnk(s, qf, sK[j & 1], lane, g16);
+    mm_a_bnk(s, qf, sK[j & 1], lane);
     // scale to log2 domain, mask keys >= N
+    const int key0 = j * BR;
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -218,7 +208,7 @@ attn_fwd_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensorOut o, float
     }
     uint32_t pf[4][4];
     acc_to_afrag(pf, s);
-    mm_a_bkn(oacc, pf, sV[j & 1], lane, g16);
+    mm_a_bkn(oacc, pf, sV[j & 1], lane);
   }
   // finalise: reduce row sums across the 4 lanes of a quad, normalise, store
 #pragma unroll
@@ -309,7 +299,6 @@ attn_bwd_dkv_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensor dO, con
   zero_acc(dk_acc);
   zero_acc(dv_acc);
   const int key_lo = k0 + warp * 16 + g;  // rows g and g+8 of this warp's slice
-  const bool warp_active = k0 + warp * 16 < N;
 
   for (int j = 0; j < nq; ++j) {
     cp_async_wait<0>();
@@ -331,14 +320,12 @@ attn_bwd_dkv_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensor dO, con
     const uint8_t* sd = sm.d[j & 1];
     const float* s_lse2 = sm.lse2[j & 1];
     const float* s_delta = sm.delta[j & 1];
-    if (!warp_active) continue;  // this warp's 16 keys are all padding
-    const int g16 = (min(BR, N - j * BR) + 15) >> 4;  // 16-query groups with valid rows in this block
     float st[8][4];  // S^T tile: 16 keys x 64 queries
     zero_acc(st);
-    mm_a_bnk(st, kf, sq, lane, g16);
+    mm_a_bnk(st, kf, sq, lane);
     float dpt[8][4];
     zero_acc(dpt);
-    mm_a_bnk(dpt, vf, sd, lane, g16);
+    mm_a_bnk(dpt, vf, sd, lane);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -351,9 +338,9 @@ attn_bwd_dkv_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensor dO, con
       }
     uint32_t pf[4][4];
     acc_to_afrag(pf, st);
-    mm_a_bkn(dv_acc, pf, sd, lane, g16);  // dV += P^T dO
+    mm_a_bkn(dv_acc, pf, sd, lane);  // dV += P^T dO
     acc_to_afrag(pf, dpt);
-    mm_a_bkn(dk_acc, pf, sq, lane, g16);  // dK += dS^T Q
+    mm_a_bkn(dk_acc, pf, sq, lane);  // dK += dS^T Q
   }
   bf16* dkp = dk.ptr + (int64_t)b * dk.batch_stride + h * HD;
   bf16* dvp = dv.ptr + (int64_t)b * dv.batch_stride + h * HD;
@@ -413,7 +400,6 @@ attn_bwd_dq_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensor dO, cons
   uint32_t qf[4][4], df[4][4];
   float dq_acc[8][4];
   zero_acc(dq_acc);
-  const bool warp_active = q0 + warp * 16 < N;
 
   for (int j = 0; j < nkv; ++j) {
     cp_async_wait<0>();
@@ -432,14 +418,12 @@ attn_bwd_dq_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensor dO, cons
     }
     const uint8_t* sk = sm.k[j & 1];
     const uint8_t* sv = sm.v[j & 1];
-    if (!warp_active) continue;  // padding rows only
-    const int key0 = j * BR;
-    const int g16 = (min(BR, N - key0) + 15) >> 4;
     float s[8][4], dp[8][4];
     zero_acc(s);
     zero_acc(dp);
-    mm_a_bnk(s, qf, sk, lane, g16);   // S = Q K^T
-    mm_a_bnk(dp, df, sv, lane, g16);  // dP = dO V^T
+    mm_a_bnk(s, qf, sk, lane);   // S = Q K^T
+    mm_a_bnk(dp, df, sv, lane);  // dP = dO V^T
+    const int key0 = j * BR;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -450,7 +434,7 @@ attn_bwd_dq_kernel(AttnTensor q, AttnTensor k, AttnTensor v, AttnTensor dO, cons
       }
     uint32_t dsf[4][4];
     acc_to_afrag(dsf, s);
-    mm_a_bkn(dq_acc, dsf, sk, lane, g16);  // dQ += dS K
+    mm_a_bkn(dq_acc, dsf, sk, lane);  // dQ += dS K
   }
   bf16* dqp = dq.ptr + (int64_t)b * dq.batch_stride + h * HD;
 #pragma unroll
