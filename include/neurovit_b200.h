@@ -101,16 +101,24 @@ int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_
 /* ---- attention --------------------------------------------------------------------------------------
  * replaces: vit_3d.py:51-59. q/k/v are read in place from the QKV projection output
  * [B, N, 3*H*64] (pointers to the q, k, v column blocks; shared batch/row strides), O is written as
- * [B, N, H*64]; lse [B,H,N] fp32 is saved for backward. head_dim must be 64 (bf16 flash kernels). */
+ * [B, N, H*64]; lse [B,H,N] fp32 is saved for backward. head_dim must be 64 (bf16 flash kernels,
+ * tcgen05 / TMEM). dropout_p > 0 applies nn.Dropout to the probabilities (vit_3d.py:56): forward draws the
+ * keep bits from (seed) and saves them in drop_mask, uint32 [B*H, N, ceil(N/32)] (bit k of word w of row q =
+ * score (q, 32w+k) survives); backward reads them. drop_mask may be NULL when dropout_p == 0. */
 int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse,
-                     int B, int N, int H, int head_dim, float scale, void* stream);
+                     int B, int N, int H, int head_dim, float scale, float dropout_p, int64_t seed,
+                     void* drop_mask, void* stream);
 /* delta_ws: fp32 workspace of B*H*N elements */
 int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      const void* o, const void* dO, int64_t o_batch_stride, int64_t o_row_stride,
                      const float* lse, float* delta_ws,
                      void* dq, void* dk, void* dv, int64_t dqkv_batch_stride, int64_t dqkv_row_stride,
-                     int B, int N, int H, int head_dim, float scale, void* stream);
+                     int B, int N, int H, int head_dim, float scale, float dropout_p, const void* drop_mask,
+                     void* stream);
+/* kernel variant behind nv_attention_*: 0 = tcgen05/TMEM (default), 1 = mma.sync (no dropout; kept as an
+ * on-device cross-check for the tests and probes) */
+int nv_set_attention_impl(int impl);
 /* fp32 verification path: materialised softmax (vit_3d.py:55) and its backward, in place */
 int nv_softmax_fwd(float* s, int64_t rows, int n, void* stream);
 int nv_softmax_bwd(const float* P, float* dP, int64_t rows, int n, void* stream);

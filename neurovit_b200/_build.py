@@ -24,6 +24,7 @@ SOURCES = [
     "layernorm.cu",
     "patch_embed.cu",
     "attention.cu",
+    "attention_tc.cu",
     "misc.cu",
     "temporal.cu",
     "api.cu",

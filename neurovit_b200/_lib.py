@@ -33,9 +33,10 @@ SIGNATURES = {
     "nv_cls_row": [_p, _p, _p, _l, _i, _i, _p],
     "nv_patch_gather_ln": [_p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p, _f, _p],
     "nv_patch_ln_param_grad": [_p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
-    "nv_attention_fwd": [_p, _p, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _p],
+    "nv_attention_fwd": [_p, _p, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _l, _p, _p],
     "nv_attention_bwd": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _p, _p, _p, _p, _l, _l,
-                         _i, _i, _i, _i, _f, _p],
+                         _i, _i, _i, _i, _f, _f, _p, _p],
+    "nv_set_attention_impl": [_i],
     "nv_softmax_fwd": [_p, _l, _i, _p],
     "nv_softmax_bwd": [_p, _p, _l, _i, _p],
     "nv_cast_f32_bf16": [_p, _p, _l, _p],
@@ -106,7 +107,7 @@ def require_device(device_index: int) -> None:
 
 class _LaunchCounter:
     """Counts the CUDA kernels launched through the C ABI (bench.py reports it as `gpu_launches`)."""
-    KERNELS_PER_CALL = {"nv_attention_bwd": 3, "nv_version": 0, "nv_device_check": 0}
+    KERNELS_PER_CALL = {"nv_attention_bwd": 3, "nv_version": 0, "nv_device_check": 0, "nv_set_attention_impl": 0}
 
     def __init__(self):
         self.count = 0

@@ -1,0 +1,840 @@
+// tcgen05 / TMEM flash attention, forward and backward, head_dim = 64, bf16 operands, fp32 statistics.
+// Reference: src/models/vit_3d.py:51-59 (dots = q k^T * scale; softmax(dim=-1); dropout; attn v;
+// 'b h n d -> b n (h d)'), SURVEY 8a row A8. No mask, not causal; [B,h,N,N] is never materialised.
+//
+// All three kernels share one skeleton: a CTA owns 128 rows (= the 128 TMEM lanes) of one (batch, head),
+//   warps 0-3  "row" warps: thread i owns TMEM lane i, i.e. one query (fwd, dQ) or one key (dK/dV) row.
+//              tcgen05.ld gives the thread its whole score row, so the softmax statistics (row max, row
+//              sum, LSE, delta) live in that thread's registers with no cross-thread reduction at all;
+//              probabilities go back to shared memory as a bf16 K-major 128B-swizzled MMA operand.
+//   warp  4    TMA producer: 64-row x 64-col bf16 boxes of q / k / v / dO read IN PLACE from the QKV GEMM
+//              output through 3-D tensor maps (col, token, batch); rows past N are zero-filled by TMA.
+//   warp  5    TMEM allocator + tcgen05.mma issuer.
+// TMEM budget is 256 columns and shared memory <= 113 KB per CTA, so two CTAs are co-resident per SM:
+// one CTA's exponentials (MUFU-bound at head_dim 64) overlap the other CTA's MMAs and TMA waits.
+// Ragged sizes (N = 385 = 3*128 + 1): row warps whose 32 rows are all >= N skip their work, the last
+// column block shrinks to a multiple of 16, so the extra token costs MMA issue slots but almost no MUFU.
+//
+//   fwd : per key block j (128 keys): S = Q K_j^T -> TMEM; rows: m, p = 2^(S*c - m), l; P -> smem;
+//         O_j = P V_j -> TMEM (fresh accumulator, double-buffered); rows fold O_j into registers with the
+//         usual 2^(m_old - m_new) rescale, so TMEM is never rescaled in place.
+//   dQ  : per key block j (64 keys): S = Q K_j^T, dP = dO V_j^T -> TMEM; dS = P o (dP - delta) -> smem;
+//         dQ += dS K_j accumulates in TMEM (K_j tile reused as the MN-major B operand).
+//   dKV : per query block i (64 queries): S^T = K Q_i^T, dP^T = V dO_i^T -> TMEM (lane = key);
+//         P^T, dS^T -> smem; dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM.
+#include "nv_common.cuh"
+#include "nv_rng.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int BQ = 128;               // rows per CTA (TMEM lanes)
+constexpr int SLAB = BQ * 128;        // 16 KB: [128 rows x 64 bf16], K-major, 128B swizzle
+constexpr int BOX = 64 * 128;         // 8 KB: one TMA box (64 rows x 64 bf16)
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+constexpr int NTHREADS = 192;
+constexpr int TMA_WARP = 4, MMA_WARP = 5;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 32 consecutive bf16 of row `row` of a K-major SW128 operand tile, columns [32*chunk, 32*chunk+32)
+__device__ __forceinline__ void store_operand_chunk(uint32_t tile_base, int row, int chunk, const uint32_t (&w)[16]) {
+  const uint32_t slab = tile_base + (uint32_t)(chunk >> 1) * SLAB + (uint32_t)row * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = ((chunk & 1) << 2) + i;
+    st_shared_v4(slab + (uint32_t)((ch ^ (row & 7)) << 4), w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+}
+// rows [row0, row0 + 64*nbox) x 64 columns at column `col` of batch `b` -> consecutive 8 KB boxes
+__device__ __forceinline__ void load_rows(uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int col, int row0, int b,
+                                          int nbox) {
+  for (int i = 0; i < nbox; ++i) tma_load_3d(dst + i * BOX, m, bar, col, row0 + 64 * i, b);
+}
+__device__ __forceinline__ uint64_t kmajor_desc(const uint8_t* tile) { return umma_smem_desc_sw128(smem_u32(tile), 16, 1024); }
+__device__ __forceinline__ uint64_t mnmajor_desc(const uint8_t* tile) { return umma_smem_desc_sw128(smem_u32(tile), SLAB, 1024); }
+// D[128 x n] (+)= A[128 x 64 (one slab, K-major)] * B[n x 64 (K-major)]^T : 4 k-steps of 16
+__device__ __forceinline__ void mma_k64(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k > 0);
+}
+// D[128 x 64] (+)= A[128 x 16*ksteps (K-major slabs of 64)] * B[16*ksteps x 64 (MN-major: rows = k)]
+__device__ __forceinline__ void mma_rows(uint32_t d_tmem, const uint8_t* a_tile, const uint8_t* b_tile, uint32_t idesc,
+                                         int ksteps, bool accumulate) {
+  const uint64_t a0 = kmajor_desc(a_tile), b0 = mnmajor_desc(b_tile);
+  for (int k = 0; k < ksteps; ++k)
+    umma_f16_ss(d_tmem, a0 + (uint64_t)((k >> 2) * (SLAB >> 4) + (k & 3) * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc,
+                (accumulate || k > 0) ? 1u : 0u);
+}
+
+struct Common {
+  int N, H;
+  float scale;        // dim_head^-0.5
+  // dropout on the attention probabilities (vit_3d.py:56). Forward draws the keep bits (Philox, keyed by
+  // seed and (batch*head, query, key / 8)) and saves them, one bit per score, as mask[B*H, N, mask_words];
+  // both backward kernels read the saved bits (dK/dV walks the score matrix transposed).
+  uint32_t drop_thr;  // 0 = off
+  float keep_scale;   // 1 / (1 - p_eff)
+  uint64_t seed;
+  uint32_t* mask;
+  int mask_words;     // ceil(N / 32)
+};
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+struct FwdParams {
+  Common c;
+  bf16* o;
+  int64_t o_bs, o_rs;
+  float* lse;
+};
+constexpr int FWD_KB = 128;
+constexpr int FWD_SMEM_TILES = SLAB /*Q*/ + 2 * 2 * SLAB /*K,V x 2 stages*/ + 2 * SLAB /*P*/;
+constexpr int FWD_SMEM = FWD_SMEM_TILES + 128;
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + SLAB;                 // stage s: K at s*2*SLAB, V at s*2*SLAB + SLAB
+  uint8_t* sP = smem + SLAB + 4 * SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_SMEM_TILES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* kv_full = bars + 1;     // 2
+  uint64_t* kv_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;      // 1
+  uint64_t* sp_ready = bars + 6;    // 1
+  uint64_t* o_full = bars + 7;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.c.N;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int nblk = (N + FWD_KB - 1) / FWD_KB;
+  const int rows_here = min(BQ, N - q0);
+  const int nactive = (rows_here + 31) >> 5;  // row warps with at least one valid query
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("attn_tc_fwd: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&o_full[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(sp_ready, 32 * nactive);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;  // O buffers at +128, +192
+
+  if (warp == TMA_WARP) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, SLAB);
+      load_rows(sQ, &tq, q_full, h * HD, q0, b, 2);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[s], 2 * SLAB);
+        load_rows(sKV + s * 2 * SLAB, &tk, &kv_full[s], h * HD, j * FWD_KB, b, 2);
+        load_rows(sKV + s * 2 * SLAB + SLAB, &tv, &kv_full[s], h * HD, j * FWD_KB, b, 2);
+      }
+      __syncwarp();
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
+    const uint64_t q_desc = kmajor_desc(sQ);
+    auto cols16 = [&](int j) { return (min(FWD_KB, N - j * FWD_KB) + 15) & ~15; };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      mma_k64(tS, q_desc, kmajor_desc(sKV), umma_idesc_bf16(128, cols16(0), 0, 0));
+      umma_commit(s_full);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(sp_ready, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        mma_rows(tO + (uint32_t)(s * HD), sP, sKV + s * 2 * SLAB + SLAB, idesc_pv, cols16(j) >> 4, false);
+        umma_commit(&o_full[s]);
+        umma_commit(&kv_empty[s]);
+      }
+      __syncwarp();
+      if (j + 1 < nblk) {
+        const int s1 = (j + 1) & 1;
+        mbar_wait(&kv_full[s1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          mma_k64(tS, q_desc, kmajor_desc(sKV + s1 * 2 * SLAB), umma_idesc_bf16(128, cols16(j + 1), 0, 0));
+          umma_commit(s_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < nactive) {
+    const int row = warp * 32 + lane;  // row within the tile == TMEM lane
+    const int qrow = q0 + row;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t sP_u32 = smem_u32(sP);
+    const float cs = p.c.scale * LOG2E;
+    const bool dropout = p.c.drop_thr != 0;
+    const int bh = b * p.c.H + h;
+    float o_acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+
+    for (int j = 0; j < nblk; ++j) {
+      const int key0 = j * FWD_KB;
+      const int nvalid = min(FWD_KB, N - key0);
+      const int nch = (nvalid + 31) >> 5;
+      const bool full = nvalid == FWD_KB;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: block row max (raw scores)
+      float mx = -INFINITY;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, key0 + c * 32 + i < N ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * cs);  // finite: every block holds >= 1 valid key
+      const float alpha = ex2(m_run - m_new);
+      // fold the previous block's P V into the register accumulator (also proves P's smem buffer is free)
+      if (j > 0) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tO + lane_base + ((j - 1) & 1) * HD + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+        }
+      }
+      alpha_prev = alpha;
+      // pass 2: p = 2^(s*c - m), row sum, bf16 operand tile
+      float rs0 = 0.f, rs1 = 0.f;
+      for (int c = 0; c < nch; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tS + lane_base + c * 32, v);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = ex2(fmaf(__uint_as_float(v[i]), cs, -m_new));
+          if (!full) e = key0 + c * 32 + i < N ? e : 0.f;
+          pv[i] = e;
+          if (i & 1) rs1 += e; else rs0 += e;
+        }
+        if (dropout) {
+          const uint64_t mrow = (uint64_t)bh * N + min(qrow, N - 1);
+          uint32_t km = 0;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8)
+            km |= nv_keep_bits8(p.c.seed, mrow * (uint64_t)(p.c.mask_words * 4) + (uint64_t)((key0 >> 3) + c * 4 + g8), 0u,
+                                p.c.drop_thr) << (8 * g8);
+          if (qrow < N) p.c.mask[mrow * p.c.mask_words + (key0 >> 5) + c] = km;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = (km >> i) & 1u ? pv[i] * p.c.keep_scale : 0.f;
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
+        store_operand_chunk(sP_u32, row, c, w);
+      }
+      l_run = fmaf(l_run, alpha, rs0 + rs1);
+      m_run = m_new;
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(sp_ready);
+    }
+    // last block's P V
+    {
+      const int jl = nblk - 1;
+      mbar_wait(&o_full[jl & 1], (jl >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tO + lane_base + (jl & 1) * HD + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
+      }
+    }
+    if (qrow < N) {
+      const float inv = 1.0f / l_run;
+      bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)qrow * p.o_rs + h * HD;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 t;
+        t.x = pack_bf16x2(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
+        t.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
+        t.z = pack_bf16x2(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
+        t.w = pack_bf16x2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
+        *reinterpret_cast<uint4*>(op + 8 * i) = t;
+      }
+      p.lse[((int64_t)b * p.c.H + h) * N + qrow] = (m_run + log2f(l_run)) * LN2;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =====================================================================================================
+// backward, dQ: CTA = 128 queries; loop over 64-key blocks
+// =====================================================================================================
+struct BwdParams {
+  Common c;
+  const float* lse;    // [B,H,N] natural log
+  const float* delta;  // [B,H,N]
+  bf16* dq; bf16* dk; bf16* dv;
+  int64_t d_bs, d_rs;
+};
+constexpr int BWD_CB = 64;  // columns per block (keys in dQ, queries in dKV)
+constexpr int DQ_SMEM_TILES = 2 * SLAB /*Q, dO*/ + 2 * 2 * BOX /*K,V x 2 stages*/ + SLAB /*dS*/;
+constexpr int DQ_SMEM = DQ_SMEM_TILES + 128 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                      const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + SLAB;
+  uint8_t* sKV = smem + 2 * SLAB;            // stage s: K at s*2*BOX, V at s*2*BOX + BOX
+  uint8_t* sdS = smem + 2 * SLAB + 4 * BOX;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_TILES);
+  uint64_t* qd_full = bars;         // 1
+  uint64_t* kv_full = bars + 1;     // 2
+  uint64_t* kv_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;      // 1
+  uint64_t* ds_ready = bars + 6;    // 1
+  uint64_t* ds_free = bars + 7;     // 1  (also "dQ accumulated" after the last block)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.c.N;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int nblk = (N + BWD_CB - 1) / BWD_CB;
+  const int nactive = (min(BQ, N - q0) + 31) >> 5;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    mbar_init(qd_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(ds_ready, 32 * nactive);
+    mbar_init(ds_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdQ = tmem_base + 128;
+
+  if (warp == TMA_WARP) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(qd_full, 2 * SLAB);
+      load_rows(sQ, &tq, qd_full, h * HD, q0, b, 2);
+      load_rows(sdO, &tdo, qd_full, h * HD, q0, b, 2);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[s], 2 * BOX);
+        load_rows(sKV + s * 2 * BOX, &tk, &kv_full[s], h * HD, j * BWD_CB, b, 1);
+        load_rows(sKV + s * 2 * BOX + BOX, &tv, &kv_full[s], h * HD, j * BWD_CB, b, 1);
+      }
+      __syncwarp();
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 0, 1);
+    const uint64_t q_desc = kmajor_desc(sQ), do_desc = kmajor_desc(sdO);
+    auto cols16 = [&](int j) { return (min(BWD_CB, N - j * BWD_CB) + 15) & ~15; };
+    auto issue_scores = [&](int j) {
+      const uint8_t* kt = sKV + (j & 1) * 2 * BOX;
+      const uint32_t idesc = umma_idesc_bf16(128, cols16(j), 0, 0);
+      mma_k64(tS, q_desc, kmajor_desc(kt), idesc);         // S  = Q  K_j^T
+      mma_k64(tdP, do_desc, kmajor_desc(kt + BOX), idesc);  // dP = dO V_j^T
+      umma_commit(s_full);
+    };
+    mbar_wait(qd_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_scores(0);
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j & 1;
+      mbar_wait(ds_ready, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        mma_rows(tdQ, sdS, sKV + s * 2 * BOX, idesc_dq, cols16(j) >> 4, j > 0);  // dQ += dS K_j
+        umma_commit(&kv_empty[s]);
+        umma_commit(ds_free);
+      }
+      __syncwarp();
+      if (j + 1 < nblk) {
+        mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) issue_scores(j + 1);
+        __syncwarp();
+      }
+    }
+  } else if (warp < nactive) {
+    const int row = warp * 32 + lane;
+    const int qrow = q0 + row;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t sdS_u32 = smem_u32(sdS);
+    const float cs = p.c.scale * LOG2E;
+    const bool dropout = p.c.drop_thr != 0;
+    const int64_t stat = ((int64_t)b * p.c.H + h) * N + min(qrow, N - 1);
+    const uint64_t mrow = (uint64_t)stat;
+    const float lse2 = p.lse[stat] * LOG2E;
+    const float dl = p.delta[stat];
+    for (int j = 0; j < nblk; ++j) {
+      const int key0 = j * BWD_CB;
+      const int nch = (min(BWD_CB, N - key0) + 31) >> 5;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(ds_free, (j - 1) & 1);  // dS tile consumed by the previous dQ MMA
+      for (int c = 0; c < nch; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tS + lane_base + c * 32, sv);
+        tmem_ld_32x32(tdP + lane_base + c * 32, dv);
+        tmem_ld_wait();
+        float ds[32];
+        // keys >= N: K rows are zero-filled, so whatever finite dS lands there multiplies zeros in dS K
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ds[i] = ex2(fmaf(__uint_as_float(sv[i]), cs, -lse2));
+        if (dropout) {
+          const uint32_t km = p.c.mask[mrow * p.c.mask_words + (key0 >> 5) + c];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ds[i] *= ((km >> i) & 1u ? __uint_as_float(dv[i]) * p.c.keep_scale : 0.f) - dl;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ds[i] *= __uint_as_float(dv[i]) - dl;
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
+        store_operand_chunk(sdS_u32, row, c, w);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(ds_ready);
+    }
+    mbar_wait(ds_free, (nblk - 1) & 1);  // last dQ MMA retired
+    tc_fence_after();
+    {  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows store
+      bf16* dst = p.dq + (int64_t)b * p.d_bs + (int64_t)min(qrow, N - 1) * p.d_rs + h * HD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tdQ + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (qrow < N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t;
+            t.x = pack_bf16x2(__uint_as_float(v[8 * i]) * p.c.scale, __uint_as_float(v[8 * i + 1]) * p.c.scale);
+            t.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * p.c.scale, __uint_as_float(v[8 * i + 3]) * p.c.scale);
+            t.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * p.c.scale, __uint_as_float(v[8 * i + 5]) * p.c.scale);
+            t.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * p.c.scale, __uint_as_float(v[8 * i + 7]) * p.c.scale);
+            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = t;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =====================================================================================================
+// backward, dK / dV: CTA = 128 keys (TMEM lane = key); loop over 64-query blocks
+// =====================================================================================================
+constexpr int DKV_SMEM_TILES = 2 * SLAB /*K, V*/ + 2 * 2 * BOX /*Q_i, dO_i x 2 stages*/ + 2 * SLAB /*P^T, dS^T*/;
+constexpr int DKV_SMEM = DKV_SMEM_TILES + 128 + 4 * 768 /*per-warp lse/delta/mask staging*/ + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                       const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                       const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + SLAB;
+  uint8_t* sQD = smem + 2 * SLAB;            // stage s: Q_i at s*2*BOX, dO_i at s*2*BOX + BOX
+  uint8_t* sPT = smem + 2 * SLAB + 4 * BOX;
+  uint8_t* sdST = sPT + SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DKV_SMEM_TILES);
+  uint64_t* kv_full = bars;         // 1
+  uint64_t* qd_full = bars + 1;     // 2
+  uint64_t* qd_empty = bars + 3;    // 2
+  uint64_t* s_full = bars + 5;      // 1
+  uint64_t* pds_ready = bars + 6;   // 1
+  uint64_t* pds_free = bars + 7;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.c.N;
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BQ;
+  const int nblk = (N + BWD_CB - 1) / BWD_CB;
+  const int nactive = (min(BQ, N - k0) + 31) >> 5;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(pds_ready, 32 * nactive);
+    mbar_init(pds_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tST = tmem_base, tdPT = tmem_base + 64, tdV = tmem_base + 128, tdK = tmem_base + 192;
+
+  if (warp == TMA_WARP) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(kv_full, 2 * SLAB);
+      load_rows(sK, &tk, kv_full, h * HD, k0, b, 2);
+      load_rows(sV, &tv, kv_full, h * HD, k0, b, 2);
+    }
+    __syncwarp();
+    for (int i = 0; i < nblk; ++i) {
+      const int s = i & 1;
+      mbar_wait(&qd_empty[s], ((i >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&qd_full[s], 2 * BOX);
+        load_rows(sQD + s * 2 * BOX, &tq, &qd_full[s], h * HD, i * BWD_CB, b, 1);
+        load_rows(sQD + s * 2 * BOX + BOX, &tdo, &qd_full[s], h * HD, i * BWD_CB, b, 1);
+      }
+      __syncwarp();
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(128, HD, 0, 1);
+    const uint64_t k_desc = kmajor_desc(sK), v_desc = kmajor_desc(sV);
+    auto cols16 = [&](int i) { return (min(BWD_CB, N - i * BWD_CB) + 15) & ~15; };
+    auto issue_scores = [&](int i) {
+      const uint8_t* qt = sQD + (i & 1) * 2 * BOX;
+      const uint32_t idesc = umma_idesc_bf16(128, cols16(i), 0, 0);
+      mma_k64(tST, k_desc, kmajor_desc(qt), idesc);         // S^T  = K Q_i^T
+      mma_k64(tdPT, v_desc, kmajor_desc(qt + BOX), idesc);   // dP^T = V dO_i^T
+      umma_commit(s_full);
+    };
+    mbar_wait(kv_full, 0);
+    mbar_wait(&qd_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) issue_scores(0);
+    __syncwarp();
+    for (int i = 0; i < nblk; ++i) {
+      const int s = i & 1;
+      mbar_wait(pds_ready, i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint8_t* qt = sQD + s * 2 * BOX;
+        mma_rows(tdV, sPT, qt + BOX, idesc_acc, cols16(i) >> 4, i > 0);  // dV += P^T  dO_i
+        mma_rows(tdK, sdST, qt, idesc_acc, cols16(i) >> 4, i > 0);       // dK += dS^T Q_i
+        umma_commit(&qd_empty[s]);
+        umma_commit(pds_free);
+      }
+      __syncwarp();
+      if (i + 1 < nblk) {
+        mbar_wait(&qd_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) issue_scores(i + 1);
+        __syncwarp();
+      }
+    }
+  } else if (warp < nactive) {
+    const int row = warp * 32 + lane;
+    const int krow = k0 + row;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t sPT_u32 = smem_u32(sPT), sdST_u32 = smem_u32(sdST);
+    const float cs = p.c.scale * LOG2E;
+    const float* lse_bh = p.lse + ((int64_t)b * p.c.H + h) * N;
+    const float* delta_bh = p.delta + ((int64_t)b * p.c.H + h) * N;
+    // per-warp staging of the block's 64 per-query statistics: [lse*log2e | delta], read back as broadcasts
+    float* stats = reinterpret_cast<float*>(smem + DKV_SMEM_TILES + 128) + warp * 192;
+    uint32_t* mwords = reinterpret_cast<uint32_t*>(stats + 128);  // dropout: the 64 queries' mask words of this warp's keys
+    const bool dropout = p.c.drop_thr != 0;
+    const uint64_t mbase = ((uint64_t)b * p.c.H + h) * N;
+    for (int i = 0; i < nblk; ++i) {
+      const int qb = i * BWD_CB;
+      const int nvalid = min(BWD_CB, N - qb);
+      const int nch = (nvalid + 31) >> 5;
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int q = qb + t * 32 + lane;
+        const int qc = min(q, N - 1);
+        // padded queries: lse = +inf makes P exactly 0 (their dO / Q rows are zero-filled anyway)
+        stats[t * 32 + lane] = q < N ? __ldg(lse_bh + qc) * LOG2E : INFINITY;
+        stats[64 + t * 32 + lane] = __ldg(delta_bh + qc);
+        if (dropout) mwords[t * 32 + lane] = p.c.mask[(mbase + qc) * p.c.mask_words + ((k0 + warp * 32) >> 5)];
+      }
+      __syncwarp();
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      if (i > 0) mbar_wait(pds_free, (i - 1) & 1);  // P^T / dS^T tiles consumed by the previous dV / dK MMAs
+      for (int c = 0; c < nch; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tST + lane_base + c * 32, sv);
+        tmem_ld_32x32(tdPT + lane_base + c * 32, dv);
+        tmem_ld_wait();
+        float pt[32], ds[32];
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 l2 = *reinterpret_cast<const float4*>(stats + c * 32 + e4 * 4);
+          const float4 dl = *reinterpret_cast<const float4*>(stats + 64 + c * 32 + e4 * 4);
+          const float l2v[4] = {l2.x, l2.y, l2.z, l2.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int e = e4 * 4 + k;
+            const float pe = ex2(fmaf(__uint_as_float(sv[e]), cs, -l2v[k]));
+            pt[e] = pe;
+            ds[e] = pe * (__uint_as_float(dv[e]) - dlv[k]);
+          }
+        }
+        if (dropout) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const bool keep = (mwords[c * 32 + e] >> lane) & 1u;
+            const float pe = pt[e];
+            // ds was pe * (dp - dl); with the mask it is pe * (keep ? dp * ks : 0 - dl)
+            const float dl_pe = fmaf(-pe, __uint_as_float(dv[e]), ds[e]);  // = -pe * dl
+            ds[e] = keep ? fmaf(pe * p.c.keep_scale, __uint_as_float(dv[e]), dl_pe) : dl_pe;
+            pt[e] = keep ? pe * p.c.keep_scale : 0.f;
+          }
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(pt[2 * e], pt[2 * e + 1]);
+        store_operand_chunk(sPT_u32, row, c, w);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
+        store_operand_chunk(sdST_u32, row, c, w);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(pds_ready);
+    }
+    mbar_wait(pds_free, (nblk - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      bf16* base = which == 0 ? p.dv : p.dk;
+      const float mul = which == 0 ? 1.0f : p.c.scale;
+      bf16* dst = base + (int64_t)b * p.d_bs + (int64_t)min(krow, N - 1) * p.d_rs + h * HD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32((which == 0 ? tdV : tdK) + lane_base + c * 32, v);
+        tmem_ld_wait();
+        if (krow < N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t;
+            t.x = pack_bf16x2(__uint_as_float(v[8 * i]) * mul, __uint_as_float(v[8 * i + 1]) * mul);
+            t.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * mul, __uint_as_float(v[8 * i + 3]) * mul);
+            t.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * mul, __uint_as_float(v[8 * i + 5]) * mul);
+            t.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * mul, __uint_as_float(v[8 * i + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = t;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]: one warp per (b, token), all heads of the token in one
+// pass (the token's 8 x 128 B head slices are contiguous), lanes own 16-byte chunks.
+__global__ void attn_tc_delta_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, int64_t bs, int64_t rs,
+                                     float* __restrict__ delta, int B, int N, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)B * N) return;
+  const int i = (int)(w % N), b = (int)(w / N);
+  const bf16* a = dO + (int64_t)b * bs + (int64_t)i * rs;
+  const bf16* c = O + (int64_t)b * bs + (int64_t)i * rs;
+  for (int base = 0; base < H * HD; base += 256) {  // 32 lanes x 8 elements
+    const int col = base + lane * 8;
+    float s = 0.f;
+    if (col < H * HD) {
+      const uint4 x = *reinterpret_cast<const uint4*>(a + col), y = *reinterpret_cast<const uint4*>(c + col);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = unpack_bf16x2(xs[k]), fb = unpack_bf16x2(ys[k]);
+        s = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, s));
+      }
+    }
+    // 8 lanes share a head
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0 && col < H * HD) delta[((int64_t)b * H + (col >> 6)) * N + i] = s;
+  }
+}
+
+int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, int N, int H) {
+  const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)N, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)rs * 2, (uint64_t)bs * 2};
+  const uint32_t box[3] = {64, 64, 1};
+  return nv_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int fill_common(Common& c, int N, int H, float scale, float dropout_p, uint64_t seed, uint32_t* mask) {
+  NV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p %f out of range [0, 1)", dropout_p);
+  c.N = N; c.H = H; c.scale = scale; c.seed = seed;
+  c.drop_thr = nv_dropout_threshold(dropout_p);
+  c.keep_scale = nv_dropout_keep_scale(c.drop_thr);
+  c.mask = mask;
+  c.mask_words = (N + 31) / 32;
+  NV_REQUIRE(c.drop_thr == 0 || mask != nullptr, "attention: dropout needs the mask buffer [B*H, N, ceil(N/32)] uint32");
+  return NV_OK;
+}
+
+int check_args(const void* p, int64_t bs, int64_t rs, const char* name) {
+  NV_REQUIRE(p != nullptr, "attention: %s is null", name);
+  NV_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && bs % 8 == 0 && rs % 8 == 0,
+             "attention: %s must be 16-byte aligned with strides that are multiples of 8 elements", name);
+  return NV_OK;
+}
+
+template <typename K>
+int set_smem(K kern, int bytes) {
+  NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  return NV_OK;
+}
+
+}  // namespace
+
+int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
+                          int64_t o_bs, int64_t o_rs, float* lse, int B, int N, int H, int head_dim, float scale,
+                          float dropout_p, uint64_t seed, uint32_t* drop_mask, cudaStream_t stream) {
+  NV_REQUIRE(head_dim == HD, "attention: head_dim %d unsupported by the bf16 flash kernel (needs 64)", head_dim);
+  NV_REQUIRE(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad sizes B=%d N=%d H=%d", B, N, H);
+  if (B == 0) return NV_OK;
+  int s;
+  if ((s = check_args(q, qkv_bs, qkv_rs, "q")) != NV_OK) return s;
+  if ((s = check_args(k, qkv_bs, qkv_rs, "k")) != NV_OK) return s;
+  if ((s = check_args(v, qkv_bs, qkv_rs, "v")) != NV_OK) return s;
+  if ((s = check_args(o, o_bs, o_rs, "o")) != NV_OK) return s;
+  NV_REQUIRE(lse != nullptr, "attention: lse is null");
+  CUtensorMap tq, tk, tv;
+  if ((s = make_map(&tq, q, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  FwdParams p;
+  if ((s = fill_common(p.c, N, H, scale, dropout_p, seed, drop_mask)) != NV_OK) return s;
+  p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if ((s = set_smem(attn_tc_fwd_kernel, FWD_SMEM)) != NV_OK) return s;
+    attr_set = true;
+  }
+  dim3 grid((N + BQ - 1) / BQ, H, B);
+  attn_tc_fwd_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  NV_LAUNCH_CHECK("attn_tc_fwd_kernel");
+  return NV_OK;
+}
+
+int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
+                          const bf16* dO, int64_t o_bs, int64_t o_rs, const float* lse, float* delta_ws, bf16* dq,
+                          bf16* dk, bf16* dv, int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim,
+                          float scale, float dropout_p, const uint32_t* drop_mask, cudaStream_t stream) {
+  NV_REQUIRE(head_dim == HD, "attention: head_dim %d unsupported by the bf16 flash kernel (needs 64)", head_dim);
+  NV_REQUIRE(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad sizes B=%d N=%d H=%d", B, N, H);
+  if (B == 0) return NV_OK;
+  int s;
+  if ((s = check_args(q, qkv_bs, qkv_rs, "q")) != NV_OK) return s;
+  if ((s = check_args(k, qkv_bs, qkv_rs, "k")) != NV_OK) return s;
+  if ((s = check_args(v, qkv_bs, qkv_rs, "v")) != NV_OK) return s;
+  if ((s = check_args(o, o_bs, o_rs, "o")) != NV_OK) return s;
+  if ((s = check_args(dO, o_bs, o_rs, "dO")) != NV_OK) return s;
+  if ((s = check_args(dq, d_bs, d_rs, "dq")) != NV_OK) return s;
+  if ((s = check_args(dk, d_bs, d_rs, "dk")) != NV_OK) return s;
+  if ((s = check_args(dv, d_bs, d_rs, "dv")) != NV_OK) return s;
+  NV_REQUIRE(lse != nullptr && delta_ws != nullptr, "attention: lse / delta workspace is null");
+  CUtensorMap tq, tk, tv, tdo;
+  if ((s = make_map(&tq, q, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  if ((s = make_map(&tdo, dO, o_bs, o_rs, B, N, H)) != NV_OK) return s;
+  BwdParams p;
+  if ((s = fill_common(p.c, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
+  p.lse = lse; p.delta = delta_ws; p.dq = dq; p.dk = dk; p.dv = dv; p.d_bs = d_bs; p.d_rs = d_rs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if ((s = set_smem(attn_tc_bwd_dq_kernel, DQ_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_bwd_dkv_kernel, DKV_SMEM)) != NV_OK) return s;
+    attr_set = true;
+  }
+  const int64_t tokens = (int64_t)B * N;
+  attn_tc_delta_kernel<<<(unsigned)((tokens + 7) / 8), 256, 0, stream>>>(dO, o, o_bs, o_rs, delta_ws, B, N, H);
+  NV_LAUNCH_CHECK("attn_tc_delta_kernel");
+  dim3 grid((N + BQ - 1) / BQ, H, B);
+  attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  NV_LAUNCH_CHECK("attn_tc_bwd_dq_kernel");
+  attn_tc_bwd_dkv_kernel<<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  NV_LAUNCH_CHECK("attn_tc_bwd_dkv_kernel");
+  return NV_OK;
+}

@@ -96,14 +96,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error), never as a hang.
+__device__ __forceinline__ uint64_t nv_globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_timeout_trap(uint64_t* bar, uint32_t parity) {
+  printf("neurovit_b200: mbarrier timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
+         (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x, smem_u32(bar), parity);
+  __trap();
+}
+// (try_wait suspends the thread for a hardware time slice per call, so the bound is wall-clock, ~4 s.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = nv_globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("neurovit_b200: mbarrier timeout (block %d thread %d bar@%u parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if ((++spins & 1023u) == 0 && nv_globaltimer_ns() - t0 > 4000000000ull) mbar_timeout_trap(bar, parity);
   }
 }
 

@@ -202,24 +202,32 @@ def _off(t, elems):
     return ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
 
 
-def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale):
-    """qkv [B*N, 3*H*hd] bf16 (q|k|v column blocks), o [B*N, H*hd] bf16, lse [B,H,N] fp32."""
+def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale, dropout_p=0.0, seed=0, drop_mask=None):
+    """qkv [B*N, 3*H*hd] bf16 (q|k|v column blocks), o [B*N, H*hd] bf16, lse [B,H,N] fp32;
+    drop_mask uint32-as-int32 [B*H, N, ceil(N/32)] when dropout_p > 0."""
     _dev(qkv)
     assert qkv.dtype == BF16 and o.dtype == BF16 and lse.dtype == F32
     inner = H * head_dim
     rs = qkv.stride(0)
     _lib.call("nv_attention_fwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
-              N * o.stride(0), o.stride(0), _ptr(lse), B, N, H, head_dim, float(scale), _stream())
+              N * o.stride(0), o.stride(0), _ptr(lse), B, N, H, head_dim, float(scale), float(dropout_p), int(seed),
+              _ptr(drop_mask), _stream())
 
 
-def attention_bwd(qkv, o, dO, lse, delta_ws, dqkv, *, B, N, H, head_dim, scale):
+def attention_bwd(qkv, o, dO, lse, delta_ws, dqkv, *, B, N, H, head_dim, scale, dropout_p=0.0, drop_mask=None):
     _dev(qkv)
     inner = H * head_dim
     rs, drs = qkv.stride(0), dqkv.stride(0)
     assert o.stride(0) == dO.stride(0)
     _lib.call("nv_attention_bwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
               _ptr(dO), N * o.stride(0), o.stride(0), _ptr(lse), _ptr(delta_ws), _off(dqkv, 0), _off(dqkv, inner),
-              _off(dqkv, 2 * inner), N * drs, drs, B, N, H, head_dim, float(scale), _stream())
+              _off(dqkv, 2 * inner), N * drs, drs, B, N, H, head_dim, float(scale), float(dropout_p),
+              _ptr(drop_mask), _stream())
+
+
+def set_attention_impl(impl: int):
+    """0 = tcgen05/TMEM kernels (default), 1 = mma.sync cross-check variant."""
+    _lib.call("nv_set_attention_impl", int(impl))
 
 
 def softmax_fwd(s, rows, n):
