@@ -96,32 +96,38 @@ struct FwdParams {
   int64_t o_bs, o_rs;
   float* lse;
 };
-constexpr int FWD_KB = 128;
-constexpr int FWD_SMEM_TILES = SLAB /*Q*/ + 2 * 2 * SLAB /*K,V x 2 stages*/ + 2 * SLAB /*P*/;
+constexpr int FWD_KB = 96;                    // keys per block: 2 S buffers (2 x 96) + O (64) = 256 TMEM columns
+constexpr int FWD_KV_BYTES = FWD_KB * 128;    // 12 KB per K or V stage
+constexpr int FWD_SMEM_TILES = SLAB /*Q*/ + 4 * FWD_KV_BYTES /*K x 2, V x 2*/ + 2 * SLAB /*P: 64 + 32 keys*/;
 constexpr int FWD_SMEM = FWD_SMEM_TILES + 128;
+constexpr int FWD_NCH = FWD_KB / 32;
+
+__device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sKV = smem + SLAB;                 // stage s: K at s*2*SLAB, V at s*2*SLAB + SLAB
-  uint8_t* sP = smem + SLAB + 4 * SLAB;
+  uint8_t* sK = smem + SLAB;                       // stage s at s * FWD_KV_BYTES
+  uint8_t* sV = smem + SLAB + 2 * FWD_KV_BYTES;
+  uint8_t* sP = smem + SLAB + 4 * FWD_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_SMEM_TILES);
   uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // 2
-  uint64_t* kv_empty = bars + 3;    // 2
-  uint64_t* s_full = bars + 5;      // 1
-  uint64_t* sp_ready = bars + 6;    // 1
-  uint64_t* o_full = bars + 7;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;      // 2
+  uint64_t* sp_ready = bars + 11;   // 1
+  uint64_t* o_full = bars + 12;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.c.N;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   const int nblk = (N + FWD_KB - 1) / FWD_KB;
-  const int rows_here = min(BQ, N - q0);
-  const int nactive = (rows_here + 31) >> 5;  // row warps with at least one valid query
+  const int nactive = (min(BQ, N - q0) + 31) >> 5;  // row warps with at least one valid query
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("attn_tc_fwd: dynamic shared memory is not 1024-byte aligned\n");
@@ -130,9 +136,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&o_full[i], 1); }
-    mbar_init(s_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
     mbar_init(sp_ready, 32 * nactive);
+    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -140,21 +150,27 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;  // O buffers at +128, +192
+  const uint32_t tS = tmem_base, tO = tmem_base + 2 * FWD_KB;  // S buffers at +0, +96; O at +192
 
   if (warp == TMA_WARP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, SLAB);
-      load_rows(sQ, &tq, q_full, h * HD, q0, b, 2);
+      tma_load_3d(sQ, &tq, q_full, h * HD, q0, b);  // one 128-row box
     }
     __syncwarp();
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
-      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      const uint32_t ph = ((j >> 1) & 1) ^ 1;
+      mbar_wait(&k_empty[s], ph);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&kv_full[s], 2 * SLAB);
-        load_rows(sKV + s * 2 * SLAB, &tk, &kv_full[s], h * HD, j * FWD_KB, b, 2);
-        load_rows(sKV + s * 2 * SLAB + SLAB, &tv, &kv_full[s], h * HD, j * FWD_KB, b, 2);
+        mbar_arrive_expect_tx(&k_full[s], FWD_KV_BYTES);
+        tma_load_3d(sK + s * FWD_KV_BYTES, &tk, &k_full[s], h * HD, j * FWD_KB, b);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[s], ph);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&v_full[s], FWD_KV_BYTES);
+        tma_load_3d(sV + s * FWD_KV_BYTES, &tv, &v_full[s], h * HD, j * FWD_KB, b);
       }
       __syncwarp();
     }
@@ -162,32 +178,34 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
     const uint64_t q_desc = kmajor_desc(sQ);
     auto cols16 = [&](int j) { return (min(FWD_KB, N - j * FWD_KB) + 15) & ~15; };
+    auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j & 1; frees the K stage when done
+      const int s = j & 1;
+      mma_k64(tS + (uint32_t)(s * FWD_KB), q_desc, kmajor_desc(sK + s * FWD_KV_BYTES), umma_idesc_bf16(128, cols16(j), 0, 0));
+      umma_commit(&s_full[s]);
+      umma_commit(&k_empty[s]);
+    };
     mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) {
-      mma_k64(tS, q_desc, kmajor_desc(sKV), umma_idesc_bf16(128, cols16(0), 0, 0));
-      umma_commit(s_full);
+    for (int j = 0; j < 2 && j < nblk; ++j) {
+      mbar_wait(&k_full[j], 0);
+      tc_fence_after();
+      if (elect_one()) issue_s(j);
+      __syncwarp();
     }
-    __syncwarp();
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
-      mbar_wait(sp_ready, j & 1);
+      mbar_wait(sp_ready, j & 1);            // rows: S_j consumed, P_j in smem, O_{j-1} folded
+      mbar_wait(&v_full[s], (j >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        mma_rows(tO + (uint32_t)(s * HD), sP, sKV + s * 2 * SLAB + SLAB, idesc_pv, cols16(j) >> 4, false);
-        umma_commit(&o_full[s]);
-        umma_commit(&kv_empty[s]);
+        mma_rows(tO, sP, sV + s * FWD_KV_BYTES, idesc_pv, cols16(j) >> 4, false);
+        umma_commit(o_full);
+        umma_commit(&v_empty[s]);
       }
       __syncwarp();
-      if (j + 1 < nblk) {
-        const int s1 = (j + 1) & 1;
-        mbar_wait(&kv_full[s1], ((j + 1) >> 1) & 1);
+      if (j + 2 < nblk) {
+        mbar_wait(&k_full[s], ((j + 2) >> 1) & 1);
         tc_fence_after();
-        if (elect_one()) {
-          mma_k64(tS, q_desc, kmajor_desc(sKV + s1 * 2 * SLAB), umma_idesc_bf16(128, cols16(j + 1), 0, 0));
-          umma_commit(s_full);
-        }
+        if (elect_one()) issue_s(j + 2);
         __syncwarp();
       }
     }
@@ -203,94 +221,109 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 #pragma unroll
     for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    uint32_t va[32], vb[32];  // two TMEM chunks in flight: the load of chunk c+1 overlaps the math on chunk c
+
+    auto fold_o = [&]() {  // o_acc = o_acc * alpha_prev + (P V of the previous block)
+      tmem_ld_32x32(tO + lane_base, va);
+      tmem_ld_32x32(tO + lane_base + 32, vb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(va[i]));
+        o_acc[32 + i] = fmaf(o_acc[32 + i], alpha_prev, __uint_as_float(vb[i]));
+      }
+    };
 
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * FWD_KB;
       const int nvalid = min(FWD_KB, N - key0);
       const int nch = (nvalid + 31) >> 5;
       const bool full = nvalid == FWD_KB;
-      mbar_wait(s_full, j & 1);
+      const uint32_t tSj = tS + lane_base + (uint32_t)((j & 1) * FWD_KB);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: block row max (raw scores)
-      float mx = -INFINITY;
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_base + c * 32, v);
-        tmem_ld_wait();
-        if (full) {
+      // pass 1: block row max of the raw scores
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      tmem_ld_32x32(tSj, va);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+      for (int c = 0; c < FWD_NCH; ++c) {
+        if (c < nch) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld_32x32(tSj + (c + 1) * 32, nxt);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, key0 + c * 32 + i < N ? __uint_as_float(v[i]) : -INFINITY);
+          for (int i = 0; i < 32; i += 4) {
+            float x0 = __uint_as_float(cur[i]), x1 = __uint_as_float(cur[i + 1]), x2 = __uint_as_float(cur[i + 2]),
+                  x3 = __uint_as_float(cur[i + 3]);
+            if (!full) {
+              const int k = key0 + c * 32 + i;
+              x0 = k < N ? x0 : -INFINITY; x1 = k + 1 < N ? x1 : -INFINITY;
+              x2 = k + 2 < N ? x2 : -INFINITY; x3 = k + 3 < N ? x3 : -INFINITY;
+            }
+            mx0 = fmaxf(mx0, x0); mx1 = fmaxf(mx1, x1); mx2 = fmaxf(mx2, x2); mx3 = fmaxf(mx3, x3);
+          }
         }
       }
-      const float m_new = fmaxf(m_run, mx * cs);  // finite: every block holds >= 1 valid key
+      const float m_new = fmaxf(m_run, max4(mx0, mx1, mx2, mx3) * cs);  // finite: every block holds >= 1 valid key
       const float alpha = ex2(m_run - m_new);
       // fold the previous block's P V into the register accumulator (also proves P's smem buffer is free)
       if (j > 0) {
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tO + lane_base + ((j - 1) & 1) * HD + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
-        }
+        fold_o();
       }
       alpha_prev = alpha;
       // pass 2: p = 2^(s*c - m), row sum, bf16 operand tile
-      float rs0 = 0.f, rs1 = 0.f;
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tS + lane_base + c * 32, v);
-        tmem_ld_wait();
-        float pv[32];
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+      tmem_ld_32x32(tSj, va);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2(fmaf(__uint_as_float(v[i]), cs, -m_new));
-          if (!full) e = key0 + c * 32 + i < N ? e : 0.f;
-          pv[i] = e;
-          if (i & 1) rs1 += e; else rs0 += e;
+      for (int c = 0; c < FWD_NCH; ++c) {
+        if (c < nch) {
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+          tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld_32x32(tSj + (c + 1) * 32, nxt);
+          uint32_t km = 0xFFFFFFFFu;
+          if (dropout) {
+            const uint64_t mrow = (uint64_t)bh * N + min(qrow, N - 1);
+            km = 0;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8)
+              km |= nv_keep_bits8(p.c.seed, mrow * (uint64_t)(p.c.mask_words * 4) + (uint64_t)((key0 >> 3) + c * 4 + g8),
+                                  0u, p.c.drop_thr) << (8 * g8);
+            if (qrow < N) p.c.mask[mrow * p.c.mask_words + (key0 >> 5) + c] = km;
+          }
+          // 8 scores -> 8 probabilities -> one 16-byte piece of the K-major SW128 operand row
+          const uint32_t prow = sP_u32 + (uint32_t)(c >> 1) * SLAB + (uint32_t)row * 128;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2(fmaf(__uint_as_float(cur[g8 * 8 + i]), cs, -m_new));
+              if (!full) e[i] = key0 + c * 32 + g8 * 8 + i < N ? e[i] : 0.f;
+            }
+            rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
+            if (dropout) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] = (km >> (g8 * 8 + i)) & 1u ? e[i] * p.c.keep_scale : 0.f;
+            }
+            const int ch = ((c & 1) << 2) + g8;
+            st_shared_v4(prow + (uint32_t)((ch ^ (row & 7)) << 4), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                         pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          }
         }
-        if (dropout) {
-          const uint64_t mrow = (uint64_t)bh * N + min(qrow, N - 1);
-          uint32_t km = 0;
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8)
-            km |= nv_keep_bits8(p.c.seed, mrow * (uint64_t)(p.c.mask_words * 4) + (uint64_t)((key0 >> 3) + c * 4 + g8), 0u,
-                                p.c.drop_thr) << (8 * g8);
-          if (qrow < N) p.c.mask[mrow * p.c.mask_words + (key0 >> 5) + c] = km;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = (km >> i) & 1u ? pv[i] * p.c.keep_scale : 0.f;
-        }
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(pv[2 * i], pv[2 * i + 1]);
-        store_operand_chunk(sP_u32, row, c, w);
       }
-      l_run = fmaf(l_run, alpha, rs0 + rs1);
+      l_run = fmaf(l_run, alpha, (rs0 + rs1) + (rs2 + rs3));
       m_run = m_new;
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(sp_ready);
     }
-    // last block's P V
-    {
-      const int jl = nblk - 1;
-      mbar_wait(&o_full[jl & 1], (jl >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tO + lane_base + (jl & 1) * HD + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
-      }
-    }
+    mbar_wait(o_full, (nblk - 1) & 1);  // last block's P V
+    tc_fence_after();
+    fold_o();
     if (qrow < N) {
       const float inv = 1.0f / l_run;
       bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)qrow * p.o_rs + h * HD;
@@ -733,10 +766,10 @@ __global__ void attn_tc_delta_kernel(const bf16* __restrict__ dO, const bf16* __
   }
 }
 
-int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, int N, int H) {
+int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, int N, int H, int box_rows = 64) {
   const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)N, (uint64_t)B};
   const uint64_t strides[2] = {(uint64_t)rs * 2, (uint64_t)bs * 2};
-  const uint32_t box[3] = {64, 64, 1};
+  const uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return nv_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -780,9 +813,9 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   if ((s = check_args(o, o_bs, o_rs, "o")) != NV_OK) return s;
   NV_REQUIRE(lse != nullptr, "attention: lse is null");
   CUtensorMap tq, tk, tv;
-  if ((s = make_map(&tq, q, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
-  if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
-  if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
+  if ((s = make_map(&tq, q, qkv_bs, qkv_rs, B, N, H, BQ)) != NV_OK) return s;
+  if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H, FWD_KB)) != NV_OK) return s;
+  if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H, FWD_KB)) != NV_OK) return s;
   FwdParams p;
   if ((s = fill_common(p.c, N, H, scale, dropout_p, seed, drop_mask)) != NV_OK) return s;
   p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
