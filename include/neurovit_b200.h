@@ -73,8 +73,9 @@ int nv_layernorm_fwd(const float* x, int64_t ld_x, int x_group, int x_gstride, i
                      void* y, int y_is_bf16, int64_t ld_y, int y_group, int y_gstride, int y_goff,
                      float* mean, float* rstd, int M, int D, float eps, void* stream);
 /* dx = LNbwd(dy) (+ dres); dgamma/dbeta/colsum are ACCUMULATED (atomicAdd) — zero or pre-load them.
- * colsum (optional) += sum_rows dx_out: the bias gradient of the linear feeding the residual stream. */
-int nv_layernorm_bwd(const float* dy, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff,
+ * colsum (optional) += sum_rows dx_out: the bias gradient of the linear feeding the residual stream.
+ * dy is fp32, or bf16 when dy_is_bf16 (the dgrad GEMM's output in bf16 mode). */
+int nv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff,
                      const float* x, int64_t ld_x, int x_group, int x_gstride, int x_goff,
                      const float* mean, const float* rstd, const float* gamma,
                      const float* dres, int64_t ld_dres,

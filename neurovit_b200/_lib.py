@@ -28,7 +28,7 @@ SIGNATURES = {
                     _p, _p, _l, _p, _l, _p, _l, _i, _i, _f, _p],
     "nv_layernorm_fwd": [_p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _i, _l, _i, _i, _i, _p, _p,
                          _i, _i, _f, _p],
-    "nv_layernorm_bwd": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _p, _l, _i, _i, _i,
+    "nv_layernorm_bwd": [_p, _i, _l, _i, _i, _i, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _p, _l, _i, _i, _i,
                          _p, _l, _p, _p, _p, _i, _i, _p],
     "nv_cls_row": [_p, _p, _p, _l, _i, _i, _p],
     "nv_patch_gather_ln": [_p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p, _f, _p],

@@ -20,7 +20,7 @@ int nv_softmax_bwd_launch(const float* P, float* dP, int64_t rows, int n, cudaSt
 int nv_ln_fwd_launch(const float* x, int64_t ld_x, int xg, int xs, int xo, const float* gamma, const float* beta,
                      const float* add, int64_t ld_add, int add_mod, int add_off, void* y, int y_is_bf16, int64_t ld_y,
                      int yg, int ys, int yo, float* mean, float* rstd, int M, int D, float eps, cudaStream_t stream);
-int nv_ln_bwd_launch(const float* dy, int64_t ld_dy, int dyg, int dys, int dyo, const float* x, int64_t ld_x, int xg,
+int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int dys, int dyo, const float* x, int64_t ld_x, int xg,
                      int xs, int xo, const float* mean, const float* rstd, const float* gamma, const float* dres,
                      int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo, bf16* dx_bf16,
                      int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D, cudaStream_t stream);
@@ -105,12 +105,12 @@ int nv_layernorm_fwd(const float* x, int64_t ld_x, int x_group, int x_gstride, i
                           y_is_bf16, ld_y, y_group, y_gstride, y_goff, mean, rstd, M, D, eps, ST(stream));
 }
 
-int nv_layernorm_bwd(const float* dy, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff, const float* x,
+int nv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff, const float* x,
                      int64_t ld_x, int x_group, int x_gstride, int x_goff, const float* mean, const float* rstd,
                      const float* gamma, const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dx_group,
                      int dx_gstride, int dx_goff, void* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
                      float* colsum, int M, int D, void* stream) {
-  return nv_ln_bwd_launch(dy, ld_dy, dy_group, dy_gstride, dy_goff, x, ld_x, x_group, x_gstride, x_goff, mean, rstd,
+  return nv_ln_bwd_launch(dy, dy_is_bf16, ld_dy, dy_group, dy_gstride, dy_goff, x, ld_x, x_group, x_gstride, x_goff, mean, rstd,
                           gamma, dres, ld_dres, dx, ld_dx, dx_group, dx_gstride, dx_goff, (bf16*)dx_bf16, ld_dxb,
                           dgamma, dbeta, colsum, M, D, ST(stream));
 }

@@ -101,8 +101,18 @@ ln_fwd_kernel(const float* __restrict__ x, int64_t ld_x, RowMap xmap, const floa
 constexpr int LNB_ROWS = 4;
 constexpr int LNB_MAX_WARPS = 16;
 
+// dy is fp32 (autograd tensors) or bf16 (the dgrad GEMM's output in bf16 mode: half the read traffic)
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4<bf16>(const bf16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename DyT>
 __global__ void __launch_bounds__(LNB_MAX_WARPS * 32)
-ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, RowMap dymap, const float* __restrict__ x,
+ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, const float* __restrict__ x,
               int64_t ld_x, RowMap xmap, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
               const float* __restrict__ gamma, const float* __restrict__ dres, int64_t ld_dres,
               float* __restrict__ dx, int64_t ld_dx, RowMap dxmap, bf16* __restrict__ dx_bf16,
@@ -126,7 +136,7 @@ ln_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, RowMap dymap, const f
       const int r = r0 + k;
       const bool ok = active && r < M;
       xv[k] = ok ? *reinterpret_cast<const float4*>(x + xmap(r) * ld_x + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      dv[k] = ok ? *reinterpret_cast<const float4*>(dy + dymap(r) * ld_dy + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dv[k] = ok ? ld4<DyT>(dy + dymap(r) * ld_dy + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       rv[k] = (ok && dres) ? *reinterpret_cast<const float4*>(dres + (int64_t)r * ld_dres + 4 * c)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       mean[k] = r < M ? mean_in[r] : 0.f;
@@ -239,7 +249,7 @@ int nv_ln_fwd_launch(const float* x, int64_t ld_x, int xg, int xs, int xo, const
   return NV_OK;
 }
 
-int nv_ln_bwd_launch(const float* dy, int64_t ld_dy, int dyg, int dys, int dyo, const float* x, int64_t ld_x,
+int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int dys, int dyo, const float* x, int64_t ld_x,
                      int xg, int xs, int xo, const float* mean, const float* rstd, const float* gamma,
                      const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo,
                      bf16* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D,
@@ -251,13 +261,20 @@ int nv_ln_bwd_launch(const float* dy, int64_t ld_dy, int dyg, int dys, int dyo, 
   RowMap dym{dyg, dys, dyo}, xm{xg, xs, xo}, dxm{dxg, dxs, dxo};
   const int threads = ((D / 4 + 31) / 32) * 32;
   int ctas_per_sm = 1;  // size the persistent grid to exactly one resident wave
-  NV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ln_bwd_kernel, threads, 0));
+  if (dy_is_bf16) NV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ln_bwd_kernel<bf16>, threads, 0));
+  else NV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ln_bwd_kernel<float>, threads, 0));
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   int grid = (M + LNB_ROWS - 1) / LNB_ROWS;
   const int cap = nv_num_sms() * ctas_per_sm;
   if (grid > cap) grid = cap;
-  ln_bwd_kernel<<<grid, threads, 0, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
-                                              dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D);
+  if (dy_is_bf16) {
+    NV_REQUIRE(ld_dy % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0, "layernorm bwd: bf16 dy must be 8-byte aligned");
+    ln_bwd_kernel<bf16><<<grid, threads, 0, stream>>>((const bf16*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres,
+                                                      ld_dres, dx, ld_dx, dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D);
+  } else {
+    ln_bwd_kernel<float><<<grid, threads, 0, stream>>>((const float*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres,
+                                                       ld_dres, dx, ld_dx, dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D);
+  }
   NV_LAUNCH_CHECK("ln_bwd_kernel");
   return NV_OK;
 }

@@ -98,6 +98,63 @@ class GradStash:
 _STASH = GradStash()
 
 
+# ------------------------------------------------------------------------------- gradient sinks
+class GradSinks:
+    """Lets the backward kernels accumulate parameter gradients straight into a caller-owned fp32 buffer
+    (trainer.FlatGradBuckets: the all-reduce buckets) instead of returning fresh tensors that autograd then
+    adds into .grad with one elementwise kernel per parameter. Active only inside `with SINKS.active(...)`
+    (DataParallelTrainer.step wraps loss.backward()); a Function that sank a gradient returns None for that
+    input and reports the parameter through `notify` so the bucket countdown still runs. Keyed by the
+    parameter's storage address; bf16 tensor-core mode only (its wgrad / LayerNorm-backward epilogues are
+    red.global.add accumulators already)."""
+
+    def __init__(self):
+        self._views = None
+        self._notify = None
+
+    def active(self, views, notify):
+        sinks = self
+
+        class _Ctx:
+            def __enter__(self_c):
+                sinks._views, sinks._notify = views, notify
+
+            def __exit__(self_c, *exc):
+                sinks._views, sinks._notify = None, None
+                return False
+
+        return _Ctx()
+
+    def view(self, param):
+        return None if self._views is None else self._views.get(param.data_ptr())
+
+    def notify(self, key):
+        self._notify(key)
+
+
+SINKS = GradSinks()
+
+
+class GradAcc:
+    """fp32 accumulator for one parameter's gradient: the sink view (kernels add into it) or fresh zeros."""
+    __slots__ = ("buf", "key")
+
+    def __init__(self, param, mode, shape=None):
+        v = SINKS.view(param) if mode == "bf16" else None
+        shape = tuple(param.shape if shape is None else shape)
+        if v is not None and v.numel() == math.prod(shape):
+            self.buf, self.key = v.view(shape), param.data_ptr()
+        else:
+            self.buf, self.key = torch.zeros(shape, device=param.device, dtype=F32), None
+
+    def result(self):
+        """What backward returns for this input: the tensor, or None when it already sits in the sink."""
+        if self.key is None:
+            return self.buf
+        SINKS.notify(self.key)
+        return None
+
+
 def _splitk(tiles: int, k_blocks: int, workers: int = NUM_SMS) -> int:
     """Pick split-K so tiles*splits fills whole waves of the persistent workers (CTAs or CTA pairs)."""
     best, best_eff = 1, 0.0
@@ -140,13 +197,16 @@ class Engine:
             ops.linear_f32(a, weight.detach(), bias=bias, residual=residual, out=out, out_pre=pre, apply_gelu=gelu)
         return out, pre
 
-    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, want_colsum=False):
+    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, want_colsum=False, colsum_acc=None):
         """dx[M, K_in] = dy[M, N_out] @ W[N_out, K_in]  (optionally * gelu'(u)). With want_colsum the column
-        sums of dx (the bias gradient of the layer below) come out of the same GEMM epilogue."""
+        sums of dx (the bias gradient of the layer below) come out of the same GEMM epilogue (added into
+        colsum_acc.buf when given)."""
         M, K_in = dy.shape[0], weight.shape[1]
         out_dtype = out_dtype or self.act
         out = torch.empty(M, K_in, device=dy.device, dtype=out_dtype)
-        cs = torch.zeros(K_in, device=dy.device, dtype=F32) if want_colsum else None
+        cs = None
+        if want_colsum:
+            cs = colsum_acc.buf if colsum_acc is not None else torch.zeros(K_in, device=dy.device, dtype=F32)
         if self.mode == "bf16":
             ops.gemm_bf16(dy, self.w(weight), b_mn=True, gelu_u=gelu_u, colsum=cs,
                           out_f32=out if out_dtype == F32 else None, out_bf16=out if out_dtype == BF16 else None)
@@ -154,13 +214,20 @@ class Engine:
             ops.linear_f32(dy, weight.detach(), w_kn=True, gelu_u=gelu_u, out=out)
             if want_colsum:
                 ops.colsum(out, cs)
-        return (out, cs) if want_colsum else out
+        if want_colsum:
+            return out, (colsum_acc.result() if colsum_acc is not None else cs)
+        return out
 
-    def wgrad(self, dy, x, k_in=None):
-        """dW[N_out, K_in] = dy[M, N_out]^T @ x[M, K_in], fp32 (split-K red.add on the tensor-core path)."""
+    def wgrad(self, dy, x, k_in=None, acc=None):
+        """dW[N_out, K_in] = dy[M, N_out]^T @ x[M, K_in], fp32 (split-K red.add on the tensor-core path).
+        With `acc` (a GradAcc of shape [N_out, K_in]) the product is added into acc.buf; returns acc.result()."""
         M, N_out = dy.shape
         K_in = x.shape[1]
-        dW = torch.zeros(N_out, K_in, device=dy.device, dtype=F32)
+        if acc is not None and tuple(acc.buf.shape) == (N_out, K_in):
+            dW = acc.buf
+        else:
+            acc = None
+            dW = torch.zeros(N_out, K_in, device=dy.device, dtype=F32)
         if self.mode == "bf16":
             bn = 256 if K_in >= 256 else 128
             cg = 1 if (ops.GEMM_CTA_GROUP == 1 or N_out <= 128) else 2
@@ -169,6 +236,8 @@ class Engine:
                           k_splits=_splitk(tiles, math.ceil(M / 64), NUM_SMS // cg), block_n=bn, cta_group=cg)
         else:
             ops.linear_f32(dy, x, x_km=True, w_kn=True, out=dW)
+        if acc is not None:
+            return acc.result()
         if k_in is not None and k_in != K_in:
             dW = dW[:, :k_in].contiguous()
         return dW
@@ -188,18 +257,28 @@ class Engine:
         ops.layernorm_fwd(x, weight.detach(), bias.detach(), y, M=M, D=D, mean=mean, rstd=rstd, eps=eps)
         return y, mean, rstd
 
-    def ln_bwd(self, dy, x, mean, rstd, weight, dres=None, want_colsum=False):
+    def ln_bwd(self, dy, x, mean, rstd, weight, dres=None, want_colsum=False, acc_g=None, acc_b=None):
         """Returns dx (fp32), dx in the activation dtype (bf16 copy or the same fp32 tensor), dgamma, dbeta,
-        colsum(dx) or None."""
+        colsum(dx) or None. dy may be fp32 or bf16. acc_g / acc_b: GradAcc targets for dgamma / dbeta (their
+        .result() is returned in place of fresh tensors)."""
         M, D = x.shape
         dev = x.device
         dx = torch.empty(M, D, device=dev, dtype=F32)
         dxb = torch.empty(M, D, device=dev, dtype=BF16) if self.mode == "bf16" else None
-        z = torch.zeros(3 if want_colsum else 2, D, device=dev, dtype=F32)  # one fill for all accumulators
-        dg, db = z[0], z[1]
-        cs = z[2] if want_colsum else None
+        cs = None
+        if acc_g is not None and acc_b is not None:
+            dg, db = acc_g.buf, acc_b.buf
+            if want_colsum:
+                cs = torch.zeros(D, device=dev, dtype=F32)
+        else:
+            acc_g = acc_b = None
+            z = torch.zeros(3 if want_colsum else 2, D, device=dev, dtype=F32)  # one fill for all accumulators
+            dg, db = z[0], z[1]
+            cs = z[2] if want_colsum else None
         ops.layernorm_bwd(dy, x, mean, rstd, weight.detach(), M=M, D=D, dres=dres, dx=dx, dx_bf16=dxb, dgamma=dg,
                           dbeta=db, colsum=cs)
+        if acc_g is not None:
+            dg, db = acc_g.result(), acc_b.result()
         return dx, (dxb if dxb is not None else dx), dg, db, cs
 
     def as_act(self, g):
@@ -242,16 +321,16 @@ class Engine:
         y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32)
         return y, (qkv, o, aux)
 
-    def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head):
-        """Returns da (fp32 grad wrt the LN output), dWqkv, dWout, dbout. dy is the fp32 grad of the block
-        output; its residual branch is handled by the caller."""
+    def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=None):
+        """Returns da (grad wrt the LN output, fp32 or the activation dtype), dWqkv, dWout, dbout. dy is the
+        fp32 grad of the block output; its residual branch is handled by the caller."""
         qkv, o, aux = saved
         M = a.shape[0]
         inner = heads * dim_head
         scale = dim_head ** -0.5
         dev = a.device
         dO = self.dgrad(dy_act, w_out)
-        dWo = self.wgrad(dy_act, o)
+        dWo = self.wgrad(dy_act, o, acc=GradAcc(w_out, self.mode))
         dbo = self.bias_grad(dy, dy_colsum)
         dqkv = torch.empty(M, 3 * inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
@@ -274,8 +353,8 @@ class Engine:
                          (drs, N * drs, dim_head), Z1=B, Z2=heads, alpha=scale)
             ops.gemm_f32(N, dim_head, N, dP, (1, N, *zP), (qkv, 0), (1, rs, N * rs, dim_head), (dqkv, inner),
                          (drs, N * drs, dim_head), Z1=B, Z2=heads, alpha=scale)
-        da = self.dgrad(dqkv, w_qkv, out_dtype=F32)
-        dWqkv = self.wgrad(dqkv, a)
+        da = self.dgrad(dqkv, w_qkv, out_dtype=da_dtype or F32)
+        dWqkv = self.wgrad(dqkv, a, acc=GradAcc(w_qkv, self.mode))
         return da, dWqkv, dWo, dbo
 
     # -- feed-forward core -------------------------------------------------------------------------
@@ -284,13 +363,13 @@ class Engine:
         y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32)
         return y, (u, g)
 
-    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, w2):
+    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, b1, w2, da_dtype=None):
         u, g = saved
-        dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True)
-        dW2 = self.wgrad(dy_act, g)
+        dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True, colsum_acc=GradAcc(b1, self.mode))
+        dW2 = self.wgrad(dy_act, g, acc=GradAcc(w2, self.mode))
         db2 = self.bias_grad(dy, dy_colsum)
-        da = self.dgrad(dU, w1, out_dtype=F32)
-        dW1 = self.wgrad(dU, a)
+        da = self.dgrad(dU, w1, out_dtype=da_dtype or F32)
+        dW1 = self.wgrad(dU, a, acc=GradAcc(w1, self.mode))
         return da, dW1, db1, dW2, db2
 
 
@@ -349,21 +428,22 @@ class AttnBlockFn(torch.autograd.Function):
         x2, B, N = _flat(x)
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
         y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head)
-        ctx.save_for_backward(x2, mean, rstd, a, ln_w, w_qkv, w_out, *saved)
+        ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved)
         ctx.cfg = (B, N, heads, dim_head, mode)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, mean, rstd, a, ln_w, w_qkv, w_out, *saved = ctx.saved_tensors
+        x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved = ctx.saved_tensors
         B, N, heads, dim_head, mode = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy_act, cs = eng.as_act(dy)
         dy2 = dy.view(B * N, -1)
         da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w_qkv, w_out, B, N, heads,
-                                                dim_head)
-        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True)
+                                                dim_head, da_dtype=eng.act)
+        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode))
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
         return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None
@@ -406,20 +486,22 @@ class FFBlockFn(torch.autograd.Function):
         x2, B, N = _flat(x)
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
         y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2)
-        ctx.save_for_backward(x2, mean, rstd, a, ln_w, w1, w2, *saved)
+        ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved)
         ctx.cfg = (B, N, mode)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, mean, rstd, a, ln_w, w1, w2, *saved = ctx.saved_tensors
+        x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved = ctx.saved_tensors
         B, N, mode = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy_act, cs = eng.as_act(dy)
         dy2 = dy.view(B * N, -1)
-        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w1, w2)
-        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True)
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w1, b1, w2,
+                                                 da_dtype=eng.act)
+        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode))
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
         return dx, dg, db, dW1, db1, dW2, db2, None, None
@@ -436,18 +518,19 @@ class FFCoreFn(torch.autograd.Function):
         x2, _, _ = _flat(x_res)
         a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
         y, saved = eng.ff_core_fwd(a_act, x2, w1, b1, w2, b2)
-        ctx.save_for_backward(a_act, w1, w2, *saved)
+        ctx.save_for_backward(a_act, w1, b1, w2, *saved)
         ctx.cfg = (B, N, mode)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
-        a_act, w1, w2, *saved = ctx.saved_tensors
+        a_act, w1, b1, w2, *saved = ctx.saved_tensors
         B, N, mode = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy_act, cs = eng.as_act(dy)
-        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy.view(B * N, -1), dy_act.view(B * N, -1), cs, a_act, saved, w1, w2)
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy.view(B * N, -1), dy_act.view(B * N, -1), cs, a_act, saved, w1, b1,
+                                                 w2)
         return da.view(B, N, -1), dy, dW1, db1, dW2, db2, None
 
 
@@ -486,13 +569,13 @@ class PatchEmbedFn(torch.autograd.Function):
         ops.layernorm_fwd(e, ln2_w.detach(), ln2_b.detach(), x, M=B * n, D=D, ymap=(n, n + 1, 1), add=pos, ld_add=D,
                           add_mod=n, add_off=1, mean=mean2, rstd=rstd2, eps=eps)
         ops.cls_row(cls_token.detach().view(-1), pos, x, (n + 1) * D, B, D)
-        ctx.save_for_backward(video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, lin_w)
+        ctx.save_for_backward(video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, ln2_b, lin_w, lin_b)
         ctx.cfg = (B, n, P, D, patch, mode, pos_embedding.shape, cls_token.shape)
         return x
 
     @staticmethod
     def backward(ctx, dx):
-        video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, lin_w = ctx.saved_tensors
+        video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, ln2_b, lin_w, lin_b = ctx.saved_tensors
         B, n, P, D, patch, mode, pos_shape, cls_shape = ctx.cfg
         eng = engine(mode)
         dev = dx.device
@@ -505,15 +588,14 @@ class PatchEmbedFn(torch.autograd.Function):
         # LN(dim) backward on the patch rows only (token offset 1)
         de = torch.empty(B * n, D, device=dev, dtype=F32)
         deb = torch.empty(B * n, D, device=dev, dtype=BF16) if mode == "bf16" else None
-        dg2 = torch.zeros(D, device=dev, dtype=F32)
-        db2 = torch.zeros(D, device=dev, dtype=F32)
-        dlin_b = torch.zeros(D, device=dev, dtype=F32)
+        acc_g2, acc_b2, acc_lb = GradAcc(ln2_w, mode), GradAcc(ln2_b, mode), GradAcc(lin_b, mode)
         ops.layernorm_bwd(dx, e, mean2, rstd2, ln2_w.detach(), M=B * n, D=D, dymap=(n, n + 1, 1), dx=de, dx_bf16=deb,
-                          dgamma=dg2, dbeta=db2, colsum=dlin_b)
+                          dgamma=acc_g2.buf, dbeta=acc_b2.buf, colsum=acc_lb.buf)
+        dg2, db2, dlin_b = acc_g2.result(), acc_b2.result(), acc_lb.result()
         de_act = deb if mode == "bf16" else de
         Kp = patches.shape[1]
         if mode == "bf16":
-            dlin_w = eng.wgrad(de_act, patches, k_in=P)
+            dlin_w = eng.wgrad(de_act, patches, k_in=P, acc=GradAcc(lin_w, mode) if Kp == P else None)
             # dP = de @ W (fp32), only needed for the patch LayerNorm's gamma/beta
             dP = torch.empty(B * n, Kp, device=dev, dtype=F32)
             ops.gemm_bf16(de_act, eng.w(lin_w, Kp), b_mn=True, out_f32=dP)

@@ -162,8 +162,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, M, D, ld_dy=None, ld_x=None, dyma
                   dres=None, ld_dres=None, dx=None, ld_dx=None, dxmap=(0, 0, 0), dx_bf16=None, ld_dxb=None,
                   dgamma=None, dbeta=None, colsum=None):
     _dev(x)
-    assert dy.dtype == F32 and x.dtype == F32
-    _lib.call("nv_layernorm_bwd", _ptr(dy), D if ld_dy is None else ld_dy, *dymap, _ptr(x),
+    assert dy.dtype in (F32, BF16) and x.dtype == F32
+    _lib.call("nv_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), D if ld_dy is None else ld_dy, *dymap, _ptr(x),
               D if ld_x is None else ld_x, *xmap, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
               D if ld_dres is None else ld_dres, _ptr(dx), D if ld_dx is None else ld_dx, *dxmap, _ptr(dx_bf16),
               D if ld_dxb is None else ld_dxb, _ptr(dgamma), _ptr(dbeta), _ptr(colsum), M, D, _stream())

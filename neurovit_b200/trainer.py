@@ -14,6 +14,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from .functional import SINKS
+
 
 def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     """Rows [rank*B/world, (rank+1)*B/world) of the global batch (global batch must divide evenly)."""
@@ -25,25 +27,35 @@ def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
 
 
 class FlatGradBuckets:
-    """All trainable parameters' .grad are views into one flat fp32 buffer (reverse parameter order).
-    Post-accumulate hooks launch an async all-reduce per bucket as it completes."""
+    """All trainable parameters' .grad are views into one flat fp32 buffer (reverse parameter order, every
+    slot 128-byte aligned so the wgrad / LayerNorm-backward epilogues can red.add vectors straight into it:
+    functional.SINKS). Post-accumulate hooks — or the sink notification, for gradients the kernels wrote
+    in place — launch an async all-reduce per bucket as it completes."""
+
+    ALIGN = 32  # elements (128 B)
 
     def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         order = list(reversed(self.params))
-        total = sum(p.numel() for p in order)
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        total = sum(pad(p.numel()) for p in order)
         dev = order[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.bucket_of = {}
         self.buckets = []  # [start, end, n_params]
+        self.sink_views = {}   # parameter storage address -> its .grad view
+        self._by_key = {}
         off, b_start, b_count = 0, 0, 0
         for p in order:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             self.bucket_of[p] = len(self.buckets)
-            off += n
+            if p.is_contiguous():
+                self.sink_views[p.data_ptr()] = p.grad
+                self._by_key[p.data_ptr()] = p
+            off += pad(n)
             b_count += 1
             if (off - b_start) * 4 >= bucket_bytes:
                 self.buckets.append([b_start, off, b_count])
@@ -54,6 +66,11 @@ class FlatGradBuckets:
         self.handles = []
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] \
             if self.world > 1 else []
+
+    def sink_notify(self, key):
+        """A backward kernel accumulated this parameter's gradient in place (no autograd hook will fire)."""
+        if self.world > 1:
+            self._on_grad(self._by_key[key])
 
     def _on_grad(self, p):
         b = self.bucket_of[p]
@@ -106,7 +123,8 @@ class DataParallelTrainer:
         self.buckets.zero()
         out = self.model(inputs)
         loss = self.criterion(out, labels)
-        loss.backward()
+        with SINKS.active(self.buckets.sink_views, self.buckets.sink_notify):
+            loss.backward()
         self.buckets.finish()
         self.optimizer.step()
         return loss

@@ -125,6 +125,14 @@ def test_layernorm_fwd_bwd(D, out_dtype):
     assert rel_err(dg, gg) < 1e-4
     assert rel_err(db, gb) < 1e-4
     assert rel_err(cs, (gx.double() + dres.double()).sum(0)) < 1e-4
+    # bf16 dy (the dgrad GEMM's output in bf16 mode): same math on the rounded input
+    dyb = dy.to(torch.bfloat16)
+    gx2, gg2, gb2 = torch.autograd.grad(ref, (x, g, b), dyb.double())
+    dg.zero_(); db.zero_(); cs.zero_()
+    ops.layernorm_bwd(dyb, x.detach(), mean, rstd, g.detach(), M=M, D=D, dres=dres, dx=dx, dx_bf16=dxb, dgamma=dg,
+                      dbeta=db, colsum=cs)
+    assert rel_err(dx, gx2.double() + dres.double()) < 1e-5
+    assert rel_err(dg, gg2) < 1e-4 and rel_err(db, gb2) < 1e-4
 
 
 def test_layernorm_row_maps_and_pos_add():

@@ -175,3 +175,25 @@ def test_errors_and_contract():
     assert out.shape == (1, 2)
     # B = 0 (empty batch) is a no-op that keeps shapes
     assert m(torch.randn(0, 1, 16, 16, 16, device=DEV)).shape == (0, 2)
+
+
+def test_trainer_grad_sinks_match_autograd_accumulation():
+    """DataParallelTrainer.step lets the wgrad / LayerNorm-backward kernels add straight into the flat
+    gradient buffer (functional.SINKS); the result must equal plain autograd accumulation into .grad."""
+    from neurovit_b200.trainer import DataParallelTrainer
+    torch.manual_seed(3)
+    ctor = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=2, dim=128, depth=2,
+                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    m = ViT(**ctor).to(DEV)
+    x = torch.randn(6, 1, 16, 16, 16, device=DEV)
+    y = torch.randint(0, 2, (6,), device=DEV)
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    want = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    tr = DataParallelTrainer(m, optimizer=torch.optim.SGD(m.parameters(), lr=0.0))
+    for _ in range(2):  # second step: the flat buffer is re-zeroed, nothing carries over
+        tr.step(x, y)
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        assert p.grad.data_ptr() % 128 == 0
+        assert rel(p.grad, want[k]) < 1e-4, k

@@ -37,12 +37,15 @@ def _worker(rank, world, port, q):
         assert len(tr.buckets.buckets) == len(list(m.parameters()))  # bucket_mb=0: one bucket per parameter
         loss = tr.step(shard_batch(X, rank, world), shard_batch(Y, rank, world))
         grads = [p.grad.clone() for p in m.parameters()]
-        # every grad is still a view into the flat buffer, laid out in reverse parameter order
+        # every grad is still a view into the flat buffer, laid out in reverse parameter order, each slot
+        # 128-byte aligned (the backward kernels red.add vectors into it)
         flat = tr.buckets.flat
+        A = FlatGradBuckets.ALIGN
         off = 0
         for p in reversed(list(m.parameters())):
             assert p.grad.data_ptr() == flat.data_ptr() + 4 * off
-            off += p.numel()
+            assert p.grad.data_ptr() % 128 == 0
+            off += (p.numel() + A - 1) // A * A
         q.put((rank, float(loss), [g.numpy() for g in grads]))
     finally:
         dist.destroy_process_group()
@@ -80,7 +83,8 @@ def test_shard_batch_and_buckets_single_process():
         shard_batch(x, 0, 4)
     m = _model()
     b = FlatGradBuckets(list(m.parameters()), bucket_bytes=1 << 30)
-    assert len(b.buckets) == 1 and b.buckets[0][1] == sum(p.numel() for p in m.parameters())
+    A = FlatGradBuckets.ALIGN
+    assert len(b.buckets) == 1 and b.buckets[0][1] == sum((p.numel() + A - 1) // A * A for p in m.parameters())
     m(torch.randn(3, 12)).sum().backward()
     assert b.flat.abs().sum() > 0
     b.zero()
