@@ -5,6 +5,7 @@
 // One warp owns one row; a lane owns the float4 chunks {lane + 32*j}, so per-column partial sums for
 // dg/db stay in registers across the grid-stride row loop and are reduced once per CTA.
 #include "nv_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -201,6 +202,203 @@ ln_bwd_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, const flo
   }
 }
 
+// ---- LayerNorm backward, bulk-copy pipelined variant (the one the transformer blocks use) --------------
+// Same column-owner arithmetic as ln_bwd_kernel, but the three input streams (dy, x, dres) are staged
+// through shared memory by the TMA engine. Warp specialised: the LAST warp is the producer (one lane issues
+// 1-D bulk copies, one per row and tensor, 2-4 KB each, into a ring of `stages` LNP_ROWS-row stages tracked
+// by full/empty mbarriers); the other warps own one float4 column chunk per thread and synchronise among
+// themselves with a named barrier, so the copy-issue latency never sits on the compute warps' critical
+// path. Sized for two CTAs per SM (~160 KB of reads in flight per SM regardless of register pressure, and
+// one CTA's reduction latency hides behind the other's). The register-staged kernel above keeps only 16
+// warps per SM resident and tops out near 3 TB/s.
+constexpr int LNP_ROWS = 2;
+constexpr int LNP_MAX_STAGES = 8;
+
+// NT = compile-time bound on the compute threads (256 covers D <= 1024 with two CTAs per SM and up to ~112
+// registers per thread, so the shuffle / shared-memory reduction chains of the rows stay independent;
+// 512 covers D <= 2048)
+template <typename DyT, int NT>
+__global__ void __launch_bounds__(NT + 32, NT <= 256 ? 2 : 1)
+ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, const float* __restrict__ x,
+                   int64_t ld_x, RowMap xmap, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                   const float* __restrict__ gamma, const float* __restrict__ dres, int64_t ld_dres,
+                   float* __restrict__ dx, int64_t ld_dx, RowMap dxmap, bf16* __restrict__ dx_bf16,
+                   int64_t ld_dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ colsum_out, int M, int D, int stages) {
+  extern __shared__ __align__(128) uint8_t lnp_smem[];
+  __shared__ __align__(16) float red[2][2 * LNP_ROWS][LNB_MAX_WARPS];
+  __shared__ __align__(8) uint64_t full[LNP_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty[LNP_MAX_STAGES];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int ncompute = blockDim.x - 32;  // compute threads (a multiple of 32)
+  const bool producer = (int)threadIdx.x >= ncompute;
+  const int c = threadIdx.x;
+  const bool active = c < (D >> 2);
+  const float inv_d = 1.0f / (float)D;
+  const uint32_t dy_row_bytes = (uint32_t)D * sizeof(DyT), f_row_bytes = (uint32_t)D * 4u;
+  const uint32_t row_bytes = dy_row_bytes + f_row_bytes + (dres ? f_row_bytes : 0u);
+  const uint32_t stage_bytes = row_bytes * LNP_ROWS;
+  // stage layout: [dy rows | x rows | dres rows]
+  auto s_dy = [&](int s, int k) { return reinterpret_cast<const DyT*>(lnp_smem + s * stage_bytes + k * dy_row_bytes); };
+  auto s_x = [&](int s, int k) {
+    return reinterpret_cast<const float*>(lnp_smem + s * stage_bytes + LNP_ROWS * dy_row_bytes + k * f_row_bytes);
+  };
+  auto s_res = [&](int s, int k) {
+    return reinterpret_cast<const float*>(lnp_smem + s * stage_bytes + LNP_ROWS * (dy_row_bytes + f_row_bytes) + k * f_row_bytes);
+  };
+  const int iters = (M + gridDim.x * LNP_ROWS - 1) / (gridDim.x * LNP_ROWS);
+  for (int i = threadIdx.x; i < 2 * 2 * LNP_ROWS * LNB_MAX_WARPS; i += blockDim.x) (&red[0][0][0])[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ncompute >> 5); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (producer) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int r0 = (it * gridDim.x + blockIdx.x) * LNP_ROWS;
+        if (r0 >= M) break;
+        const int s = it % stages;
+        if (it >= stages) mbar_wait(&empty[s], ((it / stages) - 1) & 1);
+        const int nr = min(LNP_ROWS, M - r0);
+        mbar_arrive_expect_tx(&full[s], nr * row_bytes);
+        for (int k = 0; k < nr; ++k) {
+          const int r = r0 + k;
+          bulk_load_1d(const_cast<DyT*>(s_dy(s, k)), dy + dymap(r) * ld_dy, dy_row_bytes, &full[s]);
+          bulk_load_1d(const_cast<float*>(s_x(s, k)), x + xmap(r) * ld_x, f_row_bytes, &full[s]);
+          if (dres) bulk_load_1d(const_cast<float*>(s_res(s, k)), dres + (int64_t)r * ld_dres, f_row_bytes, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  float4 acc_g = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_g, acc_c = acc_g;
+  const float4 g = active ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  int buf = 0;
+  float mean_n[LNP_ROWS], rstd_n[LNP_ROWS];  // statistics of the NEXT row block, fetched one iteration ahead
+  auto fetch_stats = [&](int it) {
+    const int r0 = (it * gridDim.x + blockIdx.x) * LNP_ROWS;
+#pragma unroll
+    for (int k = 0; k < LNP_ROWS; ++k) {
+      const int r = min(r0 + k, M - 1);
+      mean_n[k] = __ldg(mean_in + r);
+      rstd_n[k] = __ldg(rstd_in + r);
+    }
+  };
+  fetch_stats(0);
+  for (int it = 0; it < iters; ++it) {
+    const int r0 = (it * gridDim.x + blockIdx.x) * LNP_ROWS;
+    if (r0 >= M) break;  // uniform across the CTA
+    const int s = it % stages;
+    float mean[LNP_ROWS], rstd[LNP_ROWS];
+#pragma unroll
+    for (int k = 0; k < LNP_ROWS; ++k) { mean[k] = mean_n[k]; rstd[k] = rstd_n[k]; }
+    if (it + 1 < iters) fetch_stats(it + 1);
+    mbar_wait(&full[s], (it / stages) & 1);
+    float4 xh[LNP_ROWS], gh[LNP_ROWS], rv[LNP_ROWS];
+    float part[2 * LNP_ROWS];
+#pragma unroll
+    for (int k = 0; k < LNP_ROWS; ++k) {
+      const bool ok = active && (r0 + k) < M;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = xv;
+      rv[k] = xv;
+      if (ok) {
+        xv = *reinterpret_cast<const float4*>(s_x(s, k) + 4 * c);
+        dv = ld4<DyT>(s_dy(s, k) + 4 * c);
+        if (dres) rv[k] = *reinterpret_cast<const float4*>(s_res(s, k) + 4 * c);
+      }
+      xh[k].x = ok ? (xv.x - mean[k]) * rstd[k] : 0.f;
+      xh[k].y = ok ? (xv.y - mean[k]) * rstd[k] : 0.f;
+      xh[k].z = ok ? (xv.z - mean[k]) * rstd[k] : 0.f;
+      xh[k].w = ok ? (xv.w - mean[k]) * rstd[k] : 0.f;
+      acc_g.x += dv.x * xh[k].x; acc_g.y += dv.y * xh[k].y;
+      acc_g.z += dv.z * xh[k].z; acc_g.w += dv.w * xh[k].w;
+      acc_b.x += dv.x; acc_b.y += dv.y; acc_b.z += dv.z; acc_b.w += dv.w;
+      gh[k].x = dv.x * g.x; gh[k].y = dv.y * g.y; gh[k].z = dv.z * g.z; gh[k].w = dv.w * g.w;
+      part[2 * k] = (gh[k].x + gh[k].y) + (gh[k].z + gh[k].w);
+      part[2 * k + 1] = (gh[k].x * xh[k].x + gh[k].y * xh[k].y) + (gh[k].z * xh[k].z + gh[k].w * xh[k].w);
+    }
+    // this warp is done reading the stage: hand it back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+#pragma unroll
+    for (int i = 0; i < 2 * LNP_ROWS; ++i) part[i] = warp_sum(part[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 2 * LNP_ROWS; ++i) red[buf][i][warp] = part[i];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(ncompute) : "memory");  // compute warps only
+#pragma unroll
+    for (int i = 0; i < 2 * LNP_ROWS; ++i) {  // entries of warps that do not exist stay zero
+      float sacc = 0.f;
+#pragma unroll
+      for (int w4 = 0; w4 < LNB_MAX_WARPS / 4; ++w4) {
+        const float4 t = *reinterpret_cast<const float4*>(&red[buf][i][w4 * 4]);
+        sacc += (t.x + t.y) + (t.z + t.w);
+      }
+      part[i] = sacc * inv_d;
+    }
+    buf ^= 1;
+#pragma unroll
+    for (int k = 0; k < LNP_ROWS; ++k) {
+      const int r = r0 + k;
+      if (!(active && r < M)) continue;
+      const float s1 = part[2 * k], s2 = part[2 * k + 1];
+      float4 o;
+      o.x = rstd[k] * (gh[k].x - s1 - xh[k].x * s2) + rv[k].x;
+      o.y = rstd[k] * (gh[k].y - s1 - xh[k].y * s2) + rv[k].y;
+      o.z = rstd[k] * (gh[k].z - s1 - xh[k].z * s2) + rv[k].z;
+      o.w = rstd[k] * (gh[k].w - s1 - xh[k].w * s2) + rv[k].w;
+      acc_c.x += o.x; acc_c.y += o.y; acc_c.z += o.z; acc_c.w += o.w;
+      const int64_t orow = dxmap(r);
+      if (dx) *reinterpret_cast<float4*>(dx + orow * ld_dx + 4 * c) = o;
+      if (dx_bf16) OutStore<bf16>::st(dx_bf16 + orow * ld_dxb + 4 * c, o);
+    }
+  }
+  if (active) {
+    if (dgamma)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + 4 * c), "f"(acc_g.x), "f"(acc_g.y),
+                   "f"(acc_g.z), "f"(acc_g.w) : "memory");
+    if (dbeta)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + 4 * c), "f"(acc_b.x), "f"(acc_b.y),
+                   "f"(acc_b.z), "f"(acc_b.w) : "memory");
+    if (colsum_out)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum_out + 4 * c), "f"(acc_c.x),
+                   "f"(acc_c.y), "f"(acc_c.z), "f"(acc_c.w) : "memory");
+  }
+}
+
+template <typename DyT>
+int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x, int64_t ld_x, RowMap xm,
+                       const float* mean, const float* rstd, const float* gamma, const float* dres, int64_t ld_dres,
+                       float* dx, int64_t ld_dx, RowMap dxm, bf16* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
+                       float* colsum, int M, int D, int threads, cudaStream_t stream) {
+  const int stage_bytes = (D * (int)sizeof(DyT) + D * 4 + (dres ? D * 4 : 0)) * LNP_ROWS;
+  int stages = (108 * 1024) / stage_bytes;  // two CTAs per SM
+  if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
+  if (const char* e = getenv("NV_LNP_STAGES")) stages = atoi(e);
+  if (stages < 3) stages = 3;
+  const int smem = stage_bytes * stages;
+  auto kern = threads <= 256 ? ln_bwd_pipe_kernel<DyT, 256> : ln_bwd_pipe_kernel<DyT, 512>;
+  static int smem_set[2] = {0, 0};
+  int& set = smem_set[threads <= 256 ? 0 : 1];
+  if (smem > set) {
+    NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    set = smem;
+  }
+  int grid = (M + LNP_ROWS - 1) / LNP_ROWS;
+  int cap = nv_num_sms() * ((smem <= 108 * 1024 && threads <= 256) ? 2 : 1);
+  if (const char* e = getenv("NV_LNP_CTAS")) cap = nv_num_sms() * atoi(e);
+  if (grid > cap) grid = cap;
+  if (getenv("NV_LNP_NOSTORE")) { dx = nullptr; dx_bf16 = nullptr; }
+  kern<<<grid, threads + 32, smem, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
+                                             dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, stages);
+  return NV_OK;
+}
+
 // cls row of the embedding: x[b, 0, :] = cls + pos[0]   (vit_3d.py:116-118)
 __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
                                float* __restrict__ x, int64_t batch_stride, int B, int D) {
@@ -260,6 +458,25 @@ int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int
     NV_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "layernorm bwd: dgamma/dbeta/colsum must be 16-byte aligned");
   RowMap dym{dyg, dys, dyo}, xm{xg, xs, xo}, dxm{dxg, dxs, dxo};
   const int threads = ((D / 4 + 31) / 32) * 32;
+  // bulk-copy pipelined kernel when every row is a 16-byte-aligned multiple of 16 bytes and the problem is
+  // big enough to be bandwidth-bound; the register-staged kernel covers the rest (tiny M, odd D / strides)
+  const int dy_es = dy_is_bf16 ? 2 : 4;
+  const bool pipe_ok = M >= 64 && (D * dy_es) % 16 == 0 && (ld_dy * dy_es) % 16 == 0 && ld_x % 4 == 0 &&
+                       ld_dres % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dres) & 15) == 0 &&
+                       (int64_t)D * (dy_es + 8) * LNP_ROWS * 3 <= 200 * 1024;
+  if (pipe_ok) {
+    int s;
+    if (dy_is_bf16)
+      s = launch_ln_bwd_pipe<bf16>((const bf16*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
+                                   dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, stream);
+    else
+      s = launch_ln_bwd_pipe<float>((const float*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx,
+                                    ld_dx, dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, stream);
+    if (s != NV_OK) return s;
+    NV_LAUNCH_CHECK("ln_bwd_pipe_kernel");
+    return NV_OK;
+  }
   int ctas_per_sm = 1;  // size the persistent grid to exactly one resident wave
   if (dy_is_bf16) NV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ln_bwd_kernel<bf16>, threads, 0));
   else NV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, ln_bwd_kernel<float>, threads, 0));

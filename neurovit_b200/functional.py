@@ -111,6 +111,7 @@ class GradSinks:
     def __init__(self):
         self._views = None
         self._notify = None
+        self.sunk = 0  # gradients accumulated in place so far (observability / tests)
 
     def active(self, views, notify):
         sinks = self
@@ -129,6 +130,7 @@ class GradSinks:
         return None if self._views is None else self._views.get(param.data_ptr())
 
     def notify(self, key):
+        self.sunk += 1
         self._notify(key)
 
 

@@ -112,7 +112,7 @@ def test_layernorm_fwd_bwd(D, out_dtype):
     assert rel_err(y, ref) < (1e-5 if out_dtype == torch.float32 else 1e-2)
     dy = torch.randn(M, D, device=DEV)
     dres = torch.randn(M, D, device=DEV)
-    gx, gg, gb = torch.autograd.grad(ref, (x, g, b), dy.double())
+    gx, gg, gb = torch.autograd.grad(ref, (x, g, b), dy.double(), retain_graph=True)
     dx = torch.empty(M, D, device=DEV)
     dxb = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
     dg = torch.zeros(D, device=DEV)

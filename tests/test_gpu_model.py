@@ -190,10 +190,13 @@ def test_trainer_grad_sinks_match_autograd_accumulation():
     torch.nn.functional.cross_entropy(m(x), y).backward()
     want = {k: p.grad.clone() for k, p in m.named_parameters()}
     m.zero_grad(set_to_none=True)
+    from neurovit_b200.functional import SINKS
     tr = DataParallelTrainer(m, optimizer=torch.optim.SGD(m.parameters(), lr=0.0))
+    sunk0 = SINKS.sunk
     for _ in range(2):  # second step: the flat buffer is re-zeroed, nothing carries over
         tr.step(x, y)
     torch.cuda.synchronize()
+    assert SINKS.sunk - sunk0 == 2 * (2 * 9 + 4), "per layer 9 tensors (2 LayerNorm pairs, w_qkv, w_out, w1, b1, w2), 4 in the patch embedding"
     for k, p in m.named_parameters():
         assert p.grad.data_ptr() % 128 == 0
         assert rel(p.grad, want[k]) < 1e-4, k
