@@ -126,16 +126,28 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 //           2 = dgrad through GELU: acc * gelu'(u) (+ column sums)
 // erf is evaluated with Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one
 // MUFU.RCP + one MUFU.EX2 + 7 FMAs; gelu' reuses the same exponential (exp(-u^2/2) is erf's exp(-x^2)).
+// (MUFU.RCP / MUFU.EX2 are issued as the bare approx instructions: the IEEE-rounded intrinsics expand to
+// range checks with slow-path calls that break the instruction-level parallelism of the unrolled epilogue.)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void erf_parts(float u, float& erf_v, float& expv) {
   const float x = u * 0.70710678118654752440f;
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  expv = exp2f(-x * x * 1.4426950408889634f);  // exp(-x^2) = exp(-u^2/2)
+  expv = ex2_approx(-x * x * 1.4426950408889634f);  // exp(-x^2) = exp(-u^2/2)
   erf_v = copysignf(fmaf(-poly, expv, 1.0f), x);
 }
 __device__ __forceinline__ float gelu_fast(float u) {
