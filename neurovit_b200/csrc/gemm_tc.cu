@@ -194,26 +194,34 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, EpiAux& x, int
   if (EPI_MODE != 2 && p.bias != nullptr) x.bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
 }
 
+// explicit shared-space accesses for the staging slab: through a generic pointer they compile to LD.E / ST.E
+// (generic path: long-scoreboard latency and the local/global queue instead of the shared-memory pipe)
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 template <int EPI_MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], float* stage, int lane,
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], uint32_t stage, int lane,
                                                int row0, int col0, const EpiAux& x) {
   const int sub_r = lane >> 3, sub_c = lane & 7;
   const int gn = col0 + sub_c * 4;
   const bool col_ok = gn < p.N;
   // row-per-thread -> swizzled staging (16B chunk j of row `lane` lands at chunk j^(lane&7))
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float4 t = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                           __uint_as_float(v[4 * j + 3]));
-    *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = t;
-  }
+  for (int j = 0; j < 8; ++j)
+    sts_v4(stage + (uint32_t)((lane * 32 + ((j ^ (lane & 7)) << 2)) * 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + sub_r;
     const int gm = row0 + r;
-    float4 a = *reinterpret_cast<const float4*>(stage + r * 32 + ((sub_c ^ (r & 7)) << 2));
+    float4 a = lds_v4(stage + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4));
     const bool ok = col_ok && gm < p.M;
     if (EPI_MODE == 0) {
       a.x = fmaf(a.x, p.alpha, x.bias4.x);
@@ -416,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------- epilogue warps -----------------------------------------
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int part = warp >> 2;   // which 32-column chunks (part, part + W, ...) this warp owns
-    float* stage = reinterpret_cast<float*>(smem + L::EPI_OFF + warp * EPI_STAGE_BYTES);
+    const uint32_t stage = smem_u32(smem + L::EPI_OFF + warp * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = worker; unit < total_units; unit += num_workers) {
