@@ -56,6 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD_DIR, exist_ok=True)
     nvcc = _nvcc()
     hdr_mtime = _deps_mtime()
+    extra = ["-DNV_PROFILE"] if os.environ.get("NV_PROFILE") == "1" else []  # in-kernel phase clocks (tools/attn_phases.py)
     jobs = []
     objs = []
     for src in SOURCES:
@@ -63,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_mtime):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", s, "-o", o])
+            jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", s, "-o", o])
 
     def run(cmd):
         if verbose:

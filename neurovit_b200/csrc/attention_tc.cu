@@ -25,6 +25,24 @@
 #include "nv_common.cuh"
 #include "nv_rng.cuh"
 
+// Optional in-kernel phase clocks (build with NV_PROFILE=1): selected threads accumulate clock64() deltas per
+// phase into nv_attn_dbg, read back through nv_debug_read (not part of the public ABI).
+#ifdef NV_PROFILE
+__device__ long long nv_attn_dbg[512];
+#define PROF_DECL long long pt_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pt0_ = clock64(), pt1_;
+#define PROF_MARK(i) do { pt1_ = clock64(); pt_[i] += pt1_ - pt0_; pt0_ = pt1_; } while (0)
+#define PROF_RESET() do { pt0_ = clock64(); } while (0)
+#define PROF_DUMP(slot) do { for (int i_ = 0; i_ < 12; ++i_) nv_attn_dbg[(slot) * 12 + i_] = pt_[i_]; } while (0)
+extern "C" int nv_debug_read(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, nv_attn_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : 3;
+}
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_RESET()
+#define PROF_DUMP(slot)
+#endif
+
 namespace {
 
 constexpr int HD = 64;
@@ -98,12 +116,75 @@ struct FwdParams {
 };
 constexpr int FWD_KB = 96;                    // keys per block: 2 S buffers (2 x 96) + O (64) = 256 TMEM columns
 constexpr int FWD_KV_BYTES = FWD_KB * 128;    // 12 KB per K or V stage
-constexpr int FWD_SMEM_TILES = SLAB /*Q*/ + 4 * FWD_KV_BYTES /*K x 2, V x 2*/ + 2 * SLAB /*P: 64 + 32 keys*/;
+// P operand tile of one block: two 64-key slabs (rows are 128 B apart in both; the second is half used)
+constexpr int FWD_SMEM_TILES = SLAB /*Q*/ + 4 * FWD_KV_BYTES /*K x 2, V x 2*/ + 2 * SLAB /*P*/;
 constexpr int FWD_SMEM = FWD_SMEM_TILES + 128;
 constexpr int FWD_NCH = FWD_KB / 32;
+// Lazy rescale: the exponentials use a reference m_used that is only raised when the block maximum exceeds
+// it by more than 2^FWD_TAU (log2 domain). Probabilities then stay <= 2^FWD_TAU (exact in fp32 / bf16), O and
+// the row sum are rescaled only on those rare raises, and the final O / l is mathematically unchanged.
+constexpr float FWD_TAU = 8.0f;
 
-__device__ __forceinline__ float max4(float a, float b, float c, float d) { return fmaxf(fmaxf(a, b), fmaxf(c, d)); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// One 32-key chunk of one query row: raw scores (registers) -> probabilities, packed as 16 bf16x2 words, and
+// the chunk's row-sum. FULL = all 32 keys valid (branch-free); otherwise keys >= nvalid (chunk-local) give 0.
+template <bool FULL, bool DROPOUT>
+__device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float cs, float m_used, int nvalid,
+                                                 const Common& c, uint64_t mrow, int key0, bool row_ok,
+                                                 uint32_t (&w)[16]) {
+  float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      e[i] = ex2(fmaf(__uint_as_float(sv[g8 * 8 + i]), cs, -m_used));
+      if (!FULL) e[i] = (g8 * 8 + i) < nvalid ? e[i] : 0.f;
+    }
+    rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
+    if (DROPOUT) {
+      const uint32_t km = nv_keep_bits8(c.seed, mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
+                                        c.drop_thr);
+      if (row_ok) reinterpret_cast<uint8_t*>(c.mask + mrow * c.mask_words)[(key0 >> 3) + g8] = (uint8_t)km;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = (km >> i) & 1u ? e[i] * c.keep_scale : 0.f;
+    }
+    w[g8 * 4 + 0] = pack_bf16x2(e[0], e[1]);
+    w[g8 * 4 + 1] = pack_bf16x2(e[2], e[3]);
+    w[g8 * 4 + 2] = pack_bf16x2(e[4], e[5]);
+    w[g8 * 4 + 3] = pack_bf16x2(e[6], e[7]);
+  }
+  return (rs0 + rs1) + (rs2 + rs3);
+}
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    a0 = max3(a0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+    a1 = max3(a1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+    a2 = max3(a2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+    a3 = max3(a3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+  }
+  return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+}
+__device__ __forceinline__ float max32_masked(const uint32_t (&v)[32], int nvalid) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mx = i < nvalid ? fmaxf(mx, __uint_as_float(v[i])) : mx;
+  return mx;
+}
+// 16 packed words = 32 probabilities of row `row`, keys [32*chunk, 32*chunk+32) of the block -> operand tile
+__device__ __forceinline__ void store_p_chunk(uint32_t sP_u32, int row, int chunk, const uint32_t (&w)[16]) {
+  const uint32_t prow = sP_u32 + (uint32_t)(chunk >> 1) * SLAB + (uint32_t)row * 128;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int ch = ((chunk & 1) << 2) + g;
+    st_shared_v4(prow + (uint32_t)((ch ^ (row & 7)) << 4), w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]);
+  }
+}
+
+template <bool DROPOUT>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const FwdParams p) {
@@ -193,11 +274,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     }
     for (int j = 0; j < nblk; ++j) {
       const int s = j & 1;
-      mbar_wait(sp_ready, j & 1);            // rows: S_j consumed, P_j in smem, O_{j-1} folded
+      mbar_wait(sp_ready, j & 1);            // rows: S_j consumed, P_j in smem, O rescaled if it had to be
       mbar_wait(&v_full[s], (j >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        mma_rows(tO, sP, sV + s * FWD_KV_BYTES, idesc_pv, cols16(j) >> 4, false);
+        mma_rows(tO, sP, sV + s * FWD_KV_BYTES, idesc_pv, cols16(j) >> 4, j > 0);  // O += P_j V_j
         umma_commit(o_full);
         umma_commit(&v_empty[s]);
       }
@@ -215,129 +296,116 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t sP_u32 = smem_u32(sP);
     const float cs = p.c.scale * LOG2E;
-    const bool dropout = p.c.drop_thr != 0;
     const int bh = b * p.c.H + h;
-    float o_acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    uint32_t va[32], vb[32];  // two TMEM chunks in flight: the load of chunk c+1 overlaps the math on chunk c
-
-    auto fold_o = [&]() {  // o_acc = o_acc * alpha_prev + (P V of the previous block)
-      tmem_ld_32x32(tO + lane_base, va);
-      tmem_ld_32x32(tO + lane_base + 32, vb);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o_acc[i] = fmaf(o_acc[i], alpha_prev, __uint_as_float(va[i]));
-        o_acc[32 + i] = fmaf(o_acc[32 + i], alpha_prev, __uint_as_float(vb[i]));
-      }
-    };
+    const uint64_t mrow = (uint64_t)bh * N + min(qrow, N - 1);
+    float m_used = -INFINITY, l_run = 0.f;
+    PROF_DECL
 
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * FWD_KB;
       const int nvalid = min(FWD_KB, N - key0);
-      const int nch = (nvalid + 31) >> 5;
       const bool full = nvalid == FWD_KB;
       const uint32_t tSj = tS + lane_base + (uint32_t)((j & 1) * FWD_KB);
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: block row max of the raw scores
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      tmem_ld_32x32(tSj, va);
-#pragma unroll
-      for (int c = 0; c < FWD_NCH; ++c) {
-        if (c < nch) {
-          uint32_t (&cur)[32] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-          tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld_32x32(tSj + (c + 1) * 32, nxt);
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float x0 = __uint_as_float(cur[i]), x1 = __uint_as_float(cur[i + 1]), x2 = __uint_as_float(cur[i + 2]),
-                  x3 = __uint_as_float(cur[i + 3]);
-            if (!full) {
-              const int k = key0 + c * 32 + i;
-              x0 = k < N ? x0 : -INFINITY; x1 = k + 1 < N ? x1 : -INFINITY;
-              x2 = k + 2 < N ? x2 : -INFINITY; x3 = k + 3 < N ? x3 : -INFINITY;
-            }
-            mx0 = fmaxf(mx0, x0); mx1 = fmaxf(mx1, x1); mx2 = fmaxf(mx2, x2); mx3 = fmaxf(mx3, x3);
-          }
-        }
+      PROF_MARK(j == 0 ? 0 : 1);
+      // the whole block of raw scores of this row -> registers (one TMEM pass)
+      uint32_t c0[32], c1[32], c2[32];
+      tmem_ld_32x32(tSj, c0);
+      if (nvalid > 32) tmem_ld_32x32(tSj + 32, c1);
+      if (nvalid > 64) tmem_ld_32x32(tSj + 64, c2);
+      tmem_ld_wait();
+      float mx;
+      if (full) {
+        mx = max3(max32(c0), max32(c1), max32(c2));
+      } else {
+        mx = max32_masked(c0, nvalid);
+        if (nvalid > 32) mx = fmaxf(mx, max32_masked(c1, nvalid - 32));
+        if (nvalid > 64) mx = fmaxf(mx, max32_masked(c2, nvalid - 64));
       }
-      const float m_new = fmaxf(m_run, max4(mx0, mx1, mx2, mx3) * cs);  // finite: every block holds >= 1 valid key
-      const float alpha = ex2(m_run - m_new);
-      // fold the previous block's P V into the register accumulator (also proves P's smem buffer is free)
+      const float m_blk = mx * cs;  // finite: every block holds >= 1 valid key
+      const bool raise = m_blk > m_used + FWD_TAU;  // always true for the first block (m_used = -inf)
+      const float m_new = raise ? m_blk : m_used;
+      const float alpha = raise ? ex2(m_used - m_new) : 1.0f;
+      m_used = m_new;
+      PROF_MARK(2);
+      // probabilities -> K-major SW128 operand rows; the P V MMA reads ceil16(nvalid) key columns.
+      // The first chunk's exponentials are computed before waiting for the previous P V (which still reads
+      // P's buffer), so that wait is normally already satisfied.
+      const bool row_ok = qrow < N;
+      uint32_t w[16];
+      float rs;
+      if (full) rs = fwd_chunk_probs<true, DROPOUT>(c0, cs, m_used, 32, p.c, mrow, key0, row_ok, w);
+      else      rs = fwd_chunk_probs<false, DROPOUT>(c0, cs, m_used, nvalid, p.c, mrow, key0, row_ok, w);
+      PROF_MARK(3);
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-        fold_o();
       }
-      alpha_prev = alpha;
-      // pass 2: p = 2^(s*c - m), row sum, bf16 operand tile
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-      tmem_ld_32x32(tSj, va);
-#pragma unroll
-      for (int c = 0; c < FWD_NCH; ++c) {
-        if (c < nch) {
-          uint32_t (&cur)[32] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
-          tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld_32x32(tSj + (c + 1) * 32, nxt);
-          uint32_t km = 0xFFFFFFFFu;
-          if (dropout) {
-            const uint64_t mrow = (uint64_t)bh * N + min(qrow, N - 1);
-            km = 0;
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8)
-              km |= nv_keep_bits8(p.c.seed, mrow * (uint64_t)(p.c.mask_words * 4) + (uint64_t)((key0 >> 3) + c * 4 + g8),
-                                  0u, p.c.drop_thr) << (8 * g8);
-            if (qrow < N) p.c.mask[mrow * p.c.mask_words + (key0 >> 5) + c] = km;
-          }
-          // 8 scores -> 8 probabilities -> one 16-byte piece of the K-major SW128 operand row
-          const uint32_t prow = sP_u32 + (uint32_t)(c >> 1) * SLAB + (uint32_t)row * 128;
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              e[i] = ex2(fmaf(__uint_as_float(cur[g8 * 8 + i]), cs, -m_new));
-              if (!full) e[i] = key0 + c * 32 + g8 * 8 + i < N ? e[i] : 0.f;
-            }
-            rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
-            if (dropout) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) e[i] = (km >> (g8 * 8 + i)) & 1u ? e[i] * p.c.keep_scale : 0.f;
-            }
-            const int ch = ((c & 1) << 2) + g8;
-            st_shared_v4(prow + (uint32_t)((ch ^ (row & 7)) << 4), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
-                         pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-          }
+      PROF_MARK(4);
+      store_p_chunk(sP_u32, row, 0, w);
+      if (full) {
+        rs += fwd_chunk_probs<true, DROPOUT>(c1, cs, m_used, 32, p.c, mrow, key0 + 32, row_ok, w);
+        store_p_chunk(sP_u32, row, 1, w);
+        rs += fwd_chunk_probs<true, DROPOUT>(c2, cs, m_used, 32, p.c, mrow, key0 + 64, row_ok, w);
+        store_p_chunk(sP_u32, row, 2, w);
+      } else {
+        if (nvalid > 32) {
+          rs += fwd_chunk_probs<false, DROPOUT>(c1, cs, m_used, nvalid - 32, p.c, mrow, key0 + 32, row_ok, w);
+          store_p_chunk(sP_u32, row, 1, w);
+        }
+        if (nvalid > 64) {
+          rs += fwd_chunk_probs<false, DROPOUT>(c2, cs, m_used, nvalid - 64, p.c, mrow, key0 + 64, row_ok, w);
+          store_p_chunk(sP_u32, row, 2, w);
         }
       }
-      l_run = fmaf(l_run, alpha, (rs0 + rs1) + (rs2 + rs3));
-      m_run = m_new;
+      l_run = fmaf(l_run, alpha, rs);
+      if (j > 0 && __any_sync(0xffffffffu, raise)) {  // rare: bring the TMEM accumulator to the new reference
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tmem_ld_32x32(tO + lane_base + hh * 32, c0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) c0[i] = __float_as_uint(__uint_as_float(c0[i]) * alpha);
+          tmem_st_32x32(tO + lane_base + hh * 32, c0);
+        }
+        tmem_st_wait();
+      }
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(sp_ready);
+      PROF_MARK(5);
     }
     mbar_wait(o_full, (nblk - 1) & 1);  // last block's P V
     tc_fence_after();
-    fold_o();
-    if (qrow < N) {
+    PROF_MARK(6);
+    {
       const float inv = 1.0f / l_run;
-      bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)qrow * p.o_rs + h * HD;
+      bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)min(qrow, N - 1) * p.o_rs + h * HD;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint4 t;
-        t.x = pack_bf16x2(o_acc[8 * i] * inv, o_acc[8 * i + 1] * inv);
-        t.y = pack_bf16x2(o_acc[8 * i + 2] * inv, o_acc[8 * i + 3] * inv);
-        t.z = pack_bf16x2(o_acc[8 * i + 4] * inv, o_acc[8 * i + 5] * inv);
-        t.w = pack_bf16x2(o_acc[8 * i + 6] * inv, o_acc[8 * i + 7] * inv);
-        *reinterpret_cast<uint4*>(op + 8 * i) = t;
+      for (int hh = 0; hh < 2; ++hh) {  // tcgen05.ld is warp-collective: every lane loads, valid rows store
+        uint32_t v[32];
+        tmem_ld_32x32(tO + lane_base + hh * 32, v);
+        tmem_ld_wait();
+        if (qrow < N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t;
+            t.x = pack_bf16x2(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv);
+            t.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
+            t.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
+            t.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + hh * 32 + 8 * i) = t;
+          }
+        }
       }
-      p.lse[((int64_t)b * p.c.H + h) * N + qrow] = (m_run + log2f(l_run)) * LN2;
+      if (qrow < N) p.lse[((int64_t)b * p.c.H + h) * N + qrow] = (m_used + log2f(l_run)) * LN2;
     }
+    PROF_MARK(7);
+#ifdef NV_PROFILE
+    if (blockIdx.x == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+      PROF_DUMP((b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
+#endif
   }
 
   tc_fence_before();
@@ -464,12 +532,15 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     const uint64_t mrow = (uint64_t)stat;
     const float lse2 = p.lse[stat] * LOG2E;
     const float dl = p.delta[stat];
+    PROF_DECL
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * BWD_CB;
       const int nch = (min(BWD_CB, N - key0) + 31) >> 5;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      PROF_MARK(j == 0 ? 0 : 1);
       if (j > 0) mbar_wait(ds_free, (j - 1) & 1);  // dS tile consumed by the previous dQ MMA
+      PROF_MARK(2);
       for (int c = 0; c < nch; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tS + lane_base + c * 32, sv);
@@ -495,9 +566,11 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(ds_ready);
+      PROF_MARK(3);
     }
     mbar_wait(ds_free, (nblk - 1) & 1);  // last dQ MMA retired
     tc_fence_after();
+    PROF_MARK(4);
     {  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows store
       bf16* dst = p.dq + (int64_t)b * p.d_bs + (int64_t)min(qrow, N - 1) * p.d_rs + h * HD;
 #pragma unroll
@@ -518,6 +591,11 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
         }
       }
     }
+    PROF_MARK(5);
+#ifdef NV_PROFILE
+    if (blockIdx.x == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+      PROF_DUMP(4 + (b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
+#endif
   }
 
   tc_fence_before();
@@ -641,6 +719,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     uint32_t* mwords = reinterpret_cast<uint32_t*>(stats + 128);  // dropout: the 64 queries' mask words of this warp's keys
     const bool dropout = p.c.drop_thr != 0;
     const uint64_t mbase = ((uint64_t)b * p.c.H + h) * N;
+    PROF_DECL
     for (int i = 0; i < nblk; ++i) {
       const int qb = i * BWD_CB;
       const int nvalid = min(BWD_CB, N - qb);
@@ -656,9 +735,12 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         if (dropout) mwords[t * 32 + lane] = p.c.mask[(mbase + qc) * p.c.mask_words + ((k0 + warp * 32) >> 5)];
       }
       __syncwarp();
+      PROF_MARK(0);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
+      PROF_MARK(1);
       if (i > 0) mbar_wait(pds_free, (i - 1) & 1);  // P^T / dS^T tiles consumed by the previous dV / dK MMAs
+      PROF_MARK(2);
       for (int c = 0; c < nch; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32(tST + lane_base + c * 32, sv);
@@ -700,9 +782,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(pds_ready);
+      PROF_MARK(3);
     }
     mbar_wait(pds_free, (nblk - 1) & 1);
     tc_fence_after();
+    PROF_MARK(4);
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       bf16* base = which == 0 ? p.dv : p.dk;
@@ -726,6 +810,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         }
       }
     }
+    PROF_MARK(5);
+#ifdef NV_PROFILE
+    if (blockIdx.x == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+      PROF_DUMP(8 + (b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
+#endif
   }
 
   tc_fence_before();
@@ -821,11 +910,13 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
   static bool attr_set = false;
   if (!attr_set) {
-    if ((s = set_smem(attn_tc_fwd_kernel, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<false>, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<true>, FWD_SMEM)) != NV_OK) return s;
     attr_set = true;
   }
   dim3 grid((N + BQ - 1) / BQ, H, B);
-  attn_tc_fwd_kernel<<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  if (p.c.drop_thr != 0) attn_tc_fwd_kernel<true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  else attn_tc_fwd_kernel<false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
   NV_LAUNCH_CHECK("attn_tc_fwd_kernel");
   return NV_OK;
 }
