@@ -720,6 +720,23 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     const bool dropout = p.c.drop_thr != 0;
     const uint64_t mbase = ((uint64_t)b * p.c.H + h) * N;
     PROF_DECL
+    // per-query statistics of a block: fetched one block ahead into registers (the global-load latency hides
+    // behind the previous block's exponentials), then staged in shared memory and read back as broadcasts
+    float st_l[2], st_d[2];
+    uint32_t st_m[2] = {0u, 0u};
+    auto fetch_stats = [&](int blk) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int q = blk * BWD_CB + t * 32 + lane;
+        const int qc = min(q, N - 1);
+        // padded queries: lse = +inf makes P exactly 0 (their dO / Q rows are zero-filled anyway)
+        st_l[t] = q < N ? __ldg(lse_bh + qc) * LOG2E : INFINITY;
+        st_d[t] = __ldg(delta_bh + qc);
+        if (dropout) st_m[t] = p.c.mask[(mbase + qc) * p.c.mask_words + ((k0 + warp * 32) >> 5)];
+      }
+    };
+    const uint32_t stats_u32 = smem_u32(stats), mwords_u32 = smem_u32(mwords);
+    fetch_stats(0);
     for (int i = 0; i < nblk; ++i) {
       const int qb = i * BWD_CB;
       const int nvalid = min(BWD_CB, N - qb);
@@ -727,13 +744,12 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       __syncwarp();
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int q = qb + t * 32 + lane;
-        const int qc = min(q, N - 1);
-        // padded queries: lse = +inf makes P exactly 0 (their dO / Q rows are zero-filled anyway)
-        stats[t * 32 + lane] = q < N ? __ldg(lse_bh + qc) * LOG2E : INFINITY;
-        stats[64 + t * 32 + lane] = __ldg(delta_bh + qc);
-        if (dropout) mwords[t * 32 + lane] = p.c.mask[(mbase + qc) * p.c.mask_words + ((k0 + warp * 32) >> 5)];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(stats_u32 + (uint32_t)(t * 32 + lane) * 4), "f"(st_l[t]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(stats_u32 + (uint32_t)(64 + t * 32 + lane) * 4), "f"(st_d[t]) : "memory");
+        if (dropout)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(mwords_u32 + (uint32_t)(t * 32 + lane) * 4), "r"(st_m[t]) : "memory");
       }
+      if (i + 1 < nblk) fetch_stats(i + 1);
       __syncwarp();
       PROF_MARK(0);
       mbar_wait(s_full, i & 1);
@@ -749,8 +765,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         float pt[32], ds[32];
 #pragma unroll
         for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 l2 = *reinterpret_cast<const float4*>(stats + c * 32 + e4 * 4);
-          const float4 dl = *reinterpret_cast<const float4*>(stats + 64 + c * 32 + e4 * 4);
+          float4 l2, dl;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(l2.x), "=f"(l2.y), "=f"(l2.z), "=f"(l2.w)
+                       : "r"(stats_u32 + (uint32_t)(c * 32 + e4 * 4) * 4));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w)
+                       : "r"(stats_u32 + (uint32_t)(64 + c * 32 + e4 * 4) * 4));
           const float l2v[4] = {l2.x, l2.y, l2.z, l2.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {

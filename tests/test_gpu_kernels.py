@@ -220,6 +220,29 @@ def test_attention_fwd_bwd(B, N, H):
         assert rel_err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
 
 
+def test_attention_fwd_rising_scores_rescale_path():
+    """The forward keeps a lazily raised softmax reference (TMEM accumulator rescaled only when a block's
+    maximum exceeds it by 2^8): scores that climb along the key axis force that path in every block for the
+    rows with a positive query, while rows with a negative query never raise after the first block — both
+    kinds share warps."""
+    hd, B, N, H = 64, 2, 385, 2
+    torch.manual_seed(11)
+    inner = H * hd
+    qkv = torch.randn(B * N, 3 * inner, device=DEV) * 0.05
+    sign = torch.where(torch.rand(B * N, 1, device=DEV) < 0.5, -1.0, 1.0)
+    ramp = (torch.arange(N, device=DEV, dtype=torch.float32) / N).repeat(B).unsqueeze(1)
+    qkv[:, :inner] += sign                          # q = +-1 (+ noise)
+    qkv[:, inner:2 * inner] += 8.0 * ramp           # k_j grows with j: scores span ~0 .. +-64 per row
+    qkv = qkv.to(torch.bfloat16)
+    o = torch.empty(B * N, inner, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=DEV)
+    ops.attention_fwd(qkv, o, lse, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5)
+    oref, lref = _attn_ref(qkv.double(), B, N, H, hd)
+    assert torch.isfinite(o.float()).all()
+    assert rel_err(o, oref) < 1e-2
+    assert rel_err(lse, lref) < 1e-3
+
+
 def test_softmax_fwd_bwd():
     torch.manual_seed(8)
     rows, n = 333, 385
