@@ -41,6 +41,9 @@ int nv_device_check(void);
  * value = gelu(value) when apply_gelu, +residual[M,N] (fp32), then store: out_f32 (or red.add into it
  * when accumulate=1 — required for k_splits > 1) and/or the bf16 copy out_bf16; colsum[N] (optional)
  * += sum over rows of the stored value (the bias gradient of the layer below, fused into the dgrad).
+ * dropout_p > 0: nn.Dropout on the value (vit_3d.py:21,23,45), applied after bias / GELU and BEFORE the
+ * residual add; with gelu_u it multiplies the gradient by the forward mask of the activation. The keep
+ * mask is a pure function of (dropout_seed, dropout_stream, row * N + col) — nv_dropout draws the same one.
  * block_n: 0 = auto, or 128 / 256 (CTA tile 128 x block_n). */
 int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -48,7 +51,16 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  const void* gelu_u, int64_t ld_u,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
                  void* out_pre, int64_t ld_pre, float* colsum,
-                 int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group, void* stream);
+                 int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
+                 float dropout_p, int64_t dropout_seed, int dropout_stream, void* stream);
+
+/* ---- element-wise dropout ---------------------------------------------------------------------------
+ * replaces: nn.Dropout on the embedding (vit_3d.py:100,119) and, in backward, the mask applied to the
+ * gradient of a dropped-out linear output.  v = in * keep / (1 - p_eff); out_f32 / out_bf16 = v (+ residual);
+ * colsum[N] += column sums of v. p = 0 turns it into a copy / cast / column sum. N % 8 == 0. */
+int nv_dropout(const float* in, int64_t ld_in, const float* residual, int64_t ld_res,
+               float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, float* colsum,
+               int M, int N, float p, int64_t seed, int stream_id, void* stream);
 
 /* fp32 verification GEMM (CUDA-core FMA, arbitrary strides, batch index z = z1*Z2 + z2):
  * C[z][m][n] = epilogue(alpha * sum_k A[z][m,k] * B[z][n,k]); same epilogue order as nv_gemm_bf16, all

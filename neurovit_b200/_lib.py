@@ -23,7 +23,8 @@ SIGNATURES = {
     "nv_version": [],
     "nv_device_check": [],
     "nv_gemm_bf16": [_i, _i, _i, _i, _i, _p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p,
-                     _i, _i, _f, _i, _i, _i, _p],
+                     _i, _i, _f, _i, _i, _i, _f, _l, _i, _p],
+    "nv_dropout": [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _f, _l, _i, _p],
     "nv_gemm_f32": [_i, _i, _i, _i, _i, _p, _l, _l, _l, _l, _p, _l, _l, _l, _l, _p, _l, _l, _l,
                     _p, _p, _l, _p, _l, _p, _l, _i, _i, _f, _p],
     "nv_layernorm_fwd": [_p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _i, _l, _i, _i, _i, _p, _p,

@@ -21,6 +21,7 @@
 //         MMA for both, each CTA's TMEM holds its 128 accumulator rows. Per-SM L2->smem traffic drops by a
 //         third (the 1-CTA 128x256 tile is L2-bandwidth bound on B200: 96 B/clk/SM x 148 SMs > L2's ~6.3 KB/clk).
 #include "nv_common.cuh"
+#include "nv_rng.cuh"
 
 namespace {
 
@@ -50,6 +51,12 @@ struct GemmParams {
   int64_t ld_res, ld_u, ld_f32, ld_bf16, ld_pre;
   int flags;
   float alpha;
+  // dropout on the value (nn.Dropout after to_out / GELU / the MLP down projection, vit_3d.py:21,23,45;
+  // applied before the residual add). Mask = f(seed, stream, row * N + col): backward regenerates it.
+  uint32_t drop_thr;  // 0 = off
+  float keep_scale;
+  uint64_t drop_seed;
+  uint32_t drop_stream;
 };
 
 template <int BLOCK_N, int STAGES, int CG, int NUM_EPI_WARPS>
@@ -228,6 +235,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       a.y = fmaf(a.y, p.alpha, x.bias4.y);
       a.z = fmaf(a.z, p.alpha, x.bias4.z);
       a.w = fmaf(a.w, p.alpha, x.bias4.w);
+      if (p.drop_thr != 0)
+        a = nv_dropout4(a, nv_keep_bits4(p.drop_seed, (uint64_t)gm * p.N + gn, p.drop_stream, p.drop_thr), p.keep_scale);
       if (p.residual != nullptr) {
         a.x += x.res[i].x; a.y += x.res[i].y; a.z += x.res[i].z; a.w += x.res[i].w;
       }
@@ -237,11 +246,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
             make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
       a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
+      if (p.drop_thr != 0)
+        a = nv_dropout4(a, nv_keep_bits4(p.drop_seed, (uint64_t)gm * p.N + gn, p.drop_stream, p.drop_thr), p.keep_scale);
     } else {
       const float2 u01 = unpack_bf16x2(x.uu[i].x);
       const float2 u23 = unpack_bf16x2(x.uu[i].y);
       a.x *= gelu_grad_fast(u01.x); a.y *= gelu_grad_fast(u01.y);
       a.z *= gelu_grad_fast(u23.x); a.w *= gelu_grad_fast(u23.y);
+      if (p.drop_thr != 0)  // d/du of dropout(gelu(u)): the forward mask of the activation
+        a = nv_dropout4(a, nv_keep_bits4(p.drop_seed, (uint64_t)gm * p.N + gn, p.drop_stream, p.drop_thr), p.keep_scale);
     }
     if (ok) {
       if (EPI_MODE == 0 && (p.flags & EPI_ATOMIC)) {
@@ -549,7 +562,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       int64_t ld_res, const bf16* gelu_u, int64_t ld_u, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
-                      int cta_group, cudaStream_t stream) {
+                      int cta_group, float dropout_p, uint64_t dropout_seed, int dropout_stream, cudaStream_t stream) {
   NV_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   NV_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   NV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16B strides)");
@@ -599,6 +612,12 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   p.ld_res = ld_res; p.ld_u = ld_u; p.ld_f32 = ld_f32; p.ld_bf16 = ld_bf16; p.ld_pre = ld_pre;
   p.flags = (apply_gelu ? EPI_GELU : 0) | (accumulate ? EPI_ATOMIC : 0);
   p.alpha = alpha;
+  NV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "gemm: dropout_p %f out of range [0, 1)", dropout_p);
+  NV_REQUIRE(dropout_p == 0.f || !accumulate, "gemm: dropout and accumulate (split-K) are mutually exclusive");
+  p.drop_thr = nv_dropout_threshold(dropout_p);
+  p.keep_scale = nv_dropout_keep_scale(p.drop_thr);
+  p.drop_seed = dropout_seed;
+  p.drop_stream = (uint32_t)dropout_stream;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int max_workers = num_sms / cta_group;

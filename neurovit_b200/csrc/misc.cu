@@ -1,6 +1,7 @@
 // Small HBM-bound helpers around the GEMMs: dtype casts (weight caches), column sums (bias
 // gradients), batch sums (pos/cls gradients, vit_3d.py:98-99,116-118) and token pooling (:123).
 #include "nv_common.cuh"
+#include "nv_rng.cuh"
 
 namespace {
 
@@ -93,6 +94,36 @@ __global__ void mean_pool_bwd_kernel(const float* __restrict__ dpooled, float* _
   }
 }
 
+// Element-wise dropout with the same (seed, stream, row * N + col) mask the GEMM epilogues draw:
+//   v = in * keep * 1/(1-p);  out = v (+ residual);  colsum[c] += sum_r v[r, c]
+// Used for the embedding dropout (vit_3d.py:100,119), for masking the branch gradient in backward, and by
+// the fp32 verification mode (whose CUDA-core GEMM has no fused dropout). Column-owner threads walk rows.
+__global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, const float* __restrict__ residual,
+                               int64_t ld_res, float* __restrict__ out_f32, int64_t ld_f32, bf16* __restrict__ out_bf16,
+                               int64_t ld_bf16, float* __restrict__ colsum, int M, int N, uint32_t thr, float ks,
+                               uint64_t seed, uint32_t stream_id) {
+  const int nq = N >> 2;
+  for (int c = threadIdx.x; c < nq; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = blockIdx.x; r < M; r += gridDim.x) {
+      float4 v = *reinterpret_cast<const float4*>(in + (int64_t)r * ld_in + 4 * c);
+      if (thr != 0) v = nv_dropout4(v, nv_keep_bits4(seed, (uint64_t)r * N + 4 * c, stream_id, thr), ks);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      if (residual) {
+        const float4 rr = *reinterpret_cast<const float4*>(residual + (int64_t)r * ld_res + 4 * c);
+        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+      }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (int64_t)r * ld_f32 + 4 * c) = v;
+      if (out_bf16)
+        *reinterpret_cast<uint2*>(out_bf16 + (int64_t)r * ld_bf16 + 4 * c) =
+            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    if (colsum)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + 4 * c), "f"(acc.x), "f"(acc.y),
+                   "f"(acc.z), "f"(acc.w) : "memory");
+  }
+}
+
 }  // namespace
 
 int nv_cast_f32_bf16_launch(const float* in, bf16* out, int64_t n, cudaStream_t stream) {
@@ -155,5 +186,25 @@ int nv_mean_pool_bwd_launch(const float* dpooled, float* dx, bf16* dx_bf16, int 
   if (blocks > nv_num_sms() * 8) blocks = nv_num_sms() * 8;
   mean_pool_bwd_kernel<<<(int)blocks, 256, 0, stream>>>(dpooled, dx, dx_bf16, B, N, D);
   NV_LAUNCH_CHECK("mean_pool_bwd_kernel");
+  return NV_OK;
+}
+
+int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32,
+                      int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p,
+                      uint64_t seed, int stream_id, cudaStream_t stream) {
+  NV_REQUIRE(M >= 0 && N > 0 && N % 8 == 0, "dropout: N=%d must be a positive multiple of 8", N);
+  NV_REQUIRE(p >= 0.f && p < 1.f, "dropout: p %f out of range [0, 1)", p);
+  NV_REQUIRE(in != nullptr && (out_f32 != nullptr || out_bf16 != nullptr || colsum != nullptr), "dropout: null buffers");
+  NV_REQUIRE(ld_in % 4 == 0 && ld_res % 4 == 0 && ld_f32 % 4 == 0 && ld_bf16 % 4 == 0,
+             "dropout: row strides must be multiples of 4 elements");
+  NV_REQUIRE((reinterpret_cast<uintptr_t>(colsum) & 15) == 0, "dropout: colsum must be 16-byte aligned");
+  if (M == 0) return NV_OK;
+  const uint32_t thr = nv_dropout_threshold(p);
+  const int threads = (N / 4) >= 256 ? 256 : ((N / 4 + 31) / 32) * 32;
+  int grid = nv_num_sms() * 8;
+  if (grid > M) grid = M;
+  dropout_kernel<<<grid, threads, 0, stream>>>(in, ld_in, residual, ld_res, out_f32, ld_f32, out_bf16, ld_bf16, colsum,
+                                               M, N, thr, nv_dropout_keep_scale(thr), seed, (uint32_t)stream_id);
+  NV_LAUNCH_CHECK("dropout_kernel");
   return NV_OK;
 }

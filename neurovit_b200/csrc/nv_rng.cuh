@@ -57,4 +57,16 @@ __device__ __forceinline__ uint32_t nv_keep_bits8(uint64_t seed, uint64_t group,
   }
   return m;
 }
+// keep-bits of the 4 consecutive elements [idx, idx + 4), idx a multiple of 4 (element-indexed dropout sites:
+// GEMM epilogues and the element-wise kernel share this so forward and backward regenerate the same mask)
+__device__ __forceinline__ uint32_t nv_keep_bits4(uint64_t seed, uint64_t idx, uint32_t stream, uint32_t thr) {
+  return (nv_keep_bits8(seed, idx >> 3, stream, thr) >> ((idx & 4) ? 4 : 0)) & 0xFu;
+}
+__device__ __forceinline__ float4 nv_dropout4(float4 v, uint32_t bits, float ks) {
+  v.x = (bits & 1u) ? v.x * ks : 0.f;
+  v.y = (bits & 2u) ? v.y * ks : 0.f;
+  v.z = (bits & 4u) ? v.z * ks : 0.f;
+  v.w = (bits & 8u) ? v.w * ks : 0.f;
+  return v;
+}
 #endif

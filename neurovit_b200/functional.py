@@ -23,6 +23,29 @@ NUM_SMS = 148
 
 _VALID_MODES = ("bf16", "fp32")
 
+# dropout sites of one block (vit_3d.py:21,23,39,45; emb :100,119): distinct Philox streams under one seed
+DROP_ATTN, DROP_OUT, DROP_GELU, DROP_DOWN, DROP_EMB = 0, 1, 2, 3, 4
+
+
+def draw_seed() -> int:
+    """One 62-bit dropout seed per module call from torch's CPU generator (follows torch.manual_seed, no
+    device sync). The masks themselves are Philox bits of (seed, stream, element index): nv_rng.cuh."""
+    return int(torch.randint(0, 1 << 62, (1,)).item())
+
+
+class _DropoutTrace:
+    """Test hook: while `record` is a list, every dropout site appends (site, p, seed, stream, shape or mask)
+    so a reference implementation can replay exactly the same masks."""
+    record = None
+
+
+DROPOUT_TRACE = _DropoutTrace()
+
+
+def _trace(site, p, seed, stream, info):
+    if DROPOUT_TRACE.record is not None and p > 0:
+        DROPOUT_TRACE.record.append((site, p, seed, stream, info))
+
 
 def check_mode(mode: str) -> str:
     if mode not in _VALID_MODES:
@@ -183,23 +206,29 @@ class Engine:
     def w(self, weight, pad_k=0):
         return self.wc.bf16(weight, pad_k) if self.mode == "bf16" else weight.detach()
 
-    def linear(self, a, weight, *, bias=None, residual=None, gelu=False, out_dtype=None, pad_k=0):
-        """out = epilogue(a @ W^T). Returns (out, pre_activation or None)."""
+    def linear(self, a, weight, *, bias=None, residual=None, gelu=False, out_dtype=None, pad_k=0, drop=None):
+        """out = epilogue(a @ W^T). Returns (out, pre_activation or None). drop = (p, seed, stream): nn.Dropout
+        on the value (after bias / GELU, before the residual add)."""
         M, N = a.shape[0], weight.shape[0]
         out_dtype = out_dtype or self.act
         dev = a.device
         bias = None if bias is None else bias.detach()
         pre = torch.empty(M, N, device=dev, dtype=self.act) if gelu else None
         out = torch.empty(M, N, device=dev, dtype=out_dtype)
+        if drop is not None and drop[0] <= 0:
+            drop = None
         if self.mode == "bf16":
             ops.gemm_bf16(a, self.w(weight, pad_k), bias=bias, residual=residual,
                           out_f32=out if out_dtype == F32 else None, out_bf16=out if out_dtype == BF16 else None,
-                          out_pre=pre, apply_gelu=gelu)
-        else:
+                          out_pre=pre, apply_gelu=gelu, dropout=drop)
+        elif drop is None:
             ops.linear_f32(a, weight.detach(), bias=bias, residual=residual, out=out, out_pre=pre, apply_gelu=gelu)
+        else:  # verification mode: the CUDA-core GEMM has no fused dropout; mask (and add the residual) after it
+            ops.linear_f32(a, weight.detach(), bias=bias, out=out, out_pre=pre, apply_gelu=gelu)
+            ops.dropout(out, p=drop[0], seed=drop[1], stream=drop[2], residual=residual, out_f32=out)
         return out, pre
 
-    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, want_colsum=False, colsum_acc=None):
+    def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, want_colsum=False, colsum_acc=None, drop=None):
         """dx[M, K_in] = dy[M, N_out] @ W[N_out, K_in]  (optionally * gelu'(u)). With want_colsum the column
         sums of dx (the bias gradient of the layer below) come out of the same GEMM epilogue (added into
         colsum_acc.buf when given)."""
@@ -209,11 +238,15 @@ class Engine:
         cs = None
         if want_colsum:
             cs = colsum_acc.buf if colsum_acc is not None else torch.zeros(K_in, device=dy.device, dtype=F32)
+        if drop is not None and drop[0] <= 0:
+            drop = None
         if self.mode == "bf16":
-            ops.gemm_bf16(dy, self.w(weight), b_mn=True, gelu_u=gelu_u, colsum=cs,
+            ops.gemm_bf16(dy, self.w(weight), b_mn=True, gelu_u=gelu_u, colsum=cs, dropout=drop,
                           out_f32=out if out_dtype == F32 else None, out_bf16=out if out_dtype == BF16 else None)
         else:
             ops.linear_f32(dy, weight.detach(), w_kn=True, gelu_u=gelu_u, out=out)
+            if drop is not None:
+                ops.dropout(out, p=drop[0], seed=drop[1], stream=drop[2], out_f32=out)
             if want_colsum:
                 ops.colsum(out, cs)
         if want_colsum:
@@ -283,6 +316,24 @@ class Engine:
             dg, db = acc_g.result(), acc_b.result()
         return dx, (dxb if dxb is not None else dx), dg, db, cs
 
+    def drop_grad(self, dy, drop):
+        """Gradient of a dropped-out linear output: dy * mask / (1 - p) in the MMA operand dtype, plus its column
+        sums (the bias gradient). dy fp32 [M, N]."""
+        M, N = dy.shape
+        out = torch.empty(M, N, device=dy.device, dtype=self.act)
+        cs = torch.zeros(N, device=dy.device, dtype=F32)
+        ops.dropout(dy, p=drop[0], seed=drop[1], stream=drop[2], colsum=cs,
+                    out_f32=out if self.act == F32 else None, out_bf16=out if self.act == BF16 else None)
+        return out, cs
+
+    def branch_grad(self, dy, dy2, drop):
+        """(operand-dtype gradient, its column sums or None) of the residual branch's last linear output."""
+        if drop is not None and drop[0] > 0:
+            _STASH.take(dy)
+            return self.drop_grad(dy2, drop)
+        dy_act, cs = self.as_act(dy)
+        return dy_act.view(dy2.shape), cs
+
     def as_act(self, g):
         """fp32 gradient -> MMA operand dtype, preferring the stashed bf16 copy from the producing kernel."""
         bf, cs = _STASH.take(g)
@@ -293,7 +344,7 @@ class Engine:
         return bf, cs
 
     # -- attention core (after the pre-norm) ------------------------------------------------------
-    def attn_core_fwd(self, a, x_res, w_qkv, w_out, b_out, B, N, heads, dim_head):
+    def attn_core_fwd(self, a, x_res, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn=0.0, p_out=0.0, seed=0):
         """a = LN(x) [M,D] in act dtype; returns x_res + to_out(attention(a)) (fp32) and the saved tensors.
         vit_3d.py:50-60,73."""
         M = a.shape[0]
@@ -304,8 +355,11 @@ class Engine:
         o = torch.empty(M, inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
             lse = torch.empty(B, heads, N, device=dev, dtype=F32)
-            ops.attention_fwd(qkv, o, lse, B=B, N=N, H=heads, head_dim=dim_head, scale=scale)
-            aux = lse
+            mask = torch.zeros(B * heads, N, (N + 31) // 32, device=dev, dtype=torch.int32) if p_attn > 0 else None
+            ops.attention_fwd(qkv, o, lse, B=B, N=N, H=heads, head_dim=dim_head, scale=scale, dropout_p=p_attn,
+                              seed=seed, drop_mask=mask)
+            _trace("attn", p_attn, seed, DROP_ATTN, mask)
+            aux = (lse, mask)
         else:
             P = torch.empty(B, heads, N, N, device=dev, dtype=F32)
             rs = qkv.stride(0)
@@ -313,20 +367,27 @@ class Engine:
             ops.gemm_f32(N, N, dim_head, (qkv, 0), (rs, 1, N * rs, dim_head), (qkv, inner),
                          (rs, 1, N * rs, dim_head), P, (N, heads * N * N, N * N), Z1=B, Z2=heads, alpha=scale)
             ops.softmax_fwd(P, B * heads * N, N)
+            Pd = P
+            if p_attn > 0:  # attention dropout on the materialised probabilities (flat element index)
+                Pd = torch.empty_like(P)
+                ops.dropout_flat(P, Pd, p=p_attn, seed=seed, stream=DROP_ATTN)
+                _trace("attn_flat", p_attn, seed, DROP_ATTN, tuple(P.shape))
             # out = attn v, written as 'b n (h d)'
-            ops.gemm_f32(N, dim_head, N, P, (N, 1, heads * N * N, N * N), (qkv, 2 * inner),
+            ops.gemm_f32(N, dim_head, N, Pd, (N, 1, heads * N * N, N * N), (qkv, 2 * inner),
                          (1, rs, N * rs, dim_head), o, (inner, N * inner, dim_head), Z1=B, Z2=heads)
-            aux = P
+            aux = (P, Pd if p_attn > 0 else None)
         if w_out is None:  # project_out == False (heads == 1 and dim_head == dim): to_out is Identity
             y = torch.empty(M, inner, device=dev, dtype=F32)
             raise NotImplementedError("project_out=False (heads=1, dim_head=dim) is not on the NeuroViT hot path")
-        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32)
-        return y, (qkv, o, aux)
+        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32, drop=(p_out, seed, DROP_OUT))
+        _trace("out", p_out, seed, DROP_OUT, (M, w_out.shape[0]))
+        return y, (qkv, o, *aux)
 
-    def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=None):
+    def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=None,
+                      p_attn=0.0, seed=0):
         """Returns da (grad wrt the LN output, fp32 or the activation dtype), dWqkv, dWout, dbout. dy is the
         fp32 grad of the block output; its residual branch is handled by the caller."""
-        qkv, o, aux = saved
+        qkv, o, aux, aux2 = saved
         M = a.shape[0]
         inner = heads * dim_head
         scale = dim_head ** -0.5
@@ -337,18 +398,22 @@ class Engine:
         dqkv = torch.empty(M, 3 * inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
             ws = torch.empty(B * heads * N, device=dev, dtype=F32)
-            ops.attention_bwd(qkv, o, dO, aux, ws, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=scale)
+            ops.attention_bwd(qkv, o, dO, aux, ws, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=scale,
+                              dropout_p=p_attn if aux2 is not None else 0.0, drop_mask=aux2)
         else:
             P = aux
+            Pd = aux2 if aux2 is not None else P
             rs, drs = qkv.stride(0), dqkv.stride(0)
             zP = (heads * N * N, N * N)
             # dV[key,d] = sum_q P[q,key] dO[q,d]
-            ops.gemm_f32(N, dim_head, N, P, (1, N, *zP), dO, (1, inner, N * inner, dim_head), (dqkv, 2 * inner),
+            ops.gemm_f32(N, dim_head, N, Pd, (1, N, *zP), dO, (1, inner, N * inner, dim_head), (dqkv, 2 * inner),
                          (drs, N * drs, dim_head), Z1=B, Z2=heads)
             dP = torch.empty_like(P)
             # dP = dO V^T
             ops.gemm_f32(N, N, dim_head, dO, (inner, 1, N * inner, dim_head), (qkv, 2 * inner),
                          (rs, 1, N * rs, dim_head), dP, (N, *zP), Z1=B, Z2=heads)
+            if aux2 is not None:  # through the attention dropout: d(attn) = d(dropped) * mask / (1 - p)
+                ops.dropout_flat(dP, dP, p=p_attn, seed=seed, stream=DROP_ATTN)
             ops.softmax_bwd(P, dP, B * heads * N, N)  # dP <- dS
             # dQ = dS K * scale ; dK = dS^T Q * scale
             ops.gemm_f32(N, dim_head, N, dP, (N, 1, *zP), (qkv, inner), (1, rs, N * rs, dim_head), (dqkv, 0),
@@ -360,14 +425,17 @@ class Engine:
         return da, dWqkv, dWo, dbo
 
     # -- feed-forward core -------------------------------------------------------------------------
-    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2):
-        g, u = self.linear(a, w1, bias=b1, gelu=True)
-        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32)
+    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0):
+        g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, DROP_GELU))
+        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32, drop=(p_down, seed, DROP_DOWN))
+        _trace("gelu", p_gelu, seed, DROP_GELU, tuple(g.shape))
+        _trace("down", p_down, seed, DROP_DOWN, tuple(y.shape))
         return y, (u, g)
 
-    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, b1, w2, da_dtype=None):
+    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, b1, w2, da_dtype=None, p_gelu=0.0, seed=0):
         u, g = saved
-        dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True, colsum_acc=GradAcc(b1, self.mode))
+        dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True, colsum_acc=GradAcc(b1, self.mode),
+                             drop=(p_gelu, seed, DROP_GELU))
         dW2 = self.wgrad(dy_act, g, acc=GradAcc(w2, self.mode))
         db2 = self.bias_grad(dy, dy_colsum)
         da = self.dgrad(dU, w1, out_dtype=da_dtype or F32)
@@ -425,30 +493,30 @@ class AttnBlockFn(torch.autograd.Function):
     """x + to_out(attention(LN(x)))  — vit_3d.py:48-60 with the residual of :73 fused in."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w_qkv, w_out, b_out, heads, dim_head, eps, mode):
+    def forward(ctx, x, ln_w, ln_b, w_qkv, w_out, b_out, heads, dim_head, eps, mode, p_attn=0.0, p_out=0.0, seed=0):
         eng = engine(mode)
         x2, B, N = _flat(x)
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
-        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head)
+        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed)
         ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved)
-        ctx.cfg = (B, N, heads, dim_head, mode)
+        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved = ctx.saved_tensors
-        B, N, heads, dim_head, mode = ctx.cfg
+        B, N, heads, dim_head, mode, p_attn, p_out, seed = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
-        dy_act, cs = eng.as_act(dy)
         dy2 = dy.view(B * N, -1)
-        da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w_qkv, w_out, B, N, heads,
-                                                dim_head, da_dtype=eng.act)
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, DROP_OUT))
+        da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act, cs, a, saved, w_qkv, w_out, B, N, heads, dim_head,
+                                                da_dtype=eng.act, p_attn=p_attn, seed=seed)
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
                                           acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode))
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
-        return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None
+        return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None, None, None, None
 
 
 class AttnCoreFn(torch.autograd.Function):
@@ -456,26 +524,27 @@ class AttnCoreFn(torch.autograd.Function):
     module call (so forward/backward hooks on it fire)."""
 
     @staticmethod
-    def forward(ctx, a, x_res, w_qkv, w_out, b_out, heads, dim_head, mode):
+    def forward(ctx, a, x_res, w_qkv, w_out, b_out, heads, dim_head, mode, p_attn=0.0, p_out=0.0, seed=0):
         eng = engine(mode)
         a2, B, N = _flat(a)
         x2, _, _ = _flat(x_res)
         a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
-        y, saved = eng.attn_core_fwd(a_act, x2, w_qkv, w_out, b_out, B, N, heads, dim_head)
+        y, saved = eng.attn_core_fwd(a_act, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed)
         ctx.save_for_backward(a_act, w_qkv, w_out, *saved)
-        ctx.cfg = (B, N, heads, dim_head, mode)
+        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         a_act, w_qkv, w_out, *saved = ctx.saved_tensors
-        B, N, heads, dim_head, mode = ctx.cfg
+        B, N, heads, dim_head, mode, p_attn, p_out, seed = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
-        dy_act, cs = eng.as_act(dy)
-        da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy.view(B * N, -1), dy_act.view(B * N, -1), cs, a_act, saved, w_qkv,
-                                                w_out, B, N, heads, dim_head)
-        return da.view(B, N, -1), dy, dWqkv, dWo, dbo, None, None, None
+        dy2 = dy.view(B * N, -1)
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, DROP_OUT))
+        da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act, cs, a_act, saved, w_qkv, w_out, B, N, heads, dim_head,
+                                                p_attn=p_attn, seed=seed)
+        return da.view(B, N, -1), dy, dWqkv, dWo, dbo, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------- autograd: feed-forward block
@@ -483,30 +552,30 @@ class FFBlockFn(torch.autograd.Function):
     """x + W2 gelu(W1 LN(x) + b1) + b2  — vit_3d.py:14-26 with the residual of :74 fused in."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode):
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode, p_gelu=0.0, p_down=0.0, seed=0):
         eng = engine(mode)
         x2, B, N = _flat(x)
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
-        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2)
+        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2, p_gelu, p_down, seed)
         ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved)
-        ctx.cfg = (B, N, mode)
+        ctx.cfg = (B, N, mode, p_gelu, p_down, seed)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved = ctx.saved_tensors
-        B, N, mode = ctx.cfg
+        B, N, mode, p_gelu, p_down, seed = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
-        dy_act, cs = eng.as_act(dy)
         dy2 = dy.view(B * N, -1)
-        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act.view(B * N, -1), cs, a, saved, w1, b1, w2,
-                                                 da_dtype=eng.act)
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, DROP_DOWN))
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act, cs, a, saved, w1, b1, w2, da_dtype=eng.act,
+                                                 p_gelu=p_gelu, seed=seed)
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
                                           acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode))
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
-        return dx, dg, db, dW1, db1, dW2, db2, None, None
+        return dx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None
 
 
 class FFCoreFn(torch.autograd.Function):
@@ -514,26 +583,50 @@ class FFCoreFn(torch.autograd.Function):
     call (hooks on net[0] fire)."""
 
     @staticmethod
-    def forward(ctx, a, x_res, w1, b1, w2, b2, mode):
+    def forward(ctx, a, x_res, w1, b1, w2, b2, mode, p_gelu=0.0, p_down=0.0, seed=0):
         eng = engine(mode)
         a2, B, N = _flat(a)
         x2, _, _ = _flat(x_res)
         a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
-        y, saved = eng.ff_core_fwd(a_act, x2, w1, b1, w2, b2)
+        y, saved = eng.ff_core_fwd(a_act, x2, w1, b1, w2, b2, p_gelu, p_down, seed)
         ctx.save_for_backward(a_act, w1, b1, w2, *saved)
-        ctx.cfg = (B, N, mode)
+        ctx.cfg = (B, N, mode, p_gelu, p_down, seed)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         a_act, w1, b1, w2, *saved = ctx.saved_tensors
-        B, N, mode = ctx.cfg
+        B, N, mode, p_gelu, p_down, seed = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
-        dy_act, cs = eng.as_act(dy)
-        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy.view(B * N, -1), dy_act.view(B * N, -1), cs, a_act, saved, w1, b1,
-                                                 w2)
-        return da.view(B, N, -1), dy, dW1, db1, dW2, db2, None
+        dy2 = dy.view(B * N, -1)
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, DROP_DOWN))
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act, cs, a_act, saved, w1, b1, w2, p_gelu=p_gelu, seed=seed)
+        return da.view(B, N, -1), dy, dW1, db1, dW2, db2, None, None, None, None
+
+
+# ------------------------------------------------------------------------ autograd: nn.Dropout
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout on a [.., D] fp32 tensor (the embedding dropout, vit_3d.py:100,119); backward regenerates
+    the same Philox mask from (seed, stream)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, stream):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1]).float().contiguous()
+        out = torch.empty_like(x2)
+        ops.dropout(x2, p=p, seed=seed, stream=stream, out_f32=out)
+        _trace("emb", p, seed, stream, tuple(x2.shape))
+        ctx.cfg = (p, seed, stream, shape)
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, stream, shape = ctx.cfg
+        dy2 = dy.reshape(-1, shape[-1]).float().contiguous()
+        dx = torch.empty_like(dy2)
+        ops.dropout(dy2, p=p, seed=seed, stream=stream, out_f32=dx)
+        return dx.view(shape), None, None, None
 
 
 # ---------------------------------------------------------------------- autograd: patch embedding

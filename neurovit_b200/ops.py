@@ -77,8 +77,9 @@ def _rowmajor(t: torch.Tensor, name: str) -> int:
 # ------------------------------------------------------------------------------------------- GEMMs
 def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=None, out_f32=None,
               out_bf16=None, out_pre=None, colsum=None, apply_gelu=False, accumulate=False, alpha=1.0, k_splits=1,
-              block_n=0, cta_group=None):
-    """C[M,N] = epilogue(alpha * A @ B^T) on tcgen05. a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N])."""
+              block_n=0, cta_group=None, dropout=None):
+    """C[M,N] = epilogue(alpha * A @ B^T) on tcgen05. a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N]).
+    dropout = (p, seed, stream) applies nn.Dropout to the value before the residual add."""
     _dev(a)
     assert a.dtype == BF16 and b.dtype == BF16, "gemm_bf16 operands must be bfloat16"
     lda, ldb = _rowmajor(a, "a"), _rowmajor(b, "b")
@@ -96,17 +97,57 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     ld = lambda t: 0 if t is None else t.stride(0)
     if cta_group is None:
         cta_group = GEMM_CTA_GROUP
+    dp, dseed, dstream = dropout if dropout is not None else (0.0, 0, 0)
+    args = (int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
+            _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
+            _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
+            int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), float(dp), int(dseed),
+            int(dstream), _stream())
     if PROFILE.enabled:
         with PROFILE.region(2.0 * M * N * K):
-            _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
-                      _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
-                      _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
-                      int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), _stream())
+            _lib.call("nv_gemm_bf16", *args)
         return
-    _lib.call("nv_gemm_bf16", int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
-              _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
-              _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
-              int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), _stream())
+    _lib.call("nv_gemm_bf16", *args)
+
+
+def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, colsum=None):
+    """v = x * keep / (1 - p) with the (seed, stream, row * N + col) mask of the GEMM epilogues; out = v (+ residual);
+    colsum += column sums of v. x: fp32 [M, N] (unit inner stride), N % 8 == 0."""
+    _dev(x)
+    assert x.dtype == F32 and x.dim() == 2 and x.stride(1) == 1
+    M, N = x.shape
+    ld = lambda t: 0 if t is None else t.stride(0)
+    for t, dt in ((residual, F32), (out_f32, F32), (out_bf16, BF16)):
+        if t is not None:
+            assert t.dtype == dt and tuple(t.shape) == (M, N) and t.stride(1) == 1
+    _lib.call("nv_dropout", _ptr(x), ld(x), _ptr(residual), ld(residual), _ptr(out_f32), ld(out_f32), _ptr(out_bf16),
+              ld(out_bf16), _ptr(colsum), M, N, float(p), int(seed), int(stream), _stream())
+
+
+def dropout_flat(x, out, *, p, seed, stream):
+    """Dropout over a contiguous fp32 tensor addressed by its flat element index (the fp32 verification mode's
+    materialised attention probabilities, whose row length need not be a multiple of 8). The flat length is
+    padded up to a multiple of 8 by viewing whole rows of 8; a ragged tail is handled by a second tiny call."""
+    _dev(x)
+    assert x.dtype == F32 and out.dtype == F32 and x.is_contiguous() and out.is_contiguous() and x.shape == out.shape
+    L = x.numel()
+    body = L // 8 * 8
+    if body:
+        dropout(x.view(-1)[:body].view(-1, 8), p=p, seed=seed, stream=stream, out_f32=out.view(-1)[:body].view(-1, 8))
+    if L - body:  # < 8 trailing elements: own stream offset keeps the bits independent of the body's
+        pad = torch.zeros(1, 8, device=x.device)
+        pad[0, :L - body] = x.view(-1)[body:]
+        res = torch.empty_like(pad)
+        dropout(pad, p=p, seed=seed, stream=stream + 1000, out_f32=res)
+        out.view(-1)[body:] = res[0, :L - body]
+
+
+def dropout_keep_mask(M, N, *, p, seed, stream, device="cuda"):
+    """The keep mask (1.0 / 0.0, fp32 [M, N]) of a dropout site — test / debugging helper."""
+    ones = torch.ones(M, N, device=device)
+    out = torch.empty_like(ones)
+    dropout(ones, p=p, seed=seed, stream=stream, out_f32=out)
+    return (out != 0).float()
 
 
 def gemm_f32(M, N, K, a, sa, b, sb, c, sc, *, Z1=1, Z2=1, bias=None, residual=None, gelu_u=None, out_pre=None,

@@ -29,11 +29,9 @@ def _has_hooks(m: nn.Module) -> bool:
     return bool(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or m._backward_pre_hooks)
 
 
-def _check_dropout(mod: nn.Module, p: float):
-    if mod.training and p > 0.0:
-        raise NotImplementedError(
-            "neurovit_b200: dropout > 0 in training mode is not implemented yet in the fused sm_100a path; "
-            "construct the model with dropout=0 / emb_dropout=0 or call .eval()")
+def _p(mod: nn.Module, drop: nn.Module) -> float:
+    """Active dropout probability of an nn.Dropout child: its p in training mode, 0 in eval (vit_3d.py:21-23)."""
+    return float(drop.p) if (mod.training and drop.training) else 0.0
 
 
 class _PrecisionMixin:
@@ -96,17 +94,19 @@ class FeedForward(nn.Module, _PrecisionMixin):
     def forward(self, x, residual=None):
         """Reference semantics: returns net(x) (vit_3d.py:25-26). With residual=x the add of vit_3d.py:74 is
         fused into the last GEMM's epilogue (used by Transformer.forward)."""
-        _check_dropout(self, self.net[3].p)
         ln, l1, l2 = self.net[0], self.net[1], self.net[4]
+        p_gelu, p_down = _p(self, self.net[3]), _p(self, self.net[5])
+        seed = Fn.draw_seed() if (p_gelu > 0 or p_down > 0) else 0
         if residual is None:
             residual_t = torch.zeros_like(x, dtype=torch.float32)
         else:
             residual_t = residual
         if residual is not None and residual is x and not _has_hooks(ln):
             return Fn.FFBlockFn.apply(x, ln.weight, ln.bias, l1.weight, l1.bias, l2.weight, l2.bias, ln.eps,
-                                      self.precision)
+                                      self.precision, p_gelu, p_down, seed)
         a = ln(x)  # module call: hooks on net[0] fire
-        return Fn.FFCoreFn.apply(a, residual_t, l1.weight, l1.bias, l2.weight, l2.bias, self.precision)
+        return Fn.FFCoreFn.apply(a, residual_t, l1.weight, l1.bias, l2.weight, l2.bias, self.precision, p_gelu,
+                                 p_down, seed)
 
 
 class Attention(nn.Module, _PrecisionMixin):
@@ -133,18 +133,19 @@ class Attention(nn.Module, _PrecisionMixin):
     def forward(self, x, residual=None):
         """Reference semantics: returns to_out(attention(norm(x))) (vit_3d.py:48-60). With residual=x the add
         of vit_3d.py:73 is fused into the to_out GEMM epilogue."""
-        _check_dropout(self, self.dropout.p)
         if isinstance(self.to_out, nn.Identity):
             raise NotImplementedError("project_out=False (heads == 1 and dim_head == dim) is not on the NeuroViT "
                                       "hot path (NeuroEncoder.py:181-195 uses heads=8, dim_head=64)")
         w_out, b_out = self.to_out[0].weight, self.to_out[0].bias
+        p_attn, p_out = _p(self, self.dropout), _p(self, self.to_out[1])
+        seed = Fn.draw_seed() if (p_attn > 0 or p_out > 0) else 0
         if residual is not None and residual is x and not _has_hooks(self.norm):
             return Fn.AttnBlockFn.apply(x, self.norm.weight, self.norm.bias, self.to_qkv.weight, w_out, b_out,
-                                        self.heads, self.dim_head, self.norm.eps, self.precision)
+                                        self.heads, self.dim_head, self.norm.eps, self.precision, p_attn, p_out, seed)
         residual_t = torch.zeros_like(x, dtype=torch.float32) if residual is None else residual
         a = self.norm(x)  # real module call so Grad-CAM hooks on .norm observe output and grad_output
         return Fn.AttnCoreFn.apply(a, residual_t, self.to_qkv.weight, w_out, b_out, self.heads, self.dim_head,
-                                   self.precision)
+                                   self.precision, p_attn, p_out, seed)
 
 
 class Transformer(nn.Module):
@@ -213,7 +214,6 @@ class ViT(nn.Module, _PrecisionMixin):
         if video.shape[2] % pf or video.shape[3] % p1 or video.shape[4] % p2:
             raise ValueError(f"Shape mismatch: volume {tuple(video.shape[2:])} is not divisible by the patch size "
                              f"{(pf, p1, p2)}")
-        _check_dropout(self, self.dropout.p)
         if video.shape[0] == 0:  # empty batch: nothing to launch
             return video.new_zeros((0, self.mlp_head[1].out_features), dtype=torch.float32)
         pe = self.to_patch_embedding
@@ -223,6 +223,9 @@ class ViT(nn.Module, _PrecisionMixin):
         x = Fn.PatchEmbedFn.apply(video, pe[1].weight, pe[1].bias, pe[2].weight, pe[2].bias, pe[3].weight,
                                   pe[3].bias, self.cls_token, self.pos_embedding, self.patch, pe[1].eps,
                                   self.precision)
+        p_emb = _p(self, self.dropout)
+        if p_emb > 0:  # x = dropout(x), vit_3d.py:119
+            x = Fn.DropoutFn.apply(x, p_emb, Fn.draw_seed(), Fn.DROP_EMB)
         x = self.transformer(x)
         h = self.mlp_head
         x = self.to_latent(x)

@@ -56,10 +56,14 @@ def neuro_view(x: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------- ViT3D
-def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, pool="cls", prefix=""):
+def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, pool="cls", prefix="", masks=None):
     """Functional forward of ViT (reference src/models/vit_3d.py:112-126) from a state_dict `sd`.
-    patch = (pf, p1, p2). Dropout is the identity (p = 0 / eval), as in every parity test."""
+    patch = (pf, p1, p2). Dropout is the identity (p = 0 / eval) unless `masks` is given: a dict
+    {"emb": m, (layer, "attn" | "out" | "gelu" | "down"): m} of multiplicative masks (keep / (1 - p), already
+    scaled) applied exactly where the reference's nn.Dropout modules sit (vit_3d.py:21,23,39,45,100) — torch's
+    own Philox stream cannot be replayed by a fused kernel, so dropout parity is checked with injected masks."""
     g = lambda k: sd[prefix + k]
+    mk = (lambda key, t: t * masks[key].to(t.dtype).reshape(t.shape)) if masks is not None else (lambda key, t: t)
     pf, p1, p2 = patch
     B, C, Fr, H, W = video.shape
     # to_patch_embedding: Rearrange -> LN(patch_dim) -> Linear -> LN(dim)           vit_3d.py:91-96
@@ -72,6 +76,8 @@ def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, p
     # cls token, positional embedding sliced to n+1                                  vit_3d.py:116-118
     x = torch.cat((g("cls_token").expand(B, 1, -1), x), dim=1)
     x = x + g("pos_embedding")[:, : n + 1]
+    if masks is not None and "emb" in masks:
+        x = mk("emb", x)                                                                   # vit_3d.py:119
     depth = 0
     while f"{prefix}transformer.layers.{depth}.0.norm.weight" in sd:
         depth += 1
@@ -83,13 +89,13 @@ def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, p
         qkv = F.linear(a, g(p + "0.to_qkv.weight"))
         q, k, v = (t.reshape(B, n + 1, heads, dim_head).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
         dots = torch.matmul(q, k.transpose(-1, -2)) * scale
-        attn = dots.softmax(dim=-1)
+        attn = mk((i, "attn"), dots.softmax(dim=-1))                                        # :55-56
         out = torch.matmul(attn, v).transpose(1, 2).reshape(B, n + 1, heads * dim_head)
-        x = F.linear(out, g(p + "0.to_out.0.weight"), g(p + "0.to_out.0.bias")) + x      # :60,73
+        x = mk((i, "out"), F.linear(out, g(p + "0.to_out.0.weight"), g(p + "0.to_out.0.bias"))) + x  # :45,60,73
         # FeedForward                                                              vit_3d.py:17-26,74
         a = F.layer_norm(x, x.shape[-1:], g(p + "1.net.0.weight"), g(p + "1.net.0.bias"))
         u = F.linear(a, g(p + "1.net.1.weight"), g(p + "1.net.1.bias"))
-        x = F.linear(F.gelu(u), g(p + "1.net.4.weight"), g(p + "1.net.4.bias")) + x
+        x = mk((i, "down"), F.linear(mk((i, "gelu"), F.gelu(u)), g(p + "1.net.4.weight"), g(p + "1.net.4.bias"))) + x
     x = x.mean(dim=1) if pool == "mean" else x[:, 0]                                       # :123
     x = F.layer_norm(x, x.shape[-1:], g("mlp_head.0.weight"), g("mlp_head.0.bias"))
     return F.linear(x, g("mlp_head.1.weight"), g("mlp_head.1.bias"))                       # :108-110,126

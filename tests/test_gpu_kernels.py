@@ -317,3 +317,66 @@ def test_temporal_head_matches_torch():
     gflat = torch.cat([g.flatten() for g in grads[1:]])
     assert rel_err(ws.double().sum(0), gflat) < 1e-3
     assert rel_err(dx, grads[0]) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------- dropout
+def test_dropout_kernel_mask_statistics_and_determinism():
+    M, N, p = 1000, 1024, 0.1
+    x = torch.randn(M, N, device=DEV)
+    out = torch.empty_like(x)
+    outb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    ops.dropout(x, p=p, seed=123, stream=2, residual=res, out_f32=out, out_bf16=outb, colsum=cs)
+    keep = ops.dropout_keep_mask(M, N, p=p, seed=123, stream=2)
+    thr = int(p * 65536 + 0.5)
+    ks = 65536.0 / (65536 - thr)
+    assert abs(keep.mean().item() - (1 - thr / 65536)) < 3e-3
+    assert torch.equal(out, x * keep * ks + res)                    # same mask, exact arithmetic
+    assert rel_err(outb, out) < 1e-2
+    assert rel_err(cs, (x * keep * ks).double().sum(0)) < 1e-4
+    # a different stream or seed gives an independent mask
+    other = ops.dropout_keep_mask(M, N, p=p, seed=123, stream=3)
+    assert 0.70 < (other == keep).float().mean().item() < 0.90      # agreement of two Bernoulli(0.9) masks = 0.82
+    # p = 0: plain copy + column sums
+    cs.zero_()
+    ops.dropout(x, p=0.0, seed=1, stream=0, out_f32=out, colsum=cs)
+    assert torch.equal(out, x) and rel_err(cs, x.double().sum(0)) < 1e-4
+
+
+def test_gemm_epilogue_dropout_matches_elementwise_mask():
+    """The three GEMM epilogues draw the same (seed, stream, row * N + col) mask as nv_dropout."""
+    torch.manual_seed(12)
+    M, N, K, p, seed = 392, 512, 256, 0.25, 987654321
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    thr = int(p * 65536 + 0.5)
+    ks = 65536.0 / (65536 - thr)
+    lin = a.double() @ w.double().t() + bias.double()
+    # store epilogue: dropout(linear) + residual
+    keep = ops.dropout_keep_mask(M, N, p=p, seed=seed, stream=1).double()
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm_bf16(a, w, bias=bias, residual=res, out_f32=out, dropout=(p, seed, 1))
+    assert rel_err(out, lin * keep * ks + res.double()) < 2e-3
+    # GELU epilogue: pre-activation untouched, activation dropped
+    keep2 = ops.dropout_keep_mask(M, N, p=p, seed=seed, stream=2).double()
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    act = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_bf16(a, w, bias=bias, out_bf16=act, out_pre=pre, apply_gelu=True, dropout=(p, seed, 2))
+    assert rel_err(pre, lin) < 1e-2
+    assert rel_err(act, torch.nn.functional.gelu(lin) * keep2 * ks) < 1e-2
+    assert (act.double()[keep2 == 0] == 0).all()                    # dropped entries are exact zeros
+    # dgrad through GELU + dropout: dY W * mask/(1-p) * gelu'(u)
+    dy = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    wt = (torch.randn(K, N, device=DEV) * 0.1).to(torch.bfloat16)  # stored [N_out=K, K_in=N]
+    u = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    du = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=DEV)
+    ops.gemm_bf16(dy, wt, b_mn=True, gelu_u=u, out_bf16=du, colsum=cs, dropout=(p, seed, 2))
+    ud = u.double().requires_grad_(True)
+    gp, = torch.autograd.grad(torch.nn.functional.gelu(ud).sum(), ud)
+    ref = (dy.double() @ wt.double()) * keep2 * ks * gp
+    assert rel_err(du, ref) < 1e-2
+    assert rel_err(cs, ref.sum(0)) < 1e-2

@@ -200,3 +200,74 @@ def test_trainer_grad_sinks_match_autograd_accumulation():
     for k, p in m.named_parameters():
         assert p.grad.data_ptr() % 128 == 0
         assert rel(p.grad, want[k]) < 1e-4, k
+
+
+def _replay_masks(trace, B, N, heads, ks_of):
+    """Rebuild the oracle's mask dict from functional.DROPOUT_TRACE records (forward order: emb, then per layer
+    attn, out, gelu, down)."""
+    from neurovit_b200 import ops
+    masks, layer = {}, 0
+    for site, p, seed, stream, info in trace:
+        ks = ks_of(p)
+        if site == "emb":
+            masks["emb"] = ops.dropout_keep_mask(info[0], info[1], p=p, seed=seed, stream=stream).cpu() * ks
+        elif site == "attn":      # saved bit mask [B*H, N, ceil(N/32)] of the flash kernel
+            w = info.view(B, heads, N, -1).to(torch.int64) & 0xFFFFFFFF
+            bits = ((w.unsqueeze(-1) >> torch.arange(32, device=w.device)) & 1).reshape(B, heads, N, -1)[..., :N]
+            masks[(layer, "attn")] = bits.float().cpu() * ks
+        elif site == "attn_flat":  # fp32 mode: flat element index over [B, H, N, N]
+            L = info[0] * info[1] * info[2] * info[3]
+            body = L // 8 * 8
+            m = torch.ones(L)
+            m[:body] = ops.dropout_keep_mask(body // 8, 8, p=p, seed=seed, stream=stream).cpu().view(-1)
+            if L - body:
+                m[body:] = ops.dropout_keep_mask(1, 8, p=p, seed=seed, stream=stream + 1000).cpu().view(-1)[:L - body]
+            masks[(layer, "attn")] = m.view(info) * ks
+        else:
+            masks[(layer, site)] = ops.dropout_keep_mask(info[0], info[1], p=p, seed=seed, stream=stream).cpu() * ks
+            if site == "down":
+                layer += 1
+    return masks
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode):
+    """Dropout p > 0 in training mode (the reference's default TRAINING_DROPOUT 0.1 at all 25 sites): the masks
+    the kernels drew are replayed into the CPU oracle; logits and every gradient must then agree."""
+    from neurovit_b200 import functional as Fn
+    torch.manual_seed(21)
+    ctor = dict(image_size=16, image_patch_size=8, frames=24, frame_patch_size=8, num_classes=2, dim=64, depth=2,
+                heads=2, mlp_dim=128, channels=1, dim_head=64, dropout=0.2, emb_dropout=0.1)
+    m = ViT(**ctor)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(3, 1, 24, 16, 16)
+    y = torch.tensor([0, 1, 1])
+    m = m.to(DEV).train().set_precision(mode)
+    Fn.DROPOUT_TRACE.record = []
+    try:
+        logits = m(x.to(DEV))
+        trace = Fn.DROPOUT_TRACE.record
+    finally:
+        Fn.DROPOUT_TRACE.record = None
+    loss = torch.nn.functional.cross_entropy(logits, y.to(DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    n_tok = (24 // 8) * (16 // 8) * (16 // 8) + 1
+    assert len(trace) == 1 + 2 * 4, [t[0] for t in trace]
+    ks_of = lambda p: 65536.0 / (65536 - int(p * 65536 + 0.5))
+    masks = _replay_masks(trace, 3, n_tok, 2, ks_of)
+    for k_, v_ in masks.items():
+        assert 0.5 < (v_ != 0).float().mean().item() < 0.98, k_   # really dropping, at roughly the asked rate
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_logits = O.vit3d_forward(leaf, x, patch=(8, 8, 8), heads=2, masks=masks)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, y)
+    grads = torch.autograd.grad(ref_loss, list(leaf.values()), allow_unused=True)
+    tol = TOL[mode]
+    assert rel(logits, ref_logits) < tol["logits"] * (1 if mode == "bf16" else 3)
+    for (k, p_), gr in zip(m.named_parameters(), grads):
+        gr = torch.zeros_like(leaf[k]) if gr is None else gr
+        assert rel(p_.grad, gr) < tol["grad"] * (1.5 if mode == "bf16" else 3), k
+    # eval mode is deterministic and dropout-free
+    m.eval()
+    a, b = m(x.to(DEV)), m(x.to(DEV))
+    assert torch.equal(a, b)

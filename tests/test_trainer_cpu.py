@@ -44,7 +44,7 @@ def _worker(rank, world, port, q):
         off = 0
         for p in reversed(list(m.parameters())):
             assert p.grad.data_ptr() == flat.data_ptr() + 4 * off
-            assert p.grad.data_ptr() % 128 == 0
+            assert (p.grad.data_ptr() - flat.data_ptr()) % 128 == 0  # (CUDA allocations themselves are 512 B aligned)
             off += (p.numel() + A - 1) // A * A
         q.put((rank, float(loss), [g.numpy() for g in grads]))
     finally:
