@@ -33,7 +33,7 @@ CONFIGS = {
     "cfgB": dict(vol=(96, 96, 96), patch=8, tokens=1729, gflop_fwd_bwd=505.432),
 }
 MODEL = dict(dim=1024, depth=6, heads=8, dim_head=64, mlp_dim=2048, num_classes=2)
-DROPOUT = 0.0  # the fused path implements p=0 this round; the reference arm runs the same p
+DROPOUT = 0.1  # TRAINING_DROPOUT of the reference's configs/config.yaml:38 (all 25 sites); --dropout overrides, both arms
 
 
 def vit_ctor(cfg):
@@ -132,7 +132,7 @@ def cpu_reference_step_fn(cfg, batch, seed=42):
     def step():
         opt.zero_grad(set_to_none=True)
         logits = O.vit3d_forward(params, O.neuro_view(x), patch=(p, p, p), heads=MODEL["heads"],
-                                 dim_head=MODEL["dim_head"])
+                                 dim_head=MODEL["dim_head"], dropout_p=DROPOUT)
         loss = torch.nn.functional.cross_entropy(logits, y)
         loss.backward()
         opt.step()
@@ -308,6 +308,7 @@ def run_ours(args, cfg):
 
 
 def main():
+    global DROPOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -316,9 +317,11 @@ def main():
     ap.add_argument("--config", default="cfgA", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=2, help="volumes per CPU reference step (bounded sample)")
+    ap.add_argument("--dropout", type=float, default=DROPOUT, help="dropout p at all sites, training mode (both arms)")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    DROPOUT = args.dropout
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         if args.steps > 6:

@@ -134,6 +134,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
                                                  const Common& c, uint64_t mrow, int key0, bool row_ok,
                                                  uint32_t (&w)[16]) {
   float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+  uint32_t km32 = 0;
 #pragma unroll
   for (int g8 = 0; g8 < 4; ++g8) {
     float e[8];
@@ -146,7 +147,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     if (DROPOUT) {
       const uint32_t km = nv_keep_bits8(c.seed, mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
                                         c.drop_thr);
-      if (row_ok) reinterpret_cast<uint8_t*>(c.mask + mrow * c.mask_words)[(key0 >> 3) + g8] = (uint8_t)km;
+      km32 |= km << (8 * g8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) e[i] = (km >> i) & 1u ? e[i] * c.keep_scale : 0.f;
     }
@@ -155,6 +156,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     w[g8 * 4 + 2] = pack_bf16x2(e[4], e[5]);
     w[g8 * 4 + 3] = pack_bf16x2(e[6], e[7]);
   }
+  if (DROPOUT && row_ok) c.mask[mrow * c.mask_words + (key0 >> 5)] = km32;  // one word per 32-key chunk
   return (rs0 + rs1) + (rs2 + rs3);
 }
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {

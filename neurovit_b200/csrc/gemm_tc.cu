@@ -212,7 +212,7 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
-template <int EPI_MODE>
+template <int EPI_MODE, bool DROP>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], uint32_t stage, int lane,
                                                int row0, int col0, const EpiAux& x) {
   const int sub_r = lane >> 3, sub_c = lane & 7;
@@ -223,11 +223,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   for (int j = 0; j < 8; ++j)
     sts_v4(stage + (uint32_t)((lane * 32 + ((j ^ (lane & 7)) << 2)) * 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
+  // dropout keep-bits: one Philox call covers 8 consecutive columns = the two lanes (sub_c, sub_c ^ 1) of a row
+  // slice, so each lane draws the bits of four of its eight row slices and fetches the rest from its neighbour
+  uint32_t kb[4] = {0u, 0u, 0u, 0u};
+  if (DROP) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int gm_t = row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r;
+      kb[t] = nv_keep_bits8(p.drop_seed, ((uint64_t)gm_t * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
+    }
+  }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + sub_r;
     const int gm = row0 + r;
+    uint32_t keep4 = 0xFu;
+    if (DROP) {
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, kb[i & 3], 1);
+      const uint32_t b8 = ((sub_c & 1) == (i >> 2)) ? kb[i & 3] : other;
+      keep4 = (b8 >> ((sub_c & 1) * 4)) & 0xFu;
+    }
     float4 a = lds_v4(stage + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4));
     const bool ok = col_ok && gm < p.M;
     if (EPI_MODE == 0) {
@@ -235,8 +251,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       a.y = fmaf(a.y, p.alpha, x.bias4.y);
       a.z = fmaf(a.z, p.alpha, x.bias4.z);
       a.w = fmaf(a.w, p.alpha, x.bias4.w);
-      if (p.drop_thr != 0)
-        a = nv_dropout4(a, nv_keep_bits4(p.drop_seed, (uint64_t)gm * p.N + gn, p.drop_stream, p.drop_thr), p.keep_scale);
+      if (DROP) a = nv_dropout4(a, keep4, p.keep_scale);
       if (p.residual != nullptr) {
         a.x += x.res[i].x; a.y += x.res[i].y; a.z += x.res[i].z; a.w += x.res[i].w;
       }
@@ -246,15 +261,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
             make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
       a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
-      if (p.drop_thr != 0)
-        a = nv_dropout4(a, nv_keep_bits4(p.drop_seed, (uint64_t)gm * p.N + gn, p.drop_stream, p.drop_thr), p.keep_scale);
+      if (DROP) a = nv_dropout4(a, keep4, p.keep_scale);
     } else {
       const float2 u01 = unpack_bf16x2(x.uu[i].x);
       const float2 u23 = unpack_bf16x2(x.uu[i].y);
       a.x *= gelu_grad_fast(u01.x); a.y *= gelu_grad_fast(u01.y);
       a.z *= gelu_grad_fast(u23.x); a.w *= gelu_grad_fast(u23.y);
-      if (p.drop_thr != 0)  // d/du of dropout(gelu(u)): the forward mask of the activation
-        a = nv_dropout4(a, nv_keep_bits4(p.drop_seed, (uint64_t)gm * p.N + gn, p.drop_stream, p.drop_thr), p.keep_scale);
+      if (DROP) a = nv_dropout4(a, keep4, p.keep_scale);  // d/du of dropout(gelu(u)): the activation's forward mask
     }
     if (ok) {
       if (EPI_MODE == 0 && (p.flags & EPI_ATOMIC)) {
@@ -285,7 +298,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   __syncwarp();
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE, bool DROP>
 __global__ void __launch_bounds__(num_threads(EPI_MODE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -462,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t v[32];
             tmem_ld_32x32(tm_row + ci * 32 * W, v);
             tmem_ld_wait();
-            epilogue_chunk<EPI_MODE>(p, v, stage, lane, row0, col0, aux[ci & 1]);
+            epilogue_chunk<EPI_MODE, DROP>(p, v, stage, lane, row0, col0, aux[ci & 1]);
           }
         }
       } else {
@@ -478,7 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t v[32];
             tmem_ld_32x32(tm_row + ci * 32 * W, v);
             tmem_ld_wait();
-            epilogue_chunk<EPI_MODE>(p, v, stage, lane, row0, col0, aux);
+            epilogue_chunk<EPI_MODE, DROP>(p, v, stage, lane, row0, col0, aux);
           }
         }
       }
@@ -500,12 +513,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE>
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE, bool DROP = false>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                    cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES, CG, epi_warps(EPI_MODE)>;
   static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG, EPI_MODE>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG, EPI_MODE, DROP>;
   static bool attr_set = false;  // per instantiation; idempotent, races are benign
   if (!attr_set) {
     NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -539,15 +552,24 @@ constexpr int stages_for() {
 template <int BLOCK_N, int CG>
 int launch_major(int a_mn, int b_mn, int epi_mode, const CUtensorMap& ta, const CUtensorMap& tb,
                  const GemmParams& p, int grid, cudaStream_t stream) {
+  // dropout is a compile-time variant (the Philox code costs registers and scheduling freedom in the epilogue)
+  // built only for the three layouts that have a dropout site: forward linear, GELU forward, dgrad through GELU
+  const bool drop = p.drop_thr != 0;
   if (epi_mode == 1) {  // GELU forward: activations x weights, both K-major
     NV_REQUIRE(!a_mn && !b_mn, "gemm: apply_gelu is only built for K-major operands (forward linear)");
+    if (drop) return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 1>(), false, false, CG, 1, true>(ta, tb, p, grid, stream);
     return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 1>(), false, false, CG, 1>(ta, tb, p, grid, stream);
   }
   if (epi_mode == 2) {  // dgrad through GELU: dY [M,K] x W stored [K,N]
     NV_REQUIRE(!a_mn && b_mn, "gemm: gelu_u is only built for the dgrad layout (A K-major, B MN-major)");
+    if (drop) return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 2>(), false, true, CG, 2, true>(ta, tb, p, grid, stream);
     return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 2>(), false, true, CG, 2>(ta, tb, p, grid, stream);
   }
   constexpr int S = stages_for<BLOCK_N, CG, 0>();
+  if (drop) {
+    NV_REQUIRE(!a_mn && !b_mn, "gemm: dropout in the store epilogue is only built for K-major operands (forward linear)");
+    return launch_variant<BLOCK_N, S, false, false, CG, 0, true>(ta, tb, p, grid, stream);
+  }
   if (!a_mn && !b_mn) return launch_variant<BLOCK_N, S, false, false, CG, 0>(ta, tb, p, grid, stream);
   if (!a_mn && b_mn) return launch_variant<BLOCK_N, S, false, true, CG, 0>(ta, tb, p, grid, stream);
   if (a_mn && !b_mn) return launch_variant<BLOCK_N, S, true, false, CG, 0>(ta, tb, p, grid, stream);

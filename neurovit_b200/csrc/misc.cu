@@ -102,25 +102,53 @@ __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, cons
                                int64_t ld_res, float* __restrict__ out_f32, int64_t ld_f32, bf16* __restrict__ out_bf16,
                                int64_t ld_bf16, float* __restrict__ colsum, int M, int N, uint32_t thr, float ks,
                                uint64_t seed, uint32_t stream_id) {
-  const int nq = N >> 2;
-  for (int c = threadIdx.x; c < nq; c += blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = blockIdx.x; r < M; r += gridDim.x) {
-      float4 v = *reinterpret_cast<const float4*>(in + (int64_t)r * ld_in + 4 * c);
-      if (thr != 0) v = nv_dropout4(v, nv_keep_bits4(seed, (uint64_t)r * N + 4 * c, stream_id, thr), ks);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      if (residual) {
-        const float4 rr = *reinterpret_cast<const float4*>(residual + (int64_t)r * ld_res + 4 * c);
-        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+  const int n8 = N >> 3;  // one Philox call per thread and row: 8 consecutive columns
+  constexpr int R = 4;     // rows in flight per thread (independent 32-byte loads)
+  for (int c = threadIdx.x; c < n8; c += blockDim.x) {
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+    for (int rb = blockIdx.x * R; rb < M; rb += gridDim.x * R) {
+      float4 v0[R], v1[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int r = min(rb + k, M - 1);
+        const float* src = in + (int64_t)r * ld_in + 8 * c;
+        v0[k] = *reinterpret_cast<const float4*>(src);
+        v1[k] = *reinterpret_cast<const float4*>(src + 4);
       }
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (int64_t)r * ld_f32 + 4 * c) = v;
-      if (out_bf16)
-        *reinterpret_cast<uint2*>(out_bf16 + (int64_t)r * ld_bf16 + 4 * c) =
-            make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int r = rb + k;
+        if (r >= M) break;
+        if (thr != 0) {
+          const uint32_t b8 = nv_keep_bits8(seed, ((uint64_t)r * N + 8 * c) >> 3, stream_id, thr);
+          v0[k] = nv_dropout4(v0[k], b8 & 0xFu, ks);
+          v1[k] = nv_dropout4(v1[k], b8 >> 4, ks);
+        }
+        acc0.x += v0[k].x; acc0.y += v0[k].y; acc0.z += v0[k].z; acc0.w += v0[k].w;
+        acc1.x += v1[k].x; acc1.y += v1[k].y; acc1.z += v1[k].z; acc1.w += v1[k].w;
+        if (residual) {
+          const float* rs = residual + (int64_t)r * ld_res + 8 * c;
+          const float4 r0 = *reinterpret_cast<const float4*>(rs), r1 = *reinterpret_cast<const float4*>(rs + 4);
+          v0[k].x += r0.x; v0[k].y += r0.y; v0[k].z += r0.z; v0[k].w += r0.w;
+          v1[k].x += r1.x; v1[k].y += r1.y; v1[k].z += r1.z; v1[k].w += r1.w;
+        }
+        if (out_f32) {
+          float* dst = out_f32 + (int64_t)r * ld_f32 + 8 * c;
+          *reinterpret_cast<float4*>(dst) = v0[k];
+          *reinterpret_cast<float4*>(dst + 4) = v1[k];
+        }
+        if (out_bf16)
+          *reinterpret_cast<uint4*>(out_bf16 + (int64_t)r * ld_bf16 + 8 * c) =
+              make_uint4(pack_bf16x2(v0[k].x, v0[k].y), pack_bf16x2(v0[k].z, v0[k].w), pack_bf16x2(v1[k].x, v1[k].y),
+                         pack_bf16x2(v1[k].z, v1[k].w));
+      }
     }
-    if (colsum)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + 4 * c), "f"(acc.x), "f"(acc.y),
-                   "f"(acc.z), "f"(acc.w) : "memory");
+    if (colsum) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + 8 * c), "f"(acc0.x), "f"(acc0.y),
+                   "f"(acc0.z), "f"(acc0.w) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum + 8 * c + 4), "f"(acc1.x), "f"(acc1.y),
+                   "f"(acc1.z), "f"(acc1.w) : "memory");
+    }
   }
 }
 
@@ -195,14 +223,16 @@ int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int
   NV_REQUIRE(M >= 0 && N > 0 && N % 8 == 0, "dropout: N=%d must be a positive multiple of 8", N);
   NV_REQUIRE(p >= 0.f && p < 1.f, "dropout: p %f out of range [0, 1)", p);
   NV_REQUIRE(in != nullptr && (out_f32 != nullptr || out_bf16 != nullptr || colsum != nullptr), "dropout: null buffers");
-  NV_REQUIRE(ld_in % 4 == 0 && ld_res % 4 == 0 && ld_f32 % 4 == 0 && ld_bf16 % 4 == 0,
-             "dropout: row strides must be multiples of 4 elements");
+  NV_REQUIRE(ld_in % 4 == 0 && ld_res % 4 == 0 && ld_f32 % 4 == 0 && ld_bf16 % 8 == 0,
+             "dropout: fp32 row strides must be multiples of 4 elements, bf16 of 8");
+  NV_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(out_f32) |
+               reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0, "dropout: buffers must be 16-byte aligned");
   NV_REQUIRE((reinterpret_cast<uintptr_t>(colsum) & 15) == 0, "dropout: colsum must be 16-byte aligned");
   if (M == 0) return NV_OK;
   const uint32_t thr = nv_dropout_threshold(p);
-  const int threads = (N / 4) >= 256 ? 256 : ((N / 4 + 31) / 32) * 32;
+  const int threads = (N / 8) >= 128 ? 128 : ((N / 8 + 31) / 32) * 32;
   int grid = nv_num_sms() * 8;
-  if (grid > M) grid = M;
+  if (grid > (M + 3) / 4) grid = (M + 3) / 4;
   dropout_kernel<<<grid, threads, 0, stream>>>(in, ld_in, residual, ld_res, out_f32, ld_f32, out_bf16, ld_bf16, colsum,
                                                M, N, thr, nv_dropout_keep_scale(thr), seed, (uint32_t)stream_id);
   NV_LAUNCH_CHECK("dropout_kernel");

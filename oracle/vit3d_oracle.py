@@ -56,14 +56,20 @@ def neuro_view(x: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------- ViT3D
-def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, pool="cls", prefix="", masks=None):
+def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, pool="cls", prefix="", masks=None,
+                  dropout_p=0.0):
     """Functional forward of ViT (reference src/models/vit_3d.py:112-126) from a state_dict `sd`.
     patch = (pf, p1, p2). Dropout is the identity (p = 0 / eval) unless `masks` is given: a dict
     {"emb": m, (layer, "attn" | "out" | "gelu" | "down"): m} of multiplicative masks (keep / (1 - p), already
     scaled) applied exactly where the reference's nn.Dropout modules sit (vit_3d.py:21,23,39,45,100) — torch's
     own Philox stream cannot be replayed by a fused kernel, so dropout parity is checked with injected masks."""
     g = lambda k: sd[prefix + k]
-    mk = (lambda key, t: t * masks[key].to(t.dtype).reshape(t.shape)) if masks is not None else (lambda key, t: t)
+    if masks is not None:
+        mk = lambda key, t: t * masks[key].to(t.dtype).reshape(t.shape)
+    elif dropout_p > 0:  # training-mode nn.Dropout with torch's own generator (the timed CPU arm of bench.py)
+        mk = lambda key, t: F.dropout(t, dropout_p, training=True)
+    else:
+        mk = lambda key, t: t
     pf, p1, p2 = patch
     B, C, Fr, H, W = video.shape
     # to_patch_embedding: Rearrange -> LN(patch_dim) -> Linear -> LN(dim)           vit_3d.py:91-96
@@ -76,7 +82,7 @@ def vit3d_forward(sd: dict, video: torch.Tensor, *, patch, heads, dim_head=64, p
     # cls token, positional embedding sliced to n+1                                  vit_3d.py:116-118
     x = torch.cat((g("cls_token").expand(B, 1, -1), x), dim=1)
     x = x + g("pos_embedding")[:, : n + 1]
-    if masks is not None and "emb" in masks:
+    if (masks is not None and "emb" in masks) or (masks is None and dropout_p > 0):
         x = mk("emb", x)                                                                   # vit_3d.py:119
     depth = 0
     while f"{prefix}transformer.layers.{depth}.0.norm.weight" in sd:

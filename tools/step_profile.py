@@ -19,7 +19,9 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--config", default="cfgA")
 ap.add_argument("--out", default=None)
+ap.add_argument("--dropout", type=float, default=bench.DROPOUT)
 args = ap.parse_args()
+bench.DROPOUT = args.dropout
 
 cfg = bench.CONFIGS[args.config] if hasattr(bench, "CONFIGS") else bench.CFG
 dev = torch.device("cuda", 0)
