@@ -46,6 +46,19 @@ for i in range(4):
     tr.step(xs[i % 3], ys[i % 3])
 torch.cuda.synchronize()
 
+import time  # noqa: E402
+
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+for i in range(10):
+    tr.step(xs[i % 3], ys[i % 3])
+e1.record()
+t_issue = time.perf_counter() - t0
+torch.cuda.synchronize()
+print(f"un-profiled: {e0.elapsed_time(e1) / 10:.3f} ms/step on the device, host issue time {t_issue * 100:.3f} ms/step "
+      f"(host-bound if the two are equal)")
+
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
