@@ -86,14 +86,18 @@ int nv_layernorm_fwd(const float* x, int64_t ld_x, int x_group, int x_gstride, i
                      float* mean, float* rstd, int M, int D, float eps, void* stream);
 /* dx = LNbwd(dy) (+ dres); dgamma/dbeta/colsum are ACCUMULATED (atomicAdd) — zero or pre-load them.
  * colsum (optional) += sum_rows dx_out: the bias gradient of the linear feeding the residual stream.
- * dy is fp32, or bf16 when dy_is_bf16 (the dgrad GEMM's output in bf16 mode). */
+ * dy is fp32, or bf16 when dy_is_bf16 (the dgrad GEMM's output in bf16 mode).
+ * side_drop_p > 0: the bf16 copy dx_bf16 and colsum (NOT the fp32 dx) are multiplied by the dropout mask
+ * (side_drop_seed, side_drop_stream, row * D + col) — the forward mask of the linear layer whose backward
+ * consumes them (vit_3d.py:23,45), saving a separate masking pass. Needs M >= 64 and D % 8 == 0. */
 int nv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t ld_dy, int dy_group, int dy_gstride, int dy_goff,
                      const float* x, int64_t ld_x, int x_group, int x_gstride, int x_goff,
                      const float* mean, const float* rstd, const float* gamma,
                      const float* dres, int64_t ld_dres,
                      float* dx, int64_t ld_dx, int dx_group, int dx_gstride, int dx_goff,
                      void* dx_bf16, int64_t ld_dxb,
-                     float* dgamma, float* dbeta, float* colsum, int M, int D, void* stream);
+                     float* dgamma, float* dbeta, float* colsum, int M, int D,
+                     float side_drop_p, int64_t side_drop_seed, int side_drop_stream, void* stream);
 /* x[b, 0, :] = cls + pos[0]  (vit_3d.py:116-118) */
 int nv_cls_row(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D, void* stream);
 

@@ -30,7 +30,7 @@ SIGNATURES = {
     "nv_layernorm_fwd": [_p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _i, _l, _i, _i, _i, _p, _p,
                          _i, _i, _f, _p],
     "nv_layernorm_bwd": [_p, _i, _l, _i, _i, _i, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _p, _l, _i, _i, _i,
-                         _p, _l, _p, _p, _p, _i, _i, _p],
+                         _p, _l, _p, _p, _p, _i, _i, _f, _l, _i, _p],
     "nv_cls_row": [_p, _p, _p, _l, _i, _i, _p],
     "nv_patch_gather_ln": [_p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p, _f, _p],
     "nv_patch_ln_param_grad": [_p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p],

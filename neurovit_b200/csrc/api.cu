@@ -26,7 +26,8 @@ int nv_ln_fwd_launch(const float* x, int64_t ld_x, int xg, int xs, int xo, const
 int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int dys, int dyo, const float* x, int64_t ld_x, int xg,
                      int xs, int xo, const float* mean, const float* rstd, const float* gamma, const float* dres,
                      int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo, bf16* dx_bf16,
-                     int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D, cudaStream_t stream);
+                     int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D, float side_drop_p,
+                     uint64_t side_drop_seed, int side_drop_stream, cudaStream_t stream);
 int nv_cls_row_launch(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D,
                       cudaStream_t stream);
 int nv_patch_gather_ln_launch(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
@@ -120,10 +121,12 @@ int nv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t ld_dy, int dy_group
                      int64_t ld_x, int x_group, int x_gstride, int x_goff, const float* mean, const float* rstd,
                      const float* gamma, const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dx_group,
                      int dx_gstride, int dx_goff, void* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
-                     float* colsum, int M, int D, void* stream) {
+                     float* colsum, int M, int D, float side_drop_p, int64_t side_drop_seed, int side_drop_stream,
+                     void* stream) {
   return nv_ln_bwd_launch(dy, dy_is_bf16, ld_dy, dy_group, dy_gstride, dy_goff, x, ld_x, x_group, x_gstride, x_goff, mean, rstd,
                           gamma, dres, ld_dres, dx, ld_dx, dx_group, dx_gstride, dx_goff, (bf16*)dx_bf16, ld_dxb,
-                          dgamma, dbeta, colsum, M, D, ST(stream));
+                          dgamma, dbeta, colsum, M, D, side_drop_p, (uint64_t)side_drop_seed, side_drop_stream,
+                          ST(stream));
 }
 
 int nv_cls_row(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D, void* stream) {

@@ -5,6 +5,7 @@
 // One warp owns one row; a lane owns the float4 chunks {lane + 32*j}, so per-column partial sums for
 // dg/db stay in registers across the grid-stride row loop and are reduced once per CTA.
 #include "nv_common.cuh"
+#include "nv_rng.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -224,7 +225,8 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
                    const float* __restrict__ gamma, const float* __restrict__ dres, int64_t ld_dres,
                    float* __restrict__ dx, int64_t ld_dx, RowMap dxmap, bf16* __restrict__ dx_bf16,
                    int64_t ld_dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                   float* __restrict__ colsum_out, int M, int D, int stages) {
+                   float* __restrict__ colsum_out, int M, int D, int stages, uint32_t side_thr, float side_ks,
+                   uint64_t side_seed, uint32_t side_stream) {
   extern __shared__ __align__(128) uint8_t lnp_smem[];
   __shared__ __align__(16) float red[2][2 * LNP_ROWS][LNB_MAX_WARPS];
   __shared__ __align__(8) uint64_t full[LNP_MAX_STAGES];
@@ -342,6 +344,21 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
       part[i] = sacc * inv_d;
     }
     buf ^= 1;
+    // Side-car dropout: dx feeds (a) the residual stream, unmasked fp32, and (b) the backward of the previous
+    // block's last linear, whose output went through nn.Dropout — (b)'s operand (the bf16 copy) and its bias
+    // column sums take that layer's forward mask here, so no separate masking pass is needed. One Philox call
+    // covers 8 columns = lanes (c, c ^ 1): each lane draws the bits of one of the two rows and swaps.
+    uint32_t keep4[LNP_ROWS];
+#pragma unroll
+    for (int k = 0; k < LNP_ROWS; ++k) keep4[k] = 0xFu;
+    if (side_thr != 0) {
+      static_assert(LNP_ROWS == 2, "pair exchange below assumes two rows per iteration");
+      const int rmine = min(r0 + (c & 1), M - 1);
+      const uint32_t mine = nv_keep_bits8(side_seed, ((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3, side_stream, side_thr);
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+#pragma unroll
+      for (int k = 0; k < LNP_ROWS; ++k) keep4[k] = ((((c & 1) == k) ? mine : other) >> ((c & 1) * 4)) & 0xFu;
+    }
 #pragma unroll
     for (int k = 0; k < LNP_ROWS; ++k) {
       const int r = r0 + k;
@@ -352,9 +369,10 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
       o.y = rstd[k] * (gh[k].y - s1 - xh[k].y * s2) + rv[k].y;
       o.z = rstd[k] * (gh[k].z - s1 - xh[k].z * s2) + rv[k].z;
       o.w = rstd[k] * (gh[k].w - s1 - xh[k].w * s2) + rv[k].w;
-      acc_c.x += o.x; acc_c.y += o.y; acc_c.z += o.z; acc_c.w += o.w;
       const int64_t orow = dxmap(r);
       if (dx) *reinterpret_cast<float4*>(dx + orow * ld_dx + 4 * c) = o;
+      if (side_thr != 0) o = nv_dropout4(o, keep4[k], side_ks);
+      acc_c.x += o.x; acc_c.y += o.y; acc_c.z += o.z; acc_c.w += o.w;
       if (dx_bf16) OutStore<bf16>::st(dx_bf16 + orow * ld_dxb + 4 * c, o);
     }
   }
@@ -375,7 +393,8 @@ template <typename DyT>
 int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x, int64_t ld_x, RowMap xm,
                        const float* mean, const float* rstd, const float* gamma, const float* dres, int64_t ld_dres,
                        float* dx, int64_t ld_dx, RowMap dxm, bf16* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
-                       float* colsum, int M, int D, int threads, cudaStream_t stream) {
+                       float* colsum, int M, int D, int threads, uint32_t side_thr, uint64_t side_seed, int side_stream,
+                       cudaStream_t stream) {
   const int stage_bytes = (D * (int)sizeof(DyT) + D * 4 + (dres ? D * 4 : 0)) * LNP_ROWS;
   int stages = (108 * 1024) / stage_bytes;  // two CTAs per SM
   if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
@@ -395,7 +414,8 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
   if (grid > cap) grid = cap;
   if (getenv("NV_LNP_NOSTORE")) { dx = nullptr; dx_bf16 = nullptr; }
   kern<<<grid, threads + 32, smem, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
-                                             dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, stages);
+                                             dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, stages, side_thr,
+                                             nv_dropout_keep_scale(side_thr), side_seed, (uint32_t)side_stream);
   return NV_OK;
 }
 
@@ -451,7 +471,7 @@ int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int
                      int xg, int xs, int xo, const float* mean, const float* rstd, const float* gamma,
                      const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo,
                      bf16* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D,
-                     cudaStream_t stream) {
+                     float side_drop_p, uint64_t side_drop_seed, int side_drop_stream, cudaStream_t stream) {
   NV_REQUIRE(M >= 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm bwd: D=%d must be a multiple of 4 and <= 2048", D);
   if (M == 0) return NV_OK;
   for (const float* p : {dgamma, dbeta, colsum})
@@ -465,14 +485,20 @@ int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int
                        ld_dres % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
                        (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dres) & 15) == 0 &&
                        (int64_t)D * (dy_es + 8) * LNP_ROWS * 3 <= 200 * 1024;
+  NV_REQUIRE(side_drop_p >= 0.f && side_drop_p < 1.f, "layernorm bwd: side_drop_p %f out of range [0, 1)", side_drop_p);
+  const uint32_t side_thr = nv_dropout_threshold(side_drop_p);
+  NV_REQUIRE(side_thr == 0 || (pipe_ok && D % 8 == 0),
+             "layernorm bwd: the side-car dropout needs the pipelined kernel (M >= 64, D %% 8 == 0, 16-byte aligned rows)");
   if (pipe_ok) {
     int s;
     if (dy_is_bf16)
       s = launch_ln_bwd_pipe<bf16>((const bf16*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
-                                   dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, stream);
+                                   dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, side_thr, side_drop_seed,
+                                   side_drop_stream, stream);
     else
       s = launch_ln_bwd_pipe<float>((const float*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx,
-                                    ld_dx, dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, stream);
+                                    ld_dx, dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, side_thr,
+                                    side_drop_seed, side_drop_stream, stream);
     if (s != NV_OK) return s;
     NV_LAUNCH_CHECK("ln_bwd_pipe_kernel");
     return NV_OK;

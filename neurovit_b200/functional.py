@@ -103,17 +103,19 @@ class GradStash:
     def __init__(self):
         self._e = None
 
-    def put(self, t: torch.Tensor, bf=None, colsum=None):
-        # keep only the latest entry; holding `t` itself pins its storage so the address cannot be reused
-        self._e = (t, t._version, bf, colsum)
+    def put(self, t: torch.Tensor, bf=None, colsum=None, tag=None):
+        # keep only the latest entry; holding `t` itself pins its storage so the address cannot be reused.
+        # tag = (p, seed, stream) when bf / colsum already carry that dropout site's mask (side-car dropout).
+        self._e = (t, t._version, bf, colsum, tag)
 
-    def take(self, t: torch.Tensor):
+    def take(self, t: torch.Tensor, tag=None):
+        """(bf16 copy, column sums) stashed for `t`, only if they were produced with the same dropout tag."""
         e, self._e = self._e, None
         if e is None:
             return None, None
-        src, ver, bf, colsum = e
+        src, ver, bf, colsum, etag = e
         if src.data_ptr() == t.data_ptr() and src.shape == t.shape and src.stride() == t.stride() \
-                and src._version == ver and t._version == ver:
+                and src._version == ver and t._version == ver and etag == tag:
             return bf, colsum
         return None, None
 
@@ -292,7 +294,7 @@ class Engine:
         ops.layernorm_fwd(x, weight.detach(), bias.detach(), y, M=M, D=D, mean=mean, rstd=rstd, eps=eps)
         return y, mean, rstd
 
-    def ln_bwd(self, dy, x, mean, rstd, weight, dres=None, want_colsum=False, acc_g=None, acc_b=None):
+    def ln_bwd(self, dy, x, mean, rstd, weight, dres=None, want_colsum=False, acc_g=None, acc_b=None, side_drop=None):
         """Returns dx (fp32), dx in the activation dtype (bf16 copy or the same fp32 tensor), dgamma, dbeta,
         colsum(dx) or None. dy may be fp32 or bf16. acc_g / acc_b: GradAcc targets for dgamma / dbeta (their
         .result() is returned in place of fresh tensors)."""
@@ -311,10 +313,17 @@ class Engine:
             dg, db = z[0], z[1]
             cs = z[2] if want_colsum else None
         ops.layernorm_bwd(dy, x, mean, rstd, weight.detach(), M=M, D=D, dres=dres, dx=dx, dx_bf16=dxb, dgamma=dg,
-                          dbeta=db, colsum=cs)
+                          dbeta=db, colsum=cs, side_drop=side_drop)
         if acc_g is not None:
             dg, db = acc_g.result(), acc_b.result()
         return dx, (dxb if dxb is not None else dx), dg, db, cs
+
+    def side_drop_for(self, prev, seed, M, D):
+        """(p, seed, stream) of the dropout site whose backward consumes this block's input gradient — the
+        previous block's last linear — when the LayerNorm-backward kernel can pre-mask the side-car for it."""
+        if prev is None or prev[0] <= 0 or self.mode != "bf16" or M < 64 or D % 8:
+            return None
+        return (prev[0], seed, prev[1])
 
     def drop_grad(self, dy, drop):
         """Gradient of a dropped-out linear output: dy * mask / (1 - p) in the MMA operand dtype, plus its column
@@ -329,7 +338,9 @@ class Engine:
     def branch_grad(self, dy, dy2, drop):
         """(operand-dtype gradient, its column sums or None) of the residual branch's last linear output."""
         if drop is not None and drop[0] > 0:
-            _STASH.take(dy)
+            bf, cs = _STASH.take(dy, tag=tuple(drop))  # already masked by the producing LayerNorm backward?
+            if bf is not None and self.mode == "bf16":
+                return bf.view(dy2.shape), cs
             return self.drop_grad(dy2, drop)
         dy_act, cs = self.as_act(dy)
         return dy_act.view(dy2.shape), cs
@@ -344,7 +355,8 @@ class Engine:
         return bf, cs
 
     # -- attention core (after the pre-norm) ------------------------------------------------------
-    def attn_core_fwd(self, a, x_res, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn=0.0, p_out=0.0, seed=0):
+    def attn_core_fwd(self, a, x_res, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn=0.0, p_out=0.0, seed=0,
+                      sbase=0):
         """a = LN(x) [M,D] in act dtype; returns x_res + to_out(attention(a)) (fp32) and the saved tensors.
         vit_3d.py:50-60,73."""
         M = a.shape[0]
@@ -357,8 +369,8 @@ class Engine:
             lse = torch.empty(B, heads, N, device=dev, dtype=F32)
             mask = torch.zeros(B * heads, N, (N + 31) // 32, device=dev, dtype=torch.int32) if p_attn > 0 else None
             ops.attention_fwd(qkv, o, lse, B=B, N=N, H=heads, head_dim=dim_head, scale=scale, dropout_p=p_attn,
-                              seed=seed, drop_mask=mask)
-            _trace("attn", p_attn, seed, DROP_ATTN, mask)
+                              seed=seed + sbase + DROP_ATTN, drop_mask=mask)  # the flash kernel has one stream: offset the seed
+            _trace("attn", p_attn, seed, sbase + DROP_ATTN, mask)
             aux = (lse, mask)
         else:
             P = torch.empty(B, heads, N, N, device=dev, dtype=F32)
@@ -370,8 +382,8 @@ class Engine:
             Pd = P
             if p_attn > 0:  # attention dropout on the materialised probabilities (flat element index)
                 Pd = torch.empty_like(P)
-                ops.dropout_flat(P, Pd, p=p_attn, seed=seed, stream=DROP_ATTN)
-                _trace("attn_flat", p_attn, seed, DROP_ATTN, tuple(P.shape))
+                ops.dropout_flat(P, Pd, p=p_attn, seed=seed, stream=sbase + DROP_ATTN)
+                _trace("attn_flat", p_attn, seed, sbase + DROP_ATTN, tuple(P.shape))
             # out = attn v, written as 'b n (h d)'
             ops.gemm_f32(N, dim_head, N, Pd, (N, 1, heads * N * N, N * N), (qkv, 2 * inner),
                          (1, rs, N * rs, dim_head), o, (inner, N * inner, dim_head), Z1=B, Z2=heads)
@@ -379,12 +391,12 @@ class Engine:
         if w_out is None:  # project_out == False (heads == 1 and dim_head == dim): to_out is Identity
             y = torch.empty(M, inner, device=dev, dtype=F32)
             raise NotImplementedError("project_out=False (heads=1, dim_head=dim) is not on the NeuroViT hot path")
-        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32, drop=(p_out, seed, DROP_OUT))
-        _trace("out", p_out, seed, DROP_OUT, (M, w_out.shape[0]))
+        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32, drop=(p_out, seed, sbase + DROP_OUT))
+        _trace("out", p_out, seed, sbase + DROP_OUT, (M, w_out.shape[0]))
         return y, (qkv, o, *aux)
 
     def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=None,
-                      p_attn=0.0, seed=0):
+                      p_attn=0.0, seed=0, sbase=0):
         """Returns da (grad wrt the LN output, fp32 or the activation dtype), dWqkv, dWout, dbout. dy is the
         fp32 grad of the block output; its residual branch is handled by the caller."""
         qkv, o, aux, aux2 = saved
@@ -413,7 +425,7 @@ class Engine:
             ops.gemm_f32(N, N, dim_head, dO, (inner, 1, N * inner, dim_head), (qkv, 2 * inner),
                          (rs, 1, N * rs, dim_head), dP, (N, *zP), Z1=B, Z2=heads)
             if aux2 is not None:  # through the attention dropout: d(attn) = d(dropped) * mask / (1 - p)
-                ops.dropout_flat(dP, dP, p=p_attn, seed=seed, stream=DROP_ATTN)
+                ops.dropout_flat(dP, dP, p=p_attn, seed=seed, stream=sbase + DROP_ATTN)
             ops.softmax_bwd(P, dP, B * heads * N, N)  # dP <- dS
             # dQ = dS K * scale ; dK = dS^T Q * scale
             ops.gemm_f32(N, dim_head, N, dP, (N, 1, *zP), (qkv, inner), (1, rs, N * rs, dim_head), (dqkv, 0),
@@ -425,17 +437,17 @@ class Engine:
         return da, dWqkv, dWo, dbo
 
     # -- feed-forward core -------------------------------------------------------------------------
-    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0):
-        g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, DROP_GELU))
-        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32, drop=(p_down, seed, DROP_DOWN))
-        _trace("gelu", p_gelu, seed, DROP_GELU, tuple(g.shape))
-        _trace("down", p_down, seed, DROP_DOWN, tuple(y.shape))
+    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0, sbase=0):
+        g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU))
+        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32, drop=(p_down, seed, sbase + DROP_DOWN))
+        _trace("gelu", p_gelu, seed, sbase + DROP_GELU, tuple(g.shape))
+        _trace("down", p_down, seed, sbase + DROP_DOWN, tuple(y.shape))
         return y, (u, g)
 
-    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, b1, w2, da_dtype=None, p_gelu=0.0, seed=0):
+    def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, b1, w2, da_dtype=None, p_gelu=0.0, seed=0, sbase=0):
         u, g = saved
         dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True, colsum_acc=GradAcc(b1, self.mode),
-                             drop=(p_gelu, seed, DROP_GELU))
+                             drop=(p_gelu, seed, sbase + DROP_GELU))
         dW2 = self.wgrad(dy_act, g, acc=GradAcc(w2, self.mode))
         db2 = self.bias_grad(dy, dy_colsum)
         da = self.dgrad(dU, w1, out_dtype=da_dtype or F32)
@@ -493,30 +505,34 @@ class AttnBlockFn(torch.autograd.Function):
     """x + to_out(attention(LN(x)))  — vit_3d.py:48-60 with the residual of :73 fused in."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w_qkv, w_out, b_out, heads, dim_head, eps, mode, p_attn=0.0, p_out=0.0, seed=0):
+    def forward(ctx, x, ln_w, ln_b, w_qkv, w_out, b_out, heads, dim_head, eps, mode, p_attn=0.0, p_out=0.0, seed=0,
+                sbase=0, prev=None):
+        """sbase: stream offset of this block's dropout sites (layer index * 8 under Transformer.forward, which
+        shares one seed per forward); prev = (p, stream) of the dropout site that produced x, if any."""
         eng = engine(mode)
         x2, B, N = _flat(x)
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
-        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed)
+        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed, sbase)
         ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved)
-        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed)
+        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase, prev)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved = ctx.saved_tensors
-        B, N, heads, dim_head, mode, p_attn, p_out, seed = ctx.cfg
+        B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase, prev = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy2 = dy.view(B * N, -1)
-        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, DROP_OUT))
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, sbase + DROP_OUT))
         da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act, cs, a, saved, w_qkv, w_out, B, N, heads, dim_head,
-                                                da_dtype=eng.act, p_attn=p_attn, seed=seed)
+                                                da_dtype=eng.act, p_attn=p_attn, seed=seed, sbase=sbase)
+        side = eng.side_drop_for(prev, seed, B * N, x2.shape[1])
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
-                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode))
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode), side_drop=side)
         dx = dx.view(B, N, -1)
-        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
-        return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None, None, None, None
+        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2, tag=side)
+        return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None, None, None, None, None, None
 
 
 class AttnCoreFn(torch.autograd.Function):
@@ -524,27 +540,27 @@ class AttnCoreFn(torch.autograd.Function):
     module call (so forward/backward hooks on it fire)."""
 
     @staticmethod
-    def forward(ctx, a, x_res, w_qkv, w_out, b_out, heads, dim_head, mode, p_attn=0.0, p_out=0.0, seed=0):
+    def forward(ctx, a, x_res, w_qkv, w_out, b_out, heads, dim_head, mode, p_attn=0.0, p_out=0.0, seed=0, sbase=0):
         eng = engine(mode)
         a2, B, N = _flat(a)
         x2, _, _ = _flat(x_res)
         a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
-        y, saved = eng.attn_core_fwd(a_act, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed)
+        y, saved = eng.attn_core_fwd(a_act, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed, sbase)
         ctx.save_for_backward(a_act, w_qkv, w_out, *saved)
-        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed)
+        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         a_act, w_qkv, w_out, *saved = ctx.saved_tensors
-        B, N, heads, dim_head, mode, p_attn, p_out, seed = ctx.cfg
+        B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy2 = dy.view(B * N, -1)
-        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, DROP_OUT))
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, sbase + DROP_OUT))
         da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act, cs, a_act, saved, w_qkv, w_out, B, N, heads, dim_head,
-                                                p_attn=p_attn, seed=seed)
-        return da.view(B, N, -1), dy, dWqkv, dWo, dbo, None, None, None, None, None, None
+                                                p_attn=p_attn, seed=seed, sbase=sbase)
+        return da.view(B, N, -1), dy, dWqkv, dWo, dbo, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------- autograd: feed-forward block
@@ -552,30 +568,31 @@ class FFBlockFn(torch.autograd.Function):
     """x + W2 gelu(W1 LN(x) + b1) + b2  — vit_3d.py:14-26 with the residual of :74 fused in."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode, p_gelu=0.0, p_down=0.0, seed=0):
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode, p_gelu=0.0, p_down=0.0, seed=0, sbase=0, prev=None):
         eng = engine(mode)
         x2, B, N = _flat(x)
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
-        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2, p_gelu, p_down, seed)
+        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2, p_gelu, p_down, seed, sbase)
         ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved)
-        ctx.cfg = (B, N, mode, p_gelu, p_down, seed)
+        ctx.cfg = (B, N, mode, p_gelu, p_down, seed, sbase, prev)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved = ctx.saved_tensors
-        B, N, mode, p_gelu, p_down, seed = ctx.cfg
+        B, N, mode, p_gelu, p_down, seed, sbase, prev = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy2 = dy.view(B * N, -1)
-        dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, DROP_DOWN))
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, sbase + DROP_DOWN))
         da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act, cs, a, saved, w1, b1, w2, da_dtype=eng.act,
-                                                 p_gelu=p_gelu, seed=seed)
+                                                 p_gelu=p_gelu, seed=seed, sbase=sbase)
+        side = eng.side_drop_for(prev, seed, B * N, x2.shape[1])
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
-                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode))
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode), side_drop=side)
         dx = dx.view(B, N, -1)
-        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2)
-        return dx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None
+        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2, tag=side)
+        return dx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None, None, None
 
 
 class FFCoreFn(torch.autograd.Function):
@@ -583,26 +600,27 @@ class FFCoreFn(torch.autograd.Function):
     call (hooks on net[0] fire)."""
 
     @staticmethod
-    def forward(ctx, a, x_res, w1, b1, w2, b2, mode, p_gelu=0.0, p_down=0.0, seed=0):
+    def forward(ctx, a, x_res, w1, b1, w2, b2, mode, p_gelu=0.0, p_down=0.0, seed=0, sbase=0):
         eng = engine(mode)
         a2, B, N = _flat(a)
         x2, _, _ = _flat(x_res)
         a_act = ops.cast_bf16(a2) if mode == "bf16" else a2
-        y, saved = eng.ff_core_fwd(a_act, x2, w1, b1, w2, b2, p_gelu, p_down, seed)
+        y, saved = eng.ff_core_fwd(a_act, x2, w1, b1, w2, b2, p_gelu, p_down, seed, sbase)
         ctx.save_for_backward(a_act, w1, b1, w2, *saved)
-        ctx.cfg = (B, N, mode, p_gelu, p_down, seed)
+        ctx.cfg = (B, N, mode, p_gelu, p_down, seed, sbase)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         a_act, w1, b1, w2, *saved = ctx.saved_tensors
-        B, N, mode, p_gelu, p_down, seed = ctx.cfg
+        B, N, mode, p_gelu, p_down, seed, sbase = ctx.cfg
         eng = engine(mode)
         dy = dy.contiguous()
         dy2 = dy.view(B * N, -1)
-        dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, DROP_DOWN))
-        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act, cs, a_act, saved, w1, b1, w2, p_gelu=p_gelu, seed=seed)
-        return da.view(B, N, -1), dy, dW1, db1, dW2, db2, None, None, None, None
+        dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, sbase + DROP_DOWN))
+        da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act, cs, a_act, saved, w1, b1, w2, p_gelu=p_gelu, seed=seed,
+                                                 sbase=sbase)
+        return da.view(B, N, -1), dy, dW1, db1, dW2, db2, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------ autograd: nn.Dropout

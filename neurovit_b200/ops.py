@@ -201,13 +201,16 @@ def layernorm_fwd(x, gamma, beta, y, *, M, D, ld_x=None, ld_y=None, xmap=(0, 0, 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, M, D, ld_dy=None, ld_x=None, dymap=(0, 0, 0), xmap=(0, 0, 0),
                   dres=None, ld_dres=None, dx=None, ld_dx=None, dxmap=(0, 0, 0), dx_bf16=None, ld_dxb=None,
-                  dgamma=None, dbeta=None, colsum=None):
+                  dgamma=None, dbeta=None, colsum=None, side_drop=None):
+    """side_drop = (p, seed, stream): mask dx_bf16 / colsum (not dx) with that dropout site's forward mask."""
     _dev(x)
     assert dy.dtype in (F32, BF16) and x.dtype == F32
+    sp, sseed, sstream = side_drop if side_drop is not None else (0.0, 0, 0)
     _lib.call("nv_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), D if ld_dy is None else ld_dy, *dymap, _ptr(x),
               D if ld_x is None else ld_x, *xmap, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
               D if ld_dres is None else ld_dres, _ptr(dx), D if ld_dx is None else ld_dx, *dxmap, _ptr(dx_bf16),
-              D if ld_dxb is None else ld_dxb, _ptr(dgamma), _ptr(dbeta), _ptr(colsum), M, D, _stream())
+              D if ld_dxb is None else ld_dxb, _ptr(dgamma), _ptr(dbeta), _ptr(colsum), M, D, float(sp), int(sseed),
+              int(sstream), _stream())
 
 
 def cls_row(cls, pos, x, batch_stride, B, D):

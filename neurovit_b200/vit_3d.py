@@ -91,22 +91,31 @@ class FeedForward(nn.Module, _PrecisionMixin):
             nn.Dropout(dropout),
         )
 
-    def forward(self, x, residual=None):
+    def drop_p(self):
+        """(p after GELU, p after the down projection) active right now (0 in eval)."""
+        return _p(self, self.net[3]), _p(self, self.net[5])
+
+    def forward(self, x, residual=None, _drop=None):
         """Reference semantics: returns net(x) (vit_3d.py:25-26). With residual=x the add of vit_3d.py:74 is
-        fused into the last GEMM's epilogue (used by Transformer.forward)."""
+        fused into the last GEMM's epilogue (used by Transformer.forward). _drop = (seed, stream base, prev):
+        Transformer.forward shares one dropout seed per forward and tells each block which dropout site
+        produced its input (prev = (p, stream)), so the backward can pre-mask that site's gradient."""
         ln, l1, l2 = self.net[0], self.net[1], self.net[4]
-        p_gelu, p_down = _p(self, self.net[3]), _p(self, self.net[5])
-        seed = Fn.draw_seed() if (p_gelu > 0 or p_down > 0) else 0
+        p_gelu, p_down = self.drop_p()
+        if _drop is not None:
+            seed, sbase, prev = _drop
+        else:
+            seed, sbase, prev = (Fn.draw_seed() if (p_gelu > 0 or p_down > 0) else 0), 0, None
         if residual is None:
             residual_t = torch.zeros_like(x, dtype=torch.float32)
         else:
             residual_t = residual
         if residual is not None and residual is x and not _has_hooks(ln):
             return Fn.FFBlockFn.apply(x, ln.weight, ln.bias, l1.weight, l1.bias, l2.weight, l2.bias, ln.eps,
-                                      self.precision, p_gelu, p_down, seed)
+                                      self.precision, p_gelu, p_down, seed, sbase, prev)
         a = ln(x)  # module call: hooks on net[0] fire
         return Fn.FFCoreFn.apply(a, residual_t, l1.weight, l1.bias, l2.weight, l2.bias, self.precision, p_gelu,
-                                 p_down, seed)
+                                 p_down, seed, sbase)
 
 
 class Attention(nn.Module, _PrecisionMixin):
@@ -130,22 +139,32 @@ class Attention(nn.Module, _PrecisionMixin):
             nn.Dropout(dropout)
         ) if project_out else nn.Identity()
 
-    def forward(self, x, residual=None):
+    def drop_p(self):
+        """(p on the attention probabilities, p after to_out) active right now (0 in eval)."""
+        if isinstance(self.to_out, nn.Identity):
+            return _p(self, self.dropout), 0.0
+        return _p(self, self.dropout), _p(self, self.to_out[1])
+
+    def forward(self, x, residual=None, _drop=None):
         """Reference semantics: returns to_out(attention(norm(x))) (vit_3d.py:48-60). With residual=x the add
-        of vit_3d.py:73 is fused into the to_out GEMM epilogue."""
+        of vit_3d.py:73 is fused into the to_out GEMM epilogue. _drop: see FeedForward.forward."""
         if isinstance(self.to_out, nn.Identity):
             raise NotImplementedError("project_out=False (heads == 1 and dim_head == dim) is not on the NeuroViT "
                                       "hot path (NeuroEncoder.py:181-195 uses heads=8, dim_head=64)")
         w_out, b_out = self.to_out[0].weight, self.to_out[0].bias
-        p_attn, p_out = _p(self, self.dropout), _p(self, self.to_out[1])
-        seed = Fn.draw_seed() if (p_attn > 0 or p_out > 0) else 0
+        p_attn, p_out = self.drop_p()
+        if _drop is not None:
+            seed, sbase, prev = _drop
+        else:
+            seed, sbase, prev = (Fn.draw_seed() if (p_attn > 0 or p_out > 0) else 0), 0, None
         if residual is not None and residual is x and not _has_hooks(self.norm):
             return Fn.AttnBlockFn.apply(x, self.norm.weight, self.norm.bias, self.to_qkv.weight, w_out, b_out,
-                                        self.heads, self.dim_head, self.norm.eps, self.precision, p_attn, p_out, seed)
+                                        self.heads, self.dim_head, self.norm.eps, self.precision, p_attn, p_out, seed,
+                                        sbase, prev)
         residual_t = torch.zeros_like(x, dtype=torch.float32) if residual is None else residual
         a = self.norm(x)  # real module call so Grad-CAM hooks on .norm observe output and grad_output
         return Fn.AttnCoreFn.apply(a, residual_t, self.to_qkv.weight, w_out, b_out, self.heads, self.dim_head,
-                                   self.precision, p_attn, p_out, seed)
+                                   self.precision, p_attn, p_out, seed, sbase)
 
 
 class Transformer(nn.Module):
@@ -159,11 +178,23 @@ class Transformer(nn.Module):
             ]))
 
     def forward(self, x):
-        for attn, ff in self.layers:
+        # one dropout seed per forward; site streams = layer * 8 + {attn 0, to_out 1, gelu 2, down 3}
+        drops = [(attn.drop_p(), ff.drop_p()) for attn, ff in self.layers]
+        seed = Fn.draw_seed() if any(p > 0 for pair_ in drops for ps in pair_ for p in ps) else 0
+        prev = None  # (p, stream) of the dropout site right before the residual add that produced x
+        for i, (attn, ff) in enumerate(self.layers):
             # x = attn(x) + x ; x = ff(x) + x   (vit_3d.py:72-74) with the adds fused into the GEMM epilogues;
             # modules that carry user hooks keep the reference's unfused call shape so the hooks see attn(x)
-            x = attn(x) + x if _has_hooks(attn) else attn(x, residual=x)
-            x = ff(x) + x if _has_hooks(ff) else ff(x, residual=x)
+            if _has_hooks(attn):
+                x = attn(x, _drop=(seed, 8 * i, None)) + x
+            else:
+                x = attn(x, residual=x, _drop=(seed, 8 * i, prev))
+            prev = (drops[i][0][1], 8 * i + Fn.DROP_OUT) if not _has_hooks(attn) else None
+            if _has_hooks(ff):
+                x = ff(x, _drop=(seed, 8 * i, None)) + x
+            else:
+                x = ff(x, residual=x, _drop=(seed, 8 * i, prev))
+            prev = (drops[i][1][1], 8 * i + Fn.DROP_DOWN) if not _has_hooks(ff) else None
         return x
 
 
