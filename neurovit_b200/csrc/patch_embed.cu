@@ -10,6 +10,7 @@
 // view consecutive j are consecutive addresses: the box lands in weight-K order with no permutation).
 // One warp owns one token: gather into shared memory once, two-pass statistics, coalesced store.
 #include "nv_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -114,6 +115,157 @@ __global__ void patch_ln_param_grad_kernel(const float* __restrict__ video, Patc
   }
 }
 
+// ---- TMA variants: one 5-D box {pf, p2, p1, 1, 1} per token ---------------------------
+// For the view ViT3DEncoder builds ([B,1,D,H,W] over a contiguous [B,H,W,D] tensor: sf = 1 < sw < sh, C = 1) the
+// box lands in shared memory in exactly the Rearrange feature order j = (p1i * p2 + p2i) * pf + pfi, so the
+// gather is a single cp.async.bulk.tensor.5d per token and no per-element index arithmetic. A warp owns a
+// token and double-buffers: the box of its next token is in flight while it normalises the current one.
+// Other layouts (contiguous [B,C,F,H,W], C > 1, patch rows that are not 16-byte multiples such as patch 9) keep
+// the strided-load kernels above — same results bit for bit.
+constexpr int PG_WARPS = 8;
+
+template <typename OutT>
+__global__ void __launch_bounds__(PG_WARPS * 32)
+patch_gather_ln_tma_kernel(const __grid_constant__ CUtensorMap tmap, PatchGeom g, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, OutT* __restrict__ out, int64_t ld_out,
+                           float* __restrict__ raw, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                           float eps) {
+  extern __shared__ __align__(128) uint8_t pg_smem[];
+  __shared__ __align__(8) uint64_t bars[PG_WARPS][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t box_bytes = (uint32_t)g.P * 4u;
+  const uint32_t buf_bytes = (box_bytes + 127u) & ~127u;
+  float* buf0 = reinterpret_cast<float*>(pg_smem + (size_t)warp * 2 * buf_bytes);
+  const int n_tok = g.nf * g.nh * g.nw;
+  const int rows = g.B * n_tok;
+  const int stride = gridDim.x * PG_WARPS;
+  if (lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  auto issue = [&](int r, int slot) {  // lane 0 only
+    const int b = r / n_tok;
+    int t = r % n_tok;
+    const int wi = t % g.nw; t /= g.nw;
+    const int hi = t % g.nh;
+    const int fi = t / g.nh;
+    mbar_arrive_expect_tx(&bars[warp][slot], box_bytes);
+    tma_load_5d(reinterpret_cast<uint8_t*>(buf0) + slot * buf_bytes, &tmap, &bars[warp][slot], fi * g.pf, wi * g.p2,
+                hi * g.p1, 0, b);
+  };
+  int r = blockIdx.x * PG_WARPS + warp;
+  if (r < rows && lane == 0) issue(r, 0);
+  for (int it = 0; r < rows; r += stride, ++it) {
+    const int slot = it & 1;
+    if (r + stride < rows && lane == 0) issue(r + stride, slot ^ 1);  // that buffer was released by the __syncwarp below
+    mbar_wait(&bars[warp][slot], (it >> 1) & 1);
+    const float* buf = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(buf0) + slot * buf_bytes);
+    float s = 0.f;
+    for (int j = lane; j < g.P; j += 32) s += buf[j];
+    const float mean = warp_sum(s) / (float)g.P;
+    float q = 0.f;
+    for (int j = lane; j < g.P; j += 32) { const float d = buf[j] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)g.P + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+    OutT* o = out ? out + (int64_t)r * ld_out : nullptr;
+    for (int j = lane; j < (int)ld_out; j += 32) {
+      if (j < g.P) {
+        if (raw) raw[(int64_t)r * g.P + j] = buf[j];
+        if (o) store_out<OutT>(o + j, (buf[j] - mean) * rstd * gamma[j] + beta[j]);
+      } else if (o) {
+        store_out<OutT>(o + j, 0.f);
+      }
+    }
+    __syncwarp();  // every lane is done reading this buffer before lane 0 re-arms it two iterations later
+  }
+}
+
+// dgamma / dbeta of the patch LayerNorm with the patches re-gathered by TMA: a CTA walks its rows with the
+// volume box and the dP row (1-D bulk copy) double-buffered in shared memory; thread t owns slots t, t + 256, ..
+constexpr int PGB_THREADS = 256;
+constexpr int PGB_MAX_SLOTS = 8;  // patch_dim <= 2048
+
+__global__ void __launch_bounds__(PGB_THREADS)
+patch_ln_param_grad_tma_kernel(const __grid_constant__ CUtensorMap tmap, PatchGeom g, const float* __restrict__ dP,
+                               int64_t ld_dp, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                               float* __restrict__ dgamma, float* __restrict__ dbeta, int rows_per_block) {
+  extern __shared__ __align__(128) uint8_t pg_smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  const uint32_t box_bytes = (uint32_t)g.P * 4u;
+  const uint32_t buf_bytes = (box_bytes + 127u) & ~127u;
+  const int n_tok = g.nf * g.nh * g.nw;
+  const int rows = g.B * n_tok;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  auto vbuf = [&](int slot) { return reinterpret_cast<float*>(pg_smem + (size_t)slot * 2 * buf_bytes); };
+  auto dbuf = [&](int slot) { return reinterpret_cast<float*>(pg_smem + (size_t)slot * 2 * buf_bytes + buf_bytes); };
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int r, int slot) {  // thread 0 only
+    const int b = r / n_tok;
+    int t = r % n_tok;
+    const int wi = t % g.nw; t /= g.nw;
+    const int hi = t % g.nh;
+    const int fi = t / g.nh;
+    mbar_arrive_expect_tx(&bars[slot], 2 * box_bytes);
+    tma_load_5d(vbuf(slot), &tmap, &bars[slot], fi * g.pf, wi * g.p2, hi * g.p1, 0, b);
+    bulk_load_1d(dbuf(slot), dP + (int64_t)r * ld_dp, box_bytes, &bars[slot]);
+  };
+  float ag[PGB_MAX_SLOTS], ab[PGB_MAX_SLOTS];
+#pragma unroll
+  for (int k = 0; k < PGB_MAX_SLOTS; ++k) { ag[k] = 0.f; ab[k] = 0.f; }
+  if (threadIdx.x == 0 && r0 < r1) issue(r0, 0);
+  for (int r = r0, it = 0; r < r1; ++r, ++it) {
+    const int slot = it & 1;
+    if (threadIdx.x == 0 && r + 1 < r1) issue(r + 1, slot ^ 1);  // released by the __syncthreads of the previous iteration
+    const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
+    mbar_wait(&bars[slot], (it >> 1) & 1);
+    const float* v = vbuf(slot);
+    const float* d = dbuf(slot);
+#pragma unroll
+    for (int k = 0; k < PGB_MAX_SLOTS; ++k) {
+      const int j = threadIdx.x + k * PGB_THREADS;
+      if (j < g.P) {
+        const float dd = d[j];
+        ag[k] = fmaf(dd, (v[j] - mean) * rstd, ag[k]);
+        ab[k] += dd;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < PGB_MAX_SLOTS; ++k) {
+    const int j = threadIdx.x + k * PGB_THREADS;
+    if (j < g.P) {
+      atomicAdd(dgamma + j, ag[k]);
+      atomicAdd(dbeta + j, ab[k]);
+    }
+  }
+}
+
+// The 5-D tensor map over the view, innermost-first (F, W, H, C, B); usable when the box order equals the
+// Rearrange feature order and TMA's alignment rules hold.
+bool make_patch_tmap(CUtensorMap* m, const float* video, const PatchGeom& g) {
+  if (g.C != 1 || g.sf != 1 || !(g.sw < g.sh)) return false;
+  if ((g.pf * 4) % 16 != 0 || g.pf > 256 || g.p1 > 256 || g.p2 > 256) return false;
+  if ((g.sw * 4) % 16 != 0 || (g.sh * 4) % 16 != 0 || (g.sb * 4) % 16 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(video) & 15) != 0 || g.P > 2048) return false;
+  const uint64_t dims[5] = {(uint64_t)g.F, (uint64_t)g.W, (uint64_t)g.H, 1, (uint64_t)g.B};
+  const uint64_t sc_bytes = (uint64_t)g.sb * 4;  // C = 1: any 16-byte multiple is a valid stride for the unit dim
+  const uint64_t strides[4] = {(uint64_t)g.sw * 4, (uint64_t)g.sh * 4, sc_bytes, (uint64_t)g.sb * 4};
+  const uint32_t box[5] = {(uint32_t)g.pf, (uint32_t)g.p2, (uint32_t)g.p1, 1, 1};
+  return nv_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, video, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) == NV_OK;
+}
+
 int fill_geom(PatchGeom& g, const int64_t* dims, const int64_t* strides, const int64_t* patch) {
   g.B = (int)dims[0]; g.C = (int)dims[1]; g.F = (int)dims[2]; g.H = (int)dims[3]; g.W = (int)dims[4];
   g.pf = (int)patch[0]; g.p1 = (int)patch[1]; g.p2 = (int)patch[2];
@@ -140,6 +292,27 @@ int nv_patch_gather_ln_launch(const float* video, const int64_t* dims, const int
   if (rows == 0) return NV_OK;
   NV_REQUIRE(out == nullptr || ld_out >= g.P, "patch_embed: ld_out %lld < patch_dim %d", (long long)ld_out, g.P);
   NV_REQUIRE((size_t)g.P * 4 <= 200 * 1024, "patch_embed: patch_dim %d too large for shared memory staging", g.P);
+  CUtensorMap tmap;
+  if (!getenv("NV_PATCH_NO_TMA") && make_patch_tmap(&tmap, video, g)) {
+    const size_t buf_bytes = ((size_t)g.P * 4 + 127) & ~(size_t)127;
+    const size_t smem_t = (size_t)PG_WARPS * 2 * buf_bytes;
+    int grid_t = (rows + PG_WARPS - 1) / PG_WARPS;
+    if (grid_t > nv_num_sms() * 4) grid_t = nv_num_sms() * 4;
+    if (out_is_bf16) {
+      if (smem_t > 48 * 1024)
+        NV_CUDA(cudaFuncSetAttribute(patch_gather_ln_tma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      patch_gather_ln_tma_kernel<bf16><<<grid_t, PG_WARPS * 32, smem_t, stream>>>(tmap, g, gamma, beta, (bf16*)out, ld_out,
+                                                                                  raw, mean, rstd, eps);
+    } else {
+      if (smem_t > 48 * 1024)
+        NV_CUDA(cudaFuncSetAttribute(patch_gather_ln_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      patch_gather_ln_tma_kernel<float><<<grid_t, PG_WARPS * 32, smem_t, stream>>>(tmap, g, gamma, beta, (float*)out, ld_out,
+                                                                                   raw, mean, rstd, eps);
+    }
+    NV_LAUNCH_CHECK("patch_gather_ln_tma_kernel");
+    return NV_OK;
+  }
+  // (a failed tensor-map encode above is not an error: the strided-load kernel handles the layout)
   int warps = 8;
   while (warps > 1 && (size_t)warps * g.P * 4 > 96 * 1024) warps >>= 1;
   const size_t smem = (size_t)warps * g.P * 4;
@@ -172,6 +345,16 @@ int nv_patch_ln_param_grad_launch(const float* video, const int64_t* dims, const
   int rows_per_block = (rows + blocks - 1) / blocks;
   if (rows_per_block < 4) rows_per_block = 4;
   blocks = (rows + rows_per_block - 1) / rows_per_block;
+  CUtensorMap tmap;
+  if (!getenv("NV_PATCH_NO_TMA") && (ld_dp * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(dP) & 15) == 0 &&
+      (g.P * 4) % 16 == 0 && make_patch_tmap(&tmap, video, g)) {
+    const size_t buf_bytes = ((size_t)g.P * 4 + 127) & ~(size_t)127;
+    patch_ln_param_grad_tma_kernel<<<blocks, PGB_THREADS, 4 * buf_bytes, stream>>>(tmap, g, dP, ld_dp, mean, rstd, dgamma,
+                                                                                   dbeta, rows_per_block);
+    NV_LAUNCH_CHECK("patch_ln_param_grad_tma_kernel");
+    return NV_OK;
+  }
+
   const size_t smem = (size_t)2 * g.P * 4;
   NV_REQUIRE(smem <= 48 * 1024, "patch_embed bwd: patch_dim %d too large", g.P);
   patch_ln_param_grad_kernel<<<blocks, 256, smem, stream>>>(video, g, dP, ld_dp, mean, rstd, dgamma, dbeta,

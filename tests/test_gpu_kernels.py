@@ -154,8 +154,10 @@ def test_layernorm_row_maps_and_pos_add():
 
 # ----------------------------------------------------------------------------------- patch gather
 @pytest.mark.parametrize("layout", ["neuro_view", "contiguous"])
-@pytest.mark.parametrize("geom", [(2, 1, 16, 16, 8, 8), (2, 1, 18, 18, 18, 9), (1, 2, 8, 12, 4, 4)])
+@pytest.mark.parametrize("geom", [(2, 1, 16, 16, 8, 8), (2, 1, 18, 18, 18, 9), (1, 2, 8, 12, 4, 4),
+                                  (5, 1, 64, 64, 48, 8)])
 def test_patch_gather_bit_exact(layout, geom):
+    """(the ViT3DEncoder view with patch 8 takes the 5-D TMA box kernels, everything else the strided-load ones)"""
     B, C, H, W, D_, p = geom
     torch.manual_seed(6)
     if layout == "neuro_view":
@@ -187,6 +189,33 @@ def test_patch_gather_bit_exact(layout, geom):
     xh = torch.nn.functional.layer_norm(ref.double(), (P,)).view(B * n, P)
     assert rel_err(dg, (dP[:, :P].double() * xh).sum(0)) < 1e-4
     assert rel_err(db, dP[:, :P].double().sum(0)) < 1e-4
+
+
+def test_patch_gather_tma_and_strided_kernels_agree_bitwise():
+    import os
+    torch.manual_seed(16)
+    B, H, W, D_, p = 3, 32, 24, 16, 8
+    video = torch.randn(B, H, W, D_, device=DEV).permute(0, 3, 1, 2).unsqueeze(1)
+    n, P = (H // p) * (W // p) * (D_ // p), p ** 3
+    g, b = torch.randn(P, device=DEV), torch.randn(P, device=DEV)
+    dP = torch.randn(B * n, P, device=DEV)
+    res = []
+    for no_tma in ("", "1"):
+        if no_tma:
+            os.environ["NV_PATCH_NO_TMA"] = "1"
+        try:
+            out = torch.empty(B * n, P, device=DEV, dtype=torch.bfloat16)
+            raw = torch.empty(B * n, P, device=DEV)
+            mean, rstd = torch.empty(B * n, device=DEV), torch.empty(B * n, device=DEV)
+            ops.patch_gather_ln(video, (p, p, p), g, b, out, raw=raw, mean=mean, rstd=rstd)
+            dg, db = torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+            ops.patch_ln_param_grad(video, (p, p, p), dP, mean, rstd, dg, db)
+            res.append((out.clone(), raw.clone(), mean.clone(), rstd.clone(), dg, db))
+        finally:
+            os.environ.pop("NV_PATCH_NO_TMA", None)
+    for a, c in zip(res[0][:4], res[1][:4]):
+        assert torch.equal(a, c)
+    assert rel_err(res[0][4], res[1][4]) < 1e-5 and rel_err(res[0][5], res[1][5]) < 1e-5  # atomics: order differs
 
 
 # -------------------------------------------------------------------------------------- attention
