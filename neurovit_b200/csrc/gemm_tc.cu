@@ -358,8 +358,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int s = 0;
       uint32_t ph = 0;
       for (int unit = worker; unit < total_units; unit += num_workers) {
-        const int split = unit % p.k_splits;
-        const int tile = unit / p.k_splits;
+        // split-major unit order: the workers running at the same time share one K-slice, so the A / B rows of
+        // that slice are fetched from HBM once and re-used out of L2 by all tiles
+        const int ntiles = p.num_m_tiles * p.num_n_tiles;
+        const int split = unit / ntiles;
+        const int tile = unit % ntiles;
         const int n_blk = tile % p.num_n_tiles;
         const int m_blk = tile / p.num_n_tiles;
         const int kb0 = split * p.k_blocks_per_split;
@@ -416,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int acc = 0;
       uint32_t acc_ph = 0;
       for (int unit = worker; unit < total_units; unit += num_workers) {
-        const int split = unit % p.k_splits;
+        const int split = unit / (p.num_m_tiles * p.num_n_tiles);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks_total);
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
@@ -454,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = worker; unit < total_units; unit += num_workers) {
-      const int tile = unit / p.k_splits;
+      const int tile = unit % (p.num_m_tiles * p.num_n_tiles);
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = tile / p.num_n_tiles;
       const int row0 = (m_blk * CG + (int)cta_rank) * BLOCK_M + q * 32;
