@@ -159,11 +159,16 @@ int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int 
  * x [B,T,2] -> out [B,2] (optional) and/or seq_out [B,T,2] = the encoder layer's per-timepoint output
  * (TemporalTransformer.forward called on its own); saved [B, T*4] keeps the LN1 output and LN2 input.
  * bwd takes dout [B,2] and/or dseq [B,T,2] (either may be null), writes per-sequence parameter
- * gradients to dparams_ws [B, P] (reduce with nv_batch_sum) and dx [B,T,2] (optional). */
+ * gradients to dparams_ws [B, P] (reduce with nv_batch_sum) and dx [B,T,2] (optional).
+ * p_attn / p_drop1 / p_ffn / p_drop2: training-mode dropout of the layer's four nn.Dropout sites (attention
+ * weights, after the self-attention block, after ReLU, after linear2; torch default 0.1, 0 = eval); masks are
+ * Philox bits of (seed, site, element index) — pass the same seed to bwd. */
 int nv_temporal_fwd(const float* x, const float* params, float* out, float* seq_out, float* saved,
-                    int B, int T, int F, float eps, void* stream);
+                    int B, int T, int F, float eps,
+                    float p_attn, float p_drop1, float p_ffn, float p_drop2, int64_t seed, void* stream);
 int nv_temporal_bwd(const float* x, const float* params, const float* saved, const float* dout, const float* dseq,
-                    float* dparams_ws, float* dx, int B, int T, int F, float eps, void* stream);
+                    float* dparams_ws, float* dx, int B, int T, int F, float eps,
+                    float p_attn, float p_drop1, float p_ffn, float p_drop2, int64_t seed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,10 @@ class NeuroEncoder(nn.Module):
                 seq = tt(enc)
                 return ph(seq.mean(dim=1))
             layer = tt.transformer.layers[0]
-            return Fn.TemporalHeadFn.apply(enc, layer.norm1.eps, *temporal_param_list(layer, ph.projection_head))
+            drop = temporal_dropout(layer)
+            seed = Fn.draw_seed() if any(p > 0 for p in drop) else 0
+            return Fn.TemporalHeadFn.apply(enc, layer.norm1.eps, drop, seed,
+                                           *temporal_param_list(layer, ph.projection_head))
         raise ValueError(f"TRAINING_DIM must be 3 or 4, got {self.config['TRAINING_DIM']!r}")
 
     def register_hooks(self):
@@ -159,6 +162,15 @@ class ViT3DEncoder(nn.Module):
         return self.vit3d(volume)
 
 
+def temporal_dropout(layer: nn.TransformerEncoderLayer):
+    """(p_attn, p_dropout1, p_ffn, p_dropout2) of the layer's four nn.Dropout sites as active right now: torch's
+    default p = 0.1 each in training mode (NeuroEncoder.py:211 passes no dropout argument), all 0 in eval."""
+    if not layer.training:
+        return (0.0, 0.0, 0.0, 0.0)
+    on = lambda m: float(m.p) if m.training else 0.0
+    return (float(layer.self_attn.dropout), on(layer.dropout1), on(layer.dropout), on(layer.dropout2))
+
+
 def temporal_param_list(layer: nn.TransformerEncoderLayer, head: nn.Linear):
     """Parameter tensors in the order of functional.TEMPORAL_KEYS."""
     sa = layer.self_attn
@@ -180,10 +192,9 @@ class TemporalTransformer(nn.Module):
 
     def forward(self, x):
         layer = self.transformer.layers[0]
-        if layer.training and (layer.dropout.p > 0 or layer.dropout1.p > 0 or layer.dropout2.p > 0):
-            raise NotImplementedError("neurovit_b200: dropout inside the temporal layer is not implemented in "
-                                      "training mode; call .eval() or set the layer's dropout p to 0")
-        return Fn.TemporalSeqFn.apply(x, layer.norm1.eps, *temporal_param_list(layer, None)[:12])
+        drop = temporal_dropout(layer)
+        seed = Fn.draw_seed() if any(p > 0 for p in drop) else 0
+        return Fn.TemporalSeqFn.apply(x, layer.norm1.eps, drop, seed, *temporal_param_list(layer, None)[:12])
 
 
 class ProjectionHead(nn.Module):

@@ -46,8 +46,8 @@ SIGNATURES = {
     "nv_batch_sum": [_p, _l, _p, _i, _l, _p],
     "nv_mean_pool_fwd": [_p, _p, _i, _i, _i, _p],
     "nv_mean_pool_bwd": [_p, _p, _p, _i, _i, _i, _p],
-    "nv_temporal_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _f, _p],
-    "nv_temporal_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p],
+    "nv_temporal_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
+    "nv_temporal_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
 }
 
 _lock = threading.Lock()

@@ -57,10 +57,10 @@ int nv_batch_sum_launch(const float* in, int64_t batch_stride, float* out, int B
 int nv_mean_pool_fwd_launch(const float* x, float* pooled, int B, int N, int D, cudaStream_t stream);
 int nv_mean_pool_bwd_launch(const float* dpooled, float* dx, bf16* dx_bf16, int B, int N, int D, cudaStream_t stream);
 int nv_temporal_fwd_launch(const float* x, const float* params, float* out, float* seq_out, float* saved, int B,
-                           int T, int F, float eps, cudaStream_t stream);
+                           int T, int F, float eps, const float* drop_p4, uint64_t seed, cudaStream_t stream);
 int nv_temporal_bwd_launch(const float* x, const float* params, const float* saved, const float* dout,
                            const float* dseq, float* dparams_ws, float* dx, int B, int T, int F, float eps,
-                           cudaStream_t stream);
+                           const float* drop_p4, uint64_t seed, cudaStream_t stream);
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -210,12 +210,17 @@ int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int 
 }
 
 int nv_temporal_fwd(const float* x, const float* params, float* out, float* seq_out, float* saved, int B, int T,
-                    int F, float eps, void* stream) {
-  return nv_temporal_fwd_launch(x, params, out, seq_out, saved, B, T, F, eps, ST(stream));
+                    int F, float eps, float p_attn, float p_drop1, float p_ffn, float p_drop2, int64_t seed,
+                    void* stream) {
+  const float p4[4] = {p_attn, p_drop1, p_ffn, p_drop2};
+  return nv_temporal_fwd_launch(x, params, out, seq_out, saved, B, T, F, eps, p4, (uint64_t)seed, ST(stream));
 }
 int nv_temporal_bwd(const float* x, const float* params, const float* saved, const float* dout, const float* dseq,
-                    float* dparams_ws, float* dx, int B, int T, int F, float eps, void* stream) {
-  return nv_temporal_bwd_launch(x, params, saved, dout, dseq, dparams_ws, dx, B, T, F, eps, ST(stream));
+                    float* dparams_ws, float* dx, int B, int T, int F, float eps, float p_attn, float p_drop1,
+                    float p_ffn, float p_drop2, int64_t seed, void* stream) {
+  const float p4[4] = {p_attn, p_drop1, p_ffn, p_drop2};
+  return nv_temporal_bwd_launch(x, params, saved, dout, dseq, dparams_ws, dx, B, T, F, eps, p4, (uint64_t)seed,
+                                ST(stream));
 }
 
 }  // extern "C"

@@ -10,10 +10,41 @@
 //   in_w[6,2]@0  in_b[6]@12  out_w[2,2]@18  out_b[2]@22  l1_w[F,2]@24  l1_b[F]@24+2F  l2_w[2,F]@24+3F
 //   l2_b[2]@24+5F  n1_w@26+5F n1_b@28+5F n2_w@30+5F n2_b@32+5F  ph_w[2,2]@34+5F  ph_b[2]@38+5F ; P=40+5F
 #include "nv_common.cuh"
+#include "nv_rng.cuh"
 
 namespace {
 
 constexpr int TT = 256;  // threads per CTA
+
+// The four nn.Dropout sites of nn.TransformerEncoderLayer in training mode (torch defaults p = 0.1):
+//   0 attention probabilities [B, 2, T, T]   1 dropout1 on the self-attention output [B, T, 2]
+//   2 dropout on relu(linear1) [B, T, F]     3 dropout2 on linear2's output [B, T, 2]
+// Masks are Philox bits of (seed, site, element index) with rows padded to a multiple of 8 elements
+// (Tp, Fp), so forward and backward regenerate them and ops.dropout_keep_mask can replay them in tests.
+struct TDrop {
+  uint32_t thr[4];
+  float ks[4];
+  uint64_t seed;
+};
+// keep-scale (0 or 1/(1-p)) of one element
+__device__ __forceinline__ float tkeep(const TDrop& d, int site, uint64_t idx) {
+  if (d.thr[site] == 0) return 1.0f;
+  const uint32_t b8 = nv_keep_bits8(d.seed, idx >> 3, (uint32_t)site, d.thr[site]);
+  return (b8 >> (idx & 7)) & 1u ? d.ks[site] : 0.f;
+}
+// keep-scale of element (row, i) while i walks a row in order: one Philox call per 8 elements
+struct RowMask {
+  const TDrop& d;
+  int site;
+  uint64_t base;  // row * padded row length
+  uint32_t b8;
+  __device__ __forceinline__ RowMask(const TDrop& d_, int site_, uint64_t base_) : d(d_), site(site_), base(base_), b8(0) {}
+  __device__ __forceinline__ float operator()(int i) {
+    if (d.thr[site] == 0) return 1.0f;
+    if ((i & 7) == 0) b8 = nv_keep_bits8(d.seed, (base + i) >> 3, (uint32_t)site, d.thr[site]);
+    return (b8 >> (i & 7)) & 1u ? d.ks[site] : 0.f;
+  }
+};
 
 struct TParams {
   const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b, *ph_w, *ph_b;
@@ -59,7 +90,8 @@ __device__ __forceinline__ void ln2_bwd(float y0, float y1, const float* w, floa
 
 // shared: xs, q, k, v, o : [T][2] each
 __device__ void temporal_attn_fwd(const float* xb, const TParams& P, int T, float* xs, float* q, float* k, float* v,
-                                  float* o) {
+                                  float* o, const TDrop& drop, int b) {
+  const int Tp = (T + 7) & ~7;
   for (int t = threadIdx.x; t < T; t += TT) {
     const float x0 = xb[2 * t], x1 = xb[2 * t + 1];
     xs[2 * t] = x0; xs[2 * t + 1] = x1;
@@ -77,10 +109,11 @@ __device__ void temporal_attn_fwd(const float* xb, const TParams& P, int T, floa
     float mx = -INFINITY;
     for (int s = 0; s < T; ++s) mx = fmaxf(mx, qv * k[2 * s + hh]);
     float sum = 0.f, acc = 0.f;
+    RowMask mask(drop, 0, (((uint64_t)b * 2 + hh) * T + (idx >> 1)) * Tp);
     for (int s = 0; s < T; ++s) {
       const float e = expf(qv * k[2 * s + hh] - mx);
       sum += e;
-      acc += e * v[2 * s + hh];
+      acc += e * mask(s) * v[2 * s + hh];  // dropout on the normalised weights = masked numerator
     }
     o[idx] = acc / sum;
   }
@@ -89,26 +122,29 @@ __device__ void temporal_attn_fwd(const float* xb, const TParams& P, int T, floa
 
 __global__ void __launch_bounds__(TT)
 temporal_fwd_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ out,
-                    float* __restrict__ seq_out, float* __restrict__ saved, int T, int F, float eps) {
+                    float* __restrict__ seq_out, float* __restrict__ saved, int T, int F, float eps, const TDrop drop) {
   extern __shared__ float sm[];
   __shared__ float red[TT / 32];
   float *xs = sm, *q = sm + 2 * T, *k = sm + 4 * T, *v = sm + 6 * T, *o = sm + 8 * T;
   const int b = blockIdx.x;
   const TParams P(params, F);
-  temporal_attn_fwd(x + (int64_t)b * T * 2, P, T, xs, q, k, v, o);
+  temporal_attn_fwd(x + (int64_t)b * T * 2, P, T, xs, q, k, v, o, drop, b);
+  const int Fp = (F + 7) & ~7;
   float m0 = 0.f, m1 = 0.f;
   for (int t = threadIdx.x; t < T; t += TT) {
-    const float a0 = P.out_w[0] * o[2 * t] + P.out_w[1] * o[2 * t + 1] + P.out_b[0];
-    const float a1 = P.out_w[2] * o[2 * t] + P.out_w[3] * o[2 * t + 1] + P.out_b[1];
+    const uint64_t bt = (uint64_t)b * T + t;
+    const float a0 = (P.out_w[0] * o[2 * t] + P.out_w[1] * o[2 * t + 1] + P.out_b[0]) * tkeep(drop, 1, bt * 2);
+    const float a1 = (P.out_w[2] * o[2 * t] + P.out_w[3] * o[2 * t + 1] + P.out_b[1]) * tkeep(drop, 1, bt * 2 + 1);
     float u0, u1;
     ln2_fwd(xs[2 * t] + a0, xs[2 * t + 1] + a1, P.n1_w, P.n1_b, eps, u0, u1);
     float f0 = P.l2_b[0], f1 = P.l2_b[1];
+    RowMask hmask(drop, 2, bt * Fp);
     for (int j = 0; j < F; ++j) {
-      const float h = fmaxf(P.l1_w[2 * j] * u0 + P.l1_w[2 * j + 1] * u1 + P.l1_b[j], 0.f);
+      const float h = fmaxf(P.l1_w[2 * j] * u0 + P.l1_w[2 * j + 1] * u1 + P.l1_b[j], 0.f) * hmask(j);
       f0 += P.l2_w[j] * h;
       f1 += P.l2_w[F + j] * h;
     }
-    const float y0 = u0 + f0, y1 = u1 + f1;
+    const float y0 = u0 + f0 * tkeep(drop, 3, bt * 2), y1 = u1 + f1 * tkeep(drop, 3, bt * 2 + 1);
     float* sv = saved + ((int64_t)b * T + t) * 4;
     sv[0] = u0; sv[1] = u1; sv[2] = y0; sv[3] = y1;
     float z0, z1;
@@ -127,13 +163,15 @@ temporal_fwd_kernel(const float* __restrict__ x, const float* __restrict__ param
 __global__ void __launch_bounds__(TT)
 temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ params, const float* __restrict__ saved,
                     const float* __restrict__ dout, const float* __restrict__ dseq, float* __restrict__ dparams_ws,
-                    float* __restrict__ dx_out, int T, int F, float eps) {
+                    float* __restrict__ dx_out, int T, int F, float eps, const TDrop drop) {
   extern __shared__ float sm[];
   __shared__ float red[TT / 32];
   // [T][2] arrays: xs q k v o | x1 df dx1 da dq dk dv
   float *xs = sm, *q = sm + 2 * T, *k = sm + 4 * T, *v = sm + 6 * T, *o = sm + 8 * T;
   float *x1 = sm + 10 * T, *df = sm + 12 * T, *dx1 = sm + 14 * T, *da = sm + 16 * T;
   float *dq = sm + 18 * T, *dk = sm + 20 * T, *dv = sm + 22 * T, *dxs = sm + 24 * T;
+  float* dfm = sm + 26 * T;  // df through dropout2 (gradient of linear2's output)
+  const int Tp = (T + 7) & ~7, Fp = (F + 7) & ~7;
   const int b = blockIdx.x;
   const TParams P(params, F);
   const int PN = 40 + 5 * F;
@@ -143,7 +181,7 @@ temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ param
   float* g_n1_w = G + 26 + 5 * F; float* g_n1_b = G + 28 + 5 * F; float* g_n2_w = G + 30 + 5 * F;
   float* g_n2_b = G + 32 + 5 * F; float* g_ph_w = G + 34 + 5 * F; float* g_ph_b = G + 38 + 5 * F;
 
-  temporal_attn_fwd(x + (int64_t)b * T * 2, P, T, xs, q, k, v, o);
+  temporal_attn_fwd(x + (int64_t)b * T * 2, P, T, xs, q, k, v, o, drop, b);
 
   // ---- projection head + mean + LN2 backward ----
   const float do0 = dout ? dout[2 * b] : 0.f, do1 = dout ? dout[2 * b + 1] : 0.f;
@@ -171,8 +209,11 @@ temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ param
     float dy0, dy1, xh0, xh1;
     ln2_bwd(sv[2], sv[3], P.n2_w, eps, dz0, dz1, dy0, dy1, xh0, xh1);
     gw0 += dz0 * xh0; gw1 += dz1 * xh1; gb0 += dz0; gb1 += dz1;
-    df[2 * t] = dy0; df[2 * t + 1] = dy1;
-    sb0 += dy0; sb1 += dy1;
+    df[2 * t] = dy0; df[2 * t + 1] = dy1;           // residual path x1 -> y2
+    const uint64_t bt = (uint64_t)b * T + t;
+    const float e0 = dy0 * tkeep(drop, 3, bt * 2), e1 = dy1 * tkeep(drop, 3, bt * 2 + 1);
+    dfm[2 * t] = e0; dfm[2 * t + 1] = e1;           // through dropout2 into linear2
+    sb0 += e0; sb1 += e1;
   }
   gw0 = block_sum(gw0, red); gw1 = block_sum(gw1, red);
   gb0 = block_sum(gb0, red); gb1 = block_sum(gb1, red);
@@ -191,9 +232,10 @@ temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ param
       const float u0 = x1[2 * t], u1 = x1[2 * t + 1];
       const float pre = w0 * u0 + w1 * u1 + bj;
       if (pre > 0.f) {
-        const float d0 = df[2 * t], d1 = df[2 * t + 1];
-        const float dh = d0 * v0 + d1 * v1;
-        gv0 += d0 * pre; gv1 += d1 * pre;
+        const float mk = tkeep(drop, 2, ((uint64_t)b * T + t) * Fp + j);  // hidden-unit dropout mask
+        const float d0 = dfm[2 * t], d1 = dfm[2 * t + 1];
+        const float dh = (d0 * v0 + d1 * v1) * mk;
+        gv0 += d0 * pre * mk; gv1 += d1 * pre * mk;
         gw_0 += dh * u0; gw_1 += dh * u1; gbj += dh;
       }
     }
@@ -205,23 +247,28 @@ temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ param
   float ow[4] = {0.f, 0.f, 0.f, 0.f}, ob0 = 0.f, ob1 = 0.f;
   for (int t = threadIdx.x; t < T; t += TT) {
     const float u0 = x1[2 * t], u1 = x1[2 * t + 1];
-    const float d0 = df[2 * t], d1 = df[2 * t + 1];
-    float g0 = d0, g1 = d1;  // residual path x1 -> y2
+    const float d0 = dfm[2 * t], d1 = dfm[2 * t + 1];
+    float g0 = df[2 * t], g1 = df[2 * t + 1];  // residual path x1 -> y2
+    const uint64_t bt = (uint64_t)b * T + t;
+    RowMask hmask(drop, 2, bt * Fp);
     for (int j = 0; j < F; ++j) {
       const float w0 = P.l1_w[2 * j], w1 = P.l1_w[2 * j + 1];
       const float pre = w0 * u0 + w1 * u1 + P.l1_b[j];
+      const float mk = hmask(j);
       if (pre > 0.f) {
-        const float dh = d0 * P.l2_w[j] + d1 * P.l2_w[F + j];
+        const float dh = (d0 * P.l2_w[j] + d1 * P.l2_w[F + j]) * mk;
         g0 += dh * w0; g1 += dh * w1;
       }
     }
-    // LN1: input y1 = x + W_o o + b_o
-    const float a0 = P.out_w[0] * o[2 * t] + P.out_w[1] * o[2 * t + 1] + P.out_b[0];
-    const float a1 = P.out_w[2] * o[2 * t] + P.out_w[3] * o[2 * t + 1] + P.out_b[1];
+    // LN1: input y1 = x + dropout1(W_o o + b_o)
+    const float k0 = tkeep(drop, 1, bt * 2), k1 = tkeep(drop, 1, bt * 2 + 1);
+    const float a0 = (P.out_w[0] * o[2 * t] + P.out_w[1] * o[2 * t + 1] + P.out_b[0]) * k0;
+    const float a1 = (P.out_w[2] * o[2 * t] + P.out_w[3] * o[2 * t + 1] + P.out_b[1]) * k1;
     float dy0, dy1, xh0, xh1;
     ln2_bwd(xs[2 * t] + a0, xs[2 * t + 1] + a1, P.n1_w, eps, g0, g1, dy0, dy1, xh0, xh1);
     n1w0 += g0 * xh0; n1w1 += g1 * xh1; n1b0 += g0; n1b1 += g1;
     dxs[2 * t] = dy0; dxs[2 * t + 1] = dy1;  // residual path x -> y1
+    dy0 *= k0; dy1 *= k1;                    // through dropout1 into the attention output projection
     ow[0] += dy0 * o[2 * t]; ow[1] += dy0 * o[2 * t + 1]; ow[2] += dy1 * o[2 * t]; ow[3] += dy1 * o[2 * t + 1];
     ob0 += dy0; ob1 += dy1;
     // d o = W_o^T dy
@@ -250,14 +297,16 @@ temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ param
     float sum = 0.f;
     for (int s = 0; s < T; ++s) sum += expf(qv * k[2 * s + hh] - mx);
     const float inv = 1.0f / sum;
-    const float delta = dov * o[idx];
+    const float delta = dov * o[idx];  // = sum_s p_s dP_s also with dropout (o already holds the masked sum)
     float dqa = 0.f;
+    RowMask mask(drop, 0, (((uint64_t)b * 2 + hh) * T + (idx >> 1)) * Tp);
     for (int s = 0; s < T; ++s) {
       const float p = expf(qv * k[2 * s + hh] - mx) * inv;
-      const float ds = p * (dov * v[2 * s + hh] - delta);
+      const float mk = mask(s);
+      const float ds = p * (dov * v[2 * s + hh] * mk - delta);
       dqa += ds * k[2 * s + hh];
       atomicAdd(&dk[2 * s + hh], ds * qv);
-      atomicAdd(&dv[2 * s + hh], p * dov);
+      atomicAdd(&dv[2 * s + hh], p * mk * dov);
     }
     dq[idx] = dqa;
   }
@@ -291,29 +340,46 @@ temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ param
   }
 }
 
+int fill_tdrop(TDrop& d, const float* p4, uint64_t seed) {
+  for (int i = 0; i < 4; ++i) {
+    const float p = p4 ? p4[i] : 0.f;
+    NV_REQUIRE(p >= 0.f && p < 1.f, "temporal: dropout p[%d] = %f out of range [0, 1)", i, p);
+    d.thr[i] = nv_dropout_threshold(p);
+    d.ks[i] = nv_dropout_keep_scale(d.thr[i]);
+  }
+  d.seed = seed;
+  return NV_OK;
+}
+
 }  // namespace
 
 int nv_temporal_fwd_launch(const float* x, const float* params, float* out, float* seq_out, float* saved, int B,
-                           int T, int F, float eps, cudaStream_t stream) {
+                           int T, int F, float eps, const float* drop_p4, uint64_t seed, cudaStream_t stream) {
   NV_REQUIRE(B >= 0 && T > 0 && F > 0 && T <= 2048, "temporal: bad sizes B=%d T=%d F=%d", B, T, F);
+  TDrop drop;
+  int st = fill_tdrop(drop, drop_p4, seed);
+  if (st != NV_OK) return st;
   if (B == 0) return NV_OK;
   const size_t smem = (size_t)10 * T * sizeof(float);
   if (smem > 48 * 1024)
     NV_CUDA(cudaFuncSetAttribute(temporal_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  temporal_fwd_kernel<<<B, TT, smem, stream>>>(x, params, out, seq_out, saved, T, F, eps);
+  temporal_fwd_kernel<<<B, TT, smem, stream>>>(x, params, out, seq_out, saved, T, F, eps, drop);
   NV_LAUNCH_CHECK("temporal_fwd_kernel");
   return NV_OK;
 }
 
 int nv_temporal_bwd_launch(const float* x, const float* params, const float* saved, const float* dout,
                            const float* dseq, float* dparams_ws, float* dx, int B, int T, int F, float eps,
-                           cudaStream_t stream) {
+                           const float* drop_p4, uint64_t seed, cudaStream_t stream) {
   NV_REQUIRE(B >= 0 && T > 0 && F > 0 && T <= 2048, "temporal: bad sizes B=%d T=%d F=%d", B, T, F);
+  TDrop drop;
+  int st = fill_tdrop(drop, drop_p4, seed);
+  if (st != NV_OK) return st;
   if (B == 0) return NV_OK;
-  const size_t smem = (size_t)26 * T * sizeof(float);
+  const size_t smem = (size_t)28 * T * sizeof(float);
   if (smem > 48 * 1024)
     NV_CUDA(cudaFuncSetAttribute(temporal_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  temporal_bwd_kernel<<<B, TT, smem, stream>>>(x, params, saved, dout, dseq, dparams_ws, dx, T, F, eps);
+  temporal_bwd_kernel<<<B, TT, smem, stream>>>(x, params, saved, dout, dseq, dparams_ws, dx, T, F, eps, drop);
   NV_LAUNCH_CHECK("temporal_bwd_kernel");
   return NV_OK;
 }

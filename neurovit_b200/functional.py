@@ -792,7 +792,8 @@ class TemporalHeadFn(torch.autograd.Function):
     """TemporalTransformer -> mean over T -> ProjectionHead, NeuroEncoder.py:63-66."""
 
     @staticmethod
-    def forward(ctx, x, eps, *params):
+    def forward(ctx, x, eps, drop, seed, *params):
+        """drop = (p_attn, p_dropout1, p_ffn, p_dropout2) active right now, seed: their Philox seed."""
         B, T, E = x.shape
         if E != 2:
             raise ValueError("the temporal kernel implements d_model=2 (NeuroEncoder.py:211)")
@@ -801,19 +802,21 @@ class TemporalHeadFn(torch.autograd.Function):
         packed = pack_temporal_params(params)
         out = torch.empty(B, 2, device=x.device, dtype=F32)
         saved = torch.empty(B, T * 4, device=x.device, dtype=F32)
-        ops.temporal_fwd(x, packed, out, saved, B, T, F, eps)
+        ops.temporal_fwd(x, packed, out, saved, B, T, F, eps, drop=drop, seed=seed)
+        if any(p > 0 for p in drop):
+            _trace("temporal", max(drop), seed, 0, (B, T, F, tuple(drop)))
         ctx.save_for_backward(x, packed, saved)
-        ctx.cfg = (B, T, F, eps, [p.shape for p in params], x.requires_grad)
+        ctx.cfg = (B, T, F, eps, [p.shape for p in params], x.requires_grad, tuple(drop), seed)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, packed, saved = ctx.saved_tensors
-        B, T, F, eps, shapes, need_dx = ctx.cfg
+        B, T, F, eps, shapes, need_dx, drop, seed = ctx.cfg
         dev = x.device
         ws = torch.empty(B, packed.numel(), device=dev, dtype=F32)
         dx = torch.empty(B, T, 2, device=dev, dtype=F32) if ctx.needs_input_grad[0] else None
-        ops.temporal_bwd(x, packed, saved, dout.float().contiguous(), ws, dx, B, T, F, eps)
+        ops.temporal_bwd(x, packed, saved, dout.float().contiguous(), ws, dx, B, T, F, eps, drop=drop, seed=seed)
         flat = torch.zeros(packed.numel(), device=dev, dtype=F32)
         ops.batch_sum(ws, packed.numel(), flat, B, packed.numel())
         grads, off = [], 0
@@ -821,14 +824,14 @@ class TemporalHeadFn(torch.autograd.Function):
             n = math.prod(s)
             grads.append(flat[off:off + n].view(s))
             off += n
-        return (dx, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
 class TemporalSeqFn(torch.autograd.Function):
     """TemporalTransformer.forward on its own: [B, T, 2] -> [B, T, 2] (NeuroEncoder.py:213-216)."""
 
     @staticmethod
-    def forward(ctx, x, eps, *params):
+    def forward(ctx, x, eps, drop, seed, *params):
         B, T, E = x.shape
         if E != 2:
             raise ValueError("the temporal kernel implements d_model=2 (NeuroEncoder.py:211)")
@@ -839,19 +842,20 @@ class TemporalSeqFn(torch.autograd.Function):
         packed = pack_temporal_params(list(params) + ident)
         seq = torch.empty(B, T, 2, device=dev, dtype=F32)
         saved = torch.empty(B, T * 4, device=dev, dtype=F32)
-        ops.temporal_fwd(x, packed, None, saved, B, T, F, eps, seq_out=seq)
+        ops.temporal_fwd(x, packed, None, saved, B, T, F, eps, seq_out=seq, drop=drop, seed=seed)
         ctx.save_for_backward(x, packed, saved)
-        ctx.cfg = (B, T, F, eps, [p.shape for p in params])
+        ctx.cfg = (B, T, F, eps, [p.shape for p in params], tuple(drop), seed)
         return seq
 
     @staticmethod
     def backward(ctx, dseq):
         x, packed, saved = ctx.saved_tensors
-        B, T, F, eps, shapes = ctx.cfg
+        B, T, F, eps, shapes, drop, seed = ctx.cfg
         dev = x.device
         ws = torch.empty(B, packed.numel(), device=dev, dtype=F32)
         dx = torch.empty(B, T, 2, device=dev, dtype=F32) if ctx.needs_input_grad[0] else None
-        ops.temporal_bwd(x, packed, saved, None, ws, dx, B, T, F, eps, dseq=dseq.float().contiguous())
+        ops.temporal_bwd(x, packed, saved, None, ws, dx, B, T, F, eps, dseq=dseq.float().contiguous(), drop=drop,
+                         seed=seed)
         flat = torch.zeros(packed.numel(), device=dev, dtype=F32)
         ops.batch_sum(ws, packed.numel(), flat, B, packed.numel())
         grads, off = [], 0
@@ -859,7 +863,7 @@ class TemporalSeqFn(torch.autograd.Function):
             n = math.prod(s)
             grads.append(flat[off:off + n].view(s))
             off += n
-        return (dx, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
 class SmallLinearFn(torch.autograd.Function):

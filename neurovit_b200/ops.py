@@ -328,13 +328,15 @@ def mean_pool_bwd(dpooled, dx, dx_bf16, B, N, D):
     _lib.call("nv_mean_pool_bwd", _ptr(dpooled), _ptr(dx), _ptr(dx_bf16), B, N, D, _stream())
 
 
-def temporal_fwd(x, params, out, saved, B, T, F, eps=1e-5, seq_out=None):
+def temporal_fwd(x, params, out, saved, B, T, F, eps=1e-5, seq_out=None, drop=(0.0, 0.0, 0.0, 0.0), seed=0):
+    """drop = (p_attn, p_dropout1, p_ffn, p_dropout2) of nn.TransformerEncoderLayer in training mode."""
     _dev(x)
     _lib.call("nv_temporal_fwd", _ptr(x), _ptr(params), _ptr(out), _ptr(seq_out), _ptr(saved), B, T, F, float(eps),
-              _stream())
+              *[float(p) for p in drop], int(seed), _stream())
 
 
-def temporal_bwd(x, params, saved, dout, dparams_ws, dx, B, T, F, eps=1e-5, dseq=None):
+def temporal_bwd(x, params, saved, dout, dparams_ws, dx, B, T, F, eps=1e-5, dseq=None, drop=(0.0, 0.0, 0.0, 0.0),
+                 seed=0):
     _dev(x)
     _lib.call("nv_temporal_bwd", _ptr(x), _ptr(params), _ptr(saved), _ptr(dout), _ptr(dseq), _ptr(dparams_ws),
-              _ptr(dx), B, T, F, float(eps), _stream())
+              _ptr(dx), B, T, F, float(eps), *[float(p) for p in drop], int(seed), _stream())

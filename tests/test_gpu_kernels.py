@@ -348,6 +348,58 @@ def test_temporal_head_matches_torch():
     assert rel_err(dx, grads[0]) < 1e-3
 
 
+def test_temporal_head_training_dropout_matches_masked_reference():
+    """nn.TransformerEncoderLayer in training mode has four dropout sites (torch default p = 0.1); the kernel's
+    Philox masks are replayed (ops.dropout_keep_mask draws the same bits) into a float64 restatement."""
+    import math as _m
+    from neurovit_b200.functional import pack_temporal_params, TEMPORAL_KEYS
+    import torch.nn.functional as Fnn
+    torch.manual_seed(13)
+    B, T, F = 3, 140, 2048
+    drop, seed = (0.1, 0.2, 0.1, 0.3), 4242
+    layer = torch.nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True).to(DEV).double()
+    head = torch.nn.Linear(2, 2).to(DEV).double()
+    with torch.no_grad():
+        layer.norm1.weight.mul_(0.003)
+        layer.norm1.bias.zero_()
+    x = (0.005 * torch.randn(B, T, 2, device=DEV)).double().requires_grad_(True)
+    ks = lambda p: 65536.0 / (65536 - int(p * 65536 + 0.5))
+    Tp, Fp = (T + 7) // 8 * 8, (F + 7) // 8 * 8
+    km = lambda rows, cols, site: ops.dropout_keep_mask(rows, cols, p=drop[site], seed=seed, stream=site).double() * ks(drop[site])
+    m_attn = km(B * 2 * T, Tp, 0).view(B, 2, T, Tp)[..., :T]
+    flat2 = lambda site: km((B * T * 2 + 7) // 8, 8, site).view(-1)[:B * T * 2].view(B, T, 2)
+    m1, m2 = flat2(1), flat2(3)
+    m_ffn = km(B * T, Fp, 2).view(B, T, Fp)[..., :F]
+    sa = layer.self_attn
+    qkv = Fnn.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+    q, k, v = (t.reshape(B, T, 2, 1).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+    attn = (q @ k.transpose(-1, -2)).softmax(-1) * m_attn                       # head_dim 1: scale 1
+    o = (attn @ v).transpose(1, 2).reshape(B, T, 2)
+    a = Fnn.linear(o, sa.out_proj.weight, sa.out_proj.bias) * m1
+    x1 = Fnn.layer_norm(x + a, (2,), layer.norm1.weight, layer.norm1.bias)
+    f = Fnn.linear(Fnn.relu(Fnn.linear(x1, layer.linear1.weight, layer.linear1.bias)) * m_ffn,
+                   layer.linear2.weight, layer.linear2.bias) * m2
+    x2 = Fnn.layer_norm(x1 + f, (2,), layer.norm2.weight, layer.norm2.bias)
+    ref = head(x2.mean(1))
+    dout = torch.randn(B, 2, device=DEV).double()
+    named = {"temporal." + k_: v_ for k_, v_ in layer.named_parameters()}
+    named.update({"head.weight": head.weight, "head.bias": head.bias})
+    tensors = [named[k_] for k_ in TEMPORAL_KEYS]
+    grads = torch.autograd.grad(ref, [x] + tensors, dout)
+    params = pack_temporal_params([t.detach().float() for t in tensors])
+    out = torch.empty(B, 2, device=DEV)
+    saved = torch.empty(B, T * 4, device=DEV)
+    ops.temporal_fwd(x.detach().float(), params, out, saved, B, T, F, drop=drop, seed=seed)
+    assert rel_err(out, ref) < 1e-4
+    ws = torch.empty(B, params.numel(), device=DEV)
+    dx = torch.empty(B, T, 2, device=DEV)
+    ops.temporal_bwd(x.detach().float(), params, saved, dout.float(), ws, dx, B, T, F, drop=drop, seed=seed)
+    gflat = torch.cat([g.flatten() for g in grads[1:]])
+    assert rel_err(ws.double().sum(0), gflat) < 1e-3
+    assert rel_err(dx, grads[0]) < 1e-3
+    assert 0.85 < (m_attn != 0).double().mean().item() < 0.95 and 0.65 < (m2 != 0).double().mean().item() < 0.75
+
+
 # ---------------------------------------------------------------------------------------- dropout
 def test_dropout_kernel_mask_statistics_and_determinism():
     M, N, p = 1000, 1024, 0.1
