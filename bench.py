@@ -31,6 +31,8 @@ CONFIGS = {
     # volume [H, W, D] as delivered by the datasets (Trainer.py:66), model dims hard-coded in NeuroEncoder.py:181-195
     "cfgA": dict(vol=(64, 64, 48), patch=8, tokens=385, gflop_fwd_bwd=93.469),
     "cfgB": dict(vol=(96, 96, 96), patch=8, tokens=1729, gflop_fwd_bwd=505.432),
+    # BASELINE config 5: 4D NeuroEncoder — frozen ViT3D forward over T timepoints + temporal head fwd+bwd+AdamW
+    "cfg5": dict(vol=(64, 64, 48), patch=8, tokens=385, T=140, gflop_fwd=31.291),
 }
 MODEL = dict(dim=1024, depth=6, heads=8, dim_head=64, mlp_dim=2048, num_classes=2)
 DROPOUT = 0.1  # TRAINING_DROPOUT of the reference's configs/config.yaml:38 (all 25 sites); --dropout overrides, both arms
@@ -171,6 +173,88 @@ def workload_name(args, cfg, batch):
     H, W, D = cfg["vol"]
     return (f"ViT3D training step, batch {batch} synthetic 1x{H}x{W}x{D} volumes, patch {cfg['patch']} "
             f"({cfg['tokens'] - 1} patches + cls), dim 1024 depth 6 heads 8 mlp 2048")
+
+
+# ---- secondary workload: BASELINE config 5 (4D NeuroEncoder) -------------------------------------------
+def run_4d(args, cfg):
+    """One step = NeuroEncoder(TRAINING_DIM=4) forward on `--batch` fMRI sequences [H,W,D,T] (frozen ViT3D over
+    B*T volumes, then TemporalTransformer + ProjectionHead), CrossEntropy, backward through the temporal head
+    and AdamW on its 10 280 parameters; sequences are sharded over the ranks, the all-reduce is 41 KB."""
+    import tempfile
+    import torch.distributed as dist
+    from neurovit_b200 import _lib
+    from neurovit_b200.NeuroEncoder import NeuroEncoder
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device(local)
+    H, W, D = cfg["vol"]
+    T, B = cfg["T"], args.batch
+    base = dict(DEVICE=dev, TRAINING_DROPOUT=DROPOUT, TRAINING_VIT_INPUT_SIZE=H, GRADCAM_CUBE_SIZE=8,
+                TRAINING_VIT_PATCH_SIZE=cfg["patch"], DATASET_NAME="adni", GRADCAM_THRESHOLD=0.5, GRADCAM_SLICE_DIM=0,
+                GRADCAM_SLICE_IDX=0, GRADCAM_CAPTURE=args.gradcam)
+    with tempfile.TemporaryDirectory() as tmp:
+        torch.manual_seed(42)
+        m3 = NeuroEncoder({**base, "TRAINING_DIM": 3, "GLOBAL_BASE_PATH": tmp, "BEST_MODEL_PATH": "vit3d.pth"})
+        torch.save(m3.state_dict(), os.path.join(tmp, "vit3d.pth"))   # the 3D checkpoint the 4D model freezes
+        del m3
+        model = NeuroEncoder({**base, "TRAINING_DIM": 4, "GLOBAL_BASE_PATH": tmp, "BEST_MODEL_PATH": "vit3d.pth"})
+    model.train()
+    model.volume_encoder.eval()  # frozen ViT3D (NeuroEncoder.py:33-36)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
+    g = torch.Generator().manual_seed(42 + rank)
+    x = [torch.randn(B, H, W, D, T, generator=g).to(dev) for _ in range(2)]
+    y = [torch.randint(0, 2, (B,), generator=g).to(dev) for _ in range(2)]
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(model(x[i & 1]), y[i & 1])
+        loss.backward()
+        if world > 1:
+            for p_ in params:
+                dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        peaks = load_peaks()
+        sps = world * B * args.steps / (ms * 1e-3)
+        tfl = sps / world * T * cfg["gflop_fwd"] / 1e3
+        print(json.dumps({
+            "metric": "4D NeuroEncoder sequences/sec (frozen ViT3D fwd over T volumes + temporal head fwd+bwd+AdamW)",
+            "value": sps, "unit": "sequences/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"NeuroEncoder TRAINING_DIM=4, {B} sequences/GPU of {T} x 1x{H}x{W}x{D} volumes, patch "
+                                   f"{cfg['patch']}", "volumes_per_s": sps * T, "model_tflops_per_gpu": tfl,
+                       "model_frac_of_peak": tfl / peaks["tflops"], "dropout_temporal": 0.1,
+                       "gradcam_capture": args.gradcam,
+                       "parallelism": f"dp{world} (sequences sharded, 41 KB gradient all-reduce)"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---- our arm ------------------------------------------------------------------------------------------
@@ -349,6 +433,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=2, help="volumes per CPU reference step (bounded sample)")
     ap.add_argument("--dropout", type=float, default=DROPOUT, help="dropout p at all sites, training mode (both arms)")
+    ap.add_argument("--gradcam", default="device", choices=["host", "device", "off"],
+                    help="cfg5 only: NeuroEncoder Grad-CAM capture ('host' = the reference's per-step D2H copies)")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -360,6 +446,10 @@ def main():
         if args.warmup > 2:
             args.warmup = 2
         run_reference(args, cfg)
+    elif args.config == "cfg5":
+        if args.batch == 64:
+            args.batch = 2  # 2 sequences x 140 timepoints = 280 volumes per GPU per step
+        run_4d(args, cfg)
     else:
         if args.warmup < 3:
             args.warmup = 3

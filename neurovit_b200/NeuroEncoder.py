@@ -75,14 +75,25 @@ class NeuroEncoder(nn.Module):
 
     def register_hooks(self):
         """Capture the output of the last block's attention LayerNorm and the gradient flowing into it
-        (NeuroEncoder.py:70-82); both are moved to the host, exactly as the reference does."""
+        (NeuroEncoder.py:70-82). config['GRADCAM_CAPTURE'] (optional, not a reference key):
+          "host"   (default) move both to the host inside the hook, exactly as the reference does — one device sync
+                   and a [B, N, 1024] fp32 D2H copy per forward and per backward (SURVEY 8a row A16);
+          "device" keep the detached tensors on the GPU (get_attention_map moves the small result instead);
+          "off"    register no hooks: the last block then runs the fully fused path."""
+        mode = self.config.get('GRADCAM_CAPTURE', 'host')
+        if mode not in ('host', 'device', 'off'):
+            raise ValueError(f"GRADCAM_CAPTURE must be 'host', 'device' or 'off', got {mode!r}")
+        self.forward_handle = self.backward_handle = None
+        if mode == 'off':
+            return
         target = self.volume_encoder.vit3d.transformer.layers[-1][0].norm
+        keep = (lambda t: t.detach().cpu()) if mode == 'host' else (lambda t: t.detach())
 
         def forward_hook(module, inputs, output):
-            self.activations = output.detach().cpu()
+            self.activations = keep(output)
 
         def backward_hook(module, grad_input, grad_output):
-            self.gradients = grad_output[0].detach().cpu()
+            self.gradients = keep(grad_output[0])
 
         self.forward_handle = target.register_forward_hook(forward_hook)
         self.backward_handle = target.register_full_backward_hook(backward_hook)
@@ -100,8 +111,10 @@ class NeuroEncoder(nn.Module):
         output.backward(gradient=one_hot, retain_graph=True)
 
         grads, acts = self.gradients, self.activations
+        if not torch.is_tensor(grads) or not torch.is_tensor(acts):
+            raise RuntimeError("Grad-CAM needs the capture hooks (config GRADCAM_CAPTURE 'host' or 'device')")
         weights = grads.mean(dim=2, keepdim=True)          # importance = mean gradient over the feature axis
-        cam = (weights * acts).sum(dim=2)[:, 1:]           # weighted activation per token, cls dropped
+        cam = (weights * acts).sum(dim=2)[:, 1:].cpu()     # weighted activation per token, cls dropped
         side = grid // patch
         cam = F.relu(cam.reshape(1, side, side, side))
         cam = (cam - cam.min()) / (cam.max() - cam.min() + 1e-8)
