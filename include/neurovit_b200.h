@@ -152,6 +152,14 @@ int nv_batch_sum(const float* in, int64_t batch_stride, float* out, int B, int64
 int nv_mean_pool_fwd(const float* x, float* pooled, int B, int N, int D, void* stream);
 int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int N, int D, void* stream);
 
+/* ---- fused AdamW over flat buffers -------------------------------------------------------------------
+ * replaces: optim.AdamW(model.parameters(), lr, weight_decay) + optimizer.step() at src/Trainer.py:31,75
+ * (torch semantics: p *= 1 - lr*wd; m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)) when parameters,
+ * gradients and moments live in flat fp32 buffers of n elements (n % 4 == 0). p_bf16 (optional) receives the
+ * bf16 copy of the updated parameters — the weight cache the next forward's GEMMs read. step counts from 1. */
+int nv_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* ---- 4D temporal head -------------------------------------------------------------------------------
  * replaces: TemporalTransformer (nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True),
  * post-norm, ReLU, dim_ff = F) + mean over T + ProjectionHead Linear(2,2); NeuroEncoder.py:63-66,207-230.

@@ -63,14 +63,28 @@ class WeightCache:
 
     def __init__(self):
         self._c = collections.OrderedDict()
+        self._pinned = {}   # storage address -> [version, bf16 view kept current by trainer.FlatAdamW]
+        self.epoch = 0      # bumped by optimizers that update parameters through raw pointers (no version bump)
+
+    def pin(self, w: torch.Tensor, view: torch.Tensor):
+        """`view` (bf16, same shape) is w's bf16 copy and is rewritten by the fused optimizer kernel on every step;
+        the cache only re-casts into it when w changes through torch (load_state_dict, manual edits)."""
+        self._pinned[(w.data_ptr(), tuple(w.shape))] = [w._version, view, w.detach()]
 
     def bf16(self, w: torch.Tensor, pad_k: int = 0) -> torch.Tensor:
+        if not pad_k or pad_k == w.shape[1]:
+            pin = self._pinned.get((w.data_ptr(), tuple(w.shape)))
+            if pin is not None:
+                if pin[0] != w._version:
+                    ops.cast_bf16(w.detach(), out=pin[1])
+                    pin[0] = w._version
+                return pin[1]
         # Keyed by the storage address. Every entry keeps a reference to (an alias of) the source tensor, so
         # that address cannot be handed to a different tensor while the entry lives — a freed model's weights
         # can never be mistaken for a new model's. Entries are dropped LRU.
         key = (w.data_ptr(), tuple(w.shape), pad_k)
         hit = self._c.get(key)
-        ver = w._version
+        ver = (w._version, self.epoch)
         if hit is not None and hit[0] == ver:
             self._c.move_to_end(key)
             return hit[1]
@@ -92,6 +106,7 @@ class WeightCache:
 
     def clear(self):
         self._c.clear()
+        self._pinned.clear()
 
 
 # ------------------------------------------------------------------------------- bf16 grad side-car

@@ -110,6 +110,16 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     _lib.call("nv_gemm_bf16", *args)
 
 
+def adamw_flat(p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, weight_decay, step):
+    """One fused AdamW step over flat fp32 buffers (+ bf16 copy of the new parameters)."""
+    _dev(p)
+    n = p.numel()
+    assert all(t.dtype == F32 and t.is_contiguous() and t.numel() == n for t in (p, g, m, v))
+    assert p_bf16 is None or (p_bf16.dtype == BF16 and p_bf16.numel() == n and p_bf16.is_contiguous())
+    _lib.call("nv_adamw_flat", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), n, float(lr), float(beta1),
+              float(beta2), float(eps), float(weight_decay), int(step), _stream())
+
+
 def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, colsum=None):
     """v = x * keep / (1 - p) with the (seed, stream, row * N + col) mask of the GEMM epilogues; out = v (+ residual);
     colsum += column sums of v. x: fp32 [M, N] (unit inner stride), N % 8 == 0."""

@@ -11,6 +11,8 @@ Inference shards the batch with no communication.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -34,7 +36,10 @@ class FlatGradBuckets:
 
     ALIGN = 32  # elements (128 B)
 
-    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None, flatten_params: bool = False):
+        """flatten_params: also move the parameters themselves into one flat fp32 buffer with the same slot layout
+        (p.data becomes a view of it; values, names and state_dict are unchanged) so FlatAdamW can update
+        everything with one kernel."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -43,6 +48,17 @@ class FlatGradBuckets:
         total = sum(pad(p.numel()) for p in order)
         dev = order[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_params = None
+        if flatten_params:
+            self.flat_params = torch.zeros(total, device=dev, dtype=torch.float32)
+            off = 0
+            with torch.no_grad():
+                for p in order:
+                    n = p.numel()
+                    self.flat_params[off:off + n].copy_(p.detach().reshape(-1))
+                    p.data = self.flat_params[off:off + n].view_as(p)
+                    off += pad(n)
+        self.slot_of = {}      # parameter -> (offset, numel) in the flat buffers
         self.bucket_of = {}
         self.buckets = []  # [start, end, n_params]
         self.sink_views = {}   # parameter storage address -> its .grad view
@@ -51,6 +67,7 @@ class FlatGradBuckets:
         for p in order:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
+            self.slot_of[p] = (off, n)
             self.bucket_of[p] = len(self.buckets)
             if p.is_contiguous():
                 self.sink_views[p.data_ptr()] = p.grad
@@ -104,16 +121,64 @@ class FlatGradBuckets:
             h.remove()
 
 
+class FlatAdamW:
+    """torch.optim.AdamW semantics (src/Trainer.py:31: lr, weight_decay; default betas / eps) as ONE kernel over the
+    trainer's flat parameter / gradient / moment buffers (nv_adamw_flat), which also rewrites the bf16 weight copies
+    the next forward's tensor-core GEMMs read. CUDA only."""
+
+    def __init__(self, buckets: FlatGradBuckets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        from . import ops
+        from .functional import engine
+        assert buckets.flat_params is not None, "FlatAdamW needs FlatGradBuckets(flatten_params=True)"
+        self.buckets = buckets
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(buckets.flat)
+        self.v = torch.zeros_like(buckets.flat)
+        self.t = 0
+        self._ops = ops
+        self.shadow = torch.empty(buckets.flat.numel(), device=buckets.flat.device, dtype=torch.bfloat16)
+        ops.cast_bf16(buckets.flat_params, out=self.shadow)
+        self._wc = engine("bf16").wc
+        for p, (off, n) in buckets.slot_of.items():
+            if p.dim() == 2:  # GEMM weights: their bf16 operand copy lives in the shadow buffer from now on
+                self._wc.pin(p, self.shadow[off:off + n].view_as(p))
+
+    def step(self):
+        self.t += 1
+        b = self.buckets
+        self._ops.adamw_flat(b.flat_params, b.flat, self.m, self.v, self.shadow, lr=self.lr, beta1=self.betas[0],
+                             beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self.t)
+        self._wc.epoch += 1  # derived copies that are not pinned (K-padded patch weights) must be re-cast
+
+    def zero_grad(self, set_to_none=False):
+        self.buckets.zero()
+
+    def state_dict(self):
+        return {"t": self.t, "m": self.m, "v": self.v, "lr": self.lr, "betas": self.betas, "eps": self.eps,
+                "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.t = int(sd["t"])
+        self.m.copy_(sd["m"])
+        self.v.copy_(sd["v"])
+
+
 class DataParallelTrainer:
     """model: any nn.Module (the drop-in ViT / NeuroEncoder on GPU; a plain torch module in the CPU gloo
     tests). step(inputs, labels) runs forward, CrossEntropy, backward with overlapped bucketed all-reduce
     and the optimizer step on this rank's shard, and returns the (local) loss tensor without syncing."""
 
-    def __init__(self, model, optimizer=None, lr=1e-4, weight_decay=0.01, bucket_mb=32, group=None):
+    def __init__(self, model, optimizer=None, lr=1e-4, weight_decay=0.01, bucket_mb=None, group=None):
+        if bucket_mb is None:
+            bucket_mb = int(os.environ.get("NEUROVIT_BUCKET_MB", "80"))
         self.model = model
-        self.buckets = FlatGradBuckets(list(model.parameters()), bucket_mb << 20, group)
+        plist = list(model.parameters())
+        own_adamw = optimizer is None and plist[0].is_cuda and os.environ.get("NEUROVIT_TORCH_ADAMW") != "1"
+        self.buckets = FlatGradBuckets(plist, bucket_mb << 20, group, flatten_params=own_adamw)
         params = self.buckets.params
-        if optimizer is None:
+        if own_adamw:
+            optimizer = FlatAdamW(self.buckets, lr=lr, weight_decay=weight_decay)
+        elif optimizer is None:
             fused = params[0].is_cuda
             optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=fused)
         self.optimizer = optimizer

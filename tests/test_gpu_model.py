@@ -271,3 +271,32 @@ def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode):
     m.eval()
     a, b = m(x.to(DEV)), m(x.to(DEV))
     assert torch.equal(a, b)
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """trainer.FlatAdamW (one kernel over flat params / grads / moments + bf16 weight-copy refresh) against
+    torch.optim.AdamW on the same model, data and hyper-parameters, several steps."""
+    import copy
+    from neurovit_b200.trainer import DataParallelTrainer, FlatAdamW
+    torch.manual_seed(31)
+    ctor = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=2, dim=128, depth=2,
+                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    ma = ViT(**ctor).to(DEV)
+    mb = copy.deepcopy(ma)
+    x = torch.randn(6, 1, 16, 16, 16, device=DEV)
+    y = torch.randint(0, 2, (6,), device=DEV)
+    ta = DataParallelTrainer(ma, lr=1e-3, weight_decay=0.05)
+    assert isinstance(ta.optimizer, FlatAdamW)
+    tb = DataParallelTrainer(mb, optimizer=torch.optim.AdamW(mb.parameters(), lr=1e-3, weight_decay=0.05))
+    for _ in range(4):
+        la, lb = ta.step(x, y), tb.step(x, y)
+    torch.cuda.synchronize()
+    assert abs(la.item() - lb.item()) < 2e-3
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert (pa - pb).abs().max().item() < 1e-3 + 2e-3 * pb.abs().max().item(), k   # atomics-order noise only
+    # state_dict still has the reference's 78 tensors and round-trips
+    sd = ma.state_dict()
+    mc = ViT(**ctor).to(DEV)
+    mc.load_state_dict(sd, strict=True)
+    ma.eval(); mc.eval()
+    assert rel(mc(x), ma(x)) < 1e-3
