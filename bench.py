@@ -295,7 +295,7 @@ def run_ours(args, cfg):
 
         enc = Enc().to(dev)
     enc.train()
-    trainer = DataParallelTrainer(enc, lr=1e-4, weight_decay=0.01)
+    trainer = DataParallelTrainer(enc, lr=1e-4, weight_decay=0.01, graph=not args.no_graph)
 
     g = torch.Generator().manual_seed(42 + rank)
     n_buf = 3  # rotate host/device input buffers; one batch (50 MB) + activations (GBs) far exceed the 126 MB L2
@@ -370,7 +370,9 @@ def run_ours(args, cfg):
     ops.PROFILE.reset()
     ops.PROFILE.enabled = not args.no_kernel_events
     prof_steps = min(args.steps, 10)
+    graphed, trainer.use_graph = trainer.use_graph, False   # events cannot be recorded inside a replayed graph
     ms_prof = timed(resident_loop, prof_steps)
+    trainer.use_graph = graphed
     ops.PROFILE.enabled = False
     gemm_ms, gemm_flops, gemm_calls = ops.PROFILE.summary()
     e2e_loop(min(2, args.warmup))
@@ -387,7 +389,8 @@ def run_ours(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args, cfg, B), "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"dp{world}", "dropout": DROPOUT, "optimizer": "AdamW(fused)",
+                       "parallelism": f"dp{world}", "dropout": DROPOUT, "optimizer": "AdamW (FlatAdamW, one kernel)",
+                       "cuda_graph": bool(trainer.use_graph),
                        "l2_policy": "inputs+activations per step (>3 GB) exceed the 126 MB L2; 3 rotating input buffers",
                        "model_tflops_per_gpu": model_tflops,
                        "model_frac_of_peak": model_tflops / peaks["tflops"]},
@@ -435,6 +438,7 @@ def main():
     ap.add_argument("--dropout", type=float, default=DROPOUT, help="dropout p at all sites, training mode (both arms)")
     ap.add_argument("--gradcam", default="device", choices=["host", "device", "off"],
                     help="cfg5 only: NeuroEncoder Grad-CAM capture ('host' = the reference's per-step D2H copies)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of one CUDA graph")
     ap.add_argument("--no-kernel-events", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -156,9 +156,18 @@ int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int 
  * replaces: optim.AdamW(model.parameters(), lr, weight_decay) + optimizer.step() at src/Trainer.py:31,75
  * (torch semantics: p *= 1 - lr*wd; m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)) when parameters,
  * gradients and moments live in flat fp32 buffers of n elements (n % 4 == 0). p_bf16 (optional) receives the
- * bf16 copy of the updated parameters — the weight cache the next forward's GEMMs read. step counts from 1. */
+ * bf16 copy of the updated parameters — the weight cache the next forward's GEMMs read. step counts from 1;
+ * step_dev (optional): the step count as a device float (read by the kernel instead of `step`, so a captured
+ * CUDA graph keeps counting — bump it with nv_counter_add before the launch). */
 int nv_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
-                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  const float* step_dev, void* stream);
+/* *counter += inc on the stream (device-side step counters of captured graphs) */
+int nv_counter_add(float* counter, float inc, void* stream);
+/* Every dropout mask is Philox(seed + epoch * c, ...) where epoch is a device-resident counter (0 until advanced):
+ * a training step captured in a CUDA graph ends with nv_rng_epoch_advance so each replay draws new masks even
+ * though the host-drawn seeds are baked into the graph. Forward and backward of a step share the epoch. */
+int nv_rng_epoch_advance(void* stream);
 
 /* ---- 4D temporal head -------------------------------------------------------------------------------
  * replaces: TemporalTransformer (nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True),

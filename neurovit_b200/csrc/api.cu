@@ -11,7 +11,10 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
                       float dropout_p, uint64_t dropout_seed, int dropout_stream, cudaStream_t stream);
 int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_bf16, int64_t n, float lr, float beta1,
-                         float beta2, float eps, float weight_decay, int step, cudaStream_t stream);
+                         float beta2, float eps, float weight_decay, int step, const float* step_dev,
+                         cudaStream_t stream);
+int nv_rng_epoch_advance_launch(cudaStream_t stream);
+int nv_counter_add_launch(float* counter, float inc, cudaStream_t stream);
 int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p,
                       uint64_t seed, int stream_id, cudaStream_t stream);
@@ -95,9 +98,12 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int64_t
 }
 
 int nv_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int step, void* stream) {
-  return nv_adamw_flat_launch(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, ST(stream));
+                  float beta2, float eps, float weight_decay, int step, const float* step_dev, void* stream) {
+  return nv_adamw_flat_launch(p, g, m, v, (bf16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay, step, step_dev,
+                              ST(stream));
 }
+int nv_rng_epoch_advance(void* stream) { return nv_rng_epoch_advance_launch(ST(stream)); }
+int nv_counter_add(float* counter, float inc, void* stream) { return nv_counter_add_launch(counter, inc, ST(stream)); }
 
 int nv_dropout(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32, int64_t ld_f32,
                void* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p, int64_t seed, int stream_id,

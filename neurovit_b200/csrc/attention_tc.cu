@@ -101,6 +101,7 @@ struct Common {
   uint32_t drop_thr;  // 0 = off
   float keep_scale;   // 1 / (1 - p_eff)
   uint64_t seed;
+  const uint64_t* epoch;  // device epoch counter added to the seed (CUDA-graph replays)
   uint32_t* mask;
   int mask_words;     // ceil(N / 32)
 };
@@ -145,7 +146,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     }
     rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
     if (DROPOUT) {
-      const uint32_t km = nv_keep_bits8(c.seed, mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
+      const uint32_t km = nv_keep_bits8(nv_seed(c.seed, c.epoch), mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
                                         c.drop_thr);
       km32 |= km << (8 * g8);
 #pragma unroll
@@ -886,6 +887,7 @@ int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, in
 int fill_common(Common& c, int N, int H, float scale, float dropout_p, uint64_t seed, uint32_t* mask) {
   NV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p %f out of range [0, 1)", dropout_p);
   c.N = N; c.H = H; c.scale = scale; c.seed = seed;
+  c.epoch = dropout_p > 0.f ? nv_rng_epoch_dev() : nullptr;
   c.drop_thr = nv_dropout_threshold(dropout_p);
   c.keep_scale = nv_dropout_keep_scale(c.drop_thr);
   c.mask = mask;

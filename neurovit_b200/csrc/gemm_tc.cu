@@ -56,6 +56,7 @@ struct GemmParams {
   uint32_t drop_thr;  // 0 = off
   float keep_scale;
   uint64_t drop_seed;
+  const uint64_t* drop_epoch;  // device epoch counter added to the seed (CUDA-graph replays)
   uint32_t drop_stream;
 };
 
@@ -227,10 +228,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   // slice, so each lane draws the bits of four of its eight row slices and fetches the rest from its neighbour
   uint32_t kb[4] = {0u, 0u, 0u, 0u};
   if (DROP) {
+    const uint64_t seed = nv_seed(p.drop_seed, p.drop_epoch);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int gm_t = row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r;
-      kb[t] = nv_keep_bits8(p.drop_seed, ((uint64_t)gm_t * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
+      kb[t] = nv_keep_bits8(seed, ((uint64_t)gm_t * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
     }
   }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -642,6 +644,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   p.drop_thr = nv_dropout_threshold(dropout_p);
   p.keep_scale = nv_dropout_keep_scale(p.drop_thr);
   p.drop_seed = dropout_seed;
+  p.drop_epoch = p.drop_thr != 0 ? nv_rng_epoch_dev() : nullptr;
   p.drop_stream = (uint32_t)dropout_stream;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;

@@ -226,7 +226,7 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
                    float* __restrict__ dx, int64_t ld_dx, RowMap dxmap, bf16* __restrict__ dx_bf16,
                    int64_t ld_dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ colsum_out, int M, int D, int stages, uint32_t side_thr, float side_ks,
-                   uint64_t side_seed, uint32_t side_stream) {
+                   uint64_t side_seed_host, uint32_t side_stream, const uint64_t* side_epoch) {
   extern __shared__ __align__(128) uint8_t lnp_smem[];
   __shared__ __align__(16) float red[2][2 * LNP_ROWS][LNB_MAX_WARPS];
   __shared__ __align__(8) uint64_t full[LNP_MAX_STAGES];
@@ -352,6 +352,7 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
 #pragma unroll
     for (int k = 0; k < LNP_ROWS; ++k) keep4[k] = 0xFu;
     if (side_thr != 0) {
+      const uint64_t side_seed = nv_seed(side_seed_host, side_epoch);
       static_assert(LNP_ROWS == 2, "pair exchange below assumes two rows per iteration");
       const int rmine = min(r0 + (c & 1), M - 1);
       const uint32_t mine = nv_keep_bits8(side_seed, ((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3, side_stream, side_thr);
@@ -415,7 +416,8 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
   if (getenv("NV_LNP_NOSTORE")) { dx = nullptr; dx_bf16 = nullptr; }
   kern<<<grid, threads + 32, smem, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
                                              dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, stages, side_thr,
-                                             nv_dropout_keep_scale(side_thr), side_seed, (uint32_t)side_stream);
+                                             nv_dropout_keep_scale(side_thr), side_seed, (uint32_t)side_stream,
+                                             side_thr != 0 ? nv_rng_epoch_dev() : nullptr);
   return NV_OK;
 }
 

@@ -102,7 +102,8 @@ __global__ void mean_pool_bwd_kernel(const float* __restrict__ dpooled, float* _
 __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, const float* __restrict__ residual,
                                int64_t ld_res, float* __restrict__ out_f32, int64_t ld_f32, bf16* __restrict__ out_bf16,
                                int64_t ld_bf16, float* __restrict__ colsum, int M, int N, uint32_t thr, float ks,
-                               uint64_t seed, uint32_t stream_id) {
+                               uint64_t seed_host, uint32_t stream_id, const uint64_t* epoch) {
+  const uint64_t seed = nv_seed(seed_host, epoch);
   const int n8 = N >> 3;  // one Philox call per thread and row: 8 consecutive columns
   constexpr int R = 4;     // rows in flight per thread (independent 32-byte loads)
   for (int c = threadIdx.x; c < n8; c += blockDim.x) {
@@ -159,7 +160,13 @@ __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, cons
 // instead of ~80 per-tensor chunks in three multi-tensor launches and 25 cast kernels.
 __global__ void adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                   float* __restrict__ v, bf16* __restrict__ p_bf16, int64_t n4, float lr, float beta1,
-                                  float beta2, float eps, float decay, float inv_bc1, float inv_sqrt_bc2) {
+                                  float beta2, float eps, float decay, float inv_bc1, float inv_sqrt_bc2,
+                                  const float* __restrict__ step_dev) {
+  if (step_dev) {  // step count kept on the device (CUDA-graph replays): bias corrections computed here
+    const float t = __ldg(step_dev);
+    inv_bc1 = 1.0f / (1.0f - powf(beta1, t));
+    inv_sqrt_bc2 = rsqrtf(1.0f - powf(beta2, t));
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     const float4 gg = reinterpret_cast<const float4*>(g)[i];
@@ -263,15 +270,18 @@ int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int
   int grid = nv_num_sms() * 8;
   if (grid > (M + 3) / 4) grid = (M + 3) / 4;
   dropout_kernel<<<grid, threads, 0, stream>>>(in, ld_in, residual, ld_res, out_f32, ld_f32, out_bf16, ld_bf16, colsum,
-                                               M, N, thr, nv_dropout_keep_scale(thr), seed, (uint32_t)stream_id);
+                                               M, N, thr, nv_dropout_keep_scale(thr), seed, (uint32_t)stream_id,
+                                               thr != 0 ? nv_rng_epoch_dev() : nullptr);
   NV_LAUNCH_CHECK("dropout_kernel");
   return NV_OK;
 }
 
 int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_bf16, int64_t n, float lr, float beta1,
-                         float beta2, float eps, float weight_decay, int step, cudaStream_t stream) {
+                         float beta2, float eps, float weight_decay, int step, const float* step_dev,
+                         cudaStream_t stream) {
   NV_REQUIRE(n >= 0 && n % 4 == 0, "adamw: flat length %lld must be a multiple of 4", (long long)n);
-  NV_REQUIRE(step >= 1, "adamw: step counts from 1");
+  NV_REQUIRE(step >= 1 || step_dev != nullptr, "adamw: step counts from 1");
+  if (step < 1) step = 1;
   NV_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
              "adamw: buffers must be 16-byte aligned");
@@ -281,7 +291,7 @@ int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_b
   int grid = nv_num_sms() * 8;
   if ((int64_t)grid * 256 > n4) grid = (int)((n4 + 255) / 256);
   adamw_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, p_bf16, n4, lr, beta1, beta2, eps, 1.0f - lr * weight_decay,
-                                              (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)));
+                                              (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), step_dev);
   NV_LAUNCH_CHECK("adamw_flat_kernel");
   return NV_OK;
 }

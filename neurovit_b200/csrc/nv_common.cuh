@@ -41,6 +41,9 @@ int nv_encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const 
                    const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                    CUtensorMapSwizzle swizzle);
 
+// device address of the per-device dropout epoch counter (8 bytes, zero-initialised on first use; nv_host.cu)
+const uint64_t* nv_rng_epoch_dev();
+
 typedef __nv_bfloat16 bf16;
 
 // ---------------------------------------------------------------------------------------------

@@ -74,3 +74,41 @@ int nv_encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const 
   }
   return NV_OK;
 }
+
+// ---- dropout epoch counter -----------------------------------------------------------------------------
+namespace {
+std::mutex g_epoch_mu;
+uint64_t* g_epoch[64] = {nullptr};
+__global__ void epoch_add_kernel(uint64_t* e, uint64_t inc) { *e += inc; }
+__global__ void counter_add_kernel(float* c, float inc) { *c += inc; }
+}  // namespace
+
+const uint64_t* nv_rng_epoch_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (g_epoch[dev] == nullptr) {
+    std::lock_guard<std::mutex> lk(g_epoch_mu);
+    if (g_epoch[dev] == nullptr) {
+      uint64_t* p = nullptr;
+      if (cudaMalloc(&p, sizeof(uint64_t)) != cudaSuccess) return nullptr;
+      cudaMemset(p, 0, sizeof(uint64_t));
+      g_epoch[dev] = p;
+    }
+  }
+  return g_epoch[dev];
+}
+
+int nv_rng_epoch_advance_launch(cudaStream_t stream) {
+  uint64_t* e = const_cast<uint64_t*>(nv_rng_epoch_dev());
+  NV_REQUIRE(e != nullptr, "rng epoch: allocation failed");
+  epoch_add_kernel<<<1, 1, 0, stream>>>(e, 1);
+  NV_LAUNCH_CHECK("epoch_add_kernel");
+  return NV_OK;
+}
+
+int nv_counter_add_launch(float* counter, float inc, cudaStream_t stream) {
+  NV_REQUIRE(counter != nullptr, "counter_add: null pointer");
+  counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+  NV_LAUNCH_CHECK("counter_add_kernel");
+  return NV_OK;
+}

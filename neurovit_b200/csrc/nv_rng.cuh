@@ -57,6 +57,12 @@ __device__ __forceinline__ uint32_t nv_keep_bits8(uint64_t seed, uint64_t group,
   }
   return m;
 }
+// Effective seed of a launch: the host-drawn seed plus a device-resident epoch counter (nv_rng_epoch_*), so a
+// CUDA graph that bakes the host seeds in still draws fresh masks on every replay — the captured step ends
+// with nv_rng_epoch_advance. Forward and backward of one step see the same epoch.
+__device__ __forceinline__ uint64_t nv_seed(uint64_t seed, const uint64_t* epoch) {
+  return epoch ? seed + __ldg(epoch) * 0x9E3779B97F4A7C15ull : seed;
+}
 // keep-bits of the 4 consecutive elements [idx, idx + 4), idx a multiple of 4 (element-indexed dropout sites:
 // GEMM epilogues and the element-wise kernel share this so forward and backward regenerate the same mask)
 __device__ __forceinline__ uint32_t nv_keep_bits4(uint64_t seed, uint64_t idx, uint32_t stream, uint32_t thr) {

@@ -25,6 +25,7 @@ struct TDrop {
   uint32_t thr[4];
   float ks[4];
   uint64_t seed;
+  const uint64_t* epoch;  // device epoch counter added to the seed (CUDA-graph replays)
 };
 // keep-scale (0 or 1/(1-p)) of one element
 __device__ __forceinline__ float tkeep(const TDrop& d, int site, uint64_t idx) {
@@ -122,7 +123,9 @@ __device__ void temporal_attn_fwd(const float* xb, const TParams& P, int T, floa
 
 __global__ void __launch_bounds__(TT)
 temporal_fwd_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ out,
-                    float* __restrict__ seq_out, float* __restrict__ saved, int T, int F, float eps, const TDrop drop) {
+                    float* __restrict__ seq_out, float* __restrict__ saved, int T, int F, float eps, const TDrop drop_in) {
+  TDrop drop = drop_in;
+  drop.seed = nv_seed(drop_in.seed, drop_in.epoch);
   extern __shared__ float sm[];
   __shared__ float red[TT / 32];
   float *xs = sm, *q = sm + 2 * T, *k = sm + 4 * T, *v = sm + 6 * T, *o = sm + 8 * T;
@@ -163,7 +166,9 @@ temporal_fwd_kernel(const float* __restrict__ x, const float* __restrict__ param
 __global__ void __launch_bounds__(TT)
 temporal_bwd_kernel(const float* __restrict__ x, const float* __restrict__ params, const float* __restrict__ saved,
                     const float* __restrict__ dout, const float* __restrict__ dseq, float* __restrict__ dparams_ws,
-                    float* __restrict__ dx_out, int T, int F, float eps, const TDrop drop) {
+                    float* __restrict__ dx_out, int T, int F, float eps, const TDrop drop_in) {
+  TDrop drop = drop_in;
+  drop.seed = nv_seed(drop_in.seed, drop_in.epoch);
   extern __shared__ float sm[];
   __shared__ float red[TT / 32];
   // [T][2] arrays: xs q k v o | x1 df dx1 da dq dk dv
@@ -348,6 +353,9 @@ int fill_tdrop(TDrop& d, const float* p4, uint64_t seed) {
     d.ks[i] = nv_dropout_keep_scale(d.thr[i]);
   }
   d.seed = seed;
+  bool any = false;
+  for (int i = 0; i < 4; ++i) any = any || d.thr[i] != 0;
+  d.epoch = any ? nv_rng_epoch_dev() : nullptr;
   return NV_OK;
 }
 

@@ -110,14 +110,26 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     _lib.call("nv_gemm_bf16", *args)
 
 
-def adamw_flat(p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, weight_decay, step):
-    """One fused AdamW step over flat fp32 buffers (+ bf16 copy of the new parameters)."""
+def rng_epoch_advance():
+    """Advance the device-side dropout epoch (end of a training step that may be replayed from a CUDA graph)."""
+    _lib.call("nv_rng_epoch_advance", _stream())
+
+
+def counter_add(counter, inc=1.0):
+    _dev(counter)
+    assert counter.dtype == F32 and counter.numel() == 1
+    _lib.call("nv_counter_add", _ptr(counter), float(inc), _stream())
+
+
+def adamw_flat(p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, weight_decay, step, step_dev=None):
+    """One fused AdamW step over flat fp32 buffers (+ bf16 copy of the new parameters). step_dev: device float
+    holding the step count (read instead of `step`)."""
     _dev(p)
     n = p.numel()
     assert all(t.dtype == F32 and t.is_contiguous() and t.numel() == n for t in (p, g, m, v))
     assert p_bf16 is None or (p_bf16.dtype == BF16 and p_bf16.numel() == n and p_bf16.is_contiguous())
     _lib.call("nv_adamw_flat", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16), n, float(lr), float(beta1),
-              float(beta2), float(eps), float(weight_decay), int(step), _stream())
+              float(beta2), float(eps), float(weight_decay), int(step), _ptr(step_dev), _stream())
 
 
 def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, colsum=None):

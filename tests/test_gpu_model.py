@@ -300,3 +300,31 @@ def test_flat_adamw_matches_torch_adamw():
     mc.load_state_dict(sd, strict=True)
     ma.eval(); mc.eval()
     assert rel(mc(x), ma(x)) < 1e-3
+
+
+def test_graphed_step_matches_eager_and_redraws_dropout():
+    """DataParallelTrainer(graph=True): one CUDA graph per step. Without dropout the trajectory must follow the eager
+    trainer; with dropout every replay must draw new masks (device-side epoch) — the losses on the same batch differ."""
+    import copy
+    from neurovit_b200.trainer import DataParallelTrainer
+    torch.manual_seed(41)
+    ctor = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=2, dim=128, depth=2,
+                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    ma = ViT(**ctor).to(DEV)
+    mb = copy.deepcopy(ma)
+    xs = [torch.randn(8, 1, 16, 16, 16, device=DEV) for _ in range(3)]
+    ys = [torch.randint(0, 2, (8,), device=DEV) for _ in range(3)]
+    ta = DataParallelTrainer(ma, lr=1e-3, graph=True)
+    tb = DataParallelTrainer(mb, lr=1e-3, graph=False)
+    for i in range(5):
+        la = ta.step(xs[i % 3], ys[i % 3]).item()
+        lb = tb.step(xs[i % 3], ys[i % 3]).item()
+        assert abs(la - lb) < 5e-3, (i, la, lb)
+    assert ta.optimizer.t == 5 and tb.optimizer.t == 5   # the capture's warm-up steps were rolled back
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert (pa - pb).abs().max().item() < 2e-3 + 2e-3 * pb.abs().max().item(), k
+    # dropout: same batch, consecutive replays -> different masks -> different losses
+    mc = ViT(**{**ctor, "dropout": 0.3, "emb_dropout": 0.3}).to(DEV)
+    tc = DataParallelTrainer(mc, lr=0.0, weight_decay=0.0, graph=True)
+    losses = [tc.step(xs[0], ys[0]).item() for _ in range(4)]
+    assert len({round(v, 6) for v in losses}) == 4, losses
