@@ -179,7 +179,8 @@ class DataParallelTrainer:
         on its first call and replayed afterwards — the ~300 kernel launches of a step then cost one launch on the
         host and ~1 us instead of ~3 us of idle GPU time each. Needs static shapes (same batch size every step), the
         built-in FlatAdamW optimizer and CUDA tensors; inputs are copied into static buffers. Dropout masks still
-        change every step (device-side epoch counter, nv_rng_epoch_advance)."""
+        change every step (device-side epoch counter, nv_rng_epoch_advance). Ignored (eager launches) when the
+        process group has more than one rank."""
         if bucket_mb is None:
             bucket_mb = int(os.environ.get("NEUROVIT_BUCKET_MB", "80"))
         self.model = model
@@ -194,7 +195,9 @@ class DataParallelTrainer:
             optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=fused)
         self.optimizer = optimizer
         self.criterion = torch.nn.CrossEntropyLoss()
-        self.use_graph = bool(graph)
+        # single-process only for now: capturing the bucketed NCCL all-reduces that the backward thread launches
+        # hangs in the capture (seen at world_size 2); multi-GPU runs launch kernel by kernel
+        self.use_graph = bool(graph) and self.buckets.world == 1
         if self.use_graph and not isinstance(optimizer, FlatAdamW):
             raise ValueError("graph=True needs the built-in FlatAdamW optimizer (CUDA parameters, optimizer=None)")
         self._graph = None
