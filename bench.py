@@ -400,7 +400,11 @@ def run_ours(args, cfg):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 linear fwd/dgrad/wgrad)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["tflops"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["tflops"]) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of the
+                         # qkv-forward instance (M=24640 N=1536 K=1024; algorithmic 129 MB): profiles/r01_summary.md §3
+                         "traffic": 84.0e6 if args.config == "cfgA" and B == 64 else None,
+                         "traffic_source": "profiles/r01_summary.md §3, r01_gemm1 (qkv forward, one launch)",
                          "peak_source": f"{peaks['src']} bf16_tflops_sustained",
                          "launches_timed": gemm_calls, "avg_launch_ms": gemm_ms / max(gemm_calls, 1),
                          "share_of_step": gemm_ms / ms_prof if ms_prof > 0 else None,
