@@ -371,6 +371,10 @@ def run_ours(args, cfg):
     ops.PROFILE.enabled = not args.no_kernel_events
     prof_steps = min(args.steps, 10)
     graphed, trainer.use_graph = trainer.use_graph, False   # events cannot be recorded inside a replayed graph
+    ops.PROFILE.enabled = False
+    resident_loop(2)                                        # the eager path's own allocations, outside the graph pool
+    ops.PROFILE.reset()
+    ops.PROFILE.enabled = not args.no_kernel_events
     ms_prof = timed(resident_loop, prof_steps)
     trainer.use_graph = graphed
     ops.PROFILE.enabled = False

@@ -233,9 +233,13 @@ class DataParallelTrainer:
         for dst, src in zip((self.buckets.flat_params, opt.m, opt.v, opt.t_dev, opt.shadow), snap):
             dst.copy_(src)
         torch.cuda.synchronize()
+        from . import _lib
         self._graph = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES.count
         with torch.cuda.graph(self._graph):
             self._sloss = self._eager_step(self._sx, self._sy)
+        self._graph_launches = _lib.LAUNCHES.count - n0  # C-ABI kernels recorded in the graph = launched per replay
+        _lib.LAUNCHES.count = n0
 
     def step(self, inputs, labels):
         if not self.use_graph:
@@ -247,6 +251,8 @@ class DataParallelTrainer:
         self._sx.copy_(inputs, non_blocking=True)
         self._sy.copy_(labels, non_blocking=True)
         self._graph.replay()
+        from . import _lib
+        _lib.LAUNCHES.count += self._graph_launches
         return self._sloss
 
     @torch.no_grad()
