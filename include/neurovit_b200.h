@@ -52,7 +52,13 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
                  void* out_pre, int64_t ld_pre, float* colsum,
                  int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
-                 float dropout_p, int64_t dropout_seed, int dropout_stream, void* stream);
+                 float dropout_p, int64_t dropout_seed, int dropout_stream, const void* dropout_bits, void* stream);
+
+/* Keep bits drawn ahead of time: out[g] (one byte) = the 8 keep bits of elements [8g, 8g+8) of a dropout site
+ * with the given (seed, stream_id) — exactly the bits the consumers would draw inline. nv_gemm_bf16
+ * (dropout_bits), nv_layernorm_bwd (side_drop_bits) and nv_attention_fwd (drop_mask_ready) take them, which moves
+ * the Philox arithmetic out of their epilogues / softmax rows onto a side stream. n_groups % 4 == 0. */
+int nv_dropout_bits(void* out, int64_t n_groups, float p, int64_t seed, int stream_id, void* stream);
 
 /* ---- element-wise dropout ---------------------------------------------------------------------------
  * replaces: nn.Dropout on the embedding (vit_3d.py:100,119) and, in backward, the mask applied to the
@@ -97,7 +103,8 @@ int nv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t ld_dy, int dy_group
                      float* dx, int64_t ld_dx, int dx_group, int dx_gstride, int dx_goff,
                      void* dx_bf16, int64_t ld_dxb,
                      float* dgamma, float* dbeta, float* colsum, int M, int D,
-                     float side_drop_p, int64_t side_drop_seed, int side_drop_stream, void* stream);
+                     float side_drop_p, int64_t side_drop_seed, int side_drop_stream, const void* side_drop_bits,
+                     void* stream);
 /* x[b, 0, :] = cls + pos[0]  (vit_3d.py:116-118) */
 int nv_cls_row(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D, void* stream);
 
@@ -121,11 +128,13 @@ int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_
  * [B, N, H*64]; lse [B,H,N] fp32 is saved for backward. head_dim must be 64 (bf16 flash kernels,
  * tcgen05 / TMEM). dropout_p > 0 applies nn.Dropout to the probabilities (vit_3d.py:56): forward draws the
  * keep bits from (seed) and saves them in drop_mask, uint32 [B*H, N, ceil(N/32)] (bit k of word w of row q =
- * score (q, 32w+k) survives); backward reads them. drop_mask may be NULL when dropout_p == 0. */
+ * score (q, 32w+k) survives); backward reads them. drop_mask may be NULL when dropout_p == 0.
+ * drop_mask_ready = 1: drop_mask already holds the bits (nv_dropout_bits with the same seed, stream 0, over
+ * B*H*N*4*ceil(N/32) groups) and forward reads them instead of drawing them inside its softmax rows. */
 int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse,
                      int B, int N, int H, int head_dim, float scale, float dropout_p, int64_t seed,
-                     void* drop_mask, void* stream);
+                     void* drop_mask, int drop_mask_ready, void* stream);
 /* delta_ws: fp32 workspace of B*H*N elements */
 int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      const void* o, const void* dO, int64_t o_batch_stride, int64_t o_row_stride,

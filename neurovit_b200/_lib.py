@@ -23,7 +23,8 @@ SIGNATURES = {
     "nv_version": [],
     "nv_device_check": [],
     "nv_gemm_bf16": [_i, _i, _i, _i, _i, _p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p,
-                     _i, _i, _f, _i, _i, _i, _f, _l, _i, _p],
+                     _i, _i, _f, _i, _i, _i, _f, _l, _i, _p, _p],
+    "nv_dropout_bits": [_p, _l, _f, _l, _i, _p],
     "nv_adamw_flat": [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _p],
     "nv_counter_add": [_p, _f, _p],
     "nv_rng_epoch_advance": [_p],
@@ -33,11 +34,11 @@ SIGNATURES = {
     "nv_layernorm_fwd": [_p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _i, _l, _i, _i, _i, _p, _p,
                          _i, _i, _f, _p],
     "nv_layernorm_bwd": [_p, _i, _l, _i, _i, _i, _p, _l, _i, _i, _i, _p, _p, _p, _p, _l, _p, _l, _i, _i, _i,
-                         _p, _l, _p, _p, _p, _i, _i, _f, _l, _i, _p],
+                         _p, _l, _p, _p, _p, _i, _i, _f, _l, _i, _p, _p],
     "nv_cls_row": [_p, _p, _p, _l, _i, _i, _p],
     "nv_patch_gather_ln": [_p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p, _f, _p],
     "nv_patch_ln_param_grad": [_p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
-    "nv_attention_fwd": [_p, _p, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _l, _p, _p],
+    "nv_attention_fwd": [_p, _p, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _l, _p, _i, _p],
     "nv_attention_bwd": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _p, _p, _p, _p, _l, _l,
                          _i, _i, _i, _i, _f, _f, _p, _p],
     "nv_set_attention_impl": [_i],

@@ -9,7 +9,9 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       const float* bias, const float* residual, int64_t ld_res, const bf16* gelu_u, int64_t ld_u,
                       float* out_f32, int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
-                      float dropout_p, uint64_t dropout_seed, int dropout_stream, cudaStream_t stream);
+                      float dropout_p, uint64_t dropout_seed, int dropout_stream, const uint8_t* dropout_bits,
+                      cudaStream_t stream);
+int nv_dropout_bits_launch(uint32_t* out, int64_t n_groups, float p, uint64_t seed, int stream_id, cudaStream_t stream);
 int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_bf16, int64_t n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, const float* step_dev,
                          cudaStream_t stream);
@@ -32,7 +34,7 @@ int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int
                      int xs, int xo, const float* mean, const float* rstd, const float* gamma, const float* dres,
                      int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo, bf16* dx_bf16,
                      int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D, float side_drop_p,
-                     uint64_t side_drop_seed, int side_drop_stream, cudaStream_t stream);
+                     uint64_t side_drop_seed, int side_drop_stream, const uint8_t* side_drop_bits, cudaStream_t stream);
 int nv_cls_row_launch(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D,
                       cudaStream_t stream);
 int nv_patch_gather_ln_launch(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
@@ -50,7 +52,7 @@ int nv_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_
                        int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
 int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
                           int64_t o_bs, int64_t o_rs, float* lse, int B, int N, int H, int head_dim, float scale,
-                          float dropout_p, uint64_t seed, uint32_t* drop_mask, cudaStream_t stream);
+                          float dropout_p, uint64_t seed, uint32_t* drop_mask, int mask_ready, cudaStream_t stream);
 int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
                           const bf16* dO, int64_t o_bs, int64_t o_rs, const float* lse, float* delta_ws, bf16* dq,
                           bf16* dk, bf16* dv, int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim,
@@ -90,11 +92,15 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int64_t
                  const float* bias, const float* residual, int64_t ld_res, const void* gelu_u, int64_t ld_u,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, void* out_pre, int64_t ld_pre,
                  float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
-                 float dropout_p, int64_t dropout_seed, int dropout_stream, void* stream) {
+                 float dropout_p, int64_t dropout_seed, int dropout_stream, const void* dropout_bits, void* stream) {
   return nv_gemm_tc_launch(a_mn, b_mn, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, bias, residual, ld_res,
                            (const bf16*)gelu_u, ld_u, out_f32, ld_f32, (bf16*)out_bf16, ld_bf16, (bf16*)out_pre,
                            ld_pre, colsum, apply_gelu, accumulate, alpha, k_splits, block_n, cta_group, dropout_p,
-                           (uint64_t)dropout_seed, dropout_stream, ST(stream));
+                           (uint64_t)dropout_seed, dropout_stream, (const uint8_t*)dropout_bits, ST(stream));
+}
+
+int nv_dropout_bits(void* out, int64_t n_groups, float p, int64_t seed, int stream_id, void* stream) {
+  return nv_dropout_bits_launch((uint32_t*)out, n_groups, p, (uint64_t)seed, stream_id, ST(stream));
 }
 
 int nv_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
@@ -135,11 +141,11 @@ int nv_layernorm_bwd(const void* dy, int dy_is_bf16, int64_t ld_dy, int dy_group
                      const float* gamma, const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dx_group,
                      int dx_gstride, int dx_goff, void* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
                      float* colsum, int M, int D, float side_drop_p, int64_t side_drop_seed, int side_drop_stream,
-                     void* stream) {
+                     const void* side_drop_bits, void* stream) {
   return nv_ln_bwd_launch(dy, dy_is_bf16, ld_dy, dy_group, dy_gstride, dy_goff, x, ld_x, x_group, x_gstride, x_goff, mean, rstd,
                           gamma, dres, ld_dres, dx, ld_dx, dx_group, dx_gstride, dx_goff, (bf16*)dx_bf16, ld_dxb,
                           dgamma, dbeta, colsum, M, D, side_drop_p, (uint64_t)side_drop_seed, side_drop_stream,
-                          ST(stream));
+                          (const uint8_t*)side_drop_bits, ST(stream));
 }
 
 int nv_cls_row(const float* cls, const float* pos, float* x, int64_t batch_stride, int B, int D, void* stream) {
@@ -169,7 +175,8 @@ int nv_set_attention_impl(int impl) {
 
 int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse, int B, int N, int H,
-                     int head_dim, float scale, float dropout_p, int64_t seed, void* drop_mask, void* stream) {
+                     int head_dim, float scale, float dropout_p, int64_t seed, void* drop_mask, int drop_mask_ready,
+                     void* stream) {
   if (g_attn_impl == 1) {
     NV_REQUIRE(dropout_p == 0.f, "attention: the mma.sync cross-check variant has no dropout");
     return nv_attn_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
@@ -177,7 +184,7 @@ int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_ba
   }
   return nv_attn_tc_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
                                (bf16*)o, o_batch_stride, o_row_stride, lse, B, N, H, head_dim, scale, dropout_p,
-                               (uint64_t)seed, (uint32_t*)drop_mask, ST(stream));
+                               (uint64_t)seed, (uint32_t*)drop_mask, drop_mask_ready, ST(stream));
 }
 
 int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,

@@ -104,6 +104,7 @@ struct Common {
   const uint64_t* epoch;  // device epoch counter added to the seed (CUDA-graph replays)
   uint32_t* mask;
   int mask_words;     // ceil(N / 32)
+  int mask_ready;     // forward: the mask was drawn ahead of time (nv_dropout_bits): read it instead of drawing
 };
 
 // =====================================================================================================
@@ -146,9 +147,15 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     }
     rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
     if (DROPOUT) {
-      const uint32_t km = nv_keep_bits8(nv_seed(c.seed, c.epoch), mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
-                                        c.drop_thr);
-      km32 |= km << (8 * g8);
+      uint32_t km;
+      if (c.mask_ready) {
+        if (g8 == 0) km32 = c.mask[mrow * c.mask_words + (key0 >> 5)];
+        km = (km32 >> (8 * g8)) & 0xFFu;
+      } else {
+        km = nv_keep_bits8(nv_seed(c.seed, c.epoch), mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
+                           c.drop_thr);
+        km32 |= km << (8 * g8);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) e[i] = (km >> i) & 1u ? e[i] * c.keep_scale : 0.f;
     }
@@ -157,7 +164,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     w[g8 * 4 + 2] = pack_bf16x2(e[4], e[5]);
     w[g8 * 4 + 3] = pack_bf16x2(e[6], e[7]);
   }
-  if (DROPOUT && row_ok) c.mask[mrow * c.mask_words + (key0 >> 5)] = km32;  // one word per 32-key chunk
+  if (DROPOUT && row_ok && !c.mask_ready) c.mask[mrow * c.mask_words + (key0 >> 5)] = km32;  // one word per 32-key chunk
   return (rs0 + rs1) + (rs2 + rs3);
 }
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
@@ -884,7 +891,7 @@ int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, in
   return nv_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int fill_common(Common& c, int N, int H, float scale, float dropout_p, uint64_t seed, uint32_t* mask) {
+int fill_common(Common& c, int N, int H, float scale, float dropout_p, uint64_t seed, uint32_t* mask, int mask_ready = 0) {
   NV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p %f out of range [0, 1)", dropout_p);
   c.N = N; c.H = H; c.scale = scale; c.seed = seed;
   c.epoch = dropout_p > 0.f ? nv_rng_epoch_dev() : nullptr;
@@ -892,6 +899,7 @@ int fill_common(Common& c, int N, int H, float scale, float dropout_p, uint64_t 
   c.keep_scale = nv_dropout_keep_scale(c.drop_thr);
   c.mask = mask;
   c.mask_words = (N + 31) / 32;
+  c.mask_ready = mask_ready;
   NV_REQUIRE(c.drop_thr == 0 || mask != nullptr, "attention: dropout needs the mask buffer [B*H, N, ceil(N/32)] uint32");
   return NV_OK;
 }
@@ -914,7 +922,7 @@ int set_smem(K kern, int bytes) {
 
 int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
                           int64_t o_bs, int64_t o_rs, float* lse, int B, int N, int H, int head_dim, float scale,
-                          float dropout_p, uint64_t seed, uint32_t* drop_mask, cudaStream_t stream) {
+                          float dropout_p, uint64_t seed, uint32_t* drop_mask, int mask_ready, cudaStream_t stream) {
   NV_REQUIRE(head_dim == HD, "attention: head_dim %d unsupported by the bf16 flash kernel (needs 64)", head_dim);
   NV_REQUIRE(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad sizes B=%d N=%d H=%d", B, N, H);
   if (B == 0) return NV_OK;
@@ -929,7 +937,7 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H, FWD_KB)) != NV_OK) return s;
   if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H, FWD_KB)) != NV_OK) return s;
   FwdParams p;
-  if ((s = fill_common(p.c, N, H, scale, dropout_p, seed, drop_mask)) != NV_OK) return s;
+  if ((s = fill_common(p.c, N, H, scale, dropout_p, seed, drop_mask, mask_ready)) != NV_OK) return s;
   p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
   static bool attr_set = false;
   if (!attr_set) {

@@ -57,6 +57,7 @@ struct GemmParams {
   float keep_scale;
   uint64_t drop_seed;
   const uint64_t* drop_epoch;  // device epoch counter added to the seed (CUDA-graph replays)
+  const uint8_t* drop_bits;    // optional pre-generated keep bits, byte (row * N + col) / 8 (nv_dropout_bits)
   uint32_t drop_stream;
 };
 
@@ -173,9 +174,10 @@ struct EpiAux {  // global operands of one 32x32 chunk, prefetched one chunk ahe
   float4 res[8];
   uint2 uu[8];
   float4 bias4;
+  uint32_t kb[4];  // pre-drawn dropout keep bytes of this lane's four row slices (p.drop_bits)
 };
 
-template <int EPI_MODE>
+template <int EPI_MODE, bool DROP = false>
 __device__ __forceinline__ void epi_prefetch(const GemmParams& p, EpiAux& x, int lane, int row0, int col0) {
   // Out-of-range rows/columns are CLAMPED to a valid address instead of predicated: a "ok ? load : 0"
   // select makes the warp wait for the load right here and defeats the prefetch; clamped values are
@@ -200,6 +202,13 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, EpiAux& x, int
   }
   x.bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (EPI_MODE != 2 && p.bias != nullptr) x.bias4 = *reinterpret_cast<const float4*>(p.bias + gn);
+  if (DROP && p.drop_bits != nullptr) {  // bytes drawn ahead by nv_dropout_bits: fetched with the other operands
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int gm_t = min(row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r, p.M - 1);
+      x.kb[t] = __ldg(p.drop_bits + (((uint64_t)gm_t * p.N + (gn & ~7)) >> 3));
+    }
+  }
 }
 
 // explicit shared-space accesses for the staging slab: through a generic pointer they compile to LD.E / ST.E
@@ -228,11 +237,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   // slice, so each lane draws the bits of four of its eight row slices and fetches the rest from its neighbour
   uint32_t kb[4] = {0u, 0u, 0u, 0u};
   if (DROP) {
-    const uint64_t seed = nv_seed(p.drop_seed, p.drop_epoch);
+    if (p.drop_bits != nullptr) {  // bits drawn ahead of time by nv_dropout_bits (same values), prefetched
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int gm_t = row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r;
-      kb[t] = nv_keep_bits8(seed, ((uint64_t)gm_t * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
+      for (int t = 0; t < 4; ++t) kb[t] = x.kb[t];
+    } else {
+      const uint64_t seed = nv_seed(p.drop_seed, p.drop_epoch);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int gm_t = row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r;
+        kb[t] = nv_keep_bits8(seed, ((uint64_t)gm_t * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
+      }
     }
   }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -469,13 +483,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + part * 32;
       if constexpr (EPI_MODE == 0) {
         EpiAux aux[2];
-        epi_prefetch<EPI_MODE>(p, aux[0], lane, row0, colbase);  // overlaps the wait for the accumulator
+        epi_prefetch<EPI_MODE, DROP>(p, aux[0], lane, row0, colbase);  // overlaps the wait for the accumulator
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
 #pragma unroll
         for (int ci = 0; ci < CHUNKS; ++ci) {
           const int col0 = colbase + ci * 32 * W;
-          if (ci + 1 < CHUNKS) epi_prefetch<EPI_MODE>(p, aux[(ci + 1) & 1], lane, row0, col0 + 32 * W);
+          if (ci + 1 < CHUNKS) epi_prefetch<EPI_MODE, DROP>(p, aux[(ci + 1) & 1], lane, row0, col0 + 32 * W);
           if (col0 < p.N) {  // warp-uniform
             uint32_t v[32];
             tmem_ld_32x32(tm_row + ci * 32 * W, v);
@@ -485,13 +499,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       } else {
         EpiAux aux;
-        epi_prefetch<EPI_MODE>(p, aux, lane, row0, colbase);
+        epi_prefetch<EPI_MODE, DROP>(p, aux, lane, row0, colbase);
         mbar_wait(&tmem_full[acc], acc_ph);
         tc_fence_after();
 #pragma unroll
         for (int ci = 0; ci < CHUNKS; ++ci) {
           const int col0 = colbase + ci * 32 * W;
-          if (ci > 0) epi_prefetch<EPI_MODE>(p, aux, lane, row0, col0);
+          if (ci > 0) epi_prefetch<EPI_MODE, DROP>(p, aux, lane, row0, col0);
           if (col0 < p.N) {  // warp-uniform
             uint32_t v[32];
             tmem_ld_32x32(tm_row + ci * 32 * W, v);
@@ -589,7 +603,8 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       int64_t ld_res, const bf16* gelu_u, int64_t ld_u, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
-                      int cta_group, float dropout_p, uint64_t dropout_seed, int dropout_stream, cudaStream_t stream) {
+                      int cta_group, float dropout_p, uint64_t dropout_seed, int dropout_stream,
+                      const uint8_t* dropout_bits, cudaStream_t stream) {
   NV_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   NV_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   NV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16B strides)");
@@ -645,6 +660,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   p.keep_scale = nv_dropout_keep_scale(p.drop_thr);
   p.drop_seed = dropout_seed;
   p.drop_epoch = p.drop_thr != 0 ? nv_rng_epoch_dev() : nullptr;
+  p.drop_bits = p.drop_thr != 0 ? dropout_bits : nullptr;
   p.drop_stream = (uint32_t)dropout_stream;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;

@@ -226,7 +226,8 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
                    float* __restrict__ dx, int64_t ld_dx, RowMap dxmap, bf16* __restrict__ dx_bf16,
                    int64_t ld_dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ colsum_out, int M, int D, int stages, uint32_t side_thr, float side_ks,
-                   uint64_t side_seed_host, uint32_t side_stream, const uint64_t* side_epoch) {
+                   uint64_t side_seed_host, uint32_t side_stream, const uint64_t* side_epoch,
+                   const uint8_t* __restrict__ side_bits) {
   extern __shared__ __align__(128) uint8_t lnp_smem[];
   __shared__ __align__(16) float red[2][2 * LNP_ROWS][LNB_MAX_WARPS];
   __shared__ __align__(8) uint64_t full[LNP_MAX_STAGES];
@@ -355,7 +356,9 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
       const uint64_t side_seed = nv_seed(side_seed_host, side_epoch);
       static_assert(LNP_ROWS == 2, "pair exchange below assumes two rows per iteration");
       const int rmine = min(r0 + (c & 1), M - 1);
-      const uint32_t mine = nv_keep_bits8(side_seed, ((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3, side_stream, side_thr);
+      const uint64_t grp = ((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3;
+      const uint32_t mine = side_bits ? (active ? (uint32_t)__ldg(side_bits + grp) : 0u)  // drawn ahead (nv_dropout_bits)
+                                      : nv_keep_bits8(side_seed, grp, side_stream, side_thr);
       const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
 #pragma unroll
       for (int k = 0; k < LNP_ROWS; ++k) keep4[k] = ((((c & 1) == k) ? mine : other) >> ((c & 1) * 4)) & 0xFu;
@@ -395,7 +398,7 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
                        const float* mean, const float* rstd, const float* gamma, const float* dres, int64_t ld_dres,
                        float* dx, int64_t ld_dx, RowMap dxm, bf16* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta,
                        float* colsum, int M, int D, int threads, uint32_t side_thr, uint64_t side_seed, int side_stream,
-                       cudaStream_t stream) {
+                       const uint8_t* side_bits, cudaStream_t stream) {
   const int stage_bytes = (D * (int)sizeof(DyT) + D * 4 + (dres ? D * 4 : 0)) * LNP_ROWS;
   int stages = (108 * 1024) / stage_bytes;  // two CTAs per SM
   if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
@@ -417,7 +420,7 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
   kern<<<grid, threads + 32, smem, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
                                              dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, stages, side_thr,
                                              nv_dropout_keep_scale(side_thr), side_seed, (uint32_t)side_stream,
-                                             side_thr != 0 ? nv_rng_epoch_dev() : nullptr);
+                                             side_thr != 0 ? nv_rng_epoch_dev() : nullptr, side_thr != 0 ? side_bits : nullptr);
   return NV_OK;
 }
 
@@ -473,7 +476,8 @@ int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int
                      int xg, int xs, int xo, const float* mean, const float* rstd, const float* gamma,
                      const float* dres, int64_t ld_dres, float* dx, int64_t ld_dx, int dxg, int dxs, int dxo,
                      bf16* dx_bf16, int64_t ld_dxb, float* dgamma, float* dbeta, float* colsum, int M, int D,
-                     float side_drop_p, uint64_t side_drop_seed, int side_drop_stream, cudaStream_t stream) {
+                     float side_drop_p, uint64_t side_drop_seed, int side_drop_stream, const uint8_t* side_drop_bits,
+                     cudaStream_t stream) {
   NV_REQUIRE(M >= 0 && D > 0 && D % 4 == 0 && D <= 2048, "layernorm bwd: D=%d must be a multiple of 4 and <= 2048", D);
   if (M == 0) return NV_OK;
   for (const float* p : {dgamma, dbeta, colsum})
@@ -496,11 +500,11 @@ int nv_ln_bwd_launch(const void* dy, int dy_is_bf16, int64_t ld_dy, int dyg, int
     if (dy_is_bf16)
       s = launch_ln_bwd_pipe<bf16>((const bf16*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
                                    dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, side_thr, side_drop_seed,
-                                   side_drop_stream, stream);
+                                   side_drop_stream, side_drop_bits, stream);
     else
       s = launch_ln_bwd_pipe<float>((const float*)dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx,
                                     ld_dx, dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, threads, side_thr,
-                                    side_drop_seed, side_drop_stream, stream);
+                                    side_drop_seed, side_drop_stream, side_drop_bits, stream);
     if (s != NV_OK) return s;
     NV_LAUNCH_CHECK("ln_bwd_pipe_kernel");
     return NV_OK;

@@ -154,6 +154,22 @@ __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, cons
   }
 }
 
+// Keep-bit generator: out[g] = the 8 keep bits of Philox group g (= elements [8g, 8g+8) of a dropout site, or
+// one byte of the attention mask [B*H, N, 4*ceil(N/32)]). The consumers (GEMM epilogues, LayerNorm-backward
+// side-car, attention forward) accept these bytes instead of drawing the bits inline: the Philox arithmetic then
+// runs at full occupancy on a side stream underneath a tensor-core kernel instead of inside that kernel's
+// epilogue or its softmax rows. Bits are identical to the inline draw (same seed, stream, epoch, index).
+__global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t n_words, uint32_t thr, uint64_t seed_host,
+                                    uint32_t stream_id, const uint64_t* epoch) {
+  const uint64_t seed = nv_seed(seed_host, epoch);
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v |= nv_keep_bits8(seed, (uint64_t)(4 * w + k), stream_id, thr) << (8 * k);
+    out[w] = v;
+  }
+}
+
 // Fused AdamW over the trainer's flat buffers (reference: optim.AdamW(lr, weight_decay) at src/Trainer.py:31,75;
 // torch semantics: decoupled weight decay, bias-corrected moments, eps added to sqrt(v_hat)). One pass reads
 // p, g, m, v and writes p, m, v plus the bf16 copy of p that the next forward's GEMMs read (the weight cache),
@@ -293,5 +309,20 @@ int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_b
   adamw_flat_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, p_bf16, n4, lr, beta1, beta2, eps, 1.0f - lr * weight_decay,
                                               (float)(1.0 / bc1), (float)(1.0 / sqrt(bc2)), step_dev);
   NV_LAUNCH_CHECK("adamw_flat_kernel");
+  return NV_OK;
+}
+
+int nv_dropout_bits_launch(uint32_t* out, int64_t n_groups, float p, uint64_t seed, int stream_id, cudaStream_t stream) {
+  NV_REQUIRE(n_groups >= 0 && n_groups % 4 == 0, "dropout_bits: the number of 8-element groups (%lld) must be a multiple of 4",
+             (long long)n_groups);
+  NV_REQUIRE(p > 0.f && p < 1.f, "dropout_bits: p %f out of range (0, 1)", p);
+  NV_REQUIRE(out != nullptr && (reinterpret_cast<uintptr_t>(out) & 3) == 0, "dropout_bits: output must be 4-byte aligned");
+  if (n_groups == 0) return NV_OK;
+  const int64_t n_words = n_groups / 4;
+  int grid = nv_num_sms() * 8;
+  if ((int64_t)grid * 128 > n_words) grid = (int)((n_words + 127) / 128);
+  dropout_bits_kernel<<<grid, 128, 0, stream>>>(out, n_words, nv_dropout_threshold(p), seed, (uint32_t)stream_id,
+                                                nv_rng_epoch_dev());
+  NV_LAUNCH_CHECK("dropout_bits_kernel");
   return NV_OK;
 }

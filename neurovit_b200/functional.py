@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import collections
 import math
+import os
 
 import torch
 
@@ -51,6 +52,64 @@ def check_mode(mode: str) -> str:
     if mode not in _VALID_MODES:
         raise ValueError(f"precision mode must be one of {_VALID_MODES}, got {mode!r}")
     return mode
+
+
+# ------------------------------------------------------------------------------------ dropout bits
+class MaskGen:
+    """Draws the keep bits of a dropout site AHEAD of the kernel that applies them, on a side stream: the Philox
+    arithmetic then runs at full occupancy underneath the tensor-core kernels of the main stream instead of inside
+    a GEMM epilogue, the LayerNorm-backward loop or the attention softmax rows (where it cost 1.6 ms per step).
+    Bits are identical to the inline draw (same seed / stream / epoch / element index), so consumers may take
+    either; bits of the sites a later Function's backward needs are parked in a small LRU registry."""
+
+    MAX_PARKED = 64
+
+    def __init__(self):
+        self._side = {}
+        self._parked = collections.OrderedDict()
+        # which sites are drawn ahead: "attn" (the flash kernel's mask), "gemm" (epilogue / LayerNorm side-car sites)
+        self.sites = set(filter(None, os.environ.get("NEUROVIT_MASKGEN", "attn,gemm").split(",")))
+
+    def _stream(self, dev):
+        s = self._side.get(dev)
+        if s is None:
+            s = self._side[dev] = torch.cuda.Stream(device=dev)
+        return s
+
+    def draw(self, n_bytes, p, seed, stream_id, device, site="gemm"):
+        """(uint8 buffer of ceil4(n_bytes), event to wait for) or None when that site kind is drawn inline / p == 0."""
+        if site not in self.sites or p <= 0:
+            return None
+        buf = torch.empty((n_bytes + 3) // 4 * 4, dtype=torch.uint8, device=device)
+        cur = torch.cuda.current_stream(device)
+        side = self._stream(device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ops.dropout_bits(buf, p=p, seed=seed, stream=stream_id)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        buf.record_stream(side)
+        return buf, ev
+
+    @staticmethod
+    def ready(drawn):
+        """Make the current stream wait for a draw; returns the buffer (or None)."""
+        if drawn is None:
+            return None
+        torch.cuda.current_stream(drawn[0].device).wait_event(drawn[1])
+        return drawn[0]
+
+    def park(self, key, drawn):
+        if drawn is not None:
+            self._parked[key] = drawn
+            while len(self._parked) > self.MAX_PARKED:
+                self._parked.popitem(last=False)
+
+    def take(self, key):
+        return self._parked.pop(key, None)
+
+
+MASKS = MaskGen()
 
 
 # ------------------------------------------------------------------------------------ weight cache
@@ -242,7 +301,7 @@ class Engine:
             ops.linear_f32(a, weight.detach(), bias=bias, residual=residual, out=out, out_pre=pre, apply_gelu=gelu)
         else:  # verification mode: the CUDA-core GEMM has no fused dropout; mask (and add the residual) after it
             ops.linear_f32(a, weight.detach(), bias=bias, out=out, out_pre=pre, apply_gelu=gelu)
-            ops.dropout(out, p=drop[0], seed=drop[1], stream=drop[2], residual=residual, out_f32=out)
+            ops.dropout(out, p=drop[0], seed=drop[1], stream=drop[2], residual=residual, out_f32=out)  # inline draw
         return out, pre
 
     def dgrad(self, dy, weight, *, gelu_u=None, out_dtype=None, want_colsum=False, colsum_acc=None, drop=None):
@@ -340,6 +399,11 @@ class Engine:
             return None
         return (prev[0], seed, prev[1])
 
+    @staticmethod
+    def side_bits(side):
+        """The parked keep bits of that site (drawn during its forward), made ready on the current stream."""
+        return None if side is None else MASKS.ready(MASKS.take((side[1], side[2])))
+
     def drop_grad(self, dy, drop):
         """Gradient of a dropped-out linear output: dy * mask / (1 - p) in the MMA operand dtype, plus its column
         sums (the bias gradient). dy fp32 [M, N]."""
@@ -378,13 +442,24 @@ class Engine:
         inner = heads * dim_head
         scale = dim_head ** -0.5
         dev = a.device
+        D_out = w_out.shape[0] if w_out is not None else inner
+        mask_words = (N + 31) // 32
+        bits_attn = bits_out = None
+        if self.mode == "bf16":  # keep bits of this block's sites, drawn on the side stream under the QKV GEMM
+            bits_attn = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn")
+            bits_out = MASKS.draw(M * D_out // 8, p_out, seed, sbase + DROP_OUT, dev) if D_out % 8 == 0 else None
         qkv, _ = self.linear(a, w_qkv)
         o = torch.empty(M, inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
             lse = torch.empty(B, heads, N, device=dev, dtype=F32)
-            mask = torch.zeros(B * heads, N, (N + 31) // 32, device=dev, dtype=torch.int32) if p_attn > 0 else None
+            mask = None
+            if p_attn > 0:
+                ready = MASKS.ready(bits_attn)
+                mask = ready.view(torch.int32).view(B * heads, N, mask_words) if ready is not None else \
+                    torch.zeros(B * heads, N, mask_words, device=dev, dtype=torch.int32)
             ops.attention_fwd(qkv, o, lse, B=B, N=N, H=heads, head_dim=dim_head, scale=scale, dropout_p=p_attn,
-                              seed=seed + sbase + DROP_ATTN, drop_mask=mask)  # the flash kernel has one stream: offset the seed
+                              seed=seed + sbase + DROP_ATTN, drop_mask=mask,  # the flash kernel has one stream: offset the seed
+                              mask_ready=bits_attn is not None)
             _trace("attn", p_attn, seed, sbase + DROP_ATTN, mask)
             aux = (lse, mask)
         else:
@@ -406,7 +481,9 @@ class Engine:
         if w_out is None:  # project_out == False (heads == 1 and dim_head == dim): to_out is Identity
             y = torch.empty(M, inner, device=dev, dtype=F32)
             raise NotImplementedError("project_out=False (heads=1, dim_head=dim) is not on the NeuroViT hot path")
-        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32, drop=(p_out, seed, sbase + DROP_OUT))
+        y, _ = self.linear(o, w_out, bias=b_out, residual=x_res, out_dtype=F32,
+                           drop=(p_out, seed, sbase + DROP_OUT, MASKS.ready(bits_out)))
+        MASKS.park((seed, sbase + DROP_OUT), bits_out)  # the next block's LayerNorm backward masks its side-car with these
         _trace("out", p_out, seed, sbase + DROP_OUT, (M, w_out.shape[0]))
         return y, (qkv, o, *aux)
 
@@ -453,16 +530,24 @@ class Engine:
 
     # -- feed-forward core -------------------------------------------------------------------------
     def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0, sbase=0):
-        g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU))
-        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32, drop=(p_down, seed, sbase + DROP_DOWN))
+        M, Fh, D_out, dev = a.shape[0], w1.shape[0], w2.shape[0], a.device
+        bits_gelu = bits_down = None
+        if self.mode == "bf16":  # drawn on the side stream under the up-projection GEMM
+            bits_gelu = MASKS.draw(M * Fh // 8, p_gelu, seed, sbase + DROP_GELU, dev) if Fh % 8 == 0 else None
+            bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
+        bg = MASKS.ready(bits_gelu)
+        g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU, bg))
+        y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32,
+                           drop=(p_down, seed, sbase + DROP_DOWN, MASKS.ready(bits_down)))
+        MASKS.park((seed, sbase + DROP_DOWN), bits_down)
         _trace("gelu", p_gelu, seed, sbase + DROP_GELU, tuple(g.shape))
         _trace("down", p_down, seed, sbase + DROP_DOWN, tuple(y.shape))
-        return y, (u, g)
+        return y, (u, g, bg)
 
     def ff_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w1, b1, w2, da_dtype=None, p_gelu=0.0, seed=0, sbase=0):
-        u, g = saved
+        u, g, bits_gelu = saved
         dU, db1 = self.dgrad(dy_act, w2, gelu_u=u, want_colsum=True, colsum_acc=GradAcc(b1, self.mode),
-                             drop=(p_gelu, seed, sbase + DROP_GELU))
+                             drop=(p_gelu, seed, sbase + DROP_GELU, bits_gelu))
         dW2 = self.wgrad(dy_act, g, acc=GradAcc(w2, self.mode))
         db2 = self.bias_grad(dy, dy_colsum)
         da = self.dgrad(dU, w1, out_dtype=da_dtype or F32)
@@ -544,7 +629,8 @@ class AttnBlockFn(torch.autograd.Function):
                                                 da_dtype=eng.act, p_attn=p_attn, seed=seed, sbase=sbase)
         side = eng.side_drop_for(prev, seed, B * N, x2.shape[1])
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
-                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode), side_drop=side)
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode),
+                                          side_drop=None if side is None else (*side, eng.side_bits(side)))
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2, tag=side)
         return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None, None, None, None, None, None
@@ -604,7 +690,8 @@ class FFBlockFn(torch.autograd.Function):
                                                  p_gelu=p_gelu, seed=seed, sbase=sbase)
         side = eng.side_drop_for(prev, seed, B * N, x2.shape[1])
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
-                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode), side_drop=side)
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode),
+                                          side_drop=None if side is None else (*side, eng.side_bits(side)))
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2, tag=side)
         return dx, dg, db, dW1, db1, dW2, db2, None, None, None, None, None, None, None

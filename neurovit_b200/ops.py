@@ -97,12 +97,13 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     ld = lambda t: 0 if t is None else t.stride(0)
     if cta_group is None:
         cta_group = GEMM_CTA_GROUP
-    dp, dseed, dstream = dropout if dropout is not None else (0.0, 0, 0)
+    dp, dseed, dstream = dropout[:3] if dropout is not None else (0.0, 0, 0)
+    dbits = dropout[3] if dropout is not None and len(dropout) > 3 else None
     args = (int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
             _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
             _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
             int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), float(dp), int(dseed),
-            int(dstream), _stream())
+            int(dstream), _ptr(dbits), _stream())
     if PROFILE.enabled:
         with PROFILE.region(2.0 * M * N * K):
             _lib.call("nv_gemm_bf16", *args)
@@ -144,6 +145,15 @@ def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, c
             assert t.dtype == dt and tuple(t.shape) == (M, N) and t.stride(1) == 1
     _lib.call("nv_dropout", _ptr(x), ld(x), _ptr(residual), ld(residual), _ptr(out_f32), ld(out_f32), _ptr(out_bf16),
               ld(out_bf16), _ptr(colsum), M, N, float(p), int(seed), int(stream), _stream())
+
+
+def dropout_bits(out, *, p, seed, stream):
+    """out (uint8 / int32 buffer, numel*itemsize % 4 == 0): byte g = keep bits of elements [8g, 8g+8) of the dropout
+    site (seed, stream) — what the GEMM epilogues / LayerNorm backward / attention forward would draw inline."""
+    _dev(out)
+    assert out.is_contiguous()
+    n_groups = out.numel() * out.element_size()
+    _lib.call("nv_dropout_bits", _ptr(out), n_groups, float(p), int(seed), int(stream), _stream())
 
 
 def dropout_flat(x, out, *, p, seed, stream):
@@ -227,12 +237,13 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, *, M, D, ld_dy=None, ld_x=None, dyma
     """side_drop = (p, seed, stream): mask dx_bf16 / colsum (not dx) with that dropout site's forward mask."""
     _dev(x)
     assert dy.dtype in (F32, BF16) and x.dtype == F32
-    sp, sseed, sstream = side_drop if side_drop is not None else (0.0, 0, 0)
+    sp, sseed, sstream = side_drop[:3] if side_drop is not None else (0.0, 0, 0)
+    sbits = side_drop[3] if side_drop is not None and len(side_drop) > 3 else None
     _lib.call("nv_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), D if ld_dy is None else ld_dy, *dymap, _ptr(x),
               D if ld_x is None else ld_x, *xmap, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dres),
               D if ld_dres is None else ld_dres, _ptr(dx), D if ld_dx is None else ld_dx, *dxmap, _ptr(dx_bf16),
               D if ld_dxb is None else ld_dxb, _ptr(dgamma), _ptr(dbeta), _ptr(colsum), M, D, float(sp), int(sseed),
-              int(sstream), _stream())
+              int(sstream), _ptr(sbits), _stream())
 
 
 def cls_row(cls, pos, x, batch_stride, B, D):
@@ -268,16 +279,16 @@ def _off(t, elems):
     return ctypes.c_void_p(t.data_ptr() + elems * t.element_size())
 
 
-def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale, dropout_p=0.0, seed=0, drop_mask=None):
+def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale, dropout_p=0.0, seed=0, drop_mask=None, mask_ready=False):
     """qkv [B*N, 3*H*hd] bf16 (q|k|v column blocks), o [B*N, H*hd] bf16, lse [B,H,N] fp32;
-    drop_mask uint32-as-int32 [B*H, N, ceil(N/32)] when dropout_p > 0."""
+    drop_mask uint32-as-int32 [B*H, N, ceil(N/32)] when dropout_p > 0 (mask_ready: already drawn by dropout_bits)."""
     _dev(qkv)
     assert qkv.dtype == BF16 and o.dtype == BF16 and lse.dtype == F32
     inner = H * head_dim
     rs = qkv.stride(0)
     _lib.call("nv_attention_fwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
               N * o.stride(0), o.stride(0), _ptr(lse), B, N, H, head_dim, float(scale), float(dropout_p), int(seed),
-              _ptr(drop_mask), _stream())
+              _ptr(drop_mask), int(bool(mask_ready)), _stream())
 
 
 def attention_bwd(qkv, o, dO, lse, delta_ws, dqkv, *, B, N, H, head_dim, scale, dropout_p=0.0, drop_mask=None):
