@@ -282,6 +282,7 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
   const float4 g = active ? *reinterpret_cast<const float4*>(gamma + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
   int buf = 0;
   float mean_n[LNP_ROWS], rstd_n[LNP_ROWS];  // statistics of the NEXT row block, fetched one iteration ahead
+  uint32_t sbits_n = 0;  // pre-drawn side-car keep byte of the NEXT row block (this lane's row of the pair)
   auto fetch_stats = [&](int it) {
     const int r0 = (it * gridDim.x + blockIdx.x) * LNP_ROWS;
 #pragma unroll
@@ -289,6 +290,10 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
       const int r = min(r0 + k, M - 1);
       mean_n[k] = __ldg(mean_in + r);
       rstd_n[k] = __ldg(rstd_in + r);
+    }
+    if (side_bits != nullptr && active) {
+      const int rmine = min(r0 + (c & 1), M - 1);
+      sbits_n = __ldg(side_bits + (((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3));
     }
   };
   fetch_stats(0);
@@ -299,6 +304,7 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
     float mean[LNP_ROWS], rstd[LNP_ROWS];
 #pragma unroll
     for (int k = 0; k < LNP_ROWS; ++k) { mean[k] = mean_n[k]; rstd[k] = rstd_n[k]; }
+    const uint32_t sbits = sbits_n;
     if (it + 1 < iters) fetch_stats(it + 1);
     mbar_wait(&full[s], (it / stages) & 1);
     float4 xh[LNP_ROWS], gh[LNP_ROWS], rv[LNP_ROWS];
@@ -357,7 +363,7 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
       static_assert(LNP_ROWS == 2, "pair exchange below assumes two rows per iteration");
       const int rmine = min(r0 + (c & 1), M - 1);
       const uint64_t grp = ((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3;
-      const uint32_t mine = side_bits ? (active ? (uint32_t)__ldg(side_bits + grp) : 0u)  // drawn ahead (nv_dropout_bits)
+      const uint32_t mine = side_bits ? sbits  // drawn ahead (nv_dropout_bits), fetched one iteration early
                                       : nv_keep_bits8(side_seed, grp, side_stream, side_thr);
       const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
 #pragma unroll
