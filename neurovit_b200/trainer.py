@@ -245,7 +245,15 @@ class DataParallelTrainer:
         if not self.use_graph:
             return self._eager_step(inputs, labels)
         if self._graph is None:
-            self._capture(inputs, labels)
+            try:
+                self._capture(inputs, labels)
+            except Exception as e:  # capture is an optimisation: report loudly and launch kernel by kernel instead
+                import warnings
+                warnings.warn(f"neurovit_b200: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
+                              "continuing with eager launches")
+                self.use_graph, self._graph = False, None
+                torch.cuda.synchronize()
+                return self._eager_step(inputs, labels)
         if inputs.shape != self._sx.shape or labels.shape != self._sy.shape:
             raise ValueError(f"graph=True needs static shapes: captured {tuple(self._sx.shape)}, got {tuple(inputs.shape)}")
         self._sx.copy_(inputs, non_blocking=True)
