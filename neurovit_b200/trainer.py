@@ -89,7 +89,11 @@ class FlatGradBuckets:
         if self.world > 1:
             self._on_grad(self._by_key[key])
 
+    defer = False  # True: no all-reduce is launched from the backward thread; finish() reduces the whole buffer
+
     def _on_grad(self, p):
+        if self.defer:
+            return
         b = self.bucket_of[p]
         self.pending[b] -= 1
         if self.pending[b] == 0:
@@ -105,6 +109,9 @@ class FlatGradBuckets:
 
     def finish(self):
         """After backward: wait for the in-flight bucket all-reduces (the current stream waits, not the host)."""
+        if self.world > 1 and self.defer:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            return
         if self.world > 1 and any(n != 0 for n in self.pending):
             # parameters that received no gradient this step never fired their hook: reduce what is left
             for b, n in enumerate(self.pending):
@@ -195,9 +202,11 @@ class DataParallelTrainer:
             optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=fused)
         self.optimizer = optimizer
         self.criterion = torch.nn.CrossEntropyLoss()
-        # single-process only for now: capturing the bucketed NCCL all-reduces that the backward thread launches
-        # hangs in the capture (seen at world_size 2); multi-GPU runs launch kernel by kernel
-        self.use_graph = bool(graph) and self.buckets.world == 1
+        # with more than one rank the captured step reduces the whole gradient buffer with ONE all-reduce issued from
+        # the main thread after backward (bucketed all-reduces launched from the backward thread hang in a capture)
+        self.use_graph = bool(graph) and (self.buckets.world == 1 or os.environ.get("NEUROVIT_GRAPH_DP") == "1")
+        if self.use_graph and self.buckets.world > 1:
+            self.buckets.defer = True
         if self.use_graph and not isinstance(optimizer, FlatAdamW):
             raise ValueError("graph=True needs the built-in FlatAdamW optimizer (CUDA parameters, optimizer=None)")
         self._graph = None
