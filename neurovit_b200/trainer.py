@@ -202,27 +202,35 @@ class DataParallelTrainer:
             optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=fused)
         self.optimizer = optimizer
         self.criterion = torch.nn.CrossEntropyLoss()
-        # with more than one rank the captured step reduces the whole gradient buffer with ONE all-reduce issued from
-        # the main thread after backward (bucketed all-reduces launched from the backward thread hang in a capture)
-        self.use_graph = bool(graph) and (self.buckets.world == 1 or os.environ.get("NEUROVIT_GRAPH_DP") == "1")
+        # with more than one rank the captured step is two graphs around ONE eager all-reduce of the whole gradient
+        # buffer (NCCL inside a capture hung at world_size 2); NEUROVIT_GRAPH_DP=0 keeps multi-rank steps eager with
+        # bucketed all-reduces overlapped with backward
+        self.use_graph = bool(graph) and (self.buckets.world == 1 or os.environ.get("NEUROVIT_GRAPH_DP", "1") == "1")
         if self.use_graph and self.buckets.world > 1:
             self.buckets.defer = True
         if self.use_graph and not isinstance(optimizer, FlatAdamW):
             raise ValueError("graph=True needs the built-in FlatAdamW optimizer (CUDA parameters, optimizer=None)")
-        self._graph = None
+        self._graph = self._graph2 = None
         self._cuda = plist[0].is_cuda
 
-    def _eager_step(self, inputs, labels):
+    def _fwd_bwd(self, inputs, labels):
         self.buckets.zero()
         out = self.model(inputs)
         loss = self.criterion(out, labels)
         with SINKS.active(self.buckets.sink_views, self.buckets.sink_notify):
             loss.backward()
-        self.buckets.finish()
+        return loss
+
+    def _update(self):
         self.optimizer.step()
         if self._cuda:
             from . import ops
             ops.rng_epoch_advance()
+
+    def _eager_step(self, inputs, labels):
+        loss = self._fwd_bwd(inputs, labels)
+        self.buckets.finish()
+        self._update()
         return loss
 
     def _capture(self, inputs, labels):
@@ -243,11 +251,22 @@ class DataParallelTrainer:
             dst.copy_(src)
         torch.cuda.synchronize()
         from . import _lib
-        self._graph = torch.cuda.CUDAGraph()
         n0 = _lib.LAUNCHES.count
-        with torch.cuda.graph(self._graph):
-            self._sloss = self._eager_step(self._sx, self._sy)
-        self._graph_launches = _lib.LAUNCHES.count - n0  # C-ABI kernels recorded in the graph = launched per replay
+        self._graph = torch.cuda.CUDAGraph()
+        if self.buckets.world == 1:
+            with torch.cuda.graph(self._graph):
+                self._sloss = self._eager_step(self._sx, self._sy)
+            self._graph2 = None
+        else:
+            # several ranks: NCCL stays OUT of the capture. Graph 1 = forward + backward into the flat gradient
+            # buffer, then ONE eager all-reduce of that buffer, then graph 2 = optimizer + epoch advance.
+            # (thread_local error mode: the process group's watchdog thread may touch the CUDA API meanwhile)
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                self._sloss = self._fwd_bwd(self._sx, self._sy)
+            self._graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph2, pool=self._graph.pool(), capture_error_mode="thread_local"):
+                self._update()
+        self._graph_launches = _lib.LAUNCHES.count - n0  # C-ABI kernels recorded in the graphs = launched per step
         _lib.LAUNCHES.count = n0
 
     def step(self, inputs, labels):
@@ -268,6 +287,9 @@ class DataParallelTrainer:
         self._sx.copy_(inputs, non_blocking=True)
         self._sy.copy_(labels, non_blocking=True)
         self._graph.replay()
+        if self._graph2 is not None:
+            self.buckets.finish()   # deferred mode: one all-reduce (AVG) of the whole flat gradient buffer
+            self._graph2.replay()
         from . import _lib
         _lib.LAUNCHES.count += self._graph_launches
         return self._sloss

@@ -25,7 +25,7 @@ def _model():
                                torch.nn.Linear(32, 16), torch.nn.GELU(), torch.nn.Linear(16, 2))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, defer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -35,6 +35,7 @@ def _worker(rank, world, port, q):
         m = _model()
         tr = DataParallelTrainer(m, optimizer=torch.optim.SGD(m.parameters(), lr=0.0), bucket_mb=0)
         assert len(tr.buckets.buckets) == len(list(m.parameters()))  # bucket_mb=0: one bucket per parameter
+        tr.buckets.defer = defer  # True: what the graph-captured multi-rank step does — ONE all-reduce after backward
         loss = tr.step(shard_batch(X, rank, world), shard_batch(Y, rank, world))
         grads = [p.grad.clone() for p in m.parameters()]
         # every grad is still a view into the flat buffer, laid out in reverse parameter order, each slot
@@ -51,12 +52,13 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_dp_step_world2_gloo_matches_full_batch():
+@pytest.mark.parametrize("defer", [False, True])
+def test_dp_step_world2_gloo_matches_full_batch(defer):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, defer)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
