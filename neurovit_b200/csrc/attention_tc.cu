@@ -546,6 +546,11 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     for (int j = 0; j < nblk; ++j) {
       const int key0 = j * BWD_CB;
       const int nch = (min(BWD_CB, N - key0) + 31) >> 5;
+      uint32_t kmw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // dropout keep words of the block, fetched before the waits
+      if (dropout) {
+        kmw[0] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5));
+        if (nch > 1) kmw[1] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5) + 1);
+      }
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       PROF_MARK(j == 0 ? 0 : 1);
@@ -561,7 +566,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 #pragma unroll
         for (int i = 0; i < 32; ++i) ds[i] = ex2(fmaf(__uint_as_float(sv[i]), cs, -lse2));
         if (dropout) {
-          const uint32_t km = p.c.mask[mrow * p.c.mask_words + (key0 >> 5) + c];
+          const uint32_t km = kmw[c];
 #pragma unroll
           for (int i = 0; i < 32; ++i) ds[i] *= ((km >> i) & 1u ? __uint_as_float(dv[i]) * p.c.keep_scale : 0.f) - dl;
         } else {
@@ -790,9 +795,14 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
           }
         }
         if (dropout) {
+          uint32_t mw[32];  // the chunk's 32 queries' mask words for this warp's 32 keys (explicit shared loads)
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(mw[4 * e4]), "=r"(mw[4 * e4 + 1]),
+                         "=r"(mw[4 * e4 + 2]), "=r"(mw[4 * e4 + 3]) : "r"(mwords_u32 + (uint32_t)(c * 32 + e4 * 4) * 4));
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const bool keep = (mwords[c * 32 + e] >> lane) & 1u;
+            const bool keep = (mw[e] >> lane) & 1u;
             const float pe = pt[e];
             // ds was pe * (dp - dl); with the mask it is pe * (keep ? dp * ks : 0 - dl)
             const float dl_pe = fmaf(-pe, __uint_as_float(dv[e]), ds[e]);  // = -pe * dl
