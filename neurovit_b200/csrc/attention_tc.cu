@@ -134,7 +134,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(
 template <bool FULL, bool DROPOUT>
 __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float cs, float m_used, int nvalid,
                                                  const Common& c, uint64_t mrow, int key0, bool row_ok,
-                                                 uint32_t (&w)[16]) {
+                                                 uint32_t (&w)[16], uint32_t km_ready = 0) {
   float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
   uint32_t km32 = 0;
 #pragma unroll
@@ -149,8 +149,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     if (DROPOUT) {
       uint32_t km;
       if (c.mask_ready) {
-        if (g8 == 0) km32 = c.mask[mrow * c.mask_words + (key0 >> 5)];
-        km = (km32 >> (8 * g8)) & 0xFFu;
+        km = (km_ready >> (8 * g8)) & 0xFFu;  // drawn ahead (nv_dropout_bits), fetched before the barrier waits
       } else {
         km = nv_keep_bits8(nv_seed(c.seed, c.epoch), mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
                            c.drop_thr);
@@ -316,6 +315,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const int nvalid = min(FWD_KB, N - key0);
       const bool full = nvalid == FWD_KB;
       const uint32_t tSj = tS + lane_base + (uint32_t)((j & 1) * FWD_KB);
+      uint32_t kmw[3] = {0u, 0u, 0u};  // pre-drawn dropout keep words of this row's block
+      if (DROPOUT && p.c.mask_ready) {
+        const uint32_t* mp = p.c.mask + mrow * p.c.mask_words + (key0 >> 5);
+        kmw[0] = __ldg(mp);
+        if (nvalid > 32) kmw[1] = __ldg(mp + 1);
+        if (nvalid > 64) kmw[2] = __ldg(mp + 2);
+      }
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       PROF_MARK(j == 0 ? 0 : 1);
@@ -345,8 +351,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const bool row_ok = qrow < N;
       uint32_t w[16];
       float rs;
-      if (full) rs = fwd_chunk_probs<true, DROPOUT>(c0, cs, m_used, 32, p.c, mrow, key0, row_ok, w);
-      else      rs = fwd_chunk_probs<false, DROPOUT>(c0, cs, m_used, nvalid, p.c, mrow, key0, row_ok, w);
+      if (full) rs = fwd_chunk_probs<true, DROPOUT>(c0, cs, m_used, 32, p.c, mrow, key0, row_ok, w, kmw[0]);
+      else      rs = fwd_chunk_probs<false, DROPOUT>(c0, cs, m_used, nvalid, p.c, mrow, key0, row_ok, w, kmw[0]);
       PROF_MARK(3);
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
@@ -355,17 +361,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       PROF_MARK(4);
       store_p_chunk(sP_u32, row, 0, w);
       if (full) {
-        rs += fwd_chunk_probs<true, DROPOUT>(c1, cs, m_used, 32, p.c, mrow, key0 + 32, row_ok, w);
+        rs += fwd_chunk_probs<true, DROPOUT>(c1, cs, m_used, 32, p.c, mrow, key0 + 32, row_ok, w, kmw[1]);
         store_p_chunk(sP_u32, row, 1, w);
-        rs += fwd_chunk_probs<true, DROPOUT>(c2, cs, m_used, 32, p.c, mrow, key0 + 64, row_ok, w);
+        rs += fwd_chunk_probs<true, DROPOUT>(c2, cs, m_used, 32, p.c, mrow, key0 + 64, row_ok, w, kmw[2]);
         store_p_chunk(sP_u32, row, 2, w);
       } else {
         if (nvalid > 32) {
-          rs += fwd_chunk_probs<false, DROPOUT>(c1, cs, m_used, nvalid - 32, p.c, mrow, key0 + 32, row_ok, w);
+          rs += fwd_chunk_probs<false, DROPOUT>(c1, cs, m_used, nvalid - 32, p.c, mrow, key0 + 32, row_ok, w, kmw[1]);
           store_p_chunk(sP_u32, row, 1, w);
         }
         if (nvalid > 64) {
-          rs += fwd_chunk_probs<false, DROPOUT>(c2, cs, m_used, nvalid - 64, p.c, mrow, key0 + 64, row_ok, w);
+          rs += fwd_chunk_probs<false, DROPOUT>(c2, cs, m_used, nvalid - 64, p.c, mrow, key0 + 64, row_ok, w, kmw[2]);
           store_p_chunk(sP_u32, row, 2, w);
         }
       }
