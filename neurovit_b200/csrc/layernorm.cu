@@ -408,7 +408,6 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
   const int stage_bytes = (D * (int)sizeof(DyT) + D * 4 + (dres ? D * 4 : 0)) * LNP_ROWS;
   int stages = (108 * 1024) / stage_bytes;  // two CTAs per SM
   if (stages > LNP_MAX_STAGES) stages = LNP_MAX_STAGES;
-  if (const char* e = getenv("NV_LNP_STAGES")) stages = atoi(e);
   if (stages < 3) stages = 3;
   const int smem = stage_bytes * stages;
   auto kern = threads <= 256 ? ln_bwd_pipe_kernel<DyT, 256> : ln_bwd_pipe_kernel<DyT, 512>;
@@ -420,9 +419,7 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
   }
   int grid = (M + LNP_ROWS - 1) / LNP_ROWS;
   int cap = nv_num_sms() * ((smem <= 108 * 1024 && threads <= 256) ? 2 : 1);
-  if (const char* e = getenv("NV_LNP_CTAS")) cap = nv_num_sms() * atoi(e);
   if (grid > cap) grid = cap;
-  if (getenv("NV_LNP_NOSTORE")) { dx = nullptr; dx_bf16 = nullptr; }
   kern<<<grid, threads + 32, smem, stream>>>(dy, ld_dy, dym, x, ld_x, xm, mean, rstd, gamma, dres, ld_dres, dx, ld_dx,
                                              dxm, dx_bf16, ld_dxb, dgamma, dbeta, colsum, M, D, stages, side_thr,
                                              nv_dropout_keep_scale(side_thr), side_seed, (uint32_t)side_stream,

@@ -328,3 +328,31 @@ def test_graphed_step_matches_eager_and_redraws_dropout():
     tc = DataParallelTrainer(mc, lr=0.0, weight_decay=0.0, graph=True)
     losses = [tc.step(xs[0], ys[0]).item() for _ in range(4)]
     assert len({round(v, 6) for v in losses}) == 4, losses
+
+
+def test_predrawn_and_inline_dropout_bits_give_identical_results():
+    """Keep bits drawn ahead on the side stream (functional.MaskGen / nv_dropout_bits) are the same Philox bits the
+    kernels draw inline: with equal seeds the two paths must agree bit for bit in forward and closely in backward."""
+    from neurovit_b200 import functional as Fn
+    ctor = dict(image_size=16, image_patch_size=8, frames=24, frame_patch_size=8, num_classes=2, dim=64, depth=2,
+                heads=2, mlp_dim=128, channels=1, dim_head=64, dropout=0.25, emb_dropout=0.1)
+    torch.manual_seed(5)
+    m = ViT(**ctor).to(DEV).train()
+    x = torch.randn(6, 1, 24, 16, 16, device=DEV)
+    y = torch.tensor([0, 1, 1, 0, 1, 0], device=DEV)
+    saved_sites = set(Fn.MASKS.sites)
+    results = []
+    try:
+        for sites in ({"attn", "gemm"}, set()):
+            Fn.MASKS.sites = set(sites)
+            torch.manual_seed(77)       # same dropout seeds in both runs
+            m.zero_grad(set_to_none=True)
+            logits = m(x)
+            torch.nn.functional.cross_entropy(logits, y).backward()
+            torch.cuda.synchronize()
+            results.append((logits.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}))
+    finally:
+        Fn.MASKS.sites = saved_sites
+    assert torch.equal(results[0][0], results[1][0])
+    for k in results[0][1]:
+        assert rel(results[0][1][k], results[1][1][k]) < 1e-4, k   # split-K / column-sum atomics reorder
