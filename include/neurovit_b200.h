@@ -161,6 +161,17 @@ int nv_batch_sum(const float* in, int64_t batch_stride, float* out, int B, int64
 int nv_mean_pool_fwd(const float* x, float* pooled, int B, int N, int D, void* stream);
 int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int N, int D, void* stream);
 
+/* ---- classification head on the cls token --------------------------------------------------------------
+ * replaces: x[:, 0] -> nn.LayerNorm(dim) -> nn.Linear(dim, num_classes) at vit_3d.py:105-110,123-126 (pool='cls').
+ * x: [B, ...] fp32 with the cls row of sample b at x + b*ld_x; y [B,D] (LayerNorm output, saved), mean/rstd [B],
+ * logits [B,C]. bwd: dx rows (stride ld_dx, optional bf16 copy) get the cls-token gradient; dW [C,D], db [C],
+ * dgamma/dbeta [D] are ACCUMULATED (zero or pre-load them). fp32 in both precision modes. */
+int nv_head_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, const float* W, const float* bias,
+                float* y, float* mean, float* rstd, float* logits, int B, int D, int C, float eps, void* stream);
+int nv_head_bwd(const float* dl, const float* x, int64_t ld_x, const float* y, const float* mean, const float* rstd,
+                const float* gamma, const float* W, float* dx, int64_t ld_dx, void* dx_bf16, int64_t ld_dxb,
+                float* dW, float* db, float* dgamma, float* dbeta, int B, int D, int C, void* stream);
+
 /* ---- fused AdamW over flat buffers -------------------------------------------------------------------
  * replaces: optim.AdamW(model.parameters(), lr, weight_decay) + optimizer.step() at src/Trainer.py:31,75
  * (torch semantics: p *= 1 - lr*wd; m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)) when parameters,

@@ -24,6 +24,8 @@ SIGNATURES = {
     "nv_device_check": [],
     "nv_gemm_bf16": [_i, _i, _i, _i, _i, _p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p,
                      _i, _i, _f, _i, _i, _i, _f, _l, _i, _p, _p],
+    "nv_head_fwd": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p],
+    "nv_head_bwd": [_p, _p, _l, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p, _i, _i, _i, _p],
     "nv_dropout_bits": [_p, _l, _f, _l, _i, _p],
     "nv_adamw_flat": [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _p],
     "nv_counter_add": [_p, _f, _p],

@@ -11,6 +11,13 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
                       float dropout_p, uint64_t dropout_seed, int dropout_stream, const uint8_t* dropout_bits,
                       cudaStream_t stream);
+int nv_head_fwd_launch(const float* x, int64_t ld_x, const float* gamma, const float* beta, const float* W,
+                       const float* bias, float* y, float* mean, float* rstd, float* logits, int B, int D, int C,
+                       float eps, cudaStream_t stream);
+int nv_head_bwd_launch(const float* dl, const float* x, int64_t ld_x, const float* y, const float* mean,
+                       const float* rstd, const float* gamma, const float* W, float* dx, int64_t ld_dx, bf16* dx_bf16,
+                       int64_t ld_dxb, float* dW, float* db, float* dgamma, float* dbeta, int B, int D, int C,
+                       cudaStream_t stream);
 int nv_dropout_bits_launch(uint32_t* out, int64_t n_groups, float p, uint64_t seed, int stream_id, cudaStream_t stream);
 int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_bf16, int64_t n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int step, const float* step_dev,
@@ -97,6 +104,17 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int64_t
                            (const bf16*)gelu_u, ld_u, out_f32, ld_f32, (bf16*)out_bf16, ld_bf16, (bf16*)out_pre,
                            ld_pre, colsum, apply_gelu, accumulate, alpha, k_splits, block_n, cta_group, dropout_p,
                            (uint64_t)dropout_seed, dropout_stream, (const uint8_t*)dropout_bits, ST(stream));
+}
+
+int nv_head_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, const float* W, const float* bias,
+                float* y, float* mean, float* rstd, float* logits, int B, int D, int C, float eps, void* stream) {
+  return nv_head_fwd_launch(x, ld_x, gamma, beta, W, bias, y, mean, rstd, logits, B, D, C, eps, ST(stream));
+}
+int nv_head_bwd(const float* dl, const float* x, int64_t ld_x, const float* y, const float* mean, const float* rstd,
+                const float* gamma, const float* W, float* dx, int64_t ld_dx, void* dx_bf16, int64_t ld_dxb, float* dW,
+                float* db, float* dgamma, float* dbeta, int B, int D, int C, void* stream) {
+  return nv_head_bwd_launch(dl, x, ld_x, y, mean, rstd, gamma, W, dx, ld_dx, (bf16*)dx_bf16, ld_dxb, dW, db, dgamma,
+                            dbeta, B, D, C, ST(stream));
 }
 
 int nv_dropout_bits(void* out, int64_t n_groups, float p, int64_t seed, int stream_id, void* stream) {

@@ -154,6 +154,86 @@ __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, cons
   }
 }
 
+// ---- classification head on the cls token: LayerNorm(dim) -> Linear(dim, num_classes) (vit_3d.py:105-110,123-126) -----
+// One CTA per sample, fp32 throughout. Replaces a 64-row LayerNorm launch plus three [B,1024]x[1024,2]-sized
+// GEMM launches of the generic CUDA-core kernel (33 us each: one CTA walking K serially) in each direction.
+constexpr int HEAD_T = 256;
+__device__ __forceinline__ float head_block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HEAD_T / 32; ++i) s += red[i];
+  return s;
+}
+
+__global__ void __launch_bounds__(HEAD_T)
+head_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ y,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ logits, int D, int C,
+                float eps) {
+  __shared__ float red[HEAD_T / 32];
+  const int b = blockIdx.x;
+  const float* xr = x + (int64_t)b * ld_x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < D; i += HEAD_T) s += xr[i];
+  const float mean = head_block_sum(s, red) / (float)D;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < D; i += HEAD_T) { const float d = xr[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(head_block_sum(q, red) / (float)D + eps);
+  if (threadIdx.x == 0) { mean_out[b] = mean; rstd_out[b] = rstd; }
+  for (int i = threadIdx.x; i < D; i += HEAD_T) y[(int64_t)b * D + i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+  for (int c = 0; c < C; ++c) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < D; i += HEAD_T)
+      acc += ((xr[i] - mean) * rstd * gamma[i] + beta[i]) * W[(int64_t)c * D + i];
+    acc = head_block_sum(acc, red);
+    if (threadIdx.x == 0) logits[(int64_t)b * C + c] = acc + (bias ? bias[c] : 0.f);
+  }
+}
+
+// dx row (fp32 + optional bf16) of the cls token; dW, db, dgamma, dbeta accumulated with atomics (zero them first)
+__global__ void __launch_bounds__(HEAD_T)
+head_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ x, int64_t ld_x, const float* __restrict__ y,
+                const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ gamma,
+                const float* __restrict__ W, float* __restrict__ dx, int64_t ld_dx, bf16* __restrict__ dx_bf16,
+                int64_t ld_dxb, float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dgamma,
+                float* __restrict__ dbeta, int D, int C) {
+  __shared__ float red[HEAD_T / 32];
+  const int b = blockIdx.x;
+  const float* xr = x + (int64_t)b * ld_x;
+  const float mean = mean_in[b], rstd = rstd_in[b];
+  // pass 1: dy_i = sum_c dl[b,c] W[c,i]; LayerNorm backward sums; parameter gradients
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < D; i += HEAD_T) {
+    float dy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float g = dl[(int64_t)b * C + c];
+      dy = fmaf(g, W[(int64_t)c * D + i], dy);
+      atomicAdd(dW + (int64_t)c * D + i, g * y[(int64_t)b * D + i]);
+    }
+    const float xh = (xr[i] - mean) * rstd;
+    atomicAdd(dgamma + i, dy * xh);
+    atomicAdd(dbeta + i, dy);
+    const float gh = dy * gamma[i];
+    s1 += gh;
+    s2 += gh * xh;
+  }
+  if (threadIdx.x < C) atomicAdd(db + threadIdx.x, dl[(int64_t)b * C + threadIdx.x]);
+  s1 = head_block_sum(s1, red) / (float)D;
+  s2 = head_block_sum(s2, red) / (float)D;
+  for (int i = threadIdx.x; i < D; i += HEAD_T) {
+    float dy = 0.f;
+    for (int c = 0; c < C; ++c) dy = fmaf(dl[(int64_t)b * C + c], W[(int64_t)c * D + i], dy);
+    const float xh = (xr[i] - mean) * rstd;
+    const float o = rstd * (dy * gamma[i] - s1 - xh * s2);
+    dx[(int64_t)b * ld_dx + i] = o;
+    if (dx_bf16) dx_bf16[(int64_t)b * ld_dxb + i] = __float2bfloat16(o);
+  }
+}
+
 // Keep-bit generator: out[g] = the 8 keep bits of Philox group g (= elements [8g, 8g+8) of a dropout site, or
 // one byte of the attention mask [B*H, N, 4*ceil(N/32)]). The consumers (GEMM epilogues, LayerNorm-backward
 // side-car, attention forward) accept these bytes instead of drawing the bits inline: the Philox arithmetic then
@@ -324,5 +404,27 @@ int nv_dropout_bits_launch(uint32_t* out, int64_t n_groups, float p, uint64_t se
   dropout_bits_kernel<<<grid, 128, 0, stream>>>(out, n_words, nv_dropout_threshold(p), seed, (uint32_t)stream_id,
                                                 nv_rng_epoch_dev());
   NV_LAUNCH_CHECK("dropout_bits_kernel");
+  return NV_OK;
+}
+
+int nv_head_fwd_launch(const float* x, int64_t ld_x, const float* gamma, const float* beta, const float* W,
+                       const float* bias, float* y, float* mean, float* rstd, float* logits, int B, int D, int C,
+                       float eps, cudaStream_t stream) {
+  NV_REQUIRE(B >= 0 && D > 0 && C > 0 && C <= HEAD_T, "head: bad sizes B=%d D=%d C=%d", B, D, C);
+  if (B == 0) return NV_OK;
+  head_fwd_kernel<<<B, HEAD_T, 0, stream>>>(x, ld_x, gamma, beta, W, bias, y, mean, rstd, logits, D, C, eps);
+  NV_LAUNCH_CHECK("head_fwd_kernel");
+  return NV_OK;
+}
+
+int nv_head_bwd_launch(const float* dl, const float* x, int64_t ld_x, const float* y, const float* mean,
+                       const float* rstd, const float* gamma, const float* W, float* dx, int64_t ld_dx, bf16* dx_bf16,
+                       int64_t ld_dxb, float* dW, float* db, float* dgamma, float* dbeta, int B, int D, int C,
+                       cudaStream_t stream) {
+  NV_REQUIRE(B >= 0 && D > 0 && C > 0 && C <= HEAD_T, "head: bad sizes B=%d D=%d C=%d", B, D, C);
+  if (B == 0) return NV_OK;
+  head_bwd_kernel<<<B, HEAD_T, 0, stream>>>(dl, x, ld_x, y, mean, rstd, gamma, W, dx, ld_dx, dx_bf16, ld_dxb, dW, db,
+                                            dgamma, dbeta, D, C);
+  NV_LAUNCH_CHECK("head_bwd_kernel");
   return NV_OK;
 }

@@ -841,9 +841,14 @@ class HeadFn(torch.autograd.Function):
             pooled = torch.empty(B, D, device=dev, dtype=F32)
             ops.mean_pool_fwd(x, pooled, B, N, D)
             ops.layernorm_fwd(pooled, ln_w.detach(), ln_b.detach(), y, M=B, D=D, mean=mean, rstd=rstd, eps=eps)
-        else:
+        else:  # cls pool: LayerNorm + Linear fused, one CTA per sample
             pooled = None
-            ops.layernorm_fwd(x, ln_w.detach(), ln_b.detach(), y, M=B, D=D, ld_x=N * D, mean=mean, rstd=rstd, eps=eps)
+            logits = torch.empty(B, C, device=dev, dtype=F32)
+            ops.head_fwd(x, N * D, ln_w.detach(), ln_b.detach(), w.detach().float().contiguous(), b.detach(), y, mean,
+                         rstd, logits, B, D, C, eps)
+            ctx.save_for_backward(x, pooled, y, mean, rstd, ln_w, w)
+            ctx.cfg = (B, N, D, C, pool, mode)
+            return logits
         logits = ops.linear_f32(y, w.detach(), bias=b.detach())
         ctx.save_for_backward(x, pooled, y, mean, rstd, ln_w, w)
         ctx.cfg = (B, N, D, C, pool, mode)
@@ -855,6 +860,15 @@ class HeadFn(torch.autograd.Function):
         B, N, D, C, pool, mode = ctx.cfg
         dev = x.device
         dl = dlogits.float().contiguous()
+        if pool != "mean":
+            acc_w, acc_b = GradAcc(w, mode), torch.zeros(C, device=dev, dtype=F32)
+            acc_g, acc_be = torch.zeros(D, device=dev, dtype=F32), torch.zeros(D, device=dev, dtype=F32)
+            dx = torch.zeros(B, N, D, device=dev, dtype=F32)            # cls pool: only token 0 gets gradient
+            dxb = torch.zeros(B, N, D, device=dev, dtype=BF16) if mode == "bf16" else None
+            ops.head_bwd(dl, x, N * D, y, mean, rstd, ln_w.detach(), w.detach().float().contiguous(), dx, N * D, dxb,
+                         N * D, acc_w.buf, acc_b, acc_g, acc_be, B, D, C)
+            _STASH.put(dx, dxb)
+            return dx, acc_g, acc_be, acc_w.result(), acc_b, None, None, None
         dw = ops.linear_f32(dl, y, x_km=True, w_kn=True)            # [C, D] = dl^T y
         db = torch.zeros(C, device=dev, dtype=F32)
         ops.colsum(dl, db)

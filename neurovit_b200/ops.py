@@ -111,6 +111,18 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
     _lib.call("nv_gemm_bf16", *args)
 
 
+def head_fwd(x, ld_x, gamma, beta, W, bias, y, mean, rstd, logits, B, D, C, eps):
+    _dev(x)
+    _lib.call("nv_head_fwd", _ptr(x), ld_x, _ptr(gamma), _ptr(beta), _ptr(W), _ptr(bias), _ptr(y), _ptr(mean),
+              _ptr(rstd), _ptr(logits), B, D, C, float(eps), _stream())
+
+
+def head_bwd(dl, x, ld_x, y, mean, rstd, gamma, W, dx, ld_dx, dx_bf16, ld_dxb, dW, db, dgamma, dbeta, B, D, C):
+    _dev(x)
+    _lib.call("nv_head_bwd", _ptr(dl), _ptr(x), ld_x, _ptr(y), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(W), _ptr(dx),
+              ld_dx, _ptr(dx_bf16), ld_dxb, _ptr(dW), _ptr(db), _ptr(dgamma), _ptr(dbeta), B, D, C, _stream())
+
+
 def rng_epoch_advance():
     """Advance the device-side dropout epoch (end of a training step that may be replayed from a CUDA graph)."""
     _lib.call("nv_rng_epoch_advance", _stream())

@@ -196,7 +196,7 @@ def test_trainer_grad_sinks_match_autograd_accumulation():
     for _ in range(2):  # second step: the flat buffer is re-zeroed, nothing carries over
         tr.step(x, y)
     torch.cuda.synchronize()
-    assert SINKS.sunk - sunk0 == 2 * (2 * 9 + 4), "per layer 9 tensors (2 LayerNorm pairs, w_qkv, w_out, w1, b1, w2), 4 in the patch embedding"
+    assert SINKS.sunk - sunk0 == 2 * (2 * 9 + 4 + 1), "per layer 9 tensors (2 LayerNorm pairs, w_qkv, w_out, w1, b1, w2), 4 in the patch embedding, the head weight"
     for k, p in m.named_parameters():
         assert p.grad.data_ptr() % 128 == 0
         assert rel(p.grad, want[k]) < 1e-4, k
