@@ -867,7 +867,9 @@ class HeadFn(torch.autograd.Function):
             dxb = torch.zeros(B, N, D, device=dev, dtype=BF16) if mode == "bf16" else None
             ops.head_bwd(dl, x, N * D, y, mean, rstd, ln_w.detach(), w.detach().float().contiguous(), dx, N * D, dxb,
                          N * D, acc_w.buf, acc_b, acc_g, acc_be, B, D, C)
-            _STASH.put(dx, dxb)
+            cs = torch.zeros(D, device=dev, dtype=F32)   # column sums of dx = sum of the cls rows (bias gradient of
+            ops.batch_sum(dx, N * D, cs, B, D)           # the last block's down projection): no 100 MB colsum pass
+            _STASH.put(dx, dxb, cs)
             return dx, acc_g, acc_be, acc_w.result(), acc_b, None, None, None
         dw = ops.linear_f32(dl, y, x_km=True, w_kn=True)            # [C, D] = dl^T y
         db = torch.zeros(C, device=dev, dtype=F32)
