@@ -44,6 +44,8 @@ int nv_device_check(void);
  * dropout_p > 0: nn.Dropout on the value (vit_3d.py:21,23,45), applied after bias / GELU and BEFORE the
  * residual add; with gelu_u it multiplies the gradient by the forward mask of the activation. The keep
  * mask is a pure function of (dropout_seed, dropout_stream, row * N + col) — nv_dropout draws the same one.
+ * dropout_row_mul (>= 1): the mask row is output row * dropout_row_mul — a compact problem over every n-th row of a
+ * site (the cls rows in the last block's backward) then sees that site's forward mask.
  * block_n: 0 = auto, or 128 / 256 (CTA tile 128 x block_n). */
 int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  const void* A, int64_t lda, const void* B, int64_t ldb,
@@ -52,7 +54,8 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16,
                  void* out_pre, int64_t ld_pre, float* colsum,
                  int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
-                 float dropout_p, int64_t dropout_seed, int dropout_stream, const void* dropout_bits, void* stream);
+                 float dropout_p, int64_t dropout_seed, int dropout_stream, const void* dropout_bits,
+                 int dropout_row_mul, void* stream);
 
 /* Keep bits drawn ahead of time: out[g] (one byte) = the 8 keep bits of elements [8g, 8g+8) of a dropout site
  * with the given (seed, stream_id) — exactly the bits the consumers would draw inline. nv_gemm_bf16
@@ -66,7 +69,7 @@ int nv_dropout_bits(void* out, int64_t n_groups, float p, int64_t seed, int stre
  * colsum[N] += column sums of v. p = 0 turns it into a copy / cast / column sum. N % 8 == 0. */
 int nv_dropout(const float* in, int64_t ld_in, const float* residual, int64_t ld_res,
                float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, float* colsum,
-               int M, int N, float p, int64_t seed, int stream_id, void* stream);
+               int M, int N, float p, int64_t seed, int stream_id, int row_mul, void* stream);
 
 /* fp32 verification GEMM (CUDA-core FMA, arbitrary strides, batch index z = z1*Z2 + z2):
  * C[z][m][n] = epilogue(alpha * sum_k A[z][m,k] * B[z][n,k]); same epilogue order as nv_gemm_bf16, all

@@ -23,14 +23,14 @@ SIGNATURES = {
     "nv_version": [],
     "nv_device_check": [],
     "nv_gemm_bf16": [_i, _i, _i, _i, _i, _p, _l, _p, _l, _p, _p, _l, _p, _l, _p, _l, _p, _l, _p, _l, _p,
-                     _i, _i, _f, _i, _i, _i, _f, _l, _i, _p, _p],
+                     _i, _i, _f, _i, _i, _i, _f, _l, _i, _p, _i, _p],
     "nv_head_fwd": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p],
     "nv_head_bwd": [_p, _p, _l, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _p, _p, _p, _i, _i, _i, _p],
     "nv_dropout_bits": [_p, _l, _f, _l, _i, _p],
     "nv_adamw_flat": [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _p],
     "nv_counter_add": [_p, _f, _p],
     "nv_rng_epoch_advance": [_p],
-    "nv_dropout": [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _f, _l, _i, _p],
+    "nv_dropout": [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _f, _l, _i, _i, _p],
     "nv_gemm_f32": [_i, _i, _i, _i, _i, _p, _l, _l, _l, _l, _p, _l, _l, _l, _l, _p, _l, _l, _l,
                     _p, _p, _l, _p, _l, _p, _l, _i, _i, _f, _p],
     "nv_layernorm_fwd": [_p, _l, _i, _i, _i, _p, _p, _p, _l, _i, _i, _p, _i, _l, _i, _i, _i, _p, _p,

@@ -10,7 +10,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       float* out_f32, int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
                       float dropout_p, uint64_t dropout_seed, int dropout_stream, const uint8_t* dropout_bits,
-                      cudaStream_t stream);
+                      int dropout_row_mul, cudaStream_t stream);
 int nv_head_fwd_launch(const float* x, int64_t ld_x, const float* gamma, const float* beta, const float* W,
                        const float* bias, float* y, float* mean, float* rstd, float* logits, int B, int D, int C,
                        float eps, cudaStream_t stream);
@@ -26,7 +26,7 @@ int nv_rng_epoch_advance_launch(cudaStream_t stream);
 int nv_counter_add_launch(float* counter, float inc, cudaStream_t stream);
 int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p,
-                      uint64_t seed, int stream_id, cudaStream_t stream);
+                      uint64_t seed, int stream_id, int row_mul, cudaStream_t stream);
 int nv_simt_gemm_launch(int M, int N, int K, int Z1, int Z2, const float* A, int64_t sa_m, int64_t sa_k, int64_t sa_z1,
                         int64_t sa_z2, const float* B, int64_t sb_n, int64_t sb_k, int64_t sb_z1, int64_t sb_z2,
                         float* C, int64_t sc_m, int64_t sc_z1, int64_t sc_z2, const float* bias, const float* residual,
@@ -99,11 +99,13 @@ int nv_gemm_bf16(int a_mn, int b_mn, int M, int N, int K, const void* A, int64_t
                  const float* bias, const float* residual, int64_t ld_res, const void* gelu_u, int64_t ld_u,
                  float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, void* out_pre, int64_t ld_pre,
                  float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n, int cta_group,
-                 float dropout_p, int64_t dropout_seed, int dropout_stream, const void* dropout_bits, void* stream) {
+                 float dropout_p, int64_t dropout_seed, int dropout_stream, const void* dropout_bits,
+                 int dropout_row_mul, void* stream) {
   return nv_gemm_tc_launch(a_mn, b_mn, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, bias, residual, ld_res,
                            (const bf16*)gelu_u, ld_u, out_f32, ld_f32, (bf16*)out_bf16, ld_bf16, (bf16*)out_pre,
                            ld_pre, colsum, apply_gelu, accumulate, alpha, k_splits, block_n, cta_group, dropout_p,
-                           (uint64_t)dropout_seed, dropout_stream, (const uint8_t*)dropout_bits, ST(stream));
+                           (uint64_t)dropout_seed, dropout_stream, (const uint8_t*)dropout_bits, dropout_row_mul,
+                           ST(stream));
 }
 
 int nv_head_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta, const float* W, const float* bias,
@@ -131,9 +133,9 @@ int nv_counter_add(float* counter, float inc, void* stream) { return nv_counter_
 
 int nv_dropout(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32, int64_t ld_f32,
                void* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p, int64_t seed, int stream_id,
-               void* stream) {
+               int row_mul, void* stream) {
   return nv_dropout_launch(in, ld_in, residual, ld_res, out_f32, ld_f32, (bf16*)out_bf16, ld_bf16, colsum, M, N, p,
-                           (uint64_t)seed, stream_id, ST(stream));
+                           (uint64_t)seed, stream_id, row_mul, ST(stream));
 }
 
 int nv_gemm_f32(int M, int N, int K, int Z1, int Z2, const float* A, int64_t sa_m, int64_t sa_k, int64_t sa_z1,

@@ -58,6 +58,7 @@ struct GemmParams {
   uint64_t drop_seed;
   const uint64_t* drop_epoch;  // device epoch counter added to the seed (CUDA-graph replays)
   const uint8_t* drop_bits;    // optional pre-generated keep bits, byte (row * N + col) / 8 (nv_dropout_bits)
+  int drop_row_mul;            // mask row = output row * drop_row_mul (compact cls-row problems index the full site)
   uint32_t drop_stream;
 };
 
@@ -206,7 +207,7 @@ __device__ __forceinline__ void epi_prefetch(const GemmParams& p, EpiAux& x, int
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int gm_t = min(row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r, p.M - 1);
-      x.kb[t] = __ldg(p.drop_bits + (((uint64_t)gm_t * p.N + (gn & ~7)) >> 3));
+      x.kb[t] = __ldg(p.drop_bits + (((uint64_t)gm_t * p.drop_row_mul * p.N + (gn & ~7)) >> 3));
     }
   }
 }
@@ -245,7 +246,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int gm_t = row0 + ((sub_c & 1) * 4 + t) * 4 + sub_r;
-        kb[t] = nv_keep_bits8(seed, ((uint64_t)gm_t * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
+        kb[t] = nv_keep_bits8(seed, ((uint64_t)gm_t * p.drop_row_mul * p.N + (gn & ~7)) >> 3, p.drop_stream, p.drop_thr);
       }
     }
   }
@@ -604,7 +605,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, bf16* out_pre, int64_t ld_pre,
                       float* colsum, int apply_gelu, int accumulate, float alpha, int k_splits, int block_n,
                       int cta_group, float dropout_p, uint64_t dropout_seed, int dropout_stream,
-                      const uint8_t* dropout_bits, cudaStream_t stream) {
+                      const uint8_t* dropout_bits, int dropout_row_mul, cudaStream_t stream) {
   NV_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   NV_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
   NV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA 16B strides)");
@@ -661,6 +662,7 @@ int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, in
   p.drop_seed = dropout_seed;
   p.drop_epoch = p.drop_thr != 0 ? nv_rng_epoch_dev() : nullptr;
   p.drop_bits = p.drop_thr != 0 ? dropout_bits : nullptr;
+  p.drop_row_mul = dropout_row_mul > 0 ? dropout_row_mul : 1;
   p.drop_stream = (uint32_t)dropout_stream;
 
   const int total_units = p.num_m_tiles * p.num_n_tiles * p.k_splits;

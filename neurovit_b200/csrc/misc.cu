@@ -102,7 +102,7 @@ __global__ void mean_pool_bwd_kernel(const float* __restrict__ dpooled, float* _
 __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, const float* __restrict__ residual,
                                int64_t ld_res, float* __restrict__ out_f32, int64_t ld_f32, bf16* __restrict__ out_bf16,
                                int64_t ld_bf16, float* __restrict__ colsum, int M, int N, uint32_t thr, float ks,
-                               uint64_t seed_host, uint32_t stream_id, const uint64_t* epoch) {
+                               uint64_t seed_host, uint32_t stream_id, const uint64_t* epoch, int row_mul) {
   const uint64_t seed = nv_seed(seed_host, epoch);
   const int n8 = N >> 3;  // one Philox call per thread and row: 8 consecutive columns
   constexpr int R = 4;     // rows in flight per thread (independent 32-byte loads)
@@ -122,7 +122,7 @@ __global__ void dropout_kernel(const float* __restrict__ in, int64_t ld_in, cons
         const int r = rb + k;
         if (r >= M) break;
         if (thr != 0) {
-          const uint32_t b8 = nv_keep_bits8(seed, ((uint64_t)r * N + 8 * c) >> 3, stream_id, thr);
+          const uint32_t b8 = nv_keep_bits8(seed, ((uint64_t)r * row_mul * N + 8 * c) >> 3, stream_id, thr);
           v0[k] = nv_dropout4(v0[k], b8 & 0xFu, ks);
           v1[k] = nv_dropout4(v1[k], b8 >> 4, ks);
         }
@@ -351,7 +351,7 @@ int nv_mean_pool_bwd_launch(const float* dpooled, float* dx, bf16* dx_bf16, int 
 
 int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p,
-                      uint64_t seed, int stream_id, cudaStream_t stream) {
+                      uint64_t seed, int stream_id, int row_mul, cudaStream_t stream) {
   NV_REQUIRE(M >= 0 && N > 0 && N % 8 == 0, "dropout: N=%d must be a positive multiple of 8", N);
   NV_REQUIRE(p >= 0.f && p < 1.f, "dropout: p %f out of range [0, 1)", p);
   NV_REQUIRE(in != nullptr && (out_f32 != nullptr || out_bf16 != nullptr || colsum != nullptr), "dropout: null buffers");
@@ -367,7 +367,7 @@ int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int
   if (grid > (M + 3) / 4) grid = (M + 3) / 4;
   dropout_kernel<<<grid, threads, 0, stream>>>(in, ld_in, residual, ld_res, out_f32, ld_f32, out_bf16, ld_bf16, colsum,
                                                M, N, thr, nv_dropout_keep_scale(thr), seed, (uint32_t)stream_id,
-                                               thr != 0 ? nv_rng_epoch_dev() : nullptr);
+                                               thr != 0 ? nv_rng_epoch_dev() : nullptr, row_mul > 0 ? row_mul : 1);
   NV_LAUNCH_CHECK("dropout_kernel");
   return NV_OK;
 }

@@ -177,10 +177,18 @@ class GradStash:
     def __init__(self):
         self._e = None
 
-    def put(self, t: torch.Tensor, bf=None, colsum=None, tag=None):
+    def put(self, t: torch.Tensor, bf=None, colsum=None, tag=None, cls_only=False):
         # keep only the latest entry; holding `t` itself pins its storage so the address cannot be reused.
         # tag = (p, seed, stream) when bf / colsum already carry that dropout site's mask (side-car dropout).
+        # cls_only: t [B, N, D] is known to be zero outside token 0 of every sample (gradient of the cls-pooled
+        # head): a token-wise block can then run its backward on B rows instead of B*N.
         self._e = (t, t._version, bf, colsum, tag)
+        self._cls = bool(cls_only)
+
+    def cls_only(self, t: torch.Tensor) -> bool:
+        e = self._e
+        return bool(e is not None and getattr(self, "_cls", False) and e[0].data_ptr() == t.data_ptr()
+                    and e[0].shape == t.shape and e[0]._version == e[1] and t._version == e[1])
 
     def take(self, t: torch.Tensor, tag=None):
         """(bf16 copy, column sums) stashed for `t`, only if they were produced with the same dropout tag."""
@@ -322,7 +330,8 @@ class Engine:
         else:
             ops.linear_f32(dy, weight.detach(), w_kn=True, gelu_u=gelu_u, out=out)
             if drop is not None:
-                ops.dropout(out, p=drop[0], seed=drop[1], stream=drop[2], out_f32=out)
+                ops.dropout(out, p=drop[0], seed=drop[1], stream=drop[2], out_f32=out,
+                            row_mul=drop[4] if len(drop) > 4 else 1)
             if want_colsum:
                 ops.colsum(out, cs)
         if want_colsum:
@@ -488,7 +497,7 @@ class Engine:
         return y, (qkv, o, *aux)
 
     def attn_core_bwd(self, dy, dy_act, dy_colsum, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=None,
-                      p_attn=0.0, seed=0, sbase=0):
+                      p_attn=0.0, seed=0, sbase=0, cls_pre=None):
         """Returns da (grad wrt the LN output, fp32 or the activation dtype), dWqkv, dWout, dbout. dy is the
         fp32 grad of the block output; its residual branch is handled by the caller."""
         qkv, o, aux, aux2 = saved
@@ -496,9 +505,12 @@ class Engine:
         inner = heads * dim_head
         scale = dim_head ** -0.5
         dev = a.device
-        dO = self.dgrad(dy_act, w_out)
-        dWo = self.wgrad(dy_act, o, acc=GradAcc(w_out, self.mode))
-        dbo = self.bias_grad(dy, dy_colsum)
+        if cls_pre is not None:  # (dO with only the cls rows non-zero, dWo, dbo) computed on B rows by the caller
+            dO, dWo, dbo = cls_pre
+        else:
+            dO = self.dgrad(dy_act, w_out)
+            dWo = self.wgrad(dy_act, o, acc=GradAcc(w_out, self.mode))
+            dbo = self.bias_grad(dy, dy_colsum)
         dqkv = torch.empty(M, 3 * inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
             ws = torch.empty(B * heads * N, device=dev, dtype=F32)
@@ -553,6 +565,23 @@ class Engine:
         da = self.dgrad(dU, w1, out_dtype=da_dtype or F32)
         dW1 = self.wgrad(dU, a, acc=GradAcc(w1, self.mode))
         return da, dW1, db1, dW2, db2
+
+
+def _cls_rows(t2d, B, N):
+    """[B*N, C] -> strided [B, C] view of the rows of token 0 (row stride N*C, no copy)."""
+    return t2d.view(B, N, -1)[:, 0, :]
+
+
+def _cls_branch_grad(eng, dy2, B, N, drop):
+    """Gradient of the residual branch's last linear output on the cls rows only: (operand-dtype [B, D], column sums).
+    The dropout mask of that site is indexed with the ORIGINAL row (row_mul = N)."""
+    D = dy2.shape[1]
+    out = torch.empty(B, D, device=dy2.device, dtype=eng.act)
+    cs = torch.zeros(D, device=dy2.device, dtype=F32)
+    p, seed, stream = drop
+    ops.dropout(_cls_rows(dy2, B, N), p=max(p, 0.0), seed=seed, stream=stream, colsum=cs, row_mul=N,
+                out_f32=out if eng.act == F32 else None, out_bf16=out if eng.act == BF16 else None)
+    return out, cs
 
 
 _ENGINES = {}
@@ -624,9 +653,23 @@ class AttnBlockFn(torch.autograd.Function):
         eng = engine(mode)
         dy = dy.contiguous()
         dy2 = dy.view(B * N, -1)
-        dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, sbase + DROP_OUT))
+        cls_pre = None
+        if N > 1 and mode == "bf16" and _STASH.cls_only(dy):
+            # cls-only gradient (last block): to_out's dgrad / wgrad / bias gradient need the B cls rows only; the
+            # attention backward itself is dense (every key and value feeds the cls query)
+            _STASH.take(dy)
+            dy_act_c, cs = _cls_branch_grad(eng, dy2, B, N, (p_out, seed, sbase + DROP_OUT))
+            o = saved[1]
+            dO = torch.zeros(B * N, o.shape[1], device=dy.device, dtype=eng.act)
+            dO_c = eng.dgrad(dy_act_c, w_out)
+            _cls_rows(dO, B, N).copy_(dO_c)  # B rows of layout glue
+            cls_pre = (dO, eng.wgrad(dy_act_c, _cls_rows(o, B, N), acc=GradAcc(w_out, mode)), cs)
+            dy_act = None
+        else:
+            dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, sbase + DROP_OUT))
         da, dWqkv, dWo, dbo = eng.attn_core_bwd(dy2, dy_act, cs, a, saved, w_qkv, w_out, B, N, heads, dim_head,
-                                                da_dtype=eng.act, p_attn=p_attn, seed=seed, sbase=sbase)
+                                                da_dtype=eng.act, p_attn=p_attn, seed=seed, sbase=sbase,
+                                                cls_pre=cls_pre)
         side = eng.side_drop_for(prev, seed, B * N, x2.shape[1])
         dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy2, want_colsum=True,
                                           acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode),
@@ -685,6 +728,30 @@ class FFBlockFn(torch.autograd.Function):
         eng = engine(mode)
         dy = dy.contiguous()
         dy2 = dy.view(B * N, -1)
+        if N > 1 and mode == "bf16" and _STASH.cls_only(dy):
+            # Last block under a cls-pooled head: dy is zero outside token 0 and this block is token-wise, so the whole
+            # backward runs on the B cls rows (strided views, no gathers) and writes a cls-only dx again.
+            _STASH.take(dy)
+            D = x2.shape[1]
+            u, g, bits_gelu = saved
+            dy_act, cs = _cls_branch_grad(eng, dy2, B, N, (p_down, seed, sbase + DROP_DOWN))
+            dU, db1 = eng.dgrad(dy_act, w2, gelu_u=_cls_rows(u, B, N), want_colsum=True, colsum_acc=GradAcc(b1, mode),
+                                drop=(p_gelu, seed, sbase + DROP_GELU, bits_gelu, N))
+            dW2 = eng.wgrad(dy_act, _cls_rows(g, B, N), acc=GradAcc(w2, mode))
+            da = eng.dgrad(dU, w1, out_dtype=eng.act)
+            dW1 = eng.wgrad(dU, _cls_rows(a, B, N), acc=GradAcc(w1, mode))
+            dx = torch.zeros(B * N, D, device=dy.device, dtype=F32)
+            dxb = torch.zeros(B * N, D, device=dy.device, dtype=BF16) if mode == "bf16" else None
+            acc_g, acc_b = GradAcc(ln_w, mode), GradAcc(ln_b, mode)
+            cs2 = torch.zeros(D, device=dy.device, dtype=F32)
+            side = eng.side_drop_for(prev, seed, B, D)
+            ops.layernorm_bwd(da, x2, mean.view(B, N)[:, 0].contiguous(), rstd.view(B, N)[:, 0].contiguous(),
+                              ln_w.detach(), M=B, D=D, xmap=(1, N, 0), dres=dy2, ld_dres=N * D, dx=dx, dxmap=(1, N, 0),
+                              dx_bf16=dxb, dgamma=acc_g.buf, dbeta=acc_b.buf, colsum=cs2,
+                              side_drop=None if side is None else (*side, eng.side_bits(side)))
+            dx = dx.view(B, N, -1)
+            _STASH.put(dx, dxb.view(B, N, -1) if dxb is not None else None, cs2, tag=side, cls_only=True)
+            return dx, acc_g.result(), acc_b.result(), dW1, db1, dW2, cs, None, None, None, None, None, None, None
         dy_act, cs = eng.branch_grad(dy, dy2, (p_down, seed, sbase + DROP_DOWN))
         da, dW1, db1, dW2, db2 = eng.ff_core_bwd(dy2, dy_act, cs, a, saved, w1, b1, w2, da_dtype=eng.act,
                                                  p_gelu=p_gelu, seed=seed, sbase=sbase)
@@ -869,7 +936,7 @@ class HeadFn(torch.autograd.Function):
                          N * D, acc_w.buf, acc_b, acc_g, acc_be, B, D, C)
             cs = torch.zeros(D, device=dev, dtype=F32)   # column sums of dx = sum of the cls rows (bias gradient of
             ops.batch_sum(dx, N * D, cs, B, D)           # the last block's down projection): no 100 MB colsum pass
-            _STASH.put(dx, dxb, cs)
+            _STASH.put(dx, dxb, cs, cls_only=True)
             return dx, acc_g, acc_be, acc_w.result(), acc_b, None, None, None
         dw = ops.linear_f32(dl, y, x_km=True, w_kn=True)            # [C, D] = dl^T y
         db = torch.zeros(C, device=dev, dtype=F32)

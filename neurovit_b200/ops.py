@@ -99,11 +99,12 @@ def gemm_bf16(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, gelu_u=
         cta_group = GEMM_CTA_GROUP
     dp, dseed, dstream = dropout[:3] if dropout is not None else (0.0, 0, 0)
     dbits = dropout[3] if dropout is not None and len(dropout) > 3 else None
+    dmul = dropout[4] if dropout is not None and len(dropout) > 4 else 1
     args = (int(a_mn), int(b_mn), M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(bias),
             _ptr(residual), ld(residual), _ptr(gelu_u), ld(gelu_u), _ptr(out_f32), ld(out_f32),
             _ptr(out_bf16), ld(out_bf16), _ptr(out_pre), ld(out_pre), _ptr(colsum), int(apply_gelu),
             int(accumulate), float(alpha), int(k_splits), int(block_n), int(cta_group), float(dp), int(dseed),
-            int(dstream), _ptr(dbits), _stream())
+            int(dstream), _ptr(dbits), int(dmul), _stream())
     if PROFILE.enabled:
         with PROFILE.region(2.0 * M * N * K):
             _lib.call("nv_gemm_bf16", *args)
@@ -145,7 +146,7 @@ def adamw_flat(p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, weight_decay, step,
               float(beta2), float(eps), float(weight_decay), int(step), _ptr(step_dev), _stream())
 
 
-def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, colsum=None):
+def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, colsum=None, row_mul=1):
     """v = x * keep / (1 - p) with the (seed, stream, row * N + col) mask of the GEMM epilogues; out = v (+ residual);
     colsum += column sums of v. x: fp32 [M, N] (unit inner stride), N % 8 == 0."""
     _dev(x)
@@ -156,7 +157,7 @@ def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, c
         if t is not None:
             assert t.dtype == dt and tuple(t.shape) == (M, N) and t.stride(1) == 1
     _lib.call("nv_dropout", _ptr(x), ld(x), _ptr(residual), ld(residual), _ptr(out_f32), ld(out_f32), _ptr(out_bf16),
-              ld(out_bf16), _ptr(colsum), M, N, float(p), int(seed), int(stream), _stream())
+              ld(out_bf16), _ptr(colsum), M, N, float(p), int(seed), int(stream), int(row_mul), _stream())
 
 
 def dropout_bits(out, *, p, seed, stream):

@@ -230,8 +230,9 @@ def _replay_masks(trace, B, N, heads, ks_of):
     return masks
 
 
+@pytest.mark.parametrize("batch", [6, 64])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode):
+def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode, batch):
     """Dropout p > 0 in training mode (the reference's default TRAINING_DROPOUT 0.1 at all 25 sites): the masks
     the kernels drew are replayed into the CPU oracle; logits and every gradient must then agree."""
     from neurovit_b200 import functional as Fn
@@ -240,8 +241,10 @@ def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode):
                 heads=2, mlp_dim=128, channels=1, dim_head=64, dropout=0.2, emb_dropout=0.1)
     m = ViT(**ctor)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    x = torch.randn(6, 1, 24, 16, 16)   # 6 x 13 tokens = 78 rows >= 64: the LayerNorm-backward side-car masking path
-    y = torch.tensor([0, 1, 1, 0, 1, 0])
+    # 6 x 13 tokens = 78 rows >= 64: the LayerNorm-backward side-car masking path; batch 64 also takes the pipelined
+    # LayerNorm backward on the 64 cls rows of the last block (row maps + side-car mask with the original row index)
+    x = torch.randn(batch, 1, 24, 16, 16)
+    y = torch.randint(0, 2, (batch,))
     m = m.to(DEV).train().set_precision(mode)
     Fn.DROPOUT_TRACE.record = []
     try:
@@ -255,7 +258,7 @@ def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode):
     n_tok = (24 // 8) * (16 // 8) * (16 // 8) + 1
     assert len(trace) == 1 + 2 * 4, [t[0] for t in trace]
     ks_of = lambda p: 65536.0 / (65536 - int(p * 65536 + 0.5))
-    masks = _replay_masks(trace, 6, n_tok, 2, ks_of)
+    masks = _replay_masks(trace, batch, n_tok, 2, ks_of)
     for k_, v_ in masks.items():
         assert 0.5 < (v_ != 0).float().mean().item() < 0.98, k_   # really dropping, at roughly the asked rate
     leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
