@@ -138,6 +138,14 @@ int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_ba
                      void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse,
                      int B, int N, int H, int head_dim, float scale, float dropout_p, int64_t seed,
                      void* drop_mask, int drop_mask_ready, void* stream);
+/* Backward when only the cls query (token 0 of every sample) carries gradient (last block, pool='cls'):
+ * dO_cls [B, H*64] holds that row's dO (batch stride dO_batch_stride), o's token-0 rows are read at o + b*o_batch_stride.
+ * Writes dq (zero except token 0), dk, dv for every token: O(N d) per (batch, head). */
+int nv_attention_cls_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                         const void* o, int64_t o_batch_stride, const void* dO_cls, int64_t dO_batch_stride,
+                         const float* lse, void* dq, void* dk, void* dv, int64_t dqkv_batch_stride,
+                         int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, float dropout_p,
+                         const void* drop_mask, void* stream);
 /* delta_ws: fp32 workspace of B*H*N elements */
 int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      const void* o, const void* dO, int64_t o_batch_stride, int64_t o_row_stride,

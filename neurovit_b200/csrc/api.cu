@@ -64,6 +64,10 @@ int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
                           const bf16* dO, int64_t o_bs, int64_t o_rs, const float* lse, float* delta_ws, bf16* dq,
                           bf16* dk, bf16* dv, int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim,
                           float scale, float dropout_p, const uint32_t* drop_mask, cudaStream_t stream);
+int nv_attn_cls_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
+                           int64_t o_bs, const bf16* dO_cls, int64_t do_bs, const float* lse, bf16* dq, bf16* dk, bf16* dv,
+                           int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim, float scale, float dropout_p,
+                           const uint32_t* drop_mask, cudaStream_t stream);
 int nv_cast_f32_bf16_launch(const float* in, bf16* out, int64_t n, cudaStream_t stream);
 int nv_cast_transpose_launch(const float* in, bf16* out, bf16* outT, int R, int C, cudaStream_t stream);
 int nv_colsum_launch(const void* in, int in_is_bf16, int64_t ld, float* out, int M, int N, cudaStream_t stream);
@@ -223,6 +227,17 @@ int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_ba
                                (const bf16*)o, (const bf16*)dO, o_batch_stride, o_row_stride, lse, delta_ws,
                                (bf16*)dq, (bf16*)dk, (bf16*)dv, dqkv_batch_stride, dqkv_row_stride, B, N, H, head_dim,
                                scale, dropout_p, (const uint32_t*)drop_mask, ST(stream));
+}
+
+int nv_attention_cls_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                         const void* o, int64_t o_batch_stride, const void* dO_cls, int64_t dO_batch_stride,
+                         const float* lse, void* dq, void* dk, void* dv, int64_t dqkv_batch_stride,
+                         int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, float dropout_p,
+                         const void* drop_mask, void* stream) {
+  return nv_attn_cls_bwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
+                                (const bf16*)o, o_batch_stride, (const bf16*)dO_cls, dO_batch_stride, lse, (bf16*)dq,
+                                (bf16*)dk, (bf16*)dv, dqkv_batch_stride, dqkv_row_stride, B, N, H, head_dim, scale,
+                                dropout_p, (const uint32_t*)drop_mask, ST(stream));
 }
 
 int nv_softmax_fwd(float* s, int64_t rows, int n, void* stream) { return nv_softmax_fwd_launch(s, rows, n, ST(stream)); }

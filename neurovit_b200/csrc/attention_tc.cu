@@ -900,6 +900,79 @@ __global__ void attn_tc_delta_kernel(const bf16* __restrict__ dO, const bf16* __
   }
 }
 
+// Attention backward when only the cls query (token 0) of every sample carries gradient — the last block under a
+// cls-pooled head (vit_3d.py:123): dS has a single non-zero row, so dK and dV are rank-1 in that row and dQ is one
+// row: O(N d) per (batch, head) instead of O(N^2 d). One CTA per (head, batch), a thread per key.
+__global__ void __launch_bounds__(128)
+attn_cls_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int64_t qkv_bs,
+                    int64_t qkv_rs, const bf16* __restrict__ o, int64_t o_bs, const bf16* __restrict__ dO_cls,
+                    int64_t do_bs, const float* __restrict__ lse, bf16* __restrict__ dq, bf16* __restrict__ dk,
+                    bf16* __restrict__ dv, int64_t d_bs, int64_t d_rs, int N, int H, float scale,
+                    const uint32_t* __restrict__ mask, int mask_words, float keep_scale) {
+  __shared__ float qc[HD], doc[HD], red[4][HD];
+  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  if (t < HD) {
+    qc[t] = __bfloat162float(q[(int64_t)b * qkv_bs + h * HD + t]);             // token 0
+    doc[t] = __bfloat162float(dO_cls[(int64_t)b * do_bs + h * HD + t]);
+  }
+  __syncthreads();
+  float delta = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < HD; ++d) delta = fmaf(doc[d], __bfloat162float(o[(int64_t)b * o_bs + h * HD + d]), delta);
+  const int64_t bh = (int64_t)b * H + h;
+  const float lse2 = lse[bh * N] * LOG2E;
+  float dq_acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) dq_acc[d] = 0.f;
+  for (int key = t; key < N; key += 128) {
+    const bf16* kr = k + (int64_t)b * qkv_bs + (int64_t)key * qkv_rs + h * HD;
+    const bf16* vr = v + (int64_t)b * qkv_bs + (int64_t)key * qkv_rs + h * HD;
+    float kf[HD];
+    float s = 0.f, dp = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 kk = *reinterpret_cast<const uint4*>(kr + 8 * c), vv = *reinterpret_cast<const uint4*>(vr + 8 * c);
+      const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w}, vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(kw[j]), c2 = unpack_bf16x2(vw[j]);
+        kf[8 * c + 2 * j] = a.x; kf[8 * c + 2 * j + 1] = a.y;
+        s = fmaf(qc[8 * c + 2 * j], a.x, fmaf(qc[8 * c + 2 * j + 1], a.y, s));
+        dp = fmaf(doc[8 * c + 2 * j], c2.x, fmaf(doc[8 * c + 2 * j + 1], c2.y, dp));
+      }
+    }
+    const float p = ex2(fmaf(s, scale * LOG2E, -lse2));
+    bool keep = true;
+    if (mask != nullptr) keep = (mask[bh * N * mask_words + (key >> 5)] >> (key & 31)) & 1u;  // row of token 0
+    const float pm = keep ? p * keep_scale : 0.f;
+    const float ds = p * ((keep ? dp * keep_scale : 0.f) - delta) * scale;
+    bf16* dkr = dk + (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD;
+    bf16* dvr = dv + (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD;
+    bf16* dqr = dq + (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      uint4 a, bb;
+      a.x = pack_bf16x2(ds * qc[8 * c], ds * qc[8 * c + 1]); a.y = pack_bf16x2(ds * qc[8 * c + 2], ds * qc[8 * c + 3]);
+      a.z = pack_bf16x2(ds * qc[8 * c + 4], ds * qc[8 * c + 5]); a.w = pack_bf16x2(ds * qc[8 * c + 6], ds * qc[8 * c + 7]);
+      bb.x = pack_bf16x2(pm * doc[8 * c], pm * doc[8 * c + 1]); bb.y = pack_bf16x2(pm * doc[8 * c + 2], pm * doc[8 * c + 3]);
+      bb.z = pack_bf16x2(pm * doc[8 * c + 4], pm * doc[8 * c + 5]); bb.w = pack_bf16x2(pm * doc[8 * c + 6], pm * doc[8 * c + 7]);
+      *reinterpret_cast<uint4*>(dkr + 8 * c) = a;
+      *reinterpret_cast<uint4*>(dvr + 8 * c) = bb;
+      if (key != 0) *reinterpret_cast<uint4*>(dqr + 8 * c) = make_uint4(0u, 0u, 0u, 0u);  // queries other than the cls token
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dq_acc[d] = fmaf(ds, kf[d], dq_acc[d]);
+  }
+  // dQ of the cls row: reduce the per-thread partial sums
+#pragma unroll
+  for (int d = 0; d < HD; ++d) {
+    const float r = warp_sum(dq_acc[d]);
+    if ((t & 31) == 0) red[t >> 5][d] = r;
+  }
+  __syncthreads();
+  if (t < HD) dq[(int64_t)b * d_bs + h * HD + t] = __float2bfloat16(red[0][t] + red[1][t] + red[2][t] + red[3][t]);
+}
+
 int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, int N, int H, int box_rows = 64) {
   const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)N, (uint64_t)B};
   const uint64_t strides[2] = {(uint64_t)rs * 2, (uint64_t)bs * 2};
@@ -1007,5 +1080,29 @@ int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   NV_LAUNCH_CHECK("attn_tc_bwd_dq_kernel");
   attn_tc_bwd_dkv_kernel<<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
   NV_LAUNCH_CHECK("attn_tc_bwd_dkv_kernel");
+  return NV_OK;
+}
+
+int nv_attn_cls_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
+                           int64_t o_bs, const bf16* dO_cls, int64_t do_bs, const float* lse, bf16* dq, bf16* dk, bf16* dv,
+                           int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim, float scale, float dropout_p,
+                           const uint32_t* drop_mask, cudaStream_t stream) {
+  NV_REQUIRE(head_dim == HD, "attention: head_dim %d unsupported by the bf16 kernels (needs 64)", head_dim);
+  NV_REQUIRE(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad sizes B=%d N=%d H=%d", B, N, H);
+  if (B == 0) return NV_OK;
+  int s;
+  if ((s = check_args(q, qkv_bs, qkv_rs, "q")) != NV_OK) return s;
+  if ((s = check_args(k, qkv_bs, qkv_rs, "k")) != NV_OK) return s;
+  if ((s = check_args(v, qkv_bs, qkv_rs, "v")) != NV_OK) return s;
+  if ((s = check_args(dq, d_bs, d_rs, "dq")) != NV_OK) return s;
+  if ((s = check_args(dk, d_bs, d_rs, "dk")) != NV_OK) return s;
+  if ((s = check_args(dv, d_bs, d_rs, "dv")) != NV_OK) return s;
+  NV_REQUIRE(o != nullptr && dO_cls != nullptr && lse != nullptr, "attention: null o / dO / lse");
+  Common c;
+  if ((s = fill_common(c, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
+  attn_cls_bwd_kernel<<<dim3(H, B), 128, 0, stream>>>(q, k, v, qkv_bs, qkv_rs, o, o_bs, dO_cls, do_bs, lse, dq, dk, dv, d_bs,
+                                                      d_rs, N, H, scale, c.drop_thr != 0 ? c.mask : nullptr, c.mask_words,
+                                                      c.keep_scale);
+  NV_LAUNCH_CHECK("attn_cls_bwd_kernel");
   return NV_OK;
 }

@@ -513,9 +513,13 @@ class Engine:
             dbo = self.bias_grad(dy, dy_colsum)
         dqkv = torch.empty(M, 3 * inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
-            ws = torch.empty(B * heads * N, device=dev, dtype=F32)
-            ops.attention_bwd(qkv, o, dO, aux, ws, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=scale,
-                              dropout_p=p_attn if aux2 is not None else 0.0, drop_mask=aux2)
+            if cls_pre is not None:  # only the cls query has gradient: rank-1 dK / dV, one dQ row
+                ops.attention_cls_bwd(qkv, o, dO, aux, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=scale,
+                                      dropout_p=p_attn if aux2 is not None else 0.0, drop_mask=aux2)
+            else:
+                ws = torch.empty(B * heads * N, device=dev, dtype=F32)
+                ops.attention_bwd(qkv, o, dO, aux, ws, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=scale,
+                                  dropout_p=p_attn if aux2 is not None else 0.0, drop_mask=aux2)
         else:
             P = aux
             Pd = aux2 if aux2 is not None else P
@@ -660,10 +664,8 @@ class AttnBlockFn(torch.autograd.Function):
             _STASH.take(dy)
             dy_act_c, cs = _cls_branch_grad(eng, dy2, B, N, (p_out, seed, sbase + DROP_OUT))
             o = saved[1]
-            dO = torch.zeros(B * N, o.shape[1], device=dy.device, dtype=eng.act)
-            dO_c = eng.dgrad(dy_act_c, w_out)
-            _cls_rows(dO, B, N).copy_(dO_c)  # B rows of layout glue
-            cls_pre = (dO, eng.wgrad(dy_act_c, _cls_rows(o, B, N), acc=GradAcc(w_out, mode)), cs)
+            dO_c = eng.dgrad(dy_act_c, w_out)                      # [B, inner]: dO of the cls query only
+            cls_pre = (dO_c, eng.wgrad(dy_act_c, _cls_rows(o, B, N), acc=GradAcc(w_out, mode)), cs)
             dy_act = None
         else:
             dy_act, cs = eng.branch_grad(dy, dy2, (p_out, seed, sbase + DROP_OUT))

@@ -304,6 +304,18 @@ def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale, dropout_p=0.0, seed=
               _ptr(drop_mask), int(bool(mask_ready)), _stream())
 
 
+def attention_cls_bwd(qkv, o, dO_cls, lse, dqkv, *, B, N, H, head_dim, scale, dropout_p=0.0, drop_mask=None):
+    """Attention backward when only token 0 of every sample has gradient: dO_cls [B, H*hd] bf16 (contiguous rows)."""
+    _dev(qkv)
+    inner = H * head_dim
+    rs, drs = qkv.stride(0), dqkv.stride(0)
+    assert dO_cls.dtype == BF16 and dO_cls.stride(1) == 1 and tuple(dO_cls.shape) == (B, inner)
+    _lib.call("nv_attention_cls_bwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
+              N * o.stride(0), _ptr(dO_cls), dO_cls.stride(0), _ptr(lse), _off(dqkv, 0), _off(dqkv, inner),
+              _off(dqkv, 2 * inner), N * drs, drs, B, N, H, head_dim, float(scale), float(dropout_p), _ptr(drop_mask),
+              _stream())
+
+
 def attention_bwd(qkv, o, dO, lse, delta_ws, dqkv, *, B, N, H, head_dim, scale, dropout_p=0.0, drop_mask=None):
     _dev(qkv)
     inner = H * head_dim
