@@ -223,6 +223,21 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
+// predicated global stores: written as one `@p st` so that the eight row stores of a chunk stay straight-line code
+// (an `if (ok) *ptr = v` per row compiles to a branch + reconvergence block around every store)
+__device__ __forceinline__ void stg_v4_if(bool ok, float* ptr, const float4& v) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %5, 0; @p st.global.v4.f32 [%0], {%1, %2, %3, %4}; }" ::"l"(ptr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok) : "memory");
+}
+__device__ __forceinline__ void red_v4_if(bool ok, float* ptr, const float4& v) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %5, 0; @p red.global.add.v4.f32 [%0], {%1, %2, %3, %4}; }" ::"l"(ptr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok) : "memory");
+}
+__device__ __forceinline__ void stg_v2_if(bool ok, void* ptr, uint32_t lo, uint32_t hi) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %3, 0; @p st.global.v2.b32 [%0], {%1, %2}; }" ::"l"(ptr), "r"(lo), "r"(hi),
+               "r"((int)ok) : "memory");
+}
+
 template <int EPI_MODE, bool DROP>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], uint32_t stage, int lane,
                                                int row0, int col0, const EpiAux& x) {
@@ -250,54 +265,91 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       }
     }
   }
+  // Three straight-line passes (read the slab, arithmetic, stores) instead of one row at a time: the per-row form
+  // re-read the kernel parameters and branched on them inside every row, which left each warp waiting on a chain
+  // of LDS -> LDC -> branch -> address math -> STG eight times per chunk with nothing else to issue.
+  // G rows at a time (all eight under the 168-register budget of the store epilogue, four under the 96 of the
+  // 16-warp GELU epilogues)
+  constexpr int G = EPI_MODE == 0 ? 8 : 4;
+  const bool has_res = EPI_MODE == 0 && p.residual != nullptr;
+  const int gm0 = row0 + sub_r;
+  // rows this lane may store: gm0 + 4 i < M  <=>  i < rows_ok
+  const int rows_ok = col_ok ? min(8, (p.M - gm0 + 3) >> 2) : 0;
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + sub_r;
-    const int gm = row0 + r;
-    uint32_t keep4 = 0xFu;
-    if (DROP) {
-      const uint32_t other = __shfl_xor_sync(0xffffffffu, kb[i & 3], 1);
-      const uint32_t b8 = ((sub_c & 1) == (i >> 2)) ? kb[i & 3] : other;
-      keep4 = (b8 >> ((sub_c & 1) * 4)) & 0xFu;
+  for (int g = 0; g < 8; g += G) {
+    float4 a[G];
+    uint2 pre[EPI_MODE == 1 ? G : 1];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int r = (g + k) * 4 + sub_r;
+      a[k] = lds_v4(stage + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4));
     }
-    float4 a = lds_v4(stage + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4));
-    const bool ok = col_ok && gm < p.M;
-    if (EPI_MODE == 0) {
-      a.x = fmaf(a.x, p.alpha, x.bias4.x);
-      a.y = fmaf(a.y, p.alpha, x.bias4.y);
-      a.z = fmaf(a.z, p.alpha, x.bias4.z);
-      a.w = fmaf(a.w, p.alpha, x.bias4.w);
-      if (DROP) a = nv_dropout4(a, keep4, p.keep_scale);
-      if (p.residual != nullptr) {
-        a.x += x.res[i].x; a.y += x.res[i].y; a.z += x.res[i].z; a.w += x.res[i].w;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+      const int i = g + k;
+      uint32_t keep4 = 0xFu;
+      if (DROP) {
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, kb[i & 3], 1);
+        const uint32_t b8 = ((sub_c & 1) == (i >> 2)) ? kb[i & 3] : other;
+        keep4 = (b8 >> ((sub_c & 1) * 4)) & 0xFu;
       }
-    } else if (EPI_MODE == 1) {
-      a.x += x.bias4.x; a.y += x.bias4.y; a.z += x.bias4.z; a.w += x.bias4.w;
-      if (ok && p.out_pre != nullptr)
-        *reinterpret_cast<uint2*>(p.out_pre + (int64_t)gm * p.ld_pre + gn) =
-            make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-      a.x = gelu_fast(a.x); a.y = gelu_fast(a.y); a.z = gelu_fast(a.z); a.w = gelu_fast(a.w);
-      if (DROP) a = nv_dropout4(a, keep4, p.keep_scale);
-    } else {
-      const float2 u01 = unpack_bf16x2(x.uu[i].x);
-      const float2 u23 = unpack_bf16x2(x.uu[i].y);
-      a.x *= gelu_grad_fast(u01.x); a.y *= gelu_grad_fast(u01.y);
-      a.z *= gelu_grad_fast(u23.x); a.w *= gelu_grad_fast(u23.y);
-      if (DROP) a = nv_dropout4(a, keep4, p.keep_scale);  // d/du of dropout(gelu(u)): the activation's forward mask
+      float4 t = a[k];
+      if (EPI_MODE == 0) {
+        t.x = fmaf(t.x, p.alpha, x.bias4.x);
+        t.y = fmaf(t.y, p.alpha, x.bias4.y);
+        t.z = fmaf(t.z, p.alpha, x.bias4.z);
+        t.w = fmaf(t.w, p.alpha, x.bias4.w);
+        if (DROP) t = nv_dropout4(t, keep4, p.keep_scale);
+        if (has_res) {
+          t.x += x.res[i].x; t.y += x.res[i].y; t.z += x.res[i].z; t.w += x.res[i].w;
+        }
+      } else if (EPI_MODE == 1) {
+        t.x += x.bias4.x; t.y += x.bias4.y; t.z += x.bias4.z; t.w += x.bias4.w;
+        pre[EPI_MODE == 1 ? k : 0] = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+        t.x = gelu_fast(t.x); t.y = gelu_fast(t.y); t.z = gelu_fast(t.z); t.w = gelu_fast(t.w);
+        if (DROP) t = nv_dropout4(t, keep4, p.keep_scale);
+      } else {
+        const float2 u01 = unpack_bf16x2(x.uu[i].x);
+        const float2 u23 = unpack_bf16x2(x.uu[i].y);
+        t.x *= gelu_grad_fast(u01.x); t.y *= gelu_grad_fast(u01.y);
+        t.z *= gelu_grad_fast(u23.x); t.w *= gelu_grad_fast(u23.y);
+        if (DROP) t = nv_dropout4(t, keep4, p.keep_scale);  // d/du of dropout(gelu(u)): the activation's forward mask
+      }
+      a[k] = t;
     }
-    if (ok) {
-      if (EPI_MODE == 0 && (p.flags & EPI_ATOMIC)) {
-        float* dst = p.out_f32 + (int64_t)gm * p.ld_f32 + gn;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z),
-                     "f"(a.w) : "memory");
-      } else if (p.out_f32 != nullptr) {
-        *reinterpret_cast<float4*>(p.out_f32 + (int64_t)gm * p.ld_f32 + gn) = a;
+    if (EPI_MODE == 1 && p.out_pre != nullptr) {
+      __nv_bfloat16* dst = p.out_pre + (int64_t)gm0 * p.ld_pre + gn;
+      const int64_t step = (int64_t)4 * p.ld_pre;
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+        stg_v2_if(g + k < rows_ok, dst + (g + k) * step, pre[EPI_MODE == 1 ? k : 0].x, pre[EPI_MODE == 1 ? k : 0].y);
+    }
+    if (EPI_MODE == 0 && (p.flags & EPI_ATOMIC)) {
+      float* dst = p.out_f32 + (int64_t)gm0 * p.ld_f32 + gn;
+      const int64_t step = (int64_t)4 * p.ld_f32;
+#pragma unroll
+      for (int k = 0; k < G; ++k) red_v4_if(g + k < rows_ok, dst + (g + k) * step, a[k]);
+    } else if (p.out_f32 != nullptr) {
+      float* dst = p.out_f32 + (int64_t)gm0 * p.ld_f32 + gn;
+      const int64_t step = (int64_t)4 * p.ld_f32;
+#pragma unroll
+      for (int k = 0; k < G; ++k) stg_v4_if(g + k < rows_ok, dst + (g + k) * step, a[k]);
+    }
+    if (p.out_bf16 != nullptr) {
+      __nv_bfloat16* dst = p.out_bf16 + (int64_t)gm0 * p.ld_bf16 + gn;
+      const int64_t step = (int64_t)4 * p.ld_bf16;
+#pragma unroll
+      for (int k = 0; k < G; ++k)
+        stg_v2_if(g + k < rows_ok, dst + (g + k) * step, pack_bf16x2(a[k].x, a[k].y), pack_bf16x2(a[k].z, a[k].w));
+    }
+    if (EPI_MODE != 1 && p.colsum != nullptr) {
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const bool ok = g + k < rows_ok;
+        csum.x += ok ? a[k].x : 0.f; csum.y += ok ? a[k].y : 0.f;
+        csum.z += ok ? a[k].z : 0.f; csum.w += ok ? a[k].w : 0.f;
       }
-      if (p.out_bf16 != nullptr)
-        *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)gm * p.ld_bf16 + gn) =
-            make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-      csum.x += a.x; csum.y += a.y; csum.z += a.z; csum.w += a.w;
     }
   }
   if (EPI_MODE != 1 && p.colsum != nullptr) {  // warp-uniform: fold the 4 row groups, one vector red per chunk
