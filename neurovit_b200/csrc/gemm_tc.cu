@@ -22,6 +22,7 @@
 //         third (the 1-CTA 128x256 tile is L2-bandwidth bound on B200: 96 B/clk/SM x 148 SMs > L2's ~6.3 KB/clk).
 #include "nv_common.cuh"
 #include "nv_rng.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -30,7 +31,9 @@ constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 // epilogue warps: 8 for the store epilogue (memory-bound: residual prefetch is double-buffered in registers),
 // 16 for the two GELU epilogues (instruction-bound: four warps per SM sub-partition hide the MUFU/FMA chains)
-__host__ __device__ constexpr int epi_warps(int epi_mode) { return epi_mode == 0 ? 8 : 16; }
+__host__ __device__ constexpr int epi_warps(int epi_mode) { return (epi_mode == 0 || epi_mode == 3) ? 8 : 16; }
+// 4 KB shared-memory slabs per epilogue warp: the transpose slab, plus a two-deep residual ring in mode 3
+__host__ __device__ constexpr int epi_slabs(int epi_mode) { return epi_mode == 3 ? 3 : 1; }
 __host__ __device__ constexpr int num_threads(int epi_mode) { return (epi_warps(epi_mode) + 2) * 32; }
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;          // per epilogue warp
@@ -62,14 +65,14 @@ struct GemmParams {
   uint32_t drop_stream;
 };
 
-template <int BLOCK_N, int STAGES, int CG, int NUM_EPI_WARPS>
+template <int BLOCK_N, int STAGES, int CG, int NUM_EPI_WARPS, int EPI_SLABS = 1>
 struct SmemLayout {
   static constexpr int B_ROWS = BLOCK_N / CG;  // B rows staged by one CTA
   static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + STAGES * A_STAGE_BYTES;
   static constexpr int EPI_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + NUM_EPI_WARPS * EPI_SLABS * EPI_STAGE_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024B alignment
@@ -238,9 +241,39 @@ __device__ __forceinline__ void stg_v2_if(bool ok, void* ptr, uint32_t lo, uint3
                "r"((int)ok) : "memory");
 }
 
+// EPI_MODE 3 = mode 0 for the forward linears that add the fp32 residual stream (K-major operands, CTA pairs). Every
+// global load of an epilogue warp completes on one hardware scoreboard, so a register prefetch can never have more
+// than "everything issued so far" granularity and is one chunk deep at best. Here the residual chunk is copied by
+// cp.async (completion counted per commit group) into a two-slab ring per warp, in the swizzled layout of the
+// transposed accumulator: two chunks are in flight while a third is processed. Each lane copies exactly the
+// 16-byte pieces it reads back itself, so its own wait_group is all the synchronisation needed.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_PENDING> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+}
+__device__ __forceinline__ void residual_prefetch(const GemmParams& p, uint32_t slab, int lane, int row0, int col0) {
+  const int sub_r = lane >> 3, sub_c = lane & 7;
+  const int gn_raw = col0 + sub_c * 4;
+  const int gn = gn_raw < p.N ? gn_raw : 0;  // clamped like epi_prefetch: never stored
+  const int gm_last = p.M - 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + sub_r;
+    cp_async16(slab + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4),
+               p.residual + (int64_t)min(row0 + r, gm_last) * p.ld_res + gn);
+  }
+  cp_async_commit();
+}
+
+// next_col0 >= 0 (mode 3): once this chunk's residual has been read out of `res_slab`, refill the slab with the
+// residual of the chunk at column next_col0
 template <int EPI_MODE, bool DROP>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&v)[32], uint32_t stage, int lane,
-                                               int row0, int col0, const EpiAux& x) {
+                                               int row0, int col0, const EpiAux& x, uint32_t res_slab = 0,
+                                               int next_col0 = -1) {
   const int sub_r = lane >> 3, sub_c = lane & 7;
   const int gn = col0 + sub_c * 4;
   const bool col_ok = gn < p.N;
@@ -270,7 +303,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   // of LDS -> LDC -> branch -> address math -> STG eight times per chunk with nothing else to issue.
   // G rows at a time (all eight under the 168-register budget of the store epilogue, four under the 96 of the
   // 16-warp GELU epilogues)
-  constexpr int G = EPI_MODE == 0 ? 8 : 4;
+  constexpr bool STORE = EPI_MODE == 0 || EPI_MODE == 3;
+  constexpr int G = STORE ? 8 : 4;
   const bool has_res = EPI_MODE == 0 && p.residual != nullptr;
   const int gm0 = row0 + sub_r;
   // rows this lane may store: gm0 + 4 i < M  <=>  i < rows_ok
@@ -279,12 +313,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
   for (int g = 0; g < 8; g += G) {
     float4 a[G];
+    float4 rr[EPI_MODE == 3 ? G : 1];
     uint2 pre[EPI_MODE == 1 ? G : 1];
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int r = (g + k) * 4 + sub_r;
       a[k] = lds_v4(stage + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4));
+      if (EPI_MODE == 3) rr[EPI_MODE == 3 ? k : 0] = lds_v4(res_slab + (uint32_t)((r * 32 + ((sub_c ^ (r & 7)) << 2)) * 4));
     }
+    if (EPI_MODE == 3 && next_col0 >= 0) residual_prefetch(p, res_slab, lane, row0, next_col0);
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int i = g + k;
@@ -295,13 +332,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         keep4 = (b8 >> ((sub_c & 1) * 4)) & 0xFu;
       }
       float4 t = a[k];
-      if (EPI_MODE == 0) {
+      if (STORE) {
         t.x = fmaf(t.x, p.alpha, x.bias4.x);
         t.y = fmaf(t.y, p.alpha, x.bias4.y);
         t.z = fmaf(t.z, p.alpha, x.bias4.z);
         t.w = fmaf(t.w, p.alpha, x.bias4.w);
         if (DROP) t = nv_dropout4(t, keep4, p.keep_scale);
-        if (has_res) {
+        if (EPI_MODE == 3) {
+          const float4 r4 = rr[EPI_MODE == 3 ? k : 0];
+          t.x += r4.x; t.y += r4.y; t.z += r4.z; t.w += r4.w;
+        } else if (has_res) {
           t.x += x.res[i].x; t.y += x.res[i].y; t.z += x.res[i].z; t.w += x.res[i].w;
         }
       } else if (EPI_MODE == 1) {
@@ -374,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int NUM_EPI_WARPS = epi_warps(EPI_MODE);
   constexpr int TMA_WARP = NUM_EPI_WARPS;
   constexpr int MMA_WARP = NUM_EPI_WARPS + 1;
-  using L = SmemLayout<BLOCK_N, STAGES, CG, NUM_EPI_WARPS>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG, NUM_EPI_WARPS, epi_slabs(EPI_MODE)>;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem window starts at the same offset in every CTA, so the aligned layout (and therefore
   // every barrier / tile offset) is identical in both CTAs of a pair
@@ -522,7 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ------------------------------- epilogue warps -----------------------------------------
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int part = warp >> 2;   // which 32-column chunks (part, part + W, ...) this warp owns
-    const uint32_t stage = smem_u32(smem + L::EPI_OFF + warp * EPI_STAGE_BYTES);
+    const uint32_t stage = smem_u32(smem + L::EPI_OFF + warp * epi_slabs(EPI_MODE) * EPI_STAGE_BYTES);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int unit = worker; unit < total_units; unit += num_workers) {
@@ -534,7 +574,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr int CHUNKS = BLOCK_N / (32 * W);  // 32-column chunks owned by this warp
       const int colbase = n_blk * BLOCK_N + part * 32;
       const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + part * 32;
-      if constexpr (EPI_MODE == 0) {
+      if constexpr (EPI_MODE == 3) {
+        const uint32_t ring0 = stage + EPI_STAGE_BYTES, ring1 = stage + 2 * EPI_STAGE_BYTES;
+        residual_prefetch(p, ring0, lane, row0, colbase);
+        if (CHUNKS > 1) residual_prefetch(p, ring1, lane, row0, colbase + 32 * W);
+        EpiAux aux[CHUNKS];  // bias / keep bytes of every chunk of the tile: one scoreboard wait per tile
+#pragma unroll
+        for (int ci = 0; ci < CHUNKS; ++ci) epi_prefetch<EPI_MODE, DROP>(p, aux[ci], lane, row0, colbase + ci * 32 * W);
+        mbar_wait(&tmem_full[acc], acc_ph);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          const int col0 = colbase + ci * 32 * W;
+          uint32_t v[32];
+          tmem_ld_32x32(tm_row + ci * 32 * W, v);
+          if (ci + 1 < CHUNKS) cp_async_wait<1>(); else cp_async_wait<0>();  // this chunk's residual has landed
+          tmem_ld_wait();
+          epilogue_chunk<EPI_MODE, DROP>(p, v, stage, lane, row0, col0, aux[ci], (ci & 1) ? ring1 : ring0,
+                                         ci + 2 < CHUNKS ? col0 + 2 * 32 * W : -1);
+        }
+      } else if constexpr (EPI_MODE == 0) {
         EpiAux aux[2];
         epi_prefetch<EPI_MODE, DROP>(p, aux[0], lane, row0, colbase);  // overlaps the wait for the accumulator
         mbar_wait(&tmem_full[acc], acc_ph);
@@ -588,7 +647,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int CG, int EPI_MODE, bool DROP = false>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                    cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES, CG, epi_warps(EPI_MODE)>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG, epi_warps(EPI_MODE), epi_slabs(EPI_MODE)>;
   static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG, EPI_MODE, DROP>;
   static bool attr_set = false;  // per instantiation; idempotent, races are benign
@@ -616,7 +675,7 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
 template <int BLOCK_N, int CG, int EPI_MODE>
 constexpr int stages_for() {
   constexpr int stage_bytes = A_STAGE_BYTES + (BLOCK_N / CG) * BLOCK_K * 2;
-  constexpr int budget = 232448 - 1024 - 256 - epi_warps(EPI_MODE) * EPI_STAGE_BYTES;
+  constexpr int budget = 232448 - 1024 - 256 - epi_warps(EPI_MODE) * epi_slabs(EPI_MODE) * EPI_STAGE_BYTES;
   constexpr int n = budget / stage_bytes;
   return n > 8 ? 8 : n;
 }
@@ -638,6 +697,17 @@ int launch_major(int a_mn, int b_mn, int epi_mode, const CUtensorMap& ta, const 
     return launch_variant<BLOCK_N, stages_for<BLOCK_N, CG, 2>(), false, true, CG, 2>(ta, tb, p, grid, stream);
   }
   constexpr int S = stages_for<BLOCK_N, CG, 0>();
+  if constexpr (CG == 2) {
+    // forward linear that adds the fp32 residual stream: residual staged by cp.async (mode 3). The ring costs two
+    // pipeline stages, which only a short K loop can spare (K = 2048: 84 -> 98 us with four stages).
+    static const bool res_async = getenv("NV_GEMM_NO_RES_ASYNC") == nullptr;
+    if (res_async && !a_mn && !b_mn && p.residual != nullptr && !(p.flags & EPI_ATOMIC) && p.K <= 1024 &&
+        p.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) {
+      constexpr int S3 = stages_for<BLOCK_N, CG, 3>();
+      if (drop) return launch_variant<BLOCK_N, S3, false, false, CG, 3, true>(ta, tb, p, grid, stream);
+      return launch_variant<BLOCK_N, S3, false, false, CG, 3>(ta, tb, p, grid, stream);
+    }
+  }
   if (drop) {
     NV_REQUIRE(!a_mn && !b_mn, "gemm: dropout in the store epilogue is only built for K-major operands (forward linear)");
     return launch_variant<BLOCK_N, S, false, false, CG, 0, true>(ta, tb, p, grid, stream);

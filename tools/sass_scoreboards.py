@@ -1,0 +1,39 @@
+"""Offline check of the GEMM store epilogue's scoreboard use (no GPU needed).
+
+ptxas gives every global load of the epilogue warps ONE hardware scoreboard. An instruction that waits on it waits for
+everything in flight, including the residual prefetch of the next chunk. The kernel therefore forces that wait to
+happen right before the prefetch is issued (an STS of one prefetched register); this script decodes the control bits
+of `cuobjdump -sass` and lists, per gemm_tc_kernel variant, every instruction that waits on the load scoreboard and
+every non-load instruction that signals it, so that a rebuild which breaks the arrangement is seen before GPU time is
+spent.   Usage: python tools/sass_scoreboards.py [lib.so | file.o] [substring of the mangled kernel name]"""
+import re
+import subprocess
+import sys
+
+path = sys.argv[1] if len(sys.argv) > 1 else "neurovit_b200/libneurovit_b200.so"
+want = sys.argv[2] if len(sys.argv) > 2 else "ILi256ELi6ELb0ELb0ELi2ELi0ELb0EE"
+text = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout.split("\n")
+starts = [i for i, l in enumerate(text) if "Function :" in l]
+for si, st in enumerate(starts):
+    if "gemm_tc_kernel" not in text[st] or want not in text[st]:
+        continue
+    body = text[st:(starts[si + 1] if si + 1 < len(starts) else len(text))]
+    ins, i = [], 0
+    while i < len(body) - 1:
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);\s+/\* (0x[0-9a-f]+) \*/", body[i])
+        m2 = re.match(r"\s+/\* (0x[0-9a-f]+) \*/", body[i + 1]) if m else None
+        if m and m2:
+            hi = int(m2.group(1), 16)
+            ins.append((m.group(1), m.group(2), (hi >> 46) & 7, (hi >> 52) & 0x3F))   # write barrier, wait mask
+            i += 2
+        else:
+            i += 1
+    ldg_sb = {wb for _, t, wb, _ in ins if re.match(r"(@!?U?P\d+\s+)?(LDG|LD)\.E", t) and wb != 7}
+    print(text[st].strip()[:150])
+    print("  instructions", len(ins), " scoreboards used by global loads:", sorted(ldg_sb))
+    for k, (addr, t, wb, wait) in enumerate(ins):
+        is_ld = re.match(r"(@!?U?P\d+\s+)?(LDG|LD)\.E", t) is not None
+        waits = any(wait & (1 << sb) for sb in ldg_sb)
+        if (waits and not is_ld) or (wb in ldg_sb and not is_ld) or "LDTM" in t:
+            tag = "WAITS" if waits else ("signals" if wb in ldg_sb else "")
+            print(f"  {k:5d} {addr} {t[:70]:70s} wb{wb if wb != 7 else '-'} wait{wait:06b} {tag}")
