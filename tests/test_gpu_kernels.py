@@ -78,6 +78,27 @@ def test_gemm_bf16_epilogues():
     assert rel_err(dw, dy.double().t() @ x.double() + 0.5) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(385, 264, 520), (770, 1024, 1024), (130, 72, 64), (1000, 520, 136)])
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_gemm_residual_ring_ragged(shape, block_n, inplace):
+    """Forward linear + fp32 residual on CTA pairs with K <= 1024 takes the cp.async residual ring (store mode 3):
+    ragged last row tile, a last column tile that is partly (or, for whole 32-column chunks, entirely) outside N, and
+    the in-place form x = x + linear(a) the transformer blocks use (vit_3d.py:60,73 `x = attn(x) + x`)."""
+    M, N, K = shape
+    torch.manual_seed(5)
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    out = res if inplace else torch.full((M, N), float("nan"), device=DEV)
+    cs = torch.zeros(N, device=DEV)
+    ops.gemm_bf16(a, w, bias=bias, residual=res, out_f32=out, colsum=cs, block_n=block_n, cta_group=2)
+    assert rel_err(out, ref) < 1e-3
+    assert rel_err(cs, ref.sum(0)) < 1e-3
+
+
 def test_gemm_f32_matches_torch():
     torch.manual_seed(3)
     M, N, K = 200, 136, 300

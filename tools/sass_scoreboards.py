@@ -1,11 +1,12 @@
-"""Offline check of the GEMM store epilogue's scoreboard use (no GPU needed).
+"""Offline look at the scoreboards of a gemm_tc_kernel variant (no GPU needed).
 
-ptxas gives every global load of the epilogue warps ONE hardware scoreboard. An instruction that waits on it waits for
-everything in flight, including the residual prefetch of the next chunk. The kernel therefore forces that wait to
-happen right before the prefetch is issued (an STS of one prefetched register); this script decodes the control bits
-of `cuobjdump -sass` and lists, per gemm_tc_kernel variant, every instruction that waits on the load scoreboard and
-every non-load instruction that signals it, so that a rebuild which breaks the arrangement is seen before GPU time is
-spent.   Usage: python tools/sass_scoreboards.py [lib.so | file.o] [substring of the mangled kernel name]"""
+ptxas gives every global load of the epilogue warps ONE hardware scoreboard (a counter): an instruction that waits on
+it waits for everything in flight, including a register prefetch issued just before, and constant-bank reads (LDC /
+LDCU) can land on the same scoreboard. This script decodes the control bits of `cuobjdump -sass` (write barrier =
+bits 110-112, wait mask = bits 116-121 of each 128-bit instruction) and lists, per matching variant, every non-load
+instruction that waits on a scoreboard used by global loads, every non-load instruction that signals one, and the
+LDTM positions (= chunk boundaries). It is how the out-projection epilogue was analysed in profiles/r01_summary.md
+section 3.   Usage: python tools/sass_scoreboards.py [lib.so | file.o] [substring of the mangled kernel name]"""
 import re
 import subprocess
 import sys
