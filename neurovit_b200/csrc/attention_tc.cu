@@ -902,75 +902,99 @@ __global__ void attn_tc_delta_kernel(const bf16* __restrict__ dO, const bf16* __
 
 // Attention backward when only the cls query (token 0) of every sample carries gradient — the last block under a
 // cls-pooled head (vit_3d.py:123): dS has a single non-zero row, so dK and dV are rank-1 in that row and dQ is one
-// row: O(N d) per (batch, head) instead of O(N^2 d). One CTA per (head, batch), a thread per key.
-__global__ void __launch_bounds__(128)
+// row: O(N d) per (batch, head) instead of O(N^2 d). One CTA per (head, batch); eight lanes share a key, each owning
+// one 16-byte piece of its 128-byte k / v / dk / dv / dq rows, so a warp instruction moves four whole rows.
+constexpr int CLS_THREADS = 256;
+__global__ void __launch_bounds__(CLS_THREADS)
 attn_cls_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int64_t qkv_bs,
                     int64_t qkv_rs, const bf16* __restrict__ o, int64_t o_bs, const bf16* __restrict__ dO_cls,
                     int64_t do_bs, const float* __restrict__ lse, bf16* __restrict__ dq, bf16* __restrict__ dk,
                     bf16* __restrict__ dv, int64_t d_bs, int64_t d_rs, int N, int H, float scale,
                     const uint32_t* __restrict__ mask, int mask_words, float keep_scale) {
-  __shared__ float qc[HD], doc[HD], red[4][HD];
+  static_assert(HD == 64, "eight lanes x eight dims per key row");
+  __shared__ float red[CLS_THREADS / 32][HD];
   const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
-  if (t < HD) {
-    qc[t] = __bfloat162float(q[(int64_t)b * qkv_bs + h * HD + t]);             // token 0
-    doc[t] = __bfloat162float(dO_cls[(int64_t)b * do_bs + h * HD + t]);
-  }
-  __syncthreads();
+  const int sub = t & 7;        // which 8 dims of the head this lane owns
+  const int grp = t >> 3;       // key slot within the CTA's stride
+  // this lane's slice of the cls query, its dO and O (delta = dO . O over the whole head: 8-lane reduction)
+  float qc[8], doc[8];
   float delta = 0.f;
-#pragma unroll 8
-  for (int d = 0; d < HD; ++d) delta = fmaf(doc[d], __bfloat162float(o[(int64_t)b * o_bs + h * HD + d]), delta);
+  {
+    const uint4 qq = *reinterpret_cast<const uint4*>(q + (int64_t)b * qkv_bs + h * HD + 8 * sub);   // token 0
+    const uint4 dd = *reinterpret_cast<const uint4*>(dO_cls + (int64_t)b * do_bs + h * HD + 8 * sub);
+    const uint4 oo = *reinterpret_cast<const uint4*>(o + (int64_t)b * o_bs + h * HD + 8 * sub);
+    const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w}, ow[4] = {oo.x, oo.y, oo.z, oo.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(qw[j]), c = unpack_bf16x2(dw[j]), e = unpack_bf16x2(ow[j]);
+      qc[2 * j] = a.x; qc[2 * j + 1] = a.y;
+      doc[2 * j] = c.x; doc[2 * j + 1] = c.y;
+      delta = fmaf(c.x, e.x, fmaf(c.y, e.y, delta));
+    }
+    delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+    delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+    delta += __shfl_xor_sync(0xffffffffu, delta, 4);
+  }
   const int64_t bh = (int64_t)b * H + h;
   const float lse2 = lse[bh * N] * LOG2E;
-  float dq_acc[HD];
+  float dq_acc[8];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) dq_acc[d] = 0.f;
-  for (int key = t; key < N; key += 128) {
-    const bf16* kr = k + (int64_t)b * qkv_bs + (int64_t)key * qkv_rs + h * HD;
-    const bf16* vr = v + (int64_t)b * qkv_bs + (int64_t)key * qkv_rs + h * HD;
-    float kf[HD];
+  for (int d = 0; d < 8; ++d) dq_acc[d] = 0.f;
+  for (int key0 = 0; key0 < N; key0 += CLS_THREADS / 8) {   // uniform trip count: the shuffles below need whole warps
+    const int key = key0 + grp;
+    const bool live = key < N;
+    const int64_t row = (int64_t)(live ? key : 0) * qkv_rs + h * HD + 8 * sub;
+    const uint4 kk = *reinterpret_cast<const uint4*>(k + (int64_t)b * qkv_bs + row);
+    const uint4 vv = *reinterpret_cast<const uint4*>(v + (int64_t)b * qkv_bs + row);
+    const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w}, vw[4] = {vv.x, vv.y, vv.z, vv.w};
+    float kf[8];
     float s = 0.f, dp = 0.f;
 #pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
-      const uint4 kk = *reinterpret_cast<const uint4*>(kr + 8 * c), vv = *reinterpret_cast<const uint4*>(vr + 8 * c);
-      const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w}, vw[4] = {vv.x, vv.y, vv.z, vv.w};
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(kw[j]), c2 = unpack_bf16x2(vw[j]);
+      kf[2 * j] = a.x; kf[2 * j + 1] = a.y;
+      s = fmaf(qc[2 * j], a.x, fmaf(qc[2 * j + 1], a.y, s));
+      dp = fmaf(doc[2 * j], c2.x, fmaf(doc[2 * j + 1], c2.y, dp));
+    }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16x2(kw[j]), c2 = unpack_bf16x2(vw[j]);
-        kf[8 * c + 2 * j] = a.x; kf[8 * c + 2 * j + 1] = a.y;
-        s = fmaf(qc[8 * c + 2 * j], a.x, fmaf(qc[8 * c + 2 * j + 1], a.y, s));
-        dp = fmaf(doc[8 * c + 2 * j], c2.x, fmaf(doc[8 * c + 2 * j + 1], c2.y, dp));
-      }
+    for (int m = 1; m <= 4; m <<= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, m);
+      dp += __shfl_xor_sync(0xffffffffu, dp, m);
     }
     const float p = ex2(fmaf(s, scale * LOG2E, -lse2));
     bool keep = true;
-    if (mask != nullptr) keep = (mask[bh * N * mask_words + (key >> 5)] >> (key & 31)) & 1u;  // row of token 0
+    if (mask != nullptr && live) keep = (mask[bh * N * mask_words + (key >> 5)] >> (key & 31)) & 1u;  // row of token 0
     const float pm = keep ? p * keep_scale : 0.f;
-    const float ds = p * ((keep ? dp * keep_scale : 0.f) - delta) * scale;
-    bf16* dkr = dk + (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD;
-    bf16* dvr = dv + (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD;
-    bf16* dqr = dq + (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD;
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
+    const float ds = live ? p * ((keep ? dp * keep_scale : 0.f) - delta) * scale : 0.f;
+    if (live) {
+      const int64_t drow = (int64_t)b * d_bs + (int64_t)key * d_rs + h * HD + 8 * sub;
       uint4 a, bb;
-      a.x = pack_bf16x2(ds * qc[8 * c], ds * qc[8 * c + 1]); a.y = pack_bf16x2(ds * qc[8 * c + 2], ds * qc[8 * c + 3]);
-      a.z = pack_bf16x2(ds * qc[8 * c + 4], ds * qc[8 * c + 5]); a.w = pack_bf16x2(ds * qc[8 * c + 6], ds * qc[8 * c + 7]);
-      bb.x = pack_bf16x2(pm * doc[8 * c], pm * doc[8 * c + 1]); bb.y = pack_bf16x2(pm * doc[8 * c + 2], pm * doc[8 * c + 3]);
-      bb.z = pack_bf16x2(pm * doc[8 * c + 4], pm * doc[8 * c + 5]); bb.w = pack_bf16x2(pm * doc[8 * c + 6], pm * doc[8 * c + 7]);
-      *reinterpret_cast<uint4*>(dkr + 8 * c) = a;
-      *reinterpret_cast<uint4*>(dvr + 8 * c) = bb;
-      if (key != 0) *reinterpret_cast<uint4*>(dqr + 8 * c) = make_uint4(0u, 0u, 0u, 0u);  // queries other than the cls token
+      a.x = pack_bf16x2(ds * qc[0], ds * qc[1]); a.y = pack_bf16x2(ds * qc[2], ds * qc[3]);
+      a.z = pack_bf16x2(ds * qc[4], ds * qc[5]); a.w = pack_bf16x2(ds * qc[6], ds * qc[7]);
+      bb.x = pack_bf16x2(pm * doc[0], pm * doc[1]); bb.y = pack_bf16x2(pm * doc[2], pm * doc[3]);
+      bb.z = pack_bf16x2(pm * doc[4], pm * doc[5]); bb.w = pack_bf16x2(pm * doc[6], pm * doc[7]);
+      *reinterpret_cast<uint4*>(dk + drow) = a;
+      *reinterpret_cast<uint4*>(dv + drow) = bb;
+      if (key != 0) *reinterpret_cast<uint4*>(dq + drow) = make_uint4(0u, 0u, 0u, 0u);  // queries other than the cls token
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) dq_acc[d] = fmaf(ds, kf[d], dq_acc[d]);
+    for (int d = 0; d < 8; ++d) dq_acc[d] = fmaf(ds, kf[d], dq_acc[d]);
   }
-  // dQ of the cls row: reduce the per-thread partial sums
+  // dQ of the cls row: fold the four key slots of a warp (lanes with equal `sub`), then the warps
 #pragma unroll
-  for (int d = 0; d < HD; ++d) {
-    const float r = warp_sum(dq_acc[d]);
-    if ((t & 31) == 0) red[t >> 5][d] = r;
+  for (int d = 0; d < 8; ++d) {
+    float r = dq_acc[d];
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    if ((t & 31) < 8) red[t >> 5][8 * sub + d] = r;
   }
   __syncthreads();
-  if (t < HD) dq[(int64_t)b * d_bs + h * HD + t] = __float2bfloat16(red[0][t] + red[1][t] + red[2][t] + red[3][t]);
+  if (t < HD) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < CLS_THREADS / 32; ++w) r += red[w][t];
+    dq[(int64_t)b * d_bs + h * HD + t] = __float2bfloat16(r);
+  }
 }
 
 int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, int N, int H, int box_rows = 64) {
@@ -1098,9 +1122,11 @@ int nv_attn_cls_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t 
   if ((s = check_args(dk, d_bs, d_rs, "dk")) != NV_OK) return s;
   if ((s = check_args(dv, d_bs, d_rs, "dv")) != NV_OK) return s;
   NV_REQUIRE(o != nullptr && dO_cls != nullptr && lse != nullptr, "attention: null o / dO / lse");
+  NV_REQUIRE(((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dO_cls)) & 15) == 0 && o_bs % 8 == 0 &&
+                 do_bs % 8 == 0, "attention: o / dO of the cls row must be 16-byte aligned (16-byte vector loads)");
   Common c;
   if ((s = fill_common(c, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
-  attn_cls_bwd_kernel<<<dim3(H, B), 128, 0, stream>>>(q, k, v, qkv_bs, qkv_rs, o, o_bs, dO_cls, do_bs, lse, dq, dk, dv, d_bs,
+  attn_cls_bwd_kernel<<<dim3(H, B), CLS_THREADS, 0, stream>>>(q, k, v, qkv_bs, qkv_rs, o, o_bs, dO_cls, do_bs, lse, dq, dk, dv, d_bs,
                                                       d_rs, N, H, scale, c.drop_thr != 0 ? c.mask : nullptr, c.mask_words,
                                                       c.keep_scale);
   NV_LAUNCH_CHECK("attn_cls_bwd_kernel");

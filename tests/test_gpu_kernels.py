@@ -270,6 +270,40 @@ def test_attention_fwd_bwd(B, N, H):
         assert rel_err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
 
 
+@pytest.mark.parametrize("B,N,H", [(3, 385, 8), (2, 64, 2), (2, 9, 1), (1, 1729, 2)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.25])
+def test_attention_cls_bwd_matches_full_backward(B, N, H, p_drop):
+    """nv_attention_cls_bwd (only token 0 of every sample has gradient: the last block under pool='cls',
+    vit_3d.py:123) against nv_attention_bwd fed the same dO with every other row zero, and against autograd."""
+    hd = 64
+    inner = H * hd
+    torch.manual_seed(21)
+    qkv = torch.randn(B * N, 3 * inner, device=DEV).to(torch.bfloat16)
+    o = torch.empty(B * N, inner, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=DEV)
+    mask = torch.zeros(B * H, N, (N + 31) // 32, device=DEV, dtype=torch.int32) if p_drop > 0 else None
+    ops.attention_fwd(qkv, o, lse, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5, dropout_p=p_drop, seed=77, drop_mask=mask)
+    dO_cls = torch.randn(B, inner, device=DEV).to(torch.bfloat16)
+    dO = torch.zeros(B * N, inner, device=DEV, dtype=torch.bfloat16)
+    dO.view(B, N, inner)[:, 0] = dO_cls
+    full = torch.zeros_like(qkv)
+    ws = torch.empty(B * H * N, device=DEV)
+    ops.attention_bwd(qkv, o, dO, lse, ws, full, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5, dropout_p=p_drop,
+                      drop_mask=mask)
+    got = torch.full_like(qkv, float("nan"))   # the kernel must write every element, zeros included
+    ops.attention_cls_bwd(qkv, o, dO_cls, lse, got, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5, dropout_p=p_drop,
+                          drop_mask=mask)
+    assert torch.isfinite(got.float()).all()
+    for nm, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
+        assert rel_err(got[:, sl], full[:, sl]) < 1e-2, nm
+    assert (got.view(B, N, 3 * inner)[:, 1:, :inner] == 0).all()      # dQ rows of the other tokens
+    if p_drop == 0.0:
+        qd = qkv.double().requires_grad_(True)
+        oref, _ = _attn_ref(qd, B, N, H, hd)
+        gref, = torch.autograd.grad(oref, qd, dO.double())
+        assert rel_err(got, gref) < 2e-2
+
+
 def test_attention_fwd_rising_scores_rescale_path():
     """The forward keeps a lazily raised softmax reference (TMEM accumulator rescaled only when a block's
     maximum exceeds it by 2^8): scores that climb along the key axis force that path in every block for the
