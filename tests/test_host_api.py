@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference interface (no GPU): constructor checks and messages (vit_3d.py:83-89), module
+tree / state_dict keys as saved by the unmodified reference (tests/golden/*.npz, oracle/gen_golden.py), argument
+validation in forward, and the rule that nothing computes without the CUDA library's device (no CPU fallback)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from neurovit_b200._lib import NeuroViTLibraryError
+from neurovit_b200.vit_3d import ViT
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _vit(**kw):
+    args = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=2, dim=64, depth=2,
+                heads=2, mlp_dim=128, channels=1, dim_head=64, dropout=0.0, emb_dropout=0.0)   # = vit3d_small.npz
+    args.update(kw)
+    return ViT(**args)
+
+
+def test_state_dict_keys_and_shapes_match_the_reference_checkpoint():
+    g = np.load(os.path.join(GOLD, "vit3d_small.npz"))
+    ref = {k[3:]: g[k].shape for k in g.files if k.startswith("sd.")}
+    sd = _vit().state_dict()
+    assert list(sd.keys()) == list(ref.keys())          # same names in the same order: load_state_dict both ways
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k]), k
+    m = _vit()
+    m.load_state_dict({k: torch.from_numpy(g["sd." + k]) for k in ref}, strict=True)
+
+
+def test_module_tree_keeps_the_hook_points_of_the_reference():
+    m = _vit()
+    # explainability hooks attach to transformer.layers[i][0].attend (gradcam3DViT_fmris.py:25-26)
+    attn, ff = m.transformer.layers[-1]
+    assert isinstance(attn.attend, torch.nn.Softmax) and isinstance(attn.dropout, torch.nn.Dropout)
+    assert isinstance(attn.to_qkv, torch.nn.Linear) and attn.to_qkv.bias is None
+    assert isinstance(m.to_patch_embedding[2], torch.nn.Linear) and isinstance(m.mlp_head[1], torch.nn.Linear)
+    assert m.pos_embedding.shape == (1, 2 * 2 * 2 + 1, 64) and m.cls_token.shape == (1, 1, 64)
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(image_size=20), "Image dimensions must be divisible by the patch size"),
+    (dict(frames=12), "Frames must be divisible by frame patch size"),
+    (dict(pool="max"), "pool type must be either cls"),
+])
+def test_constructor_rejects_what_the_reference_rejects(kw, msg):
+    with pytest.raises(AssertionError, match=msg):
+        _vit(**kw)
+
+
+def test_forward_validates_shapes_before_touching_the_device():
+    m = _vit()
+    with pytest.raises(ValueError, match="5-D"):
+        m(torch.zeros(2, 16, 16, 16))
+    with pytest.raises(ValueError, match="not divisible by the patch size"):
+        m(torch.zeros(2, 1, 16, 16, 12))
+    with pytest.raises(ValueError, match="channels differ"):
+        m(torch.zeros(2, 3, 16, 16, 16))
+    assert m(torch.zeros(0, 1, 16, 16, 16)).shape == (0, 2)      # empty batch: nothing to launch
+
+
+def test_cpu_tensors_fail_loudly_instead_of_falling_back():
+    m = _vit()
+    with pytest.raises(NeuroViTLibraryError, match="no CPU fallback"):
+        m(torch.zeros(2, 1, 16, 16, 16))
+
+
+# ------------------------------------------------------------------------------------ NeuroEncoder (config dict)
+def _cfg(tmp, **kw):
+    cfg = {"DEVICE": "cpu", "TRAINING_DIM": 3, "TRAINING_DROPOUT": 0.0, "TRAINING_VIT_INPUT_SIZE": 16,
+           "GRADCAM_CUBE_SIZE": 8, "TRAINING_VIT_PATCH_SIZE": 8, "DATASET_NAME": "adni", "GLOBAL_BASE_PATH": str(tmp),
+           "BEST_MODEL_PATH": "best.pth", "GRADCAM_THRESHOLD": 10, "GRADCAM_SLICE_DIM": 0, "GRADCAM_SLICE_IDX": 0}
+    cfg.update(kw)
+    return cfg
+
+
+def test_neuroencoder_takes_the_reference_config_and_registers_the_gradcam_hooks(tmp_path):
+    from neurovit_b200.NeuroEncoder import NeuroEncoder
+    m = NeuroEncoder(_cfg(tmp_path))
+    assert m.forward_handle is not None and m.backward_handle is not None       # NeuroEncoder.py:70-82
+    keys = set(m.state_dict().keys())
+    g = np.load(os.path.join(GOLD, "neuro3d.npz"))       # holds gradients of a sample of the reference's parameters
+    assert len(keys) == 78 and {k[5:] for k in g.files if k.startswith("grad.")} <= keys
+    off = NeuroEncoder(_cfg(tmp_path, GRADCAM_CAPTURE="off"))
+    assert off.forward_handle is None and off.backward_handle is None
+    with pytest.raises(ValueError, match="GRADCAM_CAPTURE"):
+        NeuroEncoder(_cfg(tmp_path, GRADCAM_CAPTURE="disk"))
+
+
+def test_neuroencoder_rejects_an_unknown_training_dim(tmp_path):
+    from neurovit_b200.NeuroEncoder import NeuroEncoder
+    m = NeuroEncoder(_cfg(tmp_path))
+    m.config["TRAINING_DIM"] = 5
+    with pytest.raises(ValueError, match="TRAINING_DIM must be 3 or 4"):
+        m(torch.zeros(1, 16, 16, 16))
