@@ -6,7 +6,8 @@ LDCU) can land on the same scoreboard. This script decodes the control bits of `
 bits 110-112, wait mask = bits 116-121 of each 128-bit instruction) and lists, per matching variant, every non-load
 instruction that waits on a scoreboard used by global loads, every non-load instruction that signals one, and the
 LDTM positions (= chunk boundaries). It is how the out-projection epilogue was analysed in profiles/r01_summary.md
-section 3.   Usage: python tools/sass_scoreboards.py [lib.so | file.o] [substring of the mangled kernel name]"""
+section 3.   Usage: python tools/sass_scoreboards.py [lib.so | file.o] [substring of the mangled kernel name,
+e.g. attn_tc_bwd_dq_kernel; default: the K-major CTA-pair store-epilogue GEMM]"""
 import re
 import subprocess
 import sys
@@ -16,7 +17,7 @@ want = sys.argv[2] if len(sys.argv) > 2 else "ILi256ELi6ELb0ELb0ELi2ELi0ELb0EE"
 text = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout.split("\n")
 starts = [i for i, l in enumerate(text) if "Function :" in l]
 for si, st in enumerate(starts):
-    if "gemm_tc_kernel" not in text[st] or want not in text[st]:
+    if want not in text[st]:
         continue
     body = text[st:(starts[si + 1] if si + 1 < len(starts) else len(text))]
     ins, i = [], 0
