@@ -8,7 +8,9 @@
 //   B K-major : B[N, K]          B MN-major : B stored as [K, N]   (wgrad: X, dgrad: W)
 //
 // Structure (persistent, one CTA per SM, 320 threads):
-//   warps 0-7  epilogue: tcgen05.ld -> regs -> swizzled smem transpose -> coalesced global I/O
+//   warps 0-7  epilogue: tcgen05.ld -> regs -> swizzled smem transpose -> coalesced global I/O, one 32x32 chunk
+//              at a time in three straight-line passes (8 LDS, arithmetic, 8 predicated STG); 16 warps in the
+//              GELU modes. Store mode 3 stages the fp32 residual through a cp.async ring (see epilogue_chunk)
 //   warp  8    TMA producer (one lane): 128B-swizzled tiles into a STAGES-deep mbarrier ring
 //   warp  9    TMEM allocator + MMA issuer (one lane): tcgen05.mma kind::f16, K=16 per instruction
 // The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
