@@ -129,9 +129,11 @@ int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_
  * replaces: vit_3d.py:51-59. q/k/v are read in place from the QKV projection output
  * [B, N, 3*H*64] (pointers to the q, k, v column blocks; shared batch/row strides), O is written as
  * [B, N, H*64]; lse [B,H,N] fp32 is saved for backward. head_dim must be 64 (bf16 flash kernels,
- * tcgen05 / TMEM). dropout_p > 0 applies nn.Dropout to the probabilities (vit_3d.py:56): forward draws the
- * keep bits from (seed) and saves them in drop_mask, uint32 [B*H, N, ceil(N/32)] (bit k of word w of row q =
- * score (q, 32w+k) survives); backward reads them. drop_mask may be NULL when dropout_p == 0.
+ * tcgen05 / TMEM; token 0 of every sample — the cls token — is handled outside the 128-row tiles, which cover
+ * tokens 1..N-1). dropout_p > 0 applies nn.Dropout to the probabilities (vit_3d.py:56): forward draws the
+ * keep bits from (seed) and saves them in drop_mask, uint32 [B*H, N, ceil(N/32)]: bit k of word w of row q =
+ * the score of query token q and the key at position 32w+k survives, where key token t sits at position t-1
+ * for t >= 1 and key token 0 at position N-1; backward reads them. drop_mask may be NULL when dropout_p == 0.
  * drop_mask_ready = 1: drop_mask already holds the bits (nv_dropout_bits with the same seed, stream 0, over
  * B*H*N*4*ceil(N/32) groups) and forward reads them instead of drawing them inside its softmax rows. */
 int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
@@ -146,16 +148,14 @@ int nv_attention_cls_bwd(const void* q, const void* k, const void* v, int64_t qk
                          const float* lse, void* dq, void* dk, void* dv, int64_t dqkv_batch_stride,
                          int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, float dropout_p,
                          const void* drop_mask, void* stream);
-/* delta_ws: fp32 workspace of B*H*N elements */
+/* delta_ws: fp32 workspace of B*H*N elements (delta_i = dO_i . O_i, written by the dQ kernel's prologue, read by
+ * the dK/dV kernel: no separate pass) */
 int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      const void* o, const void* dO, int64_t o_batch_stride, int64_t o_row_stride,
                      const float* lse, float* delta_ws,
                      void* dq, void* dk, void* dv, int64_t dqkv_batch_stride, int64_t dqkv_row_stride,
                      int B, int N, int H, int head_dim, float scale, float dropout_p, const void* drop_mask,
                      void* stream);
-/* kernel variant behind nv_attention_*: 0 = tcgen05/TMEM (default), 1 = mma.sync (no dropout; kept as an
- * on-device cross-check for the tests and probes) */
-int nv_set_attention_impl(int impl);
 /* fp32 verification path: materialised softmax (vit_3d.py:55) and its backward, in place */
 int nv_softmax_fwd(float* s, int64_t rows, int n, void* stream);
 int nv_softmax_bwd(const float* P, float* dP, int64_t rows, int n, void* stream);
@@ -217,6 +217,29 @@ int nv_temporal_fwd(const float* x, const float* params, float* out, float* seq_
 int nv_temporal_bwd(const float* x, const float* params, const float* saved, const float* dout, const float* dseq,
                     float* dparams_ws, float* dx, int B, int T, int F, float eps,
                     float p_attn, float p_drop1, float p_ffn, float p_drop2, int64_t seed, void* stream);
+
+/* ---- data-parallel exchange step ---------------------------------------------------------------------
+ * New work (the reference is single-GPU): the gradient all-reduce at the step boundary of
+ * src/Trainer.py:65-76, over NCCL on NVLink 5 / NVSwitch. The library owns one communicator per device; NCCL is
+ * resolved with dlopen (the copy PyTorch ships; no link-time dependency). The all-reduce is enqueued on the caller's
+ * stream like any kernel, so it can be captured into the training step's CUDA graph and overlapped with backward
+ * (neurovit_b200/trainer.py launches one per gradient bucket on a side stream, followed by that bucket's AdamW).
+ *   nv_dp_load(path)            dlopen NCCL (path NULL/"" = "libnccl.so.2"); 4 (not initialised) if unavailable
+ *   nv_dp_nccl_version()        NCCL version code (22809 = 2.28.9), 0 when not loaded   [returns the value]
+ *   nv_dp_unique_id(out128)     rank 0: 128-byte id (HOST pointer) to hand to every rank
+ *   nv_dp_init(uid128, r, w)    collective: create the communicator of rank r of w on the current device
+ *   nv_dp_register(buf, bytes)  register a long-lived DEVICE buffer (the flat gradient buffer): zero-copy / NVLS
+ *   nv_dp_allreduce_bucket      in place over `count` elements; dtype 0 = fp32, 1 = bf16; op 0 = sum, 1 = average
+ *   nv_dp_world(rank*, world*)  HOST int pointers
+ *   nv_dp_destroy()             */
+int nv_dp_load(const char* path);
+int nv_dp_nccl_version(void);
+int nv_dp_unique_id(void* out128);
+int nv_dp_init(const void* uid128, int rank, int world);
+int nv_dp_register(void* buf, int64_t bytes);
+int nv_dp_allreduce_bucket(void* buf, int64_t count, int dtype, int op, void* stream);
+int nv_dp_world(int* rank, int* world);
+int nv_dp_destroy(void);
 
 #ifdef __cplusplus
 }

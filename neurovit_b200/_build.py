@@ -23,10 +23,10 @@ SOURCES = [
     "simt_gemm.cu",
     "layernorm.cu",
     "patch_embed.cu",
-    "attention.cu",
     "attention_tc.cu",
     "misc.cu",
     "temporal.cu",
+    "nv_dp.cu",
     "api.cu",
 ]
 
@@ -52,16 +52,21 @@ def _deps_mtime() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
-    os.makedirs(BUILD_DIR, exist_ok=True)
+    """Compile every CUDA source for sm_100a and link the shared library. Returns its path.
+    NV_PROFILE=1 / NV_DEBUG_PROGRESS=1 build an instrumented variant next to the product library
+    (libneurovit_b200_prof.so, objects under build/prof/); load it with NEUROVIT_LIB=<path>."""
     nvcc = _nvcc()
     hdr_mtime = _deps_mtime()
     extra = ["-DNV_PROFILE"] if os.environ.get("NV_PROFILE") == "1" else []  # in-kernel phase clocks (tools/attn_phases.py)
+    if os.environ.get("NV_DEBUG_PROGRESS") == "1":  # progress markers into a host-mapped buffer
+        extra.append("-DNV_DEBUG_PROGRESS")
+    build_dir, lib_path = (os.path.join(BUILD_DIR, "prof"), LIB_PATH.replace(".so", "_prof.so")) if extra else (BUILD_DIR, LIB_PATH)
+    os.makedirs(build_dir, exist_ok=True)
     jobs = []
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        o = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_mtime):
             jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", s, "-o", o])
@@ -77,12 +82,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             list(ex.map(run, jobs))
-    need_link = force or bool(jobs) or not os.path.exists(LIB_PATH) or any(
-        os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs)
+    need_link = force or bool(jobs) or not os.path.exists(lib_path) or any(
+        os.path.getmtime(o) > os.path.getmtime(lib_path) for o in objs)
     if need_link:
-        run([nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC", "-cudart", "static"])
-    return LIB_PATH
+        run([nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+             "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"])
+    return lib_path
 
 
 if __name__ == "__main__":

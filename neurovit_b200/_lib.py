@@ -11,7 +11,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneurovit_b200.so")
+# NEUROVIT_LIB: load an instrumented build instead (the profiling tools; see _build.build)
+LIB_PATH = os.environ.get("NEUROVIT_LIB") or os.path.join(_HERE, "libneurovit_b200.so")
 
 _i = ctypes.c_int
 _l = ctypes.c_int64
@@ -44,7 +45,6 @@ SIGNATURES = {
     "nv_attention_bwd": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _p, _p, _p, _p, _l, _l,
                          _i, _i, _i, _i, _f, _f, _p, _p],
     "nv_attention_cls_bwd": [_p, _p, _p, _l, _l, _p, _l, _p, _l, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _f, _f, _p, _p],
-    "nv_set_attention_impl": [_i],
     "nv_softmax_fwd": [_p, _l, _i, _p],
     "nv_softmax_bwd": [_p, _p, _l, _i, _p],
     "nv_cast_f32_bf16": [_p, _p, _l, _p],
@@ -55,6 +55,14 @@ SIGNATURES = {
     "nv_mean_pool_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "nv_temporal_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
     "nv_temporal_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
+    "nv_dp_load": [_p],
+    "nv_dp_nccl_version": [],
+    "nv_dp_unique_id": [_p],
+    "nv_dp_init": [_p, _i, _i],
+    "nv_dp_register": [_p, _l],
+    "nv_dp_allreduce_bucket": [_p, _l, _i, _i, _p],
+    "nv_dp_world": [_p, _p],
+    "nv_dp_destroy": [],
 }
 
 _lock = threading.Lock()
@@ -115,7 +123,9 @@ def require_device(device_index: int) -> None:
 
 class _LaunchCounter:
     """Counts the CUDA kernels launched through the C ABI (bench.py reports it as `gpu_launches`)."""
-    KERNELS_PER_CALL = {"nv_attention_bwd": 3, "nv_version": 0, "nv_device_check": 0, "nv_set_attention_impl": 0}
+    KERNELS_PER_CALL = {"nv_attention_bwd": 2, "nv_version": 0, "nv_device_check": 0, "nv_dp_load": 0,
+                        "nv_dp_nccl_version": 0, "nv_dp_unique_id": 0, "nv_dp_init": 0, "nv_dp_register": 0,
+                        "nv_dp_world": 0, "nv_dp_destroy": 0}
 
     def __init__(self):
         self.count = 0

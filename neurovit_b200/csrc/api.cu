@@ -50,13 +50,6 @@ int nv_patch_gather_ln_launch(const float* video, const int64_t* dims, const int
 int nv_patch_ln_param_grad_launch(const float* video, const int64_t* dims, const int64_t* strides,
                                   const int64_t* patch, const float* dP, int64_t ld_dp, const float* mean,
                                   const float* rstd, float* dgamma, float* dbeta, cudaStream_t stream);
-int nv_attn_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
-                       bf16* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse, int B, int N, int H,
-                       int head_dim, float scale, cudaStream_t stream);
-int nv_attn_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
-                       const bf16* o, const bf16* dO, int64_t o_batch_stride, int64_t o_row_stride, const float* lse,
-                       float* delta_ws, bf16* dq, bf16* dk, bf16* dv, int64_t dqkv_batch_stride,
-                       int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, cudaStream_t stream);
 int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
                           int64_t o_bs, int64_t o_rs, float* lse, int B, int N, int H, int head_dim, float scale,
                           float dropout_p, uint64_t seed, uint32_t* drop_mask, int mask_ready, cudaStream_t stream);
@@ -189,23 +182,10 @@ int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_
   return nv_patch_ln_param_grad_launch(video, dims, strides, patch, dP, ld_dp, mean, rstd, dgamma, dbeta, ST(stream));
 }
 
-static int g_attn_impl = 0;  // 0 = tcgen05 / TMEM, 1 = mma.sync cross-check
-
-int nv_set_attention_impl(int impl) {
-  NV_REQUIRE(impl == 0 || impl == 1, "nv_set_attention_impl: impl must be 0 (tcgen05) or 1 (mma.sync), got %d", impl);
-  g_attn_impl = impl;
-  return NV_OK;
-}
-
 int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
                      void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse, int B, int N, int H,
                      int head_dim, float scale, float dropout_p, int64_t seed, void* drop_mask, int drop_mask_ready,
                      void* stream) {
-  if (g_attn_impl == 1) {
-    NV_REQUIRE(dropout_p == 0.f, "attention: the mma.sync cross-check variant has no dropout");
-    return nv_attn_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
-                              (bf16*)o, o_batch_stride, o_row_stride, lse, B, N, H, head_dim, scale, ST(stream));
-  }
   return nv_attn_tc_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
                                (bf16*)o, o_batch_stride, o_row_stride, lse, B, N, H, head_dim, scale, dropout_p,
                                (uint64_t)seed, (uint32_t*)drop_mask, drop_mask_ready, ST(stream));
@@ -216,13 +196,6 @@ int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_ba
                      float* delta_ws, void* dq, void* dk, void* dv, int64_t dqkv_batch_stride,
                      int64_t dqkv_row_stride, int B, int N, int H, int head_dim, float scale, float dropout_p,
                      const void* drop_mask, void* stream) {
-  if (g_attn_impl == 1) {
-    NV_REQUIRE(dropout_p == 0.f, "attention: the mma.sync cross-check variant has no dropout");
-    return nv_attn_bwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
-                              (const bf16*)o, (const bf16*)dO, o_batch_stride, o_row_stride, lse, delta_ws, (bf16*)dq,
-                              (bf16*)dk, (bf16*)dv, dqkv_batch_stride, dqkv_row_stride, B, N, H, head_dim, scale,
-                              ST(stream));
-  }
   return nv_attn_tc_bwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
                                (const bf16*)o, (const bf16*)dO, o_batch_stride, o_row_stride, lse, delta_ws,
                                (bf16*)dq, (bf16*)dk, (bf16*)dv, dqkv_batch_stride, dqkv_row_stride, B, N, H, head_dim,

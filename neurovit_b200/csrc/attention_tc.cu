@@ -2,28 +2,44 @@
 // Reference: src/models/vit_3d.py:51-59 (dots = q k^T * scale; softmax(dim=-1); dropout; attn v;
 // 'b h n d -> b n (h d)'), SURVEY 8a row A8. No mask, not causal; [B,h,N,N] is never materialised.
 //
-// All three kernels share one skeleton: a CTA owns 128 rows (= the 128 TMEM lanes) of one (batch, head),
+// Token 0 (the cls token, vit_3d.py:116) is kept OUT of the tensor-core tiles: every ViT3D geometry has
+// N = n + 1 tokens with n a product of grid sizes (384, 1000, 1728), so tiling N itself left a 1-row fourth query
+// tile and a 1-key last block at N = 385 (a quarter of the CTAs nearly empty, a fifth of the key blocks one
+// column wide). The tiles cover tokens 1..n; token 0 is
+//   - as a KEY: one extra score per row, computed by the row's own thread from its Q (dO) row in shared memory
+//     (64 FMAs) and folded into the row's softmax / dQ in registers (fwd, dQ); its dK / dV are a reduction over
+//     all queries done by one SIMT CTA per (batch, head) at the end of the dK/dV grid;
+//   - as a QUERY: one SIMT CTA per (batch, head) at the end of the forward and dQ grids (385 x 64 dot products),
+//     and a rank-1 update added by each key's thread in the dK/dV epilogue.
+// Dropout mask layout [B*H, N, ceil(N/32)] words: row = query token, bit position = key token - 1 for the tiled
+// keys and N - 1 for key token 0 (so 32-key chunks of the tiles stay word-aligned).
+//
+// All three tile kernels share one skeleton: a CTA owns 128 rows (= the 128 TMEM lanes) of one (batch, head),
 //   warps 0-3  "row" warps: thread i owns TMEM lane i, i.e. one query (fwd, dQ) or one key (dK/dV) row.
 //              tcgen05.ld gives the thread its whole score row, so the softmax statistics (row max, row
 //              sum, LSE, delta) live in that thread's registers with no cross-thread reduction at all;
 //              probabilities go back to shared memory as a bf16 K-major 128B-swizzled MMA operand.
-//   warp  4    TMA producer: 64-row x 64-col bf16 boxes of q / k / v / dO read IN PLACE from the QKV GEMM
+//   warp  4    TMA producer: 64-col bf16 boxes of q / k / v / dO read IN PLACE from the QKV GEMM
 //              output through 3-D tensor maps (col, token, batch); rows past N are zero-filled by TMA.
 //   warp  5    TMEM allocator + tcgen05.mma issuer.
 // TMEM budget is 256 columns and shared memory <= 113 KB per CTA, so two CTAs are co-resident per SM:
 // one CTA's exponentials (MUFU-bound at head_dim 64) overlap the other CTA's MMAs and TMA waits.
-// Ragged sizes (N = 385 = 3*128 + 1): row warps whose 32 rows are all >= N skip their work, the last
-// column block shrinks to a multiple of 16, so the extra token costs MMA issue slots but almost no MUFU.
+// Ragged n: row warps whose 32 rows are all >= n skip their work, the last column block shrinks to a multiple
+// of 16.
 //
-//   fwd : per key block j (128 keys): S = Q K_j^T -> TMEM; rows: m, p = 2^(S*c - m), l; P -> smem;
-//         O_j = P V_j -> TMEM (fresh accumulator, double-buffered); rows fold O_j into registers with the
-//         usual 2^(m_old - m_new) rescale, so TMEM is never rescaled in place.
-//   dQ  : per key block j (64 keys): S = Q K_j^T, dP = dO V_j^T -> TMEM; dS = P o (dP - delta) -> smem;
-//         dQ += dS K_j accumulates in TMEM (K_j tile reused as the MN-major B operand).
+//   fwd : per key block j (96 keys): S_j = Q K_j^T -> TMEM (double-buffered); the row thread pulls its 96 scores
+//         into registers in one TMEM pass, p = 2^(S*c - m) with a lazily raised reference m (only when the block
+//         maximum exceeds it by 2^8), P -> smem, O += P V_j accumulates in TMEM across blocks (rescaled in place
+//         on the rare raises).
+//   dQ  : prologue: delta_i = dO_i . O_i (written for the dK/dV kernel), the extra key's dS; per key block j
+//         (64 keys): S = Q K_j^T, dP = dO V_j^T -> TMEM; dS = P o (dP - delta) -> smem; dQ += dS K_j in TMEM.
 //   dKV : per query block i (64 queries): S^T = K Q_i^T, dP^T = V dO_i^T -> TMEM (lane = key);
-//         P^T, dS^T -> smem; dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM.
+//         P^T, dS^T -> smem; dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM; epilogue adds the cls query's
+//         rank-1 term.
 #include "nv_common.cuh"
 #include "nv_rng.cuh"
+#include <cstdlib>
+#include <cstring>
 
 // Optional in-kernel phase clocks (build with NV_PROFILE=1): selected threads accumulate clock64() deltas per
 // phase into nv_attn_dbg, read back through nv_debug_read (not part of the public ABI).
@@ -41,6 +57,18 @@ extern "C" int nv_debug_read(long long* out, int n) {
 #define PROF_MARK(i)
 #define PROF_RESET()
 #define PROF_DUMP(slot)
+#endif
+
+// Optional progress markers for debugging a hang (build with NV_DEBUG_PROGRESS=1): threads store a code into a
+// host-mapped buffer (nv_debug_set_progress_buffer) that the host can read while the kernel is still running.
+#ifdef NV_DEBUG_PROGRESS
+__device__ volatile int* nv_dbg_progress = nullptr;
+extern "C" int nv_debug_set_progress_buffer(int* host_mapped) {
+  return cudaMemcpyToSymbol(nv_dbg_progress, &host_mapped, sizeof(int*)) == cudaSuccess ? 0 : 3;
+}
+#define DBG_MARK(slot, code) do { if (nv_dbg_progress) { nv_dbg_progress[(slot)] = (code); __threadfence_system(); } } while (0)
+#else
+#define DBG_MARK(slot, code)
 #endif
 
 namespace {
@@ -93,11 +121,12 @@ __device__ __forceinline__ void mma_rows(uint32_t d_tmem, const uint8_t* a_tile,
 }
 
 struct Common {
-  int N, H;
+  int N, H, B;        // N tokens per sample INCLUDING token 0; the tiles cover tokens 1 .. N-1
   float scale;        // dim_head^-0.5
   // dropout on the attention probabilities (vit_3d.py:56). Forward draws the keep bits (Philox, keyed by
-  // seed and (batch*head, query, key / 8)) and saves them, one bit per score, as mask[B*H, N, mask_words];
-  // both backward kernels read the saved bits (dK/dV walks the score matrix transposed).
+  // seed and (batch*head, query, position / 8)) and saves them, one bit per score, as mask[B*H, N, mask_words];
+  // both backward kernels read the saved bits (dK/dV walks the score matrix transposed). Bit position of key
+  // token t: t - 1 for t >= 1, N - 1 for t = 0 (key_pos).
   uint32_t drop_thr;  // 0 = off
   float keep_scale;   // 1 / (1 - p_eff)
   uint64_t seed;
@@ -105,7 +134,159 @@ struct Common {
   uint32_t* mask;
   int mask_words;     // ceil(N / 32)
   int mask_ready;     // forward: the mask was drawn ahead of time (nv_dropout_bits): read it instead of drawing
+  int ntile_ctas;     // B * H * ceil((N-1)/128): CTAs [0, ntile_ctas) run tiles, the rest token 0 (cta_role)
+  // raw operands, for the SIMT handling of token 0 (the tiles go through the tensor maps)
+  const bf16 *q, *k, *v;
+  int64_t qkv_bs, qkv_rs;
 };
+
+__device__ __forceinline__ int key_pos(int token, int N) { return token == 0 ? N - 1 : token - 1; }
+
+// ---- SIMT helpers for token 0 -------------------------------------------------------------------------
+// 64 bf16 (one head slice of one token) held as eight 16-byte registers; loaded from one global address by every
+// thread of the CTA (a broadcast)
+struct Vec64 { uint4 c[8]; };
+__device__ __forceinline__ void load_vec64(Vec64& v, const bf16* g) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v.c[i] = __ldg(reinterpret_cast<const uint4*>(g) + i);
+}
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+    acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+  }
+  return acc;
+}
+// 16-byte piece c of row `row` of a [rows x 64 bf16] K-major SW128 tile (as TMA wrote it)
+__device__ __forceinline__ uint4 lds_row16(uint32_t tile_u32, int row, int c) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(tile_u32 + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4)));
+  return v;
+}
+// this thread's row of a swizzled tile . a 64-vector in registers
+__device__ __forceinline__ float row_dot(uint32_t tile_u32, int row, const Vec64& v) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    a0 = dot8(lds_row16(tile_u32, row, c), v.c[c], a0);
+    a1 = dot8(lds_row16(tile_u32, row, c + 1), v.c[c + 1], a1);
+  }
+  return a0 + a1;
+}
+// this thread's row of tile A . the same row of tile B (both [rows x 64 bf16] SW128 tiles)
+__device__ __forceinline__ float row_dot2(uint32_t a_u32, uint32_t b_u32, int row) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; c += 2) {
+    a0 = dot8(lds_row16(a_u32, row, c), lds_row16(b_u32, row, c), a0);
+    a1 = dot8(lds_row16(a_u32, row, c + 1), lds_row16(b_u32, row, c + 1), a1);
+  }
+  return a0 + a1;
+}
+// acc[i] += w * v[32*half + i], i < 32 (TMEM accumulator columns of one half of the head)
+__device__ __forceinline__ void axpy_half(uint32_t (&acc)[32], float w, const Vec64& v, int half) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 x = v.c[half * 4 + c];
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(xw[j]);
+      acc[8 * c + 2 * j] = __float_as_uint(fmaf(w, f.x, __uint_as_float(acc[8 * c + 2 * j])));
+      acc[8 * c + 2 * j + 1] = __float_as_uint(fmaf(w, f.y, __uint_as_float(acc[8 * c + 2 * j + 1])));
+    }
+  }
+}
+// eight bf16 -> fp32 (a 16-bit shift each)
+__device__ __forceinline__ void unpack8(const uint4& x, float (&f)[8]) {
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
+}
+// A SIMT CTA serves SIMT_GROUPS (batch, head) pairs at once, two warps each. These CTAs are instruction-bound (bf16
+// unpacking and the dot-product shuffles, not the loads), and what they cost is the slot-time they hold — a slot is
+// half an SM's shared memory and registers. Two lanes per token (32 dims each: one shuffle per dot product, 64 FMAs
+// per 64 unpacks) and three pairs per CTA keep them few and short enough to run in the slots the last partial wave
+// of tile CTAs leaves idle (cfgA: 171 CTAs for 240 idle slots).
+constexpr int SIMT_GROUPS = 3;
+constexpr int SIMT_GTHREADS = NTHREADS / SIMT_GROUPS;   // 64 threads per pair
+constexpr int SIMT_LPT = 2;                             // lanes per token
+constexpr int SIMT_DPL = HD / SIMT_LPT;                 // dims per lane (32 = four 16-byte loads)
+constexpr int SIMT_SLOTS = SIMT_GTHREADS / SIMT_LPT;    // tokens processed per pass by one pair's threads
+constexpr int SIMT_GWARPS = SIMT_GTHREADS / 32;
+constexpr int SIMT_WARPS = NTHREADS / 32;
+struct SimtWho { int g, tl, half, slot, b, h; bool valid; };
+__device__ __forceinline__ SimtWho simt_who(int cta_j, int B, int H) {
+  SimtWho w;
+  w.g = threadIdx.x / SIMT_GTHREADS;
+  w.tl = threadIdx.x % SIMT_GTHREADS;
+  w.half = w.tl & 1;
+  w.slot = w.tl >> 1;
+  const int pair = cta_j * SIMT_GROUPS + w.g;
+  w.valid = pair < B * H;
+  const int pc = w.valid ? pair : B * H - 1;   // idle groups shadow the last pair (loads only) to keep barriers uniform
+  w.h = pc % H;
+  w.b = pc / H;
+  return w;
+}
+struct Row32 { uint4 c[4]; };   // this lane's 32 dims of one token's head slice
+__device__ __forceinline__ void load_row32(Row32& r, const bf16* g) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.c[i] = __ldg(reinterpret_cast<const uint4*>(g) + i);
+}
+__device__ __forceinline__ void unpack32(const Row32& r, float (&f)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w[4] = {r.c[i].x, r.c[i].y, r.c[i].z, r.c[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      f[8 * i + 2 * j] = __uint_as_float(w[j] << 16);            // bf16 -> fp32 is a 16-bit shift
+      f[8 * i + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+  }
+}
+__device__ __forceinline__ float dot32(const float (&a)[32], const float (&b)[32]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int d = 0; d < 32; d += 4) {
+    s0 = fmaf(a[d], b[d], s0); s1 = fmaf(a[d + 1], b[d + 1], s1);
+    s2 = fmaf(a[d + 2], b[d + 2], s2); s3 = fmaf(a[d + 3], b[d + 3], s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float sum_pair(float s) { return s + __shfl_xor_sync(0xffffffffu, s, 1); }  // the token's two lanes
+// fold per-lane partial sums acc[32] (dims 32 half .. 32 half + 31, one token slot per lane pair) over the warp and
+// leave them in red[warp][0..63]; the caller adds the pair's warps after a barrier
+__device__ __forceinline__ void warp_fold64(float (&acc)[32], float (*red)[HD + 4], int t, int half) {
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    float r = acc[d];
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 16);
+    if ((t & 31) < 2) red[t >> 5][32 * half + d] = r;
+  }
+}
+
+// 1-D grid: the tile CTAs first ((tile, head, batch), tile fastest), then the SIMT CTAs for token 0.
+// CTAs are dispatched in index order, so the short SIMT CTAs fill the slots the last partial wave of tile CTAs
+// leaves idle instead of taking a tile slot each.
+struct CtaRole { int tile, h, b; bool simt; };   // simt: tile = index among the SIMT CTAs
+__device__ __forceinline__ CtaRole cta_role(int ntiles, int H, int ntile_ctas) {
+  CtaRole r;
+  const int id = blockIdx.x;
+  r.simt = id >= ntile_ctas;
+  if (!r.simt) { r.tile = id % ntiles; r.h = (id / ntiles) % H; r.b = id / (ntiles * H); }
+  else { r.tile = id - ntile_ctas; r.h = 0; r.b = 0; }
+  return r;
+}
 
 // =====================================================================================================
 // forward
@@ -193,6 +374,115 @@ __device__ __forceinline__ void store_p_chunk(uint32_t sP_u32, int row, int chun
   }
 }
 
+// Forward of query token 0: all N keys, SIMT. Two lanes share a key (32 dims each); one pass with a running
+// (max, sum, o) per lane pair, merged over the pair-group's two warps at the end.
+template <bool DROPOUT>
+__device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int cta_j) {
+  const Common& c = p.c;
+  const SimtWho w = simt_who(cta_j, c.B, c.H);
+  const int t = threadIdx.x, b = w.b, h = w.h;
+  const int N = c.N;
+  const int64_t bh = (int64_t)b * c.H + h;
+  float (*red)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(sm);
+  uint32_t* mw_s = reinterpret_cast<uint32_t*>(red + SIMT_WARPS) + w.g * c.mask_words;  // keep words of mask row (bh, 0)
+  const float cs = c.scale * LOG2E;
+  const bf16* kb = c.k + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half;
+  const bf16* vb = c.v + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half;
+  float qc[32];
+  {
+    Row32 qr;
+    load_row32(qr, c.q + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half);
+    unpack32(qr, qc);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) qc[d] *= cs;   // scores come out in the log2 domain
+  }
+  if (DROPOUT) {
+    const int64_t mrow = bh * N;  // query token 0
+    for (int wi = w.tl; wi < c.mask_words; wi += SIMT_GTHREADS) {
+      uint32_t word;
+      if (c.mask_ready) {
+        word = __ldg(c.mask + mrow * c.mask_words + wi);
+      } else {
+        const uint64_t seed = nv_seed(c.seed, c.epoch);
+        word = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          word |= nv_keep_bits8(seed, (uint64_t)mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)(4 * wi + g), 0u, c.drop_thr) << (8 * g);
+        if (w.valid) c.mask[mrow * c.mask_words + wi] = word;
+      }
+      mw_s[wi] = word;
+    }
+    __syncthreads();
+  }
+  float m_g = -INFINITY, l_g = 0.f, oacc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) oacc[d] = 0.f;
+  // software-pipelined: the next key's rows are in flight while this key is processed (these warps are alone with
+  // their load latency: nothing else hides it)
+  Row32 kk, vv;
+  {
+    const int64_t roff = (int64_t)min(w.slot, N - 1) * c.qkv_rs;
+    load_row32(kk, kb + roff);
+    load_row32(vv, vb + roff);
+  }
+  for (int key0 = 0; key0 < N; key0 += SIMT_SLOTS) {   // uniform trip count: the shuffles need whole warps
+    const int key = key0 + w.slot;
+    Row32 kn, vn;
+    {
+      const int64_t roff = (int64_t)min(key + SIMT_SLOTS, N - 1) * c.qkv_rs;
+      load_row32(kn, kb + roff);
+      load_row32(vn, vb + roff);
+    }
+    float sj;
+    {
+      float kf[32];
+      unpack32(kk, kf);
+      const float sred = sum_pair(dot32(qc, kf));   // the shuffle must run in every lane: never under the `live` predicate
+      sj = key < N ? sred : -INFINITY;
+    }
+    const float m_new = fmaxf(m_g, sj);
+    const float m_safe = m_new == -INFINITY ? 0.f : m_new;   // a lane pair that has seen no key yet
+    const float alpha = ex2(m_g - m_safe);                   // 0 on the first key
+    const float pj = ex2(sj - m_safe);                       // 0 for keys past N
+    l_g = fmaf(l_g, alpha, pj);
+    float pd = pj;
+    if (DROPOUT) {
+      const int pos = key_pos(key < N ? key : 0, N);
+      pd = (mw_s[pos >> 5] >> (pos & 31)) & 1u ? pj * c.keep_scale : 0.f;
+    }
+    {
+      float vf[32];
+      unpack32(vv, vf);
+#pragma unroll
+      for (int d = 0; d < 32; ++d) oacc[d] = fmaf(oacc[d], alpha, pd * vf[d]);
+    }
+    m_g = m_new;
+    kk = kn; vv = vn;
+  }
+  // merge the pair-group's lane pairs: common reference M, then plain sums
+  const int w0 = w.g * SIMT_GWARPS;  // first warp of this pair-group
+  float mx = warp_max(m_g);
+  if ((t & 31) == 0) red[t >> 5][HD + 1] = mx;
+  __syncthreads();
+  float M = red[w0][HD + 1];
+#pragma unroll
+  for (int i = 1; i < SIMT_GWARPS; ++i) M = fmaxf(M, red[w0 + i][HD + 1]);
+  const float sc_g = ex2(m_g - M);  // 0 for lane pairs without keys
+#pragma unroll
+  for (int d = 0; d < 32; ++d) oacc[d] *= sc_g;
+  warp_fold64(oacc, red, t, w.half);
+  const float l = warp_sum(w.half == 0 ? l_g * sc_g : 0.f);
+  if ((t & 31) == 0) red[t >> 5][HD] = l;
+  __syncthreads();
+  if (w.tl < HD && w.valid) {
+    float r = 0.f, L = 0.f;
+#pragma unroll
+    for (int i = 0; i < SIMT_GWARPS; ++i) { r += red[w0 + i][w.tl]; L += red[w0 + i][HD]; }
+    p.o[(int64_t)b * p.o_bs + h * HD + w.tl] = __float2bfloat16(r / L);
+    if (w.tl == 0) p.lse[bh * N] = (M + log2f(L)) * LN2;
+  }
+}
+
 template <bool DROPOUT>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
@@ -215,9 +505,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.c.N;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
-  const int nblk = (N + FWD_KB - 1) / FWD_KB;
-  const int nactive = (min(BQ, N - q0) + 31) >> 5;  // row warps with at least one valid query
+  const int n = N - 1;  // tokens 1 .. n are tiled; tile-local index r <-> token r + 1
+  const CtaRole role = cta_role((n + BQ - 1) / BQ, p.c.H, p.c.ntile_ctas);
+  const int b = role.b, h = role.h, q0 = role.tile * BQ;
+  if (role.simt) {  // query token 0, SIMT (no barriers / TMEM in use yet)
+    PROF_DECL
+    fwd_cls_query<DROPOUT>(p, reinterpret_cast<float*>(smem), role.tile);
+    PROF_MARK(0);
+#ifdef NV_PROFILE
+    if (role.tile == 14 && threadIdx.x == 0) PROF_DUMP(12);
+#endif
+    return;
+  }
+  const int nblk = (n + FWD_KB - 1) / FWD_KB;
+  const int nactive = (min(BQ, n - q0) + 31) >> 5;  // row warps with at least one valid query
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("attn_tc_fwd: dynamic shared memory is not 1024-byte aligned\n");
@@ -245,7 +546,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == TMA_WARP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, SLAB);
-      tma_load_3d(sQ, &tq, q_full, h * HD, q0, b);  // one 128-row box
+      tma_load_3d(sQ, &tq, q_full, h * HD, 1 + q0, b);  // one 128-row box
     }
     __syncwarp();
     for (int j = 0; j < nblk; ++j) {
@@ -254,20 +555,20 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       mbar_wait(&k_empty[s], ph);
       if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[s], FWD_KV_BYTES);
-        tma_load_3d(sK + s * FWD_KV_BYTES, &tk, &k_full[s], h * HD, j * FWD_KB, b);
+        tma_load_3d(sK + s * FWD_KV_BYTES, &tk, &k_full[s], h * HD, 1 + j * FWD_KB, b);
       }
       __syncwarp();
       mbar_wait(&v_empty[s], ph);
       if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[s], FWD_KV_BYTES);
-        tma_load_3d(sV + s * FWD_KV_BYTES, &tv, &v_full[s], h * HD, j * FWD_KB, b);
+        tma_load_3d(sV + s * FWD_KV_BYTES, &tv, &v_full[s], h * HD, 1 + j * FWD_KB, b);
       }
       __syncwarp();
     }
   } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, HD, 0, 1);
     const uint64_t q_desc = kmajor_desc(sQ);
-    auto cols16 = [&](int j) { return (min(FWD_KB, N - j * FWD_KB) + 15) & ~15; };
+    auto cols16 = [&](int j) { return (min(FWD_KB, n - j * FWD_KB) + 15) & ~15; };
     auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j & 1; frees the K stage when done
       const int s = j & 1;
       mma_k64(tS + (uint32_t)(s * FWD_KB), q_desc, kmajor_desc(sK + s * FWD_KV_BYTES), umma_idesc_bf16(128, cols16(j), 0, 0));
@@ -301,18 +602,29 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     }
   } else if (warp < nactive) {
     const int row = warp * 32 + lane;  // row within the tile == TMEM lane
-    const int qrow = q0 + row;
+    const int qrow = q0 + row;         // tile-local query index; token = qrow + 1
+    const int token = min(qrow + 1, N - 1);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t sP_u32 = smem_u32(sP);
     const float cs = p.c.scale * LOG2E;
     const int bh = b * p.c.H + h;
-    const uint64_t mrow = (uint64_t)bh * N + min(qrow, N - 1);
-    float m_used = -INFINITY, l_run = 0.f;
+    const uint64_t mrow = (uint64_t)bh * N + token;
+    // key token 0: its raw score from this row's Q in shared memory; it also seeds the softmax reference, so the
+    // probability computed at the end (with the final reference) cannot overflow
     PROF_DECL
+    float s_x;
+    {
+      Vec64 k0;
+      load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);   // in flight while the Q tile lands
+      mbar_wait(q_full, 0);
+      s_x = row_dot(smem_u32(sQ), row, k0);
+    }
+    float m_used = s_x * cs, l_run = 0.f;
+    PROF_MARK(8);
 
     for (int j = 0; j < nblk; ++j) {
-      const int key0 = j * FWD_KB;
-      const int nvalid = min(FWD_KB, N - key0);
+      const int key0 = j * FWD_KB;     // tile-local key index == mask bit position
+      const int nvalid = min(FWD_KB, n - key0);
       const bool full = nvalid == FWD_KB;
       const uint32_t tSj = tS + lane_base + (uint32_t)((j & 1) * FWD_KB);
       uint32_t kmw[3] = {0u, 0u, 0u};  // pre-drawn dropout keep words of this row's block
@@ -348,7 +660,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       // probabilities -> K-major SW128 operand rows; the P V MMA reads ceil16(nvalid) key columns.
       // The first chunk's exponentials are computed before waiting for the previous P V (which still reads
       // P's buffer), so that wait is normally already satisfied.
-      const bool row_ok = qrow < N;
+      const bool row_ok = qrow < n;
       uint32_t w[16];
       float rs;
       if (full) rs = fwd_chunk_probs<true, DROPOUT>(c0, cs, m_used, 32, p.c, mrow, key0, row_ok, w, kmw[0]);
@@ -392,18 +704,39 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       mbar_arrive(sp_ready);
       PROF_MARK(5);
     }
+    Vec64 v0;
+    load_vec64(v0, p.c.v + (int64_t)b * p.c.qkv_bs + h * HD);   // in flight under the last P V
     mbar_wait(o_full, (nblk - 1) & 1);  // last block's P V
     tc_fence_after();
     PROF_MARK(6);
     {
+      // key token 0 joins here: p_x = 2^(s_x c - m) with the final reference, O += dropout(p_x) v_0
+      const float p_x = ex2(fmaf(s_x, cs, -m_used));
+      l_run += p_x;
+      float p_xd = p_x;
+      if (DROPOUT) {
+        const int pos = N - 1;
+        uint32_t keep;
+        if (p.c.mask_ready) {
+          keep = (__ldg(p.c.mask + mrow * p.c.mask_words + (pos >> 5)) >> (pos & 31)) & 1u;
+        } else {
+          const uint32_t byte = nv_keep_bits8(nv_seed(p.c.seed, p.c.epoch),
+                                              mrow * (uint64_t)(p.c.mask_words * 4) + (uint64_t)(pos >> 3), 0u, p.c.drop_thr);
+          keep = (byte >> (pos & 7)) & 1u;
+          // the word of position N-1 is written by the last key chunk unless that chunk ended on a word boundary
+          if ((pos & 31) == 0 && qrow < n) p.c.mask[mrow * p.c.mask_words + (pos >> 5)] = byte;
+        }
+        p_xd = keep ? p_x * p.c.keep_scale : 0.f;
+      }
       const float inv = 1.0f / l_run;
-      bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)min(qrow, N - 1) * p.o_rs + h * HD;
+      bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)token * p.o_rs + h * HD;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {  // tcgen05.ld is warp-collective: every lane loads, valid rows store
         uint32_t v[32];
         tmem_ld_32x32(tO + lane_base + hh * 32, v);
         tmem_ld_wait();
-        if (qrow < N) {
+        axpy_half(v, p_xd, v0, hh);
+        if (qrow < n) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 t;
@@ -415,11 +748,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           }
         }
       }
-      if (qrow < N) p.lse[((int64_t)b * p.c.H + h) * N + qrow] = (m_used + log2f(l_run)) * LN2;
+      if (qrow < n) p.lse[((int64_t)b * p.c.H + h) * N + token] = (m_used + log2f(l_run)) * LN2;
     }
     PROF_MARK(7);
 #ifdef NV_PROFILE
-    if (blockIdx.x == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+    if (role.tile == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
       PROF_DUMP((b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
 #endif
   }
@@ -438,10 +771,173 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 struct BwdParams {
   Common c;
   const float* lse;    // [B,H,N] natural log
-  const float* delta;  // [B,H,N]
+  float* delta;        // [B,H,N]: written by the dQ kernel (delta_i = dO_i . O_i), read by the dK/dV kernel
+  const bf16 *o, *dO;  // [B,N,H*64] (o_bs, o_rs)
+  int64_t o_bs, o_rs;
   bf16* dq; bf16* dk; bf16* dv;
   int64_t d_bs, d_rs;
 };
+
+// dQ of query token 0 (and its delta): all N keys, SIMT, two lanes per key.
+__device__ __forceinline__ void bwd_cls_query_dq(const BwdParams& p, float* sm, int cta_j) {
+  const Common& c = p.c;
+  const SimtWho w = simt_who(cta_j, c.B, c.H);
+  const int t = threadIdx.x, b = w.b, h = w.h;
+  const int N = c.N;
+  const int64_t bh = (int64_t)b * c.H + h;
+  float (*red)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(sm);
+  const float cs = c.scale * LOG2E;
+  const bool dropout = c.drop_thr != 0;
+  float qc[32], doc[32];
+  float delta;
+  {
+    Row32 r;
+    float oc[32];
+    load_row32(r, c.q + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half);
+    unpack32(r, qc);
+    load_row32(r, p.dO + (int64_t)b * p.o_bs + h * HD + SIMT_DPL * w.half);
+    unpack32(r, doc);
+    load_row32(r, p.o + (int64_t)b * p.o_bs + h * HD + SIMT_DPL * w.half);
+    unpack32(r, oc);
+    delta = sum_pair(dot32(doc, oc));
+  }
+  if (w.tl == 0 && w.valid) p.delta[bh * N] = delta;
+  const float lse2 = __ldg(p.lse + bh * N) * LOG2E;
+  const bf16* kb = c.k + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half;
+  const bf16* vb = c.v + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half;
+  const uint32_t* mrow0 = c.mask + bh * N * c.mask_words;   // mask row of query token 0
+  float acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  Row32 kk, vv;   // software-pipelined like the forward
+  {
+    const int64_t roff = (int64_t)min(w.slot, N - 1) * c.qkv_rs;
+    load_row32(kk, kb + roff);
+    load_row32(vv, vb + roff);
+  }
+  for (int key0 = 0; key0 < N; key0 += SIMT_SLOTS) {
+    const int key = key0 + w.slot;
+    const bool live = key < N;
+    const int kc = live ? key : 0;
+    Row32 kn, vn;
+    {
+      const int64_t roff = (int64_t)min(key + SIMT_SLOTS, N - 1) * c.qkv_rs;
+      load_row32(kn, kb + roff);
+      load_row32(vn, vb + roff);
+    }
+    const int pos = key_pos(kc, N);
+    const uint32_t mw = dropout ? __ldg(mrow0 + (pos >> 5)) : 0xFFFFFFFFu;
+    float kf[32], dp;
+    {
+      float vf[32];
+      unpack32(vv, vf);
+      dp = sum_pair(dot32(doc, vf));
+    }
+    unpack32(kk, kf);
+    const float sacc = sum_pair(dot32(qc, kf));
+    const float pj = ex2(fmaf(sacc, cs, -lse2));
+    const bool keep = (mw >> (pos & 31)) & 1u;
+    const float ds = live ? pj * ((keep ? dp * c.keep_scale : 0.f) - delta) : 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = fmaf(ds, kf[d], acc[d]);
+    kk = kn; vv = vn;
+  }
+  warp_fold64(acc, red, t, w.half);
+  __syncthreads();
+  if (w.tl < HD && w.valid) {
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < SIMT_GWARPS; ++i) r += red[w.g * SIMT_GWARPS + i][w.tl];
+    p.dq[(int64_t)b * p.d_bs + h * HD + w.tl] = __float2bfloat16(r * c.scale);
+  }
+}
+
+// dK and dV of key token 0: a reduction over all N queries, SIMT, two lanes per query.
+// Reads delta (all queries), so it runs in the dK/dV grid, after the dQ grid has written it.
+__device__ __forceinline__ void bwd_extra_key_dkv(const BwdParams& p, float* sm, int cta_j) {
+  const Common& c = p.c;
+  const SimtWho w = simt_who(cta_j, c.B, c.H);
+  const int t = threadIdx.x, b = w.b, h = w.h;
+  const int N = c.N;
+  const int64_t bh = (int64_t)b * c.H + h;
+  float (*red)[HD + 4] = reinterpret_cast<float (*)[HD + 4]>(sm);
+  float (*red2)[HD + 4] = red + SIMT_WARPS;
+  const float cs = c.scale * LOG2E;
+  const bool dropout = c.drop_thr != 0;
+  const int pos = N - 1;  // mask bit position of key token 0
+  // k and v of token 0 are re-read (L1 hits) piece by piece for every query: the registers go to the two accumulators
+  const uint4* k0p = reinterpret_cast<const uint4*>(c.k + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half);
+  const uint4* v0p = reinterpret_cast<const uint4*>(c.v + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half);
+  const bf16* qb = c.q + (int64_t)b * c.qkv_bs + h * HD + SIMT_DPL * w.half;
+  const bf16* dob = p.dO + (int64_t)b * p.o_bs + h * HD + SIMT_DPL * w.half;
+  float dk_acc[32], dv_acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) dk_acc[d] = dv_acc[d] = 0.f;
+  Row32 qq, dd;   // software-pipelined like the forward
+  float l2, dl;
+  uint32_t mw = 0xFFFFFFFFu;
+  {
+    const int ic = min(w.slot, N - 1);
+    load_row32(qq, qb + (int64_t)ic * c.qkv_rs);
+    load_row32(dd, dob + (int64_t)ic * p.o_rs);
+    l2 = __ldg(p.lse + bh * N + ic) * LOG2E;
+    dl = p.delta[bh * N + ic];   // written by the dQ grid: plain load
+    if (dropout) mw = __ldg(c.mask + (bh * N + ic) * c.mask_words + (pos >> 5));
+  }
+  for (int i0 = 0; i0 < N; i0 += SIMT_SLOTS) {
+    const int i = i0 + w.slot;
+    const bool live = i < N;
+    Row32 qn, dn;
+    float l2n, dln;
+    uint32_t mwn = 0xFFFFFFFFu;
+    {
+      const int ic = min(i + SIMT_SLOTS, N - 1);
+      load_row32(qn, qb + (int64_t)ic * c.qkv_rs);
+      load_row32(dn, dob + (int64_t)ic * p.o_rs);
+      l2n = __ldg(p.lse + bh * N + ic) * LOG2E;
+      dln = p.delta[bh * N + ic];
+      if (dropout) mwn = __ldg(c.mask + (bh * N + ic) * c.mask_words + (pos >> 5));
+    }
+    // 16-byte piece at a time: the rows stay packed in registers (the two accumulators need the space)
+    float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a[8], bb[8];
+      unpack8(qq.c[i], a); unpack8(__ldg(k0p + i), bb);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) { s0 = fmaf(a[j], bb[j], s0); s1 = fmaf(a[j + 1], bb[j + 1], s1); }
+      unpack8(dd.c[i], a); unpack8(__ldg(v0p + i), bb);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) { d0 = fmaf(a[j], bb[j], d0); d1 = fmaf(a[j + 1], bb[j + 1], d1); }
+    }
+    const float sacc = sum_pair(s0 + s1), dp = sum_pair(d0 + d1);
+    const float pj = ex2(fmaf(sacc, cs, -l2));
+    const bool keep = (mw >> (pos & 31)) & 1u;
+    const float pm = (live && keep) ? pj * c.keep_scale : 0.f;
+    const float ds = live ? pj * ((keep ? dp * c.keep_scale : 0.f) - dl) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a[8];
+      unpack8(qq.c[i], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dk_acc[8 * i + j] = fmaf(ds, a[j], dk_acc[8 * i + j]);
+      unpack8(dd.c[i], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv_acc[8 * i + j] = fmaf(pm, a[j], dv_acc[8 * i + j]);
+    }
+    qq = qn; dd = dn; l2 = l2n; dl = dln; mw = mwn;
+  }
+  warp_fold64(dk_acc, red, t, w.half);
+  warp_fold64(dv_acc, red2, t, w.half);
+  __syncthreads();
+  if (w.tl < HD && w.valid) {
+    float rk = 0.f, rv = 0.f;
+#pragma unroll
+    for (int i = 0; i < SIMT_GWARPS; ++i) { rk += red[w.g * SIMT_GWARPS + i][w.tl]; rv += red2[w.g * SIMT_GWARPS + i][w.tl]; }
+    p.dk[(int64_t)b * p.d_bs + h * HD + w.tl] = __float2bfloat16(rk * c.scale);
+    p.dv[(int64_t)b * p.d_bs + h * HD + w.tl] = __float2bfloat16(rv);
+  }
+}
 constexpr int BWD_CB = 64;  // columns per block (keys in dQ, queries in dKV)
 constexpr int DQ_SMEM_TILES = 2 * SLAB /*Q, dO*/ + 2 * 2 * BOX /*K,V x 2 stages*/ + SLAB /*dS*/;
 constexpr int DQ_SMEM = DQ_SMEM_TILES + 128 + 1024;
@@ -449,7 +945,7 @@ constexpr int DQ_SMEM = DQ_SMEM_TILES + 128 + 1024;
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                       const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
-                      const BwdParams p) {
+                      const __grid_constant__ CUtensorMap to, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
@@ -464,20 +960,33 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   uint64_t* ds_ready = bars + 6;    // 1
   uint64_t* ds_free = bars + 7;     // 1  (also "dQ accumulated" after the last block)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* o_full = bars + 9;      // 1  the O tile, parked in the dS slab until the rows have taken delta from it
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.c.N;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
-  const int nblk = (N + BWD_CB - 1) / BWD_CB;
-  const int nactive = (min(BQ, N - q0) + 31) >> 5;
+  const int n = N - 1;  // tokens 1 .. n are tiled; tile-local index r <-> token r + 1
+  const CtaRole role = cta_role((n + BQ - 1) / BQ, p.c.H, p.c.ntile_ctas);
+  const int b = role.b, h = role.h, q0 = role.tile * BQ;
+  if (role.simt) {  // query token 0 (delta, dQ), SIMT
+    PROF_DECL
+    bwd_cls_query_dq(p, reinterpret_cast<float*>(smem), role.tile);
+    PROF_MARK(0);
+#ifdef NV_PROFILE
+    if (role.tile == 14 && threadIdx.x == 0) PROF_DUMP(13);
+#endif
+    return;
+  }
+  const int nblk = (n + BWD_CB - 1) / BWD_CB;
+  const int nactive = (min(BQ, n - q0) + 31) >> 5;
 
   if (warp == TMA_WARP && lane == 0) {
-    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); tma_prefetch_desc(&to);
     mbar_init(qd_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(ds_ready, 32 * nactive);
     mbar_init(ds_free, 1);
+    mbar_init(o_full, 1);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
@@ -490,8 +999,12 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   if (warp == TMA_WARP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(qd_full, 2 * SLAB);
-      load_rows(sQ, &tq, qd_full, h * HD, q0, b, 2);
-      load_rows(sdO, &tdo, qd_full, h * HD, q0, b, 2);
+      load_rows(sQ, &tq, qd_full, h * HD, 1 + q0, b, 2);
+      load_rows(sdO, &tdo, qd_full, h * HD, 1 + q0, b, 2);
+      // O rows of the tile -> the dS slab (free until the first dS is written): each row thread reads delta = dO . O
+      // from its own row and only then overwrites that row with dS, so no other synchronisation is needed
+      mbar_arrive_expect_tx(o_full, SLAB);
+      load_rows(sdS, &to, o_full, h * HD, 1 + q0, b, 2);
     }
     __syncwarp();
     for (int j = 0; j < nblk; ++j) {
@@ -499,15 +1012,15 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[s], 2 * BOX);
-        load_rows(sKV + s * 2 * BOX, &tk, &kv_full[s], h * HD, j * BWD_CB, b, 1);
-        load_rows(sKV + s * 2 * BOX + BOX, &tv, &kv_full[s], h * HD, j * BWD_CB, b, 1);
+        load_rows(sKV + s * 2 * BOX, &tk, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
+        load_rows(sKV + s * 2 * BOX + BOX, &tv, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
       }
       __syncwarp();
     }
   } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 0, 1);
     const uint64_t q_desc = kmajor_desc(sQ), do_desc = kmajor_desc(sdO);
-    auto cols16 = [&](int j) { return (min(BWD_CB, N - j * BWD_CB) + 15) & ~15; };
+    auto cols16 = [&](int j) { return (min(BWD_CB, n - j * BWD_CB) + 15) & ~15; };
     auto issue_scores = [&](int j) {
       const uint8_t* kt = sKV + (j & 1) * 2 * BOX;
       const uint32_t idesc = umma_idesc_bf16(128, cols16(j), 0, 0);
@@ -539,19 +1052,38 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     }
   } else if (warp < nactive) {
     const int row = warp * 32 + lane;
-    const int qrow = q0 + row;
+    const int qrow = q0 + row;               // tile-local query index; token = qrow + 1
+    const int token = min(qrow + 1, N - 1);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t sdS_u32 = smem_u32(sdS);
     const float cs = p.c.scale * LOG2E;
     const bool dropout = p.c.drop_thr != 0;
-    const int64_t stat = ((int64_t)b * p.c.H + h) * N + min(qrow, N - 1);
+    const int64_t stat = ((int64_t)b * p.c.H + h) * N + token;
     const uint64_t mrow = (uint64_t)stat;
     const float lse2 = p.lse[stat] * LOG2E;
-    const float dl = p.delta[stat];
+    // prologue on this row's Q / dO in shared memory: delta_i = dO_i . O_i (also published for the dK/dV kernel)
+    // and the dS of key token 0, which stays outside the tiles
     PROF_DECL
+    float dl, ds_x;
+    {
+      Vec64 v0, k0;   // in flight while the Q / dO / O tiles land
+      load_vec64(v0, p.c.v + (int64_t)b * p.c.qkv_bs + h * HD);
+      load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);
+      uint32_t kw = 0xFFFFFFFFu;
+      if (dropout) kw = __ldg(p.c.mask + mrow * p.c.mask_words + ((N - 1) >> 5));
+      mbar_wait(qd_full, 0);
+      mbar_wait(o_full, 0);
+      dl = row_dot2(smem_u32(sdO), sdS_u32, row);
+      if (qrow < n) p.delta[stat] = dl;
+      const float dp_x = row_dot(smem_u32(sdO), row, v0);
+      const float p_x = ex2(fmaf(row_dot(smem_u32(sQ), row, k0), cs, -lse2));
+      const bool keep = (kw >> ((N - 1) & 31)) & 1u;
+      ds_x = p_x * ((keep ? dp_x * p.c.keep_scale : 0.f) - dl);
+    }
+    PROF_MARK(8);
     for (int j = 0; j < nblk; ++j) {
-      const int key0 = j * BWD_CB;
-      const int nch = (min(BWD_CB, N - key0) + 31) >> 5;
+      const int key0 = j * BWD_CB;           // tile-local key index == mask bit position
+      const int nch = (min(BWD_CB, n - key0) + 31) >> 5;
       uint32_t kmw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // dropout keep words of the block, fetched before the waits
       if (dropout) {
         kmw[0] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5));
@@ -589,17 +1121,20 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       mbar_arrive(ds_ready);
       PROF_MARK(3);
     }
+    Vec64 k0;
+    load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);   // in flight under the last dQ MMA
     mbar_wait(ds_free, (nblk - 1) & 1);  // last dQ MMA retired
     tc_fence_after();
     PROF_MARK(4);
     {  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows store
-      bf16* dst = p.dq + (int64_t)b * p.d_bs + (int64_t)min(qrow, N - 1) * p.d_rs + h * HD;
+      bf16* dst = p.dq + (int64_t)b * p.d_bs + (int64_t)token * p.d_rs + h * HD;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tdQ + lane_base + c * 32, v);
         tmem_ld_wait();
-        if (qrow < N) {
+        axpy_half(v, ds_x, k0, c);   // + dS_{i,0} k_0
+        if (qrow < n) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 t;
@@ -614,7 +1149,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     }
     PROF_MARK(5);
 #ifdef NV_PROFILE
-    if (blockIdx.x == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+    if (role.tile == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
       PROF_DUMP(4 + (b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
 #endif
   }
@@ -655,9 +1190,20 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.c.N;
-  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * BQ;
-  const int nblk = (N + BWD_CB - 1) / BWD_CB;
-  const int nactive = (min(BQ, N - k0) + 31) >> 5;
+  const int n = N - 1;  // tokens 1 .. n are tiled; tile-local index r <-> token r + 1
+  const CtaRole role = cta_role((n + BQ - 1) / BQ, p.c.H, p.c.ntile_ctas);
+  const int b = role.b, h = role.h, k0 = role.tile * BQ;
+  if (role.simt) {  // dK / dV of key token 0, SIMT
+    PROF_DECL
+    bwd_extra_key_dkv(p, reinterpret_cast<float*>(smem), role.tile);
+    PROF_MARK(0);
+#ifdef NV_PROFILE
+    if (role.tile == 14 && threadIdx.x == 0) PROF_DUMP(14);
+#endif
+    return;
+  }
+  const int nblk = (n + BWD_CB - 1) / BWD_CB;
+  const int nactive = (min(BQ, n - k0) + 31) >> 5;
 
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
@@ -678,8 +1224,8 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
   if (warp == TMA_WARP) {
     if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * SLAB);
-      load_rows(sK, &tk, kv_full, h * HD, k0, b, 2);
-      load_rows(sV, &tv, kv_full, h * HD, k0, b, 2);
+      load_rows(sK, &tk, kv_full, h * HD, 1 + k0, b, 2);
+      load_rows(sV, &tv, kv_full, h * HD, 1 + k0, b, 2);
     }
     __syncwarp();
     for (int i = 0; i < nblk; ++i) {
@@ -687,15 +1233,15 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       mbar_wait(&qd_empty[s], ((i >> 1) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&qd_full[s], 2 * BOX);
-        load_rows(sQD + s * 2 * BOX, &tq, &qd_full[s], h * HD, i * BWD_CB, b, 1);
-        load_rows(sQD + s * 2 * BOX + BOX, &tdo, &qd_full[s], h * HD, i * BWD_CB, b, 1);
+        load_rows(sQD + s * 2 * BOX, &tq, &qd_full[s], h * HD, 1 + i * BWD_CB, b, 1);
+        load_rows(sQD + s * 2 * BOX + BOX, &tdo, &qd_full[s], h * HD, 1 + i * BWD_CB, b, 1);
       }
       __syncwarp();
     }
   } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc_acc = umma_idesc_bf16(128, HD, 0, 1);
     const uint64_t k_desc = kmajor_desc(sK), v_desc = kmajor_desc(sV);
-    auto cols16 = [&](int i) { return (min(BWD_CB, N - i * BWD_CB) + 15) & ~15; };
+    auto cols16 = [&](int i) { return (min(BWD_CB, n - i * BWD_CB) + 15) & ~15; };
     auto issue_scores = [&](int i) {
       const uint8_t* qt = sQD + (i & 1) * 2 * BOX;
       const uint32_t idesc = umma_idesc_bf16(128, cols16(i), 0, 0);
@@ -729,12 +1275,12 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     }
   } else if (warp < nactive) {
     const int row = warp * 32 + lane;
-    const int krow = k0 + row;
+    const int krow = k0 + row;               // tile-local key index (== mask bit position); token = krow + 1
+    const int ktoken = min(krow + 1, N - 1);
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t sPT_u32 = smem_u32(sPT), sdST_u32 = smem_u32(sdST);
     const float cs = p.c.scale * LOG2E;
     const float* lse_bh = p.lse + ((int64_t)b * p.c.H + h) * N;
-    const float* delta_bh = p.delta + ((int64_t)b * p.c.H + h) * N;
     // per-warp staging of the block's 64 per-query statistics: [lse*log2e | delta], read back as broadcasts
     float* stats = reinterpret_cast<float*>(smem + DKV_SMEM_TILES + 128) + warp * 192;
     uint32_t* mwords = reinterpret_cast<uint32_t*>(stats + 128);  // dropout: the 64 queries' mask words of this warp's keys
@@ -748,11 +1294,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     auto fetch_stats = [&](int blk) {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int q = blk * BWD_CB + t * 32 + lane;
-        const int qc = min(q, N - 1);
+        const int q = blk * BWD_CB + t * 32 + lane;   // tile-local query index; token = q + 1
+        const int qc = min(q + 1, N - 1);
         // padded queries: lse = +inf makes P exactly 0 (their dO / Q rows are zero-filled anyway)
-        st_l[t] = q < N ? __ldg(lse_bh + qc) * LOG2E : INFINITY;
-        st_d[t] = __ldg(delta_bh + qc);
+        st_l[t] = q < n ? __ldg(lse_bh + qc) * LOG2E : INFINITY;
+        st_d[t] = p.delta[((int64_t)b * p.c.H + h) * N + qc];  // written by the dQ grid (plain load: not read-only data)
         if (dropout) st_m[t] = p.c.mask[(mbase + qc) * p.c.mask_words + ((k0 + warp * 32) >> 5)];
       }
     };
@@ -760,7 +1306,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     fetch_stats(0);
     for (int i = 0; i < nblk; ++i) {
       const int qb = i * BWD_CB;
-      const int nvalid = min(BWD_CB, N - qb);
+      const int nvalid = min(BWD_CB, n - qb);
       const int nch = (nvalid + 31) >> 5;
       __syncwarp();
 #pragma unroll
@@ -772,7 +1318,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       }
       if (i + 1 < nblk) fetch_stats(i + 1);
       __syncwarp();
-      PROF_MARK(0);
+      PROF_MARK(i == 0 ? 7 : 0);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       PROF_MARK(1);
@@ -829,6 +1375,25 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       mbar_arrive(pds_ready);
       PROF_MARK(3);
     }
+    // query token 0 stays outside the tiles: its row of P / dS for this key, from the key's K / V rows in
+    // shared memory (rank-1 terms p~_0j dO_0 and dS_0j q_0 added to the accumulators below)
+    float pm_x, ds_x;
+    mbar_wait(kv_full, 0);  // long since complete: orders this thread's reads of the TMA-written K / V tiles
+    Vec64 q0v, do0;   // q and dO of token 0: used for the scores here and for the rank-1 terms below
+    {
+      const int64_t stat0 = ((int64_t)b * p.c.H + h) * N;
+      load_vec64(q0v, p.c.q + (int64_t)b * p.c.qkv_bs + h * HD);
+      load_vec64(do0, p.dO + (int64_t)b * p.o_bs + h * HD);
+      uint32_t kw = 0xFFFFFFFFu;
+      if (dropout) kw = __ldg(p.c.mask + stat0 * p.c.mask_words + (min(krow, n - 1) >> 5));
+      const float lse2_0 = __ldg(p.lse + stat0) * LOG2E, dl_0 = p.delta[stat0];
+      const float p_x = ex2(fmaf(row_dot(smem_u32(sK), row, q0v), cs, -lse2_0));
+      const float dp_x = row_dot(smem_u32(sV), row, do0);
+      const bool keep = (kw >> (krow & 31)) & 1u;
+      pm_x = keep ? p_x * p.c.keep_scale : 0.f;
+      ds_x = p_x * ((keep ? dp_x * p.c.keep_scale : 0.f) - dl_0);
+    }
+    PROF_MARK(6);
     mbar_wait(pds_free, (nblk - 1) & 1);
     tc_fence_after();
     PROF_MARK(4);
@@ -836,13 +1401,14 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     for (int which = 0; which < 2; ++which) {
       bf16* base = which == 0 ? p.dv : p.dk;
       const float mul = which == 0 ? 1.0f : p.c.scale;
-      bf16* dst = base + (int64_t)b * p.d_bs + (int64_t)min(krow, N - 1) * p.d_rs + h * HD;
+      bf16* dst = base + (int64_t)b * p.d_bs + (int64_t)ktoken * p.d_rs + h * HD;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld_32x32((which == 0 ? tdV : tdK) + lane_base + c * 32, v);
         tmem_ld_wait();
-        if (krow < N) {
+        axpy_half(v, which == 0 ? pm_x : ds_x, which == 0 ? do0 : q0v, c);
+        if (krow < n) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 t;
@@ -857,7 +1423,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     }
     PROF_MARK(5);
 #ifdef NV_PROFILE
-    if (blockIdx.x == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+    if (role.tile == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
       PROF_DUMP(8 + (b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
 #endif
   }
@@ -867,36 +1433,6 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
   if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]: one warp per (b, token), all heads of the token in one
-// pass (the token's 8 x 128 B head slices are contiguous), lanes own 16-byte chunks.
-__global__ void attn_tc_delta_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, int64_t bs, int64_t rs,
-                                     float* __restrict__ delta, int B, int N, int H) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= (int64_t)B * N) return;
-  const int i = (int)(w % N), b = (int)(w / N);
-  const bf16* a = dO + (int64_t)b * bs + (int64_t)i * rs;
-  const bf16* c = O + (int64_t)b * bs + (int64_t)i * rs;
-  for (int base = 0; base < H * HD; base += 256) {  // 32 lanes x 8 elements
-    const int col = base + lane * 8;
-    float s = 0.f;
-    if (col < H * HD) {
-      const uint4 x = *reinterpret_cast<const uint4*>(a + col), y = *reinterpret_cast<const uint4*>(c + col);
-      const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = unpack_bf16x2(xs[k]), fb = unpack_bf16x2(ys[k]);
-        s = fmaf(fa.x, fb.x, fmaf(fa.y, fb.y, s));
-      }
-    }
-    // 8 lanes share a head
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if ((lane & 7) == 0 && col < H * HD) delta[((int64_t)b * H + (col >> 6)) * N + i] = s;
   }
 }
 
@@ -963,7 +1499,10 @@ attn_cls_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
     }
     const float p = ex2(fmaf(s, scale * LOG2E, -lse2));
     bool keep = true;
-    if (mask != nullptr && live) keep = (mask[bh * N * mask_words + (key >> 5)] >> (key & 31)) & 1u;  // row of token 0
+    if (mask != nullptr && live) {  // row of token 0; bit position of key token `key`
+      const int pos = key_pos(key, N);
+      keep = (mask[bh * N * mask_words + (pos >> 5)] >> (pos & 31)) & 1u;
+    }
     const float pm = keep ? p * keep_scale : 0.f;
     const float ds = live ? p * ((keep ? dp * keep_scale : 0.f) - delta) * scale : 0.f;
     if (live) {
@@ -1004,9 +1543,13 @@ int make_map(CUtensorMap* m, const bf16* base, int64_t bs, int64_t rs, int B, in
   return nv_encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int fill_common(Common& c, int N, int H, float scale, float dropout_p, uint64_t seed, uint32_t* mask, int mask_ready = 0) {
+int fill_common(Common& c, const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, int N, int H,
+                float scale, float dropout_p, uint64_t seed, uint32_t* mask, int mask_ready = 0) {
   NV_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attention: dropout_p %f out of range [0, 1)", dropout_p);
+  NV_REQUIRE(N <= 16384, "attention: N=%d tokens exceed the SIMT cls-row staging (16384)", N);
+  c.q = q; c.k = k; c.v = v; c.qkv_bs = qkv_bs; c.qkv_rs = qkv_rs;
   c.N = N; c.H = H; c.scale = scale; c.seed = seed;
+  c.ntile_ctas = 0;  // set by the launchers (tile_grid)
   c.epoch = dropout_p > 0.f ? nv_rng_epoch_dev() : nullptr;
   c.drop_thr = nv_dropout_threshold(dropout_p);
   c.keep_scale = nv_dropout_keep_scale(c.drop_thr);
@@ -1022,6 +1565,29 @@ int check_args(const void* p, int64_t bs, int64_t rs, const char* name) {
   NV_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0 && bs % 8 == 0 && rs % 8 == 0,
              "attention: %s must be 16-byte aligned with strides that are multiples of 8 elements", name);
   return NV_OK;
+}
+
+// 1-D grid of the tile kernels: tiles over tokens 1..N-1 for every (head, batch), then one SIMT CTA per SIMT_GROUPS
+// (head, batch) pairs for token 0. NV_ATTN_X=skipsimt drops the SIMT CTAs (timing experiments only: token 0 is then not computed).
+int tile_grid(Common& c, int B, unsigned* grid) {
+  static const char* x = getenv("NV_ATTN_X");
+  const int64_t ntile = (int64_t)((c.N - 1 + BQ - 1) / BQ) * c.H * B;
+  const int64_t ncta = ntile + ((x && strstr(x, "skipsimt")) ? 0 : ((int64_t)c.H * B + SIMT_GROUPS - 1) / SIMT_GROUPS);
+  c.B = B;
+  NV_REQUIRE(ncta < (1ll << 31) && ncta > 0, "attention: bad grid (%lld CTAs)", (long long)ncta);
+  c.ntile_ctas = (int)ntile;
+  *grid = (unsigned)ncta;
+  return NV_OK;
+}
+
+// NV_ATTN_SYNC=1: synchronise and report after every attention kernel (debugging aid for the probes)
+int dbg_sync(const char* what, cudaStream_t stream) {
+  static const bool on = getenv("NV_ATTN_SYNC") != nullptr;
+  if (!on) return NV_OK;
+  cudaError_t e = cudaStreamSynchronize(stream);
+  fprintf(stderr, "[attn] %s: %s\n", what, cudaGetErrorString(e));
+  fflush(stderr);
+  return nv_check_cuda(e, what);
 }
 
 template <typename K>
@@ -1050,19 +1616,20 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H, FWD_KB)) != NV_OK) return s;
   if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H, FWD_KB)) != NV_OK) return s;
   FwdParams p;
-  if ((s = fill_common(p.c, N, H, scale, dropout_p, seed, drop_mask, mask_ready)) != NV_OK) return s;
+  if ((s = fill_common(p.c, q, k, v, qkv_bs, qkv_rs, N, H, scale, dropout_p, seed, drop_mask, mask_ready)) != NV_OK) return s;
   p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_done = 0;  // bit per device
+  if (nv_first_on_device(&attr_done)) {
     if ((s = set_smem(attn_tc_fwd_kernel<false>, FWD_SMEM)) != NV_OK) return s;
     if ((s = set_smem(attn_tc_fwd_kernel<true>, FWD_SMEM)) != NV_OK) return s;
-    attr_set = true;
   }
-  dim3 grid((N + BQ - 1) / BQ, H, B);
+  unsigned ncta;
+  if ((s = tile_grid(p.c, B, &ncta)) != NV_OK) return s;
+  dim3 grid(ncta);
   if (p.c.drop_thr != 0) attn_tc_fwd_kernel<true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
   else attn_tc_fwd_kernel<false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
   NV_LAUNCH_CHECK("attn_tc_fwd_kernel");
-  return NV_OK;
+  return dbg_sync("fwd", stream);
 }
 
 int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
@@ -1087,24 +1654,28 @@ int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   if ((s = make_map(&tk, k, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
   if ((s = make_map(&tv, v, qkv_bs, qkv_rs, B, N, H)) != NV_OK) return s;
   if ((s = make_map(&tdo, dO, o_bs, o_rs, B, N, H)) != NV_OK) return s;
+  CUtensorMap to;
+  if ((s = make_map(&to, o, o_bs, o_rs, B, N, H)) != NV_OK) return s;
   BwdParams p;
-  if ((s = fill_common(p.c, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
+  if ((s = fill_common(p.c, q, k, v, qkv_bs, qkv_rs, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
   p.lse = lse; p.delta = delta_ws; p.dq = dq; p.dk = dk; p.dv = dv; p.d_bs = d_bs; p.d_rs = d_rs;
-  static bool attr_set = false;
-  if (!attr_set) {
+  p.o = o; p.dO = dO; p.o_bs = o_bs; p.o_rs = o_rs;
+  static uint64_t attr_done = 0;  // bit per device
+  if (nv_first_on_device(&attr_done)) {
     if ((s = set_smem(attn_tc_bwd_dq_kernel, DQ_SMEM)) != NV_OK) return s;
     if ((s = set_smem(attn_tc_bwd_dkv_kernel, DKV_SMEM)) != NV_OK) return s;
-    attr_set = true;
   }
-  const int64_t tokens = (int64_t)B * N;
-  attn_tc_delta_kernel<<<(unsigned)((tokens + 7) / 8), 256, 0, stream>>>(dO, o, o_bs, o_rs, delta_ws, B, N, H);
-  NV_LAUNCH_CHECK("attn_tc_delta_kernel");
-  dim3 grid((N + BQ - 1) / BQ, H, B);
-  attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  // dQ first (it also writes delta, which the dK/dV grid reads); the last x-slot of each grid is the SIMT CTA
+  unsigned ncta;
+  if ((s = tile_grid(p.c, B, &ncta)) != NV_OK) return s;
+  dim3 grid(ncta);
+  static const char* only = getenv("NV_ATTN_ONLY");   // timing experiments: launch one of the two kernels only
+  if (!only || !strcmp(only, "dq")) attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
   NV_LAUNCH_CHECK("attn_tc_bwd_dq_kernel");
-  attn_tc_bwd_dkv_kernel<<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  { int ds = dbg_sync("dq", stream); if (ds != NV_OK) return ds; }
+  if (!only || !strcmp(only, "dkv")) attn_tc_bwd_dkv_kernel<<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
   NV_LAUNCH_CHECK("attn_tc_bwd_dkv_kernel");
-  return NV_OK;
+  return dbg_sync("dkv", stream);
 }
 
 int nv_attn_cls_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
@@ -1125,7 +1696,7 @@ int nv_attn_cls_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t 
   NV_REQUIRE(((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(dO_cls)) & 15) == 0 && o_bs % 8 == 0 &&
                  do_bs % 8 == 0, "attention: o / dO of the cls row must be 16-byte aligned (16-byte vector loads)");
   Common c;
-  if ((s = fill_common(c, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
+  if ((s = fill_common(c, q, k, v, qkv_bs, qkv_rs, N, H, scale, dropout_p, 0, const_cast<uint32_t*>(drop_mask))) != NV_OK) return s;
   attn_cls_bwd_kernel<<<dim3(H, B), CLS_THREADS, 0, stream>>>(q, k, v, qkv_bs, qkv_rs, o, o_bs, dO_cls, do_bs, lse, dq, dk, dv, d_bs,
                                                       d_rs, N, H, scale, c.drop_thr != 0 ? c.mask : nullptr, c.mask_words,
                                                       c.keep_scale);

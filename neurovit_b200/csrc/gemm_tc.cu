@@ -652,11 +652,9 @@ int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   using L = SmemLayout<BLOCK_N, STAGES, CG, epi_warps(EPI_MODE), epi_slabs(EPI_MODE)>;
   static_assert(L::DYN_BYTES <= 232448, "shared memory budget exceeded");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN, CG, EPI_MODE, DROP>;
-  static bool attr_set = false;  // per instantiation; idempotent, races are benign
-  if (!attr_set) {
+  static uint64_t attr_done = 0;  // per instantiation, one bit per device
+  if (nv_first_on_device(&attr_done))
     NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(num_threads(EPI_MODE));

@@ -411,8 +411,10 @@ int launch_ln_bwd_pipe(const DyT* dy, int64_t ld_dy, RowMap dym, const float* x,
   if (stages < 3) stages = 3;
   const int smem = stage_bytes * stages;
   auto kern = threads <= 256 ? ln_bwd_pipe_kernel<DyT, 256> : ln_bwd_pipe_kernel<DyT, 512>;
-  static int smem_set[2] = {0, 0};
-  int& set = smem_set[threads <= 256 ? 0 : 1];
+  static int smem_set[64][2] = {};  // largest opt-in so far, per device (function attributes are per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int& set = smem_set[dev][threads <= 256 ? 0 : 1];
   if (smem > set) {
     NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     set = smem;

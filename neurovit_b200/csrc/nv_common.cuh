@@ -34,6 +34,9 @@ int nv_check_cuda(cudaError_t e, const char* what);
 
 // number of SMs of the current device (cached)
 int nv_num_sms();
+// True the first time it is called for the CURRENT device with this flag word (one static word per call site):
+// per-function attributes (cudaFuncSetAttribute) are per device, so "set once" must be tracked per device too.
+bool nv_first_on_device(uint64_t* flags);
 
 // Encode a tiled TMA descriptor (driver entry point resolved through cudart, no -lcuda needed).
 // dims/strides are innermost-first; strides in BYTES for dims 1..rank-1.

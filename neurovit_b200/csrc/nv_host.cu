@@ -8,7 +8,6 @@
 namespace {
 thread_local char g_err[1024] = "";
 std::mutex g_mu;
-int g_num_sms = 0;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 }  // namespace
 
@@ -28,13 +27,21 @@ int nv_check_cuda(cudaError_t e, const char* what) {
 }
 
 int nv_num_sms() {
-  if (g_num_sms > 0) return g_num_sms;
+  static int cached[64] = {0};
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] > 0) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
     return 148;
-  g_num_sms = n;
+  cached[dev] = n;
   return n;
+}
+
+bool nv_first_on_device(uint64_t* flags) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // unknown device: just redo the work
+  const uint64_t bit = 1ull << dev;
+  return (__atomic_fetch_or(flags, bit, __ATOMIC_ACQ_REL) & bit) == 0;
 }
 
 int nv_encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base,

@@ -23,6 +23,7 @@ F32 = torch.float32
 NUM_SMS = 148
 
 _VALID_MODES = ("bf16", "fp32")
+HEAD_FUSED_MAX_CLASSES = 256  # HEAD_T of csrc/misc.cu: the one-CTA-per-sample head kernels hold the logits in a block
 
 # dropout sites of one block (vit_3d.py:21,23,39,45; emb :100,119): distinct Philox streams under one seed
 DROP_ATTN, DROP_OUT, DROP_GELU, DROP_DOWN, DROP_EMB = 0, 1, 2, 3, 4
@@ -906,30 +907,34 @@ class HeadFn(torch.autograd.Function):
         y = torch.empty(B, D, device=dev, dtype=F32)
         mean = torch.empty(B, device=dev, dtype=F32)
         rstd = torch.empty(B, device=dev, dtype=F32)
+        fused = pool != "mean" and C <= HEAD_FUSED_MAX_CLASSES
         if pool == "mean":
             pooled = torch.empty(B, D, device=dev, dtype=F32)
             ops.mean_pool_fwd(x, pooled, B, N, D)
             ops.layernorm_fwd(pooled, ln_w.detach(), ln_b.detach(), y, M=B, D=D, mean=mean, rstd=rstd, eps=eps)
-        else:  # cls pool: LayerNorm + Linear fused, one CTA per sample
+        elif fused:  # cls pool: LayerNorm + Linear fused, one CTA per sample
             pooled = None
             logits = torch.empty(B, C, device=dev, dtype=F32)
             ops.head_fwd(x, N * D, ln_w.detach(), ln_b.detach(), w.detach().float().contiguous(), b.detach(), y, mean,
                          rstd, logits, B, D, C, eps)
             ctx.save_for_backward(x, pooled, y, mean, rstd, ln_w, w)
-            ctx.cfg = (B, N, D, C, pool, mode)
+            ctx.cfg = (B, N, D, C, pool, mode, fused)
             return logits
+        else:  # cls pool with many classes (DATASET_NAME == 'gradcam': (grid // cube)**3 of them, NeuroEncoder.py:179):
+            pooled = None  # LayerNorm on the strided token-0 rows, then the generic linear
+            ops.layernorm_fwd(x, ln_w.detach(), ln_b.detach(), y, M=B, D=D, ld_x=N * D, mean=mean, rstd=rstd, eps=eps)
         logits = ops.linear_f32(y, w.detach(), bias=b.detach())
         ctx.save_for_backward(x, pooled, y, mean, rstd, ln_w, w)
-        ctx.cfg = (B, N, D, C, pool, mode)
+        ctx.cfg = (B, N, D, C, pool, mode, fused)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         x, pooled, y, mean, rstd, ln_w, w = ctx.saved_tensors
-        B, N, D, C, pool, mode = ctx.cfg
+        B, N, D, C, pool, mode, fused = ctx.cfg
         dev = x.device
         dl = dlogits.float().contiguous()
-        if pool != "mean":
+        if fused:
             acc_w, acc_b = GradAcc(w, mode), torch.zeros(C, device=dev, dtype=F32)
             acc_g, acc_be = torch.zeros(D, device=dev, dtype=F32), torch.zeros(D, device=dev, dtype=F32)
             dx = torch.zeros(B, N, D, device=dev, dtype=F32)            # cls pool: only token 0 gets gradient
@@ -955,6 +960,10 @@ class HeadFn(torch.autograd.Function):
         else:
             ops.layernorm_bwd(dy, x, mean, rstd, ln_w.detach(), M=B, D=D, ld_x=N * D, dx=dx, ld_dx=N * D,
                               dx_bf16=dxb, ld_dxb=N * D, dgamma=dg, dbeta=dbeta)
+            cs = torch.zeros(D, device=dev, dtype=F32)
+            ops.batch_sum(dx, N * D, cs, B, D)
+            _STASH.put(dx, dxb, cs, cls_only=True)   # same contract as the fused cls head: zero outside token 0
+            return dx, dg, dbeta, dw, db, None, None, None
         _STASH.put(dx, dxb)
         return dx, dg, dbeta, dw, db, None, None, None
 

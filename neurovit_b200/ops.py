@@ -327,11 +327,6 @@ def attention_bwd(qkv, o, dO, lse, delta_ws, dqkv, *, B, N, H, head_dim, scale, 
               _ptr(drop_mask), _stream())
 
 
-def set_attention_impl(impl: int):
-    """0 = tcgen05/TMEM kernels (default), 1 = mma.sync cross-check variant."""
-    _lib.call("nv_set_attention_impl", int(impl))
-
-
 def softmax_fwd(s, rows, n):
     _dev(s)
     _lib.call("nv_softmax_fwd", _ptr(s), rows, n, _stream())

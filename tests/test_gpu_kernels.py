@@ -248,7 +248,8 @@ def _attn_ref(qkv, B, N, H, hd):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 385, 8), (1, 64, 2), (3, 9, 2), (1, 1729, 1)])
+@pytest.mark.parametrize("B,N,H", [(2, 385, 8), (1, 64, 2), (3, 9, 2), (1, 1729, 1), (2, 1001, 2), (2, 1, 2), (1, 2, 1),
+                                   (1, 129, 2), (2, 130, 1), (1, 97, 1), (1, 98, 2)])
 def test_attention_fwd_bwd(B, N, H):
     hd = 64
     torch.manual_seed(7)
@@ -268,9 +269,13 @@ def test_attention_fwd_bwd(B, N, H):
     inner = H * hd
     for nm, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
         assert rel_err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
+    # token 0 (handled outside the tensor-core tiles, as a query and as a key) and the last token, on their own
+    for tok in (0, N - 1):
+        assert rel_err(o.view(B, N, inner)[:, tok], oref.view(B, N, inner)[:, tok]) < 1e-2, tok
+        assert rel_err(dqkv.view(B, N, 3 * inner)[:, tok], gref.view(B, N, 3 * inner)[:, tok]) < 2e-2, tok
 
 
-@pytest.mark.parametrize("B,N,H", [(3, 385, 8), (2, 64, 2), (2, 9, 1), (1, 1729, 2)])
+@pytest.mark.parametrize("B,N,H", [(3, 385, 8), (2, 64, 2), (2, 9, 1), (1, 1729, 2), (2, 1, 1)])
 @pytest.mark.parametrize("p_drop", [0.0, 0.25])
 def test_attention_cls_bwd_matches_full_backward(B, N, H, p_drop):
     """nv_attention_cls_bwd (only token 0 of every sample has gradient: the last block under pool='cls',
@@ -302,6 +307,65 @@ def test_attention_cls_bwd_matches_full_backward(B, N, H, p_drop):
         oref, _ = _attn_ref(qd, B, N, H, hd)
         gref, = torch.autograd.grad(oref, qd, dO.double())
         assert rel_err(got, gref) < 2e-2
+
+
+def _mask_bits_to_keys(mask, B, H, N):
+    """Saved keep-bit words [B*H, N, ceil(N/32)] -> float keep mask [B, H, N(query), N(key)]. Bit position p of a row
+    is key token p + 1 for p < N - 1 and key token 0 for p = N - 1 (csrc/attention_tc.cu: token 0 is handled outside
+    the tiles, so the tiled keys 1..N-1 keep word-aligned positions)."""
+    w = mask.view(B, H, N, -1).to(torch.int64) & 0xFFFFFFFF
+    bits = ((w.unsqueeze(-1) >> torch.arange(32, device=w.device)) & 1).reshape(B, H, N, -1)[..., :N]
+    return torch.cat([bits[..., N - 1:N], bits[..., :N - 1]], dim=-1).double()
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 385, 4), (1, 1001, 2), (2, 64, 2), (3, 9, 1), (2, 1, 1), (1, 161, 2)])
+@pytest.mark.parametrize("predrawn", [False, True])
+def test_attention_dropout_fwd_bwd_matches_masked_reference(B, N, H, predrawn):
+    """Attention dropout (vit_3d.py:56): the keep bits the kernels drew (inline, or ahead of time by nv_dropout_bits —
+    identical bits) are replayed into an fp64 torch reference; forward and all three gradients must agree."""
+    hd, p_drop, seed = 64, 0.3, 1234
+    inner = H * hd
+    torch.manual_seed(5)
+    qkv = torch.randn(B * N, 3 * inner, device=DEV).to(torch.bfloat16)
+    o = torch.empty(B * N, inner, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=DEV)
+    mw = (N + 31) // 32
+    mask = torch.zeros(B * H, N, mw, device=DEV, dtype=torch.int32)
+    if predrawn:
+        ops.dropout_bits(mask, p=p_drop, seed=seed, stream=0)
+    ops.attention_fwd(qkv, o, lse, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5, dropout_p=p_drop, seed=seed,
+                      drop_mask=mask, mask_ready=predrawn)
+    inline = torch.zeros_like(mask)
+    ops.dropout_bits(inline, p=p_drop, seed=seed, stream=0)
+    keep = _mask_bits_to_keys(mask, B, H, N)
+    assert torch.equal(keep, _mask_bits_to_keys(inline, B, H, N))       # inline draw == nv_dropout_bits, every used bit
+    assert 0.6 < keep.mean().item() < 0.8 or N < 16
+    ks = 65536.0 / (65536 - int(p_drop * 65536 + 0.5))
+    qd = qkv.double().requires_grad_(True)
+    q, k, v = qd.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    sc = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    oref = ((sc.softmax(-1) * keep * ks) @ v).permute(0, 2, 1, 3).reshape(B * N, inner)
+    assert rel_err(o, oref) < 1e-2
+    assert rel_err(lse, torch.logsumexp(sc, -1)) < 1e-3
+    dO = torch.randn(B * N, inner, device=DEV).to(torch.bfloat16)
+    gref, = torch.autograd.grad(oref, qd, dO.double())
+    dqkv = torch.full_like(qkv, float("nan"))
+    ws = torch.empty(B * H * N, device=DEV)
+    ops.attention_bwd(qkv, o, dO, lse, ws, dqkv, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5, dropout_p=p_drop,
+                      drop_mask=mask)
+    assert torch.isfinite(dqkv.float()).all()
+    if N == 1:
+        # one key: P = 1 and dS = p (dP - delta) is exactly 0; the kernel's delta uses the bf16-rounded O, so its
+        # dq / dk are rounding noise around zero — bound them against the size of the operands instead
+        assert dqkv[:, :2 * inner].abs().max().item() < 2e-2 * dO.abs().max().item()
+        assert rel_err(dqkv[:, 2 * inner:], gref[:, 2 * inner:]) < 2e-2
+        return
+    for nm, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
+        assert rel_err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
+    # per-token check of the rows that are handled outside the tiles (token 0 as query and as key)
+    g3, r3 = dqkv.view(B, N, 3 * inner).double(), gref.view(B, N, 3 * inner)
+    assert rel_err(g3[:, 0], r3[:, 0]) < 2e-2
+    assert rel_err(o.view(B, N, inner)[:, 0], oref.view(B, N, inner)[:, 0]) < 1e-2
 
 
 def test_attention_fwd_rising_scores_rescale_path():

@@ -212,8 +212,10 @@ def _replay_masks(trace, B, N, heads, ks_of):
         if site == "emb":
             masks["emb"] = ops.dropout_keep_mask(info[0], info[1], p=p, seed=seed, stream=stream).cpu() * ks
         elif site == "attn":      # saved bit mask [B*H, N, ceil(N/32)] of the flash kernel
+            # bit position p of a row = key token p + 1 (p < N - 1) or key token 0 (p = N - 1): attention_tc.cu
             w = info.view(B, heads, N, -1).to(torch.int64) & 0xFFFFFFFF
             bits = ((w.unsqueeze(-1) >> torch.arange(32, device=w.device)) & 1).reshape(B, heads, N, -1)[..., :N]
+            bits = torch.cat([bits[..., N - 1:N], bits[..., :N - 1]], dim=-1)
             masks[(layer, "attn")] = bits.float().cpu() * ks
         elif site == "attn_flat":  # fp32 mode: flat element index over [B, H, N, N]
             L = info[0] * info[1] * info[2] * info[3]
