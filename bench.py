@@ -143,6 +143,81 @@ def cpu_reference_step_fn(cfg, batch, seed=42):
     return step, batch
 
 
+# ---- stock-PyTorch GPU arm: the kernels to beat (BASELINE.md §3 a-c) -----------------------------------------
+def torch_gpu_step_fn(cfg, batch, dev, sdpa, seed=42):
+    """One training step of the reference model's math on the GPU through stock PyTorch only: the oracle port
+    (same ATen ops the reference dispatches to) under bf16 autocast, eager, fused torch AdamW; sdpa=True swaps the
+    explicit softmax attention for F.scaled_dot_product_attention. None of this repo's kernels are involved."""
+    from oracle import vit3d_oracle as O
+    from neurovit_b200.vit_3d import ViT  # parameter container only
+    torch.manual_seed(seed)
+    m = ViT(**vit_ctor(cfg))
+    params = {k: v.detach().to(dev).requires_grad_(True) for k, v in m.state_dict().items()}
+    del m
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01, fused=True)
+    H, W, D = cfg["vol"]
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(batch, H, W, D, generator=g).to(dev) for _ in range(3)]
+    ys = [torch.randint(0, 2, (batch,), generator=g).to(dev) for _ in range(3)]
+    p = cfg["patch"]
+
+    def step(i):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = O.vit3d_forward(params, O.neuro_view(xs[i % 3]), patch=(p, p, p), heads=MODEL["heads"],
+                                     dim_head=MODEL["dim_head"], dropout_p=DROPOUT, sdpa=sdpa)
+            loss = torch.nn.functional.cross_entropy(logits.float(), ys[i % 3])
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step
+
+
+def time_torch_gpu(cfg, batch, dev, steps, warmup):
+    """{variant: volumes/s} for the explicit-softmax and the SDPA variant, CUDA events around `steps` steps."""
+    out = {}
+    for name, sdpa in (("eager_bf16_autocast", False), ("eager_bf16_autocast_sdpa", True)):
+        step = torch_gpu_step_fn(cfg, batch, dev, sdpa)
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = batch * steps / (e0.elapsed_time(e1) * 1e-3)
+        del step
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_torch_gpu(args, cfg):
+    """--impl torch_gpu: rank 0 only, one GPU (a per-GPU number; the data-parallel arm is ours)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    res = time_torch_gpu(cfg, args.batch, dev, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop()
+    best = max(res, key=res.get)
+    peaks = load_peaks()
+    tfl = res[best] * cfg["gflop_fwd_bwd"] / 1e3
+    print(json.dumps({"impl": "torch_gpu", "metric": "ViT3D training volumes/sec (fwd+bwd+AdamW)", "value": res[best],
+                      "unit": "volumes/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+                      "ms_per_step": 1e3 * args.batch / res[best], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": workload_name(args, cfg, args.batch), "variant": best, "variants": res,
+                                 "dropout": DROPOUT, "torch": torch.__version__, "model_tflops_per_gpu": tfl,
+                                 "model_frac_of_peak": tfl / peaks["tflops"],
+                                 "note": "stock PyTorch (cuBLAS + ATen + SDPA) on the same GPU, none of this repo's kernels"},
+                      "clocks": clocks}), flush=True)
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -444,7 +519,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="volumes per GPU per step")
     ap.add_argument("--config", default="cfgA", choices=sorted(CONFIGS))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--ref-batch", type=int, default=2, help="volumes per CPU reference step (bounded sample)")
     ap.add_argument("--dropout", type=float, default=DROPOUT, help="dropout p at all sites, training mode (both arms)")
     ap.add_argument("--gradcam", default="device", choices=["host", "device", "off"],
@@ -461,6 +536,8 @@ def main():
         if args.warmup > 2:
             args.warmup = 2
         run_reference(args, cfg)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args, cfg)
     elif args.config == "cfg5":
         if args.batch == 64:
             args.batch = 2  # 2 sequences x 140 timepoints = 280 volumes per GPU per step

@@ -218,6 +218,14 @@ int nv_temporal_bwd(const float* x, const float* params, const float* saved, con
                     float* dparams_ws, float* dx, int B, int T, int F, float eps,
                     float p_attn, float p_drop1, float p_ffn, float p_drop2, int64_t seed, void* stream);
 
+/* ---- 4D input pipeline ---------------------------------------------------------------------------------
+ * replaces: NeuroEncoder.py:54-56 (fmri.permute(0, 4, 1, 2, 3) + reshape(B*T, H, W, D): the time axis leaves the
+ * innermost position) and, optionally fused into the same pass, the dataset's per-sample z-score of
+ * src/data/DatasetADNI_4D.py:84-86 ((x - mean) / (std + eps) over all H*W*D*T values, population std).
+ * x [B, S, T] fp32 contiguous (S = H*W*D) -> y [B, T, S]. stats_ws NULL: plain de-interleave, bit-exact with the
+ * reference's strided copy. stats_ws = DEVICE workspace of 2*B doubles: z-score, moments accumulated in fp64. */
+int nv_fmri_deinterleave(const float* x, float* y, int B, int64_t S, int T, void* stats_ws, double eps, void* stream);
+
 /* ---- data-parallel exchange step ---------------------------------------------------------------------
  * New work (the reference is single-GPU): the gradient all-reduce at the step boundary of
  * src/Trainer.py:65-76, over NCCL on NVLink 5 / NVSwitch. The library owns one communicator per device; NCCL is

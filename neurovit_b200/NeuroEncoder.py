@@ -58,9 +58,11 @@ class NeuroEncoder(nn.Module):
         if self.config['TRAINING_DIM'] == 3:
             return self.volume_encoder(fmri)                                   # [B, num_classes]
         if self.config['TRAINING_DIM'] == 4:
-            fmri = fmri.permute(0, 4, 1, 2, 3)                                 # [B,H,W,D,T] -> [B,T,H,W,D]
-            B, T, H, W, D = fmri.shape
-            volumes = fmri.reshape(B * T, H, W, D)
+            # [B,H,W,D,T] -> permute(0, 4, 1, 2, 3) -> reshape(B*T, H, W, D) (NeuroEncoder.py:54-56) as one
+            # de-interleave kernel; config['INPUT_ZSCORE'] (optional, not a reference key) folds the dataset's
+            # per-sample z-score (DatasetADNI_4D.py:84-86) into the same pass for raw, un-normalised sequences
+            B, T = fmri.shape[0], fmri.shape[4]
+            volumes = Fn.fmri_to_volumes(fmri, zscore=self.config.get('INPUT_ZSCORE', False))
             enc = self.volume_encoder(volumes).reshape(B, T, -1)               # [B, T, 2]
             tt, ph = self.temporal_transformer, self.projection_head
             if _has_hooks(tt) or _has_hooks(ph) or _has_hooks(ph.projection_head):

@@ -26,6 +26,7 @@ SOURCES = [
     "attention_tc.cu",
     "misc.cu",
     "temporal.cu",
+    "fmri4d.cu",
     "nv_dp.cu",
     "api.cu",
 ]

@@ -55,6 +55,7 @@ SIGNATURES = {
     "nv_mean_pool_bwd": [_p, _p, _p, _i, _i, _i, _p],
     "nv_temporal_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
     "nv_temporal_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
+    "nv_fmri_deinterleave": [_p, _p, _i, _l, _i, _p, ctypes.c_double, _p],
     "nv_dp_load": [_p],
     "nv_dp_nccl_version": [],
     "nv_dp_unique_id": [_p],

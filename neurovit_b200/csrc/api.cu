@@ -67,6 +67,8 @@ int nv_colsum_launch(const void* in, int in_is_bf16, int64_t ld, float* out, int
 int nv_batch_sum_launch(const float* in, int64_t batch_stride, float* out, int B, int64_t L, cudaStream_t stream);
 int nv_mean_pool_fwd_launch(const float* x, float* pooled, int B, int N, int D, cudaStream_t stream);
 int nv_mean_pool_bwd_launch(const float* dpooled, float* dx, bf16* dx_bf16, int B, int N, int D, cudaStream_t stream);
+int nv_fmri_deinterleave_launch(const float* x, float* y, int B, int64_t S, int T, double* stats_ws, double eps,
+                                cudaStream_t stream);
 int nv_temporal_fwd_launch(const float* x, const float* params, float* out, float* seq_out, float* saved, int B,
                            int T, int F, float eps, const float* drop_p4, uint64_t seed, cudaStream_t stream);
 int nv_temporal_bwd_launch(const float* x, const float* params, const float* saved, const float* dout,
@@ -235,6 +237,10 @@ int nv_mean_pool_fwd(const float* x, float* pooled, int B, int N, int D, void* s
 }
 int nv_mean_pool_bwd(const float* dpooled, float* dx, void* dx_bf16, int B, int N, int D, void* stream) {
   return nv_mean_pool_bwd_launch(dpooled, dx, (bf16*)dx_bf16, B, N, D, ST(stream));
+}
+
+int nv_fmri_deinterleave(const float* x, float* y, int B, int64_t S, int T, void* stats_ws, double eps, void* stream) {
+  return nv_fmri_deinterleave_launch(x, y, B, S, T, static_cast<double*>(stats_ws), eps, ST(stream));
 }
 
 int nv_temporal_fwd(const float* x, const float* params, float* out, float* seq_out, float* saved, int B, int T,

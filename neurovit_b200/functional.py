@@ -984,6 +984,41 @@ def pack_temporal_params(tensors):
     return torch.cat([t.detach().reshape(-1).float() for t in tensors]).contiguous()
 
 
+class FmriToVolumesFn(torch.autograd.Function):
+    """[B, H, W, D, T] -> [B*T, H, W, D]: NeuroEncoder.py:54-56's permute(0, 4, 1, 2, 3) + reshape as one HBM-rate
+    de-interleave kernel (csrc/fmri4d.cu), optionally with the dataset's per-sample z-score folded in
+    (DatasetADNI_4D.py:84-86). Backward is the inverse interleave (times the z-score's 1/(std+eps) only when the
+    caller asks for input gradients of the plain path; the z-scored path is input preprocessing and carries none)."""
+
+    @staticmethod
+    def forward(ctx, fmri, zscore, eps):
+        if fmri.dim() != 5:
+            raise ValueError(f"NeuroEncoder (TRAINING_DIM=4) expects fmri [B, H, W, D, T], got {tuple(fmri.shape)}")
+        B, H, W, D, T = fmri.shape
+        x = fmri.detach()
+        if x.dtype != F32 or not x.is_contiguous():
+            x = x.to(F32).contiguous()
+        y = torch.empty(B * T, H, W, D, device=x.device, dtype=F32)
+        ws = torch.empty(2 * B, device=x.device, dtype=torch.float64) if zscore else None
+        ops.fmri_deinterleave(x, y, B, H * W * D, T, stats_ws=ws, eps=eps)
+        ctx.shape = (B, H, W, D, T)
+        ctx.zscore = zscore
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if ctx.zscore:
+            raise RuntimeError("the z-scored 4D input path is preprocessing: it carries no input gradient")
+        B, H, W, D, T = ctx.shape
+        dx = torch.empty(B, H, W, D, T, device=dy.device, dtype=F32)
+        ops.fmri_deinterleave(dy.to(F32).contiguous(), dx, B, T, H * W * D)   # [B, T, S] -> [B, S, T]
+        return dx, None, None
+
+
+def fmri_to_volumes(fmri, zscore=False, eps=1e-8):
+    return FmriToVolumesFn.apply(fmri, bool(zscore), float(eps))
+
+
 class TemporalHeadFn(torch.autograd.Function):
     """TemporalTransformer -> mean over T -> ProjectionHead, NeuroEncoder.py:63-66."""
 

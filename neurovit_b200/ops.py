@@ -381,6 +381,12 @@ def mean_pool_bwd(dpooled, dx, dx_bf16, B, N, D):
     _lib.call("nv_mean_pool_bwd", _ptr(dpooled), _ptr(dx), _ptr(dx_bf16), B, N, D, _stream())
 
 
+def fmri_deinterleave(x, y, B, S, T, stats_ws=None, eps=1e-8):
+    """x [B, S, T] fp32 contiguous -> y [B, T, S]; stats_ws (2*B float64, device) turns on the per-sample z-score."""
+    _dev(x)
+    _lib.call("nv_fmri_deinterleave", _ptr(x), _ptr(y), B, S, T, _ptr(stats_ws), float(eps), _stream())
+
+
 def temporal_fwd(x, params, out, saved, B, T, F, eps=1e-5, seq_out=None, drop=(0.0, 0.0, 0.0, 0.0), seed=0):
     """drop = (p_attn, p_dropout1, p_ffn, p_dropout2) of nn.TransformerEncoderLayer in training mode."""
     _dev(x)

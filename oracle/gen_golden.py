@@ -10,6 +10,7 @@ Fixtures (all fp32 unless noted):
   vit3d_p4.npz      ViT(channels=2, 8x8x12 / patch 4, pool='mean') — permuted-K layout + mean pooling
   neuro3d.npz       NeuroEncoder 3D through ViT3DEncoder's permuted view (grid 16, patch 8; dims hard-coded 1024/6/8/2048)
   neuro4d.npz       NeuroEncoder 4D (T=6) incl. TemporalTransformer/ProjectionHead gradients
+  neuro3d_cam.npz   NeuroEncoder.get_attention_map on a 32^3 volume: the Grad-CAM map, the class and the raw token scores
 """
 import os
 import sys
@@ -116,7 +117,30 @@ def gen_neuro():
         save("neuro4d.npz", **arrs)
 
 
+def gen_cam():
+    """Grad-CAM map of the unmodified reference (NeuroEncoder.get_attention_map, NeuroEncoder.py:84-133) on a 32^3
+    volume (4x4x4 patch tokens), same seeded weights as neuro3d.npz; the consumer regenerates them from the seed."""
+    with tempfile.TemporaryDirectory() as tmp:
+        torch.manual_seed(1234)
+        cfg = {**neuro_config(tmp, 3), "TRAINING_VIT_INPUT_SIZE": 32, "GRADCAM_THRESHOLD": 25}
+        m = NeuroEncoder(cfg).eval()
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle.vit3d_oracle import perturb_for_cam, gradcam_from_hooks
+        perturb_for_cam(m.volume_encoder.vit3d)   # the raw map is round-off at initialisation: see its docstring
+        g = torch.Generator().manual_seed(99)
+        x = torch.randn(1, 32, 32, 32, generator=g)
+        cam, cls = m.get_attention_map(x)
+        raw = (m.gradients.mean(dim=2, keepdim=True) * m.activations).sum(dim=2)[:, 1:]
+        again = gradcam_from_hooks(m.gradients, m.activations, 32, 8, 25)
+        assert torch.equal(again, cam), "oracle restatement of the Grad-CAM post-processing differs from the reference"
+        save("neuro3d_cam.npz", x=x.numpy(), cam=cam.numpy(), cls=cls.numpy(), raw_cam=raw.detach().numpy(),
+             sd_checksum=np.array([float(sum(v.double().sum() for v in m.state_dict().values()))]))
+
+
 if __name__ == "__main__":
+    if "--cam-only" in sys.argv:
+        gen_cam()
+        sys.exit(0)
     gen_patch_index()
     run_vit("vit3d_small.npz", 42, 3, dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8,
                                            num_classes=2, dim=64, depth=2, heads=2, mlp_dim=128, channels=1,
@@ -125,3 +149,4 @@ if __name__ == "__main__":
                                        num_classes=3, dim=64, depth=1, heads=2, mlp_dim=64, channels=2, dim_head=64,
                                        pool="mean"), (2, 4, 8, 12))
     gen_neuro()
+    gen_cam()

@@ -26,6 +26,8 @@ def _parse_header():
                     kinds.append("l")
                 elif a.startswith("float"):
                     kinds.append("f")
+                elif a.startswith("double"):
+                    kinds.append("d")
                 elif a.startswith("int"):
                     kinds.append("i")
                 else:
@@ -44,7 +46,7 @@ def test_header_declares_expected_entry_points():
 
 
 def test_ctypes_signatures_match_header():
-    kind = {ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_float: "f", ctypes.c_void_p: "p"}
+    kind = {ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_float: "f", ctypes.c_double: "d", ctypes.c_void_p: "p"}
     protos = _parse_header()
     for name, argtypes in _lib.SIGNATURES.items():
         got = [kind[a] for a in argtypes]

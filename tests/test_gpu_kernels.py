@@ -580,3 +580,43 @@ def test_gemm_epilogue_dropout_matches_elementwise_mask():
     ref = (dy.double() @ wt.double()) * keep2 * ks * gp
     assert rel_err(du, ref) < 1e-2
     assert rel_err(cs, ref.sum(0)) < 1e-2
+
+
+# ------------------------------------------------------------------------------ 4D input pipeline
+@pytest.mark.parametrize("shape", [(2, 16, 16, 12, 140), (1, 18, 18, 18, 7), (3, 8, 8, 4, 300), (2, 5, 3, 2, 1),
+                                   (1, 4, 4, 4, 257)])
+def test_fmri_deinterleave_bit_exact(shape):
+    """[B,H,W,D,T] -> [B*T,H,W,D] equals the reference's permute(0, 4, 1, 2, 3).reshape (NeuroEncoder.py:54-56)
+    bit for bit: ragged S (not a multiple of the 64-wide CTA strip), T beyond one chunk, T = 1."""
+    from neurovit_b200 import functional as Fn
+    torch.manual_seed(11)
+    B, H, W, D, T = shape
+    x = torch.randn(*shape, device=DEV)
+    y = Fn.fmri_to_volumes(x)
+    ref = x.permute(0, 4, 1, 2, 3).reshape(B * T, H, W, D)
+    assert y.shape == ref.shape and torch.equal(y, ref)
+    # non-contiguous input (a permuted view) goes through the same path
+    xv = torch.randn(B, T, H, W, D, device=DEV).permute(0, 2, 3, 4, 1)
+    assert torch.equal(Fn.fmri_to_volumes(xv), xv.permute(0, 4, 1, 2, 3).reshape(B * T, H, W, D))
+    # backward = the inverse interleave
+    xg = x.clone().requires_grad_(True)
+    g = torch.randn(B * T, H, W, D, device=DEV)
+    Fn.fmri_to_volumes(xg).backward(g)
+    xr = x.clone().requires_grad_(True)
+    xr.permute(0, 4, 1, 2, 3).reshape(B * T, H, W, D).backward(g)
+    assert torch.equal(xg.grad, xr.grad)
+
+
+def test_fmri_deinterleave_zscore_matches_numpy_fp64():
+    """Fused per-sample z-score (DatasetADNI_4D.py:84-86: (x - mean) / (std + 1e-8), numpy fp64, population std)."""
+    from neurovit_b200 import functional as Fn
+    torch.manual_seed(12)
+    B, H, W, D, T = 2, 12, 10, 6, 140
+    x = (torch.randn(B, H, W, D, T, device=DEV) * 37.0 + 410.0) * torch.tensor([1.0, 0.01], device=DEV).view(B, 1, 1, 1, 1)
+    y = Fn.fmri_to_volumes(x, zscore=True)
+    xn = x.cpu().numpy().astype("float64")
+    for b in range(B):
+        z = (xn[b] - xn[b].mean()) / (xn[b].std() + 1e-8)
+        ref = torch.from_numpy(z).permute(3, 0, 1, 2).to(torch.float32)
+        got = y[b * T:(b + 1) * T].cpu()
+        assert (got - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()

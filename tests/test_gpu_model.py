@@ -1,8 +1,8 @@
 """Module-level parity on the GPU: the drop-in ViT / NeuroEncoder (CUDA kernels through the C ABI) against
 the CPU oracle on the same seeded inputs and weights, and against the committed golden fixtures produced
 by the unmodified reference. Tolerances from BASELINE.json north_star: 2e-2 relative (bf16 operands, fp32
-accumulation), 1e-5 for the fp32 verification mode (logits; gradients 1e-4: they pass through fp32 atomics
-and long reductions), measured as max|a-b| / max|b| per tensor."""
+accumulation), 1e-5 for the fp32 verification mode, logits and every gradient, measured as max|a-b| / max|b| per
+tensor. Where a test holds a quantity to a different bound the reason is stated next to it."""
 import os
 
 import numpy as np
@@ -20,7 +20,7 @@ from oracle import vit3d_oracle as O  # noqa: E402  (checker only)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DEV = "cuda"
-TOL = {"bf16": dict(logits=2e-2, grad=2e-2), "fp32": dict(logits=1e-5, grad=1e-4)}
+TOL = {"bf16": dict(logits=2e-2, grad=2e-2), "fp32": dict(logits=1e-5, grad=1e-5)}
 
 
 def rel(a, b):
@@ -87,13 +87,13 @@ def test_neuroencoder_3d_golden_with_gradcam_hooks(tmp_path, mode):
     assert rel(logits, g["logits"]) < tol["logits"]
     params = dict(m.named_parameters())
     for k in [f[5:] for f in g.files if f.startswith("grad.")]:
-        assert rel(params[k].grad, g["grad." + k]) < tol["grad"] * 2, k
+        assert rel(params[k].grad, g["grad." + k]) < tol["grad"], k
     gn = float(sum((p.grad.double() ** 2).sum() for p in m.parameters()) ** 0.5)
     assert abs(gn - float(g["gradnorm"][0])) / float(g["gradnorm"][0]) < tol["grad"]
     # hooks observed the LayerNorm output and its gradient, on the host, like the reference
     assert m.activations.device.type == "cpu" and tuple(m.activations.shape) == (2, 9, 1024)
-    assert rel(m.activations[:, :3, :8], g["act_hook"]) < tol["logits"] * 5
-    assert rel(m.gradients[:, :3, :8], g["grad_hook"]) < tol["grad"] * 2
+    assert rel(m.activations[:, :3, :8], g["act_hook"]) < tol["logits"]
+    assert rel(m.gradients[:, :3, :8], g["grad_hook"]) < tol["grad"]
 
 
 def test_neuroencoder_gradcam_map(tmp_path):
@@ -106,6 +106,30 @@ def test_neuroencoder_gradcam_map(tmp_path):
     img, attn = m.visualize_slice(cam, x)
     assert img.shape == (16, 16) and tuple(attn.shape) == (16, 16)
     assert m.activations.shape[1] == 9 and m.gradients.shape == m.activations.shape
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_neuroencoder_gradcam_map_matches_reference(tmp_path, mode):
+    """get_attention_map against the map the unmodified reference produced (tests/golden/neuro3d_cam.npz, 32^3 volume,
+    4x4x4 patch tokens, weights regenerated from the seed + oracle.perturb_for_cam and pinned by checksum).
+    The raw token scores have condition number ~15 (sum of 1024 signed products per token), so bf16 is held to
+    15 x 0.3 % = 5e-2 on them; the fp32 verification mode to 1e-4 and to the reference's final thresholded map."""
+    g = np.load(os.path.join(GOLD, "neuro3d_cam.npz"))
+    torch.manual_seed(1234)
+    cfg = {**_cfg(3, str(tmp_path), grid=32, precision=mode), "GRADCAM_THRESHOLD": 25}
+    m = NeuroEncoder(cfg).eval()
+    O.perturb_for_cam(m.volume_encoder.vit3d)
+    checksum = float(sum(v.double().sum() for v in m.state_dict().values()))
+    assert abs(checksum - float(g["sd_checksum"][0])) < 1e-3
+    cam, cls = m.get_attention_map(torch.from_numpy(g["x"]).to(DEV))
+    assert cls.cpu().tolist() == g["cls"].tolist()
+    grads, acts = m.gradients.float().cpu(), m.activations.float().cpu()
+    raw = (grads.mean(dim=2, keepdim=True) * acts).sum(dim=2)[:, 1:]
+    assert rel(raw, g["raw_cam"]) < (1e-4 if mode == "fp32" else 5e-2)
+    # the returned map is exactly the reference's post-processing (NeuroEncoder.py:100-131) of the hooked tensors
+    assert torch.equal(cam.cpu(), O.gradcam_from_hooks(grads, acts, 32, 8, 25))
+    if mode == "fp32":
+        assert (cam.cpu() - torch.from_numpy(g["cam"])).abs().max().item() < 1e-4
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
@@ -160,6 +184,80 @@ def test_vit_vs_oracle_ragged_tokens(mode):
     assert rel(logits, ref_logits) < tol["logits"]
     bad = {k: rel(p.grad, ref_grads[k]) for k, p in m.named_parameters() if rel(p.grad, ref_grads[k]) >= tol["grad"]}
     assert not bad, bad
+
+
+FULL = dict(num_classes=2, dim=1024, depth=6, heads=8, mlp_dim=2048, channels=1, dim_head=64)
+
+
+def _perturbed_vit(ctor, seed):
+    torch.manual_seed(seed)
+    m = ViT(**ctor)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def _check_vs_oracle(m, sd, video, labels, patch, heads, mode, oracle_video=None):
+    ref_logits, _, ref_grads = O.vit3d_loss_and_grads(sd, video if oracle_video is None else oracle_video, labels,
+                                                      patch=(patch,) * 3, heads=heads)
+    m = m.to(DEV).eval().set_precision(mode)
+    logits = m(video.to(DEV))
+    torch.nn.functional.cross_entropy(logits, labels.to(DEV)).backward()
+    tol = TOL[mode]
+    assert rel(logits, ref_logits) < tol["logits"]
+    worst = {k: rel(p.grad, ref_grads[k]) for k, p in m.named_parameters()}
+    bad = {k: v for k, v in worst.items() if v >= tol["grad"]}
+    assert not bad, bad
+    return worst
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vit_vs_oracle_config4_long_sequence(mode):
+    """BASELINE configs[3]: 1x96x96x96 volume, patch 8 -> 1728 patches + cls = 1729 tokens, full model dims, one
+    volume, through the ViT3DEncoder view ([B,H,W,D] -> permute(0,3,1,2).unsqueeze(1), NeuroEncoder.py:200-202)."""
+    ctor = dict(image_size=96, image_patch_size=8, frames=96, frame_patch_size=8, **FULL)
+    m, sd = _perturbed_vit(ctor, 13)
+    x = torch.randn(1, 96, 96, 96)
+    _check_vs_oracle(m, sd, O.neuro_view(x), torch.tensor([1]), 8, 8, mode)
+
+
+@pytest.mark.parametrize("grid", [18, 90])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vit_vs_oracle_patch9(mode, grid):
+    """The reference's shipped default geometry (configs/config.yaml:39-40: 90^3 volume, patch 9 -> 1000 patches,
+    patch_dim 729 padded to 736 for the tensor-core path) and its 2x2x2-token miniature; strided-gather kernels
+    (36-byte patch rows are not a TMA box)."""
+    ctor = dict(image_size=grid, image_patch_size=9, frames=grid, frame_patch_size=9, **FULL)
+    m, sd = _perturbed_vit(ctor, 14 + grid)
+    B = 2 if grid == 18 else 1
+    x = torch.randn(B, grid, grid, grid)
+    _check_vs_oracle(m, sd, O.neuro_view(x), torch.ones(B, dtype=torch.int64), 9, 8, mode)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_vit_per_sample_gradients_opposite_labels(mode):
+    """Companion of test_vit_vs_oracle_ragged_tokens, which uses same-class labels to keep the batch-summed
+    gradients well conditioned: here the two samples carry OPPOSITE labels and each sample's gradient is checked
+    on its own (batch of one), so no cancellation between samples hides or inflates an error."""
+    ctor = dict(image_size=16, image_patch_size=8, frames=24, frame_patch_size=8, **{**FULL, "depth": 2})
+    m, sd = _perturbed_vit(ctor, 15)
+    video = torch.randn(2, 1, 24, 16, 16)
+    for i, lab in enumerate((0, 1)):
+        m.zero_grad(set_to_none=True)
+        _check_vs_oracle(m, sd, video[i:i + 1], torch.tensor([lab]), 8, 8, mode)
+
+
+def test_head_with_many_classes_gradcam_dataset():
+    """DATASET_NAME == 'gradcam' builds num_classes = (grid // cube)^3 (NeuroEncoder.py:179): 512 classes at grid 64,
+    beyond the 256 the fused one-CTA-per-sample head kernels hold; the generic LayerNorm + linear path takes over."""
+    ctor = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=512, dim=128, depth=1,
+                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    for mode in ("fp32", "bf16"):
+        m, sd = _perturbed_vit(ctor, 16)
+        video = torch.randn(3, 1, 16, 16, 16)
+        _check_vs_oracle(m, sd, video, torch.tensor([5, 300, 511]), 8, 2, mode)
 
 
 def test_errors_and_contract():
@@ -268,10 +366,10 @@ def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode, batch):
     ref_loss = torch.nn.functional.cross_entropy(ref_logits, y)
     grads = torch.autograd.grad(ref_loss, list(leaf.values()), allow_unused=True)
     tol = TOL[mode]
-    assert rel(logits, ref_logits) < tol["logits"] * (1 if mode == "bf16" else 3)
+    assert rel(logits, ref_logits) < tol["logits"]
     for (k, p_), gr in zip(m.named_parameters(), grads):
         gr = torch.zeros_like(leaf[k]) if gr is None else gr
-        assert rel(p_.grad, gr) < tol["grad"] * (1.5 if mode == "bf16" else 3), k
+        assert rel(p_.grad, gr) < tol["grad"], k
     # eval mode is deterministic and dropout-free
     m.eval()
     a, b = m(x.to(DEV)), m(x.to(DEV))

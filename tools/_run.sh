@@ -1,8 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 150 python tools/attn_probe.py --dropout 0.1 > gpurun_out/r2_attn_probe7.log 2>&1; echo "probe exit $?" >> gpurun_out/r2_attn_probe7.log
-grep -v "OK$" gpurun_out/r2_attn_probe7.log | tail -8
-run() { echo "--- $1"; env $1 timeout 60 python tools/attn_probe.py --time-only 64 385 8 2>&1 | grep "fwd"; }
-run "NV_ATTN_ONLY=dq"
-run "NV_ATTN_ONLY=dkv"
-export NEUROVIT_LIB=$PWD/neurovit_b200/libneurovit_b200_prof.so
-timeout 100 python tools/attn_phases.py 2>&1 | tail -4
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputests_a.log 2>&1; tail -n 3 gpurun_out/r2_gputests_a.log
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_a.log 2>&1; tail -n 1 gpurun_out/r2_bench_a.log | cut -c1-1500
+timeout 200 python tools/step_profile.py --out gpurun_out/r2_step_profile_a.md > gpurun_out/r2_step_profile_a.log 2>&1; tail -n 3 gpurun_out/r2_step_profile_a.log | cut -c1-200
+timeout 200 python bench.py --impl torch_gpu --steps 10 --warmup 3 > gpurun_out/r2_torchgpu_a.log 2>&1; tail -n 1 gpurun_out/r2_torchgpu_a.log | cut -c1-900
