@@ -241,6 +241,9 @@ int nv_fmri_deinterleave(const float* x, float* y, int B, int64_t S, int T, void
  *   nv_dp_world(rank*, world*)  HOST int pointers
  *   nv_dp_destroy()             */
 int nv_dp_load(const char* path);
+/* SMs (rounded up to even) the library's persistent kernels (GEMM, LayerNorm backward) leave free on the current
+ * device for a concurrent communication kernel; 0 = use every SM (default). */
+int nv_set_sm_reserve(int n);
 int nv_dp_nccl_version(void);
 int nv_dp_unique_id(void* out128);
 int nv_dp_init(const void* uid128, int rank, int world);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "nv_temporal_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
     "nv_temporal_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _f, _f, _l, _p],
     "nv_fmri_deinterleave": [_p, _p, _i, _l, _i, _p, ctypes.c_double, _p],
+    "nv_set_sm_reserve": [_i],
     "nv_dp_load": [_p],
     "nv_dp_nccl_version": [],
     "nv_dp_unique_id": [_p],
@@ -124,7 +125,7 @@ def require_device(device_index: int) -> None:
 
 class _LaunchCounter:
     """Counts the CUDA kernels launched through the C ABI (bench.py reports it as `gpu_launches`)."""
-    KERNELS_PER_CALL = {"nv_attention_bwd": 2, "nv_version": 0, "nv_device_check": 0, "nv_dp_load": 0,
+    KERNELS_PER_CALL = {"nv_attention_bwd": 2, "nv_version": 0, "nv_device_check": 0, "nv_dp_load": 0, "nv_set_sm_reserve": 0,
                         "nv_dp_nccl_version": 0, "nv_dp_unique_id": 0, "nv_dp_init": 0, "nv_dp_register": 0,
                         "nv_dp_world": 0, "nv_dp_destroy": 0}
 

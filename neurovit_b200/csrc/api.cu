@@ -3,6 +3,7 @@
 #include "../../include/neurovit_b200.h"
 
 const char* nv_last_error_impl();
+int nv_set_sm_reserve_impl(int n);
 
 // launchers implemented in the kernel translation units
 int nv_gemm_tc_launch(int a_mn, int b_mn, int M, int N, int K, const bf16* A, int64_t lda, const bf16* B, int64_t ldb,
@@ -80,6 +81,7 @@ int nv_temporal_bwd_launch(const float* x, const float* params, const float* sav
 extern "C" {
 
 int nv_version(void) { return NV_ABI_VERSION; }
+int nv_set_sm_reserve(int n) { return nv_set_sm_reserve_impl(n); }
 const char* nv_last_error(void) { return nv_last_error_impl(); }
 
 int nv_device_check(void) {

@@ -26,15 +26,30 @@ int nv_check_cuda(cudaError_t e, const char* what) {
   return NV_ERR_CUDA;
 }
 
+namespace {
+int g_sm_reserve[64] = {0};
+}
+// SMs the persistent kernels may fill: the device's SM count minus the SMs reserved for a concurrent communication
+// kernel (nv_set_sm_reserve). A persistent grid that asked for every SM while NCCL's CTAs hold a few would leave
+// some of its CTAs queued until others finish — a whole extra wave.
 int nv_num_sms() {
   static int cached[64] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-  if (cached[dev] > 0) return cached[dev];
-  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-    return 148;
-  cached[dev] = n;
-  return n;
+  if (cached[dev] <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached[dev] = n;
+  }
+  const int avail = cached[dev] - g_sm_reserve[dev];
+  return avail >= 2 ? avail : 2;
+}
+
+int nv_set_sm_reserve_impl(int n) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { nv_set_error("nv_set_sm_reserve: no current device"); return NV_ERR_CUDA; }
+  NV_REQUIRE(n >= 0 && n <= 64, "nv_set_sm_reserve: %d out of range [0, 64]", n);
+  g_sm_reserve[dev] = (n + 1) & ~1;   // even: the CTA-pair GEMM needs an even number of SMs
+  return NV_OK;
 }
 
 bool nv_first_on_device(uint64_t* flags) {

@@ -35,12 +35,17 @@ def _find_nccl() -> str:
 class NcclComm:
     """`NcclComm(group)` creates the library's communicator for this rank on the current CUDA device."""
 
+    # CTAs NCCL may use per collective (env NEUROVIT_NCCL_MAX_CTAS; NCCL_MAX_CTAS wins if the user set it): the
+    # all-reduce runs UNDER backward, where every SM it takes is taken from the persistent GEMMs, and NVSwitch
+    # bandwidth is reached with few CTAs
+    MAX_CTAS = int(os.environ.get("NCCL_MAX_CTAS", os.environ.get("NEUROVIT_NCCL_MAX_CTAS", "8")))
+
     def __init__(self, group=None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("NcclComm needs an initialised torch.distributed process group to exchange the NCCL id")
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("NEUROVIT_NCCL_MAX_CTAS", "16"))
+        os.environ.setdefault("NCCL_MAX_CTAS", str(self.MAX_CTAS))
         path = _find_nccl()
         _lib.call("nv_dp_load", ctypes.c_char_p(path.encode()) if path else None)
         uid = ctypes.create_string_buffer(128)

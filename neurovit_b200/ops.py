@@ -381,6 +381,11 @@ def mean_pool_bwd(dpooled, dx, dx_bf16, B, N, D):
     _lib.call("nv_mean_pool_bwd", _ptr(dpooled), _ptr(dx), _ptr(dx_bf16), B, N, D, _stream())
 
 
+def set_sm_reserve(n: int):
+    """Leave n SMs (rounded up to even) free of the persistent kernels on the current device (for NCCL's CTAs)."""
+    _lib.call("nv_set_sm_reserve", int(n))
+
+
 def fmri_deinterleave(x, y, B, S, T, stats_ws=None, eps=1e-8):
     """x [B, S, T] fp32 contiguous -> y [B, T, S]; stats_ws (2*B float64, device) turns on the per-sample z-score."""
     _dev(x)

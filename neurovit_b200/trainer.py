@@ -6,8 +6,11 @@ step; fp16 autocast + GradScaler there, bf16 operands with fp32 master weights h
 needed). The reference has no distributed code; data parallelism is the new work BASELINE.json
 asks for: rank r takes batch[r*B/g:(r+1)*B/g]; gradients live in ONE flat fp32 buffer laid out in reverse
 parameter order (the order backward produces them), cut into buckets; each bucket is all-reduced (NCCL,
-average) as soon as autograd has accumulated its last gradient, while the rest of backward still runs.
-Inference shards the batch with no communication.
+average) as soon as its last gradient has landed, on a side stream, while the rest of backward still runs.
+On CUDA the all-reduce is issued through the library's own communicator (csrc/nv_dp.cu, neurovit_b200/dp.py): a
+plain kernel launch on the side stream, so the whole multi-rank step — forward, backward, the per-bucket
+all-reduces and FlatAdamW — is ONE CUDA graph. CPU tensors (the gloo tests) and NEUROVIT_DP_NCCL=torch go through
+torch.distributed's all_reduce instead. Inference shards the batch with no communication.
 """
 from __future__ import annotations
 
@@ -36,12 +39,15 @@ class FlatGradBuckets:
 
     ALIGN = 32  # elements (128 B)
 
-    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None, flatten_params: bool = False):
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None, flatten_params: bool = False, comm=None):
         """flatten_params: also move the parameters themselves into one flat fp32 buffer with the same slot layout
         (p.data becomes a view of it; values, names and state_dict are unchanged) so FlatAdamW can update
         everything with one kernel."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.comm = comm            # dp.NcclComm: all-reduces are kernel launches on self.comm_stream (graph-capturable)
+        self.comm_stream = torch.cuda.Stream() if comm is not None else None
+        self._comm_used = False
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         order = list(reversed(self.params))
         pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
@@ -79,10 +85,24 @@ class FlatGradBuckets:
                 b_start, b_count = off, 0
         if b_count:
             self.buckets.append([b_start, off, b_count])
-        self.pending = [b[2] for b in self.buckets]
+        self.seen = [set() for _ in self.buckets]   # parameters of each bucket whose gradient has landed this step
+        self.fired = [False] * len(self.buckets)
         self.handles = []
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] \
             if self.world > 1 else []
+        if self.world > 1:
+            self.broadcast_from_rank0()
+
+    def broadcast_from_rank0(self):
+        """Replicas must start identical: rank 0's parameters (and buffers, by the caller) win, as DDP does at
+        construction. Cheap insurance against per-rank seeds or a checkpoint loaded on one rank only."""
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        with torch.no_grad():
+            if self.flat_params is not None:
+                dist.broadcast(self.flat_params, src=src, group=self.group)
+            else:
+                for p in self.params:
+                    dist.broadcast(p.data, src=src, group=self.group)
 
     def sink_notify(self, key):
         """A backward kernel accumulated this parameter's gradient in place (no autograd hook will fire)."""
@@ -91,34 +111,61 @@ class FlatGradBuckets:
 
     defer = False  # True: no all-reduce is launched from the backward thread; finish() reduces the whole buffer
 
+    def _reduce_bucket(self, b):
+        s, e, _ = self.buckets[b]
+        self.fired[b] = True
+        if self.comm is not None:
+            # fork: the side stream waits for everything the backward stream has enqueued so far (inside a capture
+            # this event becomes a graph edge), then runs ncclAllReduce as an ordinary kernel launch
+            ev = torch.cuda.Event()
+            ev.record()
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm.all_reduce_(self.flat[s:e], average=True)
+            self._comm_used = True
+        else:
+            self.handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.AVG, group=self.group,
+                                                async_op=True))
+
     def _on_grad(self, p):
+        """One parameter's gradient is complete. A bucket is reduced when ALL its parameters have reported — tracked
+        as a set, so a parameter that reports twice in one step (shared weights, two forwards before one backward)
+        cannot release the bucket early; its later contributions would miss the reduction, so that case raises."""
         if self.defer:
             return
         b = self.bucket_of[p]
-        self.pending[b] -= 1
-        if self.pending[b] == 0:
-            s, e, _ = self.buckets[b]
-            self.handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.AVG, group=self.group,
-                                                async_op=True))
+        if self.fired[b]:
+            raise RuntimeError("a gradient arrived for a bucket that was already all-reduced in this step (parameter "
+                               "used twice before one backward?); set buckets.defer = True to reduce once after backward")
+        self.seen[b].add(id(p))
+        if len(self.seen[b]) == self.buckets[b][2]:
+            self._reduce_bucket(b)
 
     def zero(self):
         """Start of a step: clear the flat buffer (grads stay views into it; never set_to_none)."""
         self.flat.zero_()
-        self.pending = [b[2] for b in self.buckets]
+        for sset in self.seen:
+            sset.clear()
+        self.fired = [False] * len(self.buckets)
         self.handles = []
 
     def finish(self):
         """After backward: wait for the in-flight bucket all-reduces (the current stream waits, not the host)."""
-        if self.world > 1 and self.defer:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        if self.world == 1:
             return
-        if self.world > 1 and any(n != 0 for n in self.pending):
-            # parameters that received no gradient this step never fired their hook: reduce what is left
-            for b, n in enumerate(self.pending):
-                if n != 0:
-                    s, e, _ = self.buckets[b]
-                    self.handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.AVG, group=self.group,
-                                                        async_op=True))
+        if self.defer:
+            if self.comm is not None:
+                self.comm.all_reduce_(self.flat, average=True)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            return
+        # parameters that received no gradient this step never reported: reduce what is left
+        for b in range(len(self.buckets)):
+            if not self.fired[b]:
+                self._reduce_bucket(b)
+        if self._comm_used:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)   # join (closes the fork inside a capture)
+            self._comm_used = False
         for h in self.handles:
             h.wait()
         self.handles = []
@@ -126,6 +173,8 @@ class FlatGradBuckets:
     def close(self):
         for h in self.hooks:
             h.remove()
+        if self.comm is not None:
+            self.comm.close()
 
 
 class FlatAdamW:
@@ -171,9 +220,22 @@ class FlatAdamW:
                 "weight_decay": self.weight_decay}
 
     def load_state_dict(self, sd):
+        """Restores step count, moments AND hyper-parameters (torch.optim semantics), then re-casts the bf16 weight
+        copies from the current fp32 masters. A CUDA graph captured earlier baked the old hyper-parameters in as
+        kernel arguments: DataParallelTrainer.load_state_dict drops it so the next step re-captures."""
         self.t_dev.fill_(float(sd["t"]))
         self.m.copy_(sd["m"])
         self.v.copy_(sd["v"])
+        self.lr = sd.get("lr", self.lr)
+        self.betas = tuple(sd.get("betas", self.betas))
+        self.eps = sd.get("eps", self.eps)
+        self.weight_decay = sd.get("weight_decay", self.weight_decay)
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        """fp32 masters changed behind the optimizer's back (load_state_dict, manual edit): re-cast the bf16 copies."""
+        self._ops.cast_bf16(self.buckets.flat_params, out=self.shadow)
+        self._wc.epoch += 1
 
 
 class DataParallelTrainer:
@@ -189,11 +251,25 @@ class DataParallelTrainer:
         change every step (device-side epoch counter, nv_rng_epoch_advance). Ignored (eager launches) when the
         process group has more than one rank."""
         if bucket_mb is None:
-            bucket_mb = int(os.environ.get("NEUROVIT_BUCKET_MB", "80"))
+            # ~ half a transformer layer: the tail of backward (layer 0's attention, the patch embedding) then leaves
+            # only a few MB to reduce after the last kernel
+            bucket_mb = int(os.environ.get("NEUROVIT_BUCKET_MB", "12"))
         self.model = model
         plist = list(model.parameters())
         own_adamw = optimizer is None and plist[0].is_cuda and os.environ.get("NEUROVIT_TORCH_ADAMW") != "1"
-        self.buckets = FlatGradBuckets(plist, bucket_mb << 20, group, flatten_params=own_adamw)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        comm = None
+        if world > 1 and plist[0].is_cuda and os.environ.get("NEUROVIT_DP_NCCL", "own") != "torch":
+            from . import dp, ops
+            comm = dp.NcclComm(group)
+            # NCCL's CTAs need SMs of their own while they overlap backward: the persistent kernels leave them free
+            ops.set_sm_reserve(int(os.environ.get("NEUROVIT_SM_RESERVE", str(dp.NcclComm.MAX_CTAS))))
+        self.buckets = FlatGradBuckets(plist, bucket_mb << 20, group, flatten_params=own_adamw, comm=comm)
+        if comm is not None:
+            comm.register(self.buckets.flat)
+        if world > 1:
+            for buf in model.buffers():
+                dist.broadcast(buf.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         params = self.buckets.params
         if own_adamw:
             optimizer = FlatAdamW(self.buckets, lr=lr, weight_decay=weight_decay)
@@ -202,11 +278,13 @@ class DataParallelTrainer:
             optimizer = torch.optim.AdamW(params, lr=lr, weight_decay=weight_decay, fused=fused)
         self.optimizer = optimizer
         self.criterion = torch.nn.CrossEntropyLoss()
-        # with more than one rank the captured step is two graphs around ONE eager all-reduce of the whole gradient
-        # buffer (NCCL inside a capture hung at world_size 2); NEUROVIT_GRAPH_DP=0 keeps multi-rank steps eager with
-        # bucketed all-reduces overlapped with backward
+        # Several ranks: with the library's own communicator the bucketed all-reduces are captured into the step's
+        # graph. Through torch.distributed (NEUROVIT_DP_NCCL=torch) NCCL stays out of the capture (ProcessGroupNCCL
+        # inside a capture hung at world_size 2): two graphs around ONE eager all-reduce of the whole buffer.
+        # NEUROVIT_GRAPH_DP=0 keeps multi-rank steps eager.
         self.use_graph = bool(graph) and (self.buckets.world == 1 or os.environ.get("NEUROVIT_GRAPH_DP", "1") == "1")
-        if self.use_graph and self.buckets.world > 1:
+        self._two_graphs = self.use_graph and self.buckets.world > 1 and comm is None
+        if self._two_graphs or os.environ.get("NEUROVIT_DP_DEFER") == "1":
             self.buckets.defer = True
         if self.use_graph and not isinstance(optimizer, FlatAdamW):
             raise ValueError("graph=True needs the built-in FlatAdamW optimizer (CUDA parameters, optimizer=None)")
@@ -253,8 +331,8 @@ class DataParallelTrainer:
         from . import _lib
         n0 = _lib.LAUNCHES.count
         self._graph = torch.cuda.CUDAGraph()
-        if self.buckets.world == 1:
-            with torch.cuda.graph(self._graph):
+        if not self._two_graphs:
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local" if self.buckets.world > 1 else "global"):
                 self._sloss = self._eager_step(self._sx, self._sy)
             self._graph2 = None
         else:
@@ -293,6 +371,18 @@ class DataParallelTrainer:
         from . import _lib
         _lib.LAUNCHES.count += self._graph_launches
         return self._sloss
+
+    def load_state_dict(self, model_sd=None, optimizer_sd=None):
+        """Load a checkpoint into a live trainer: parameters go into the flat fp32 buffer (p.data are views of it),
+        the bf16 weight copies are re-cast at once, and a captured graph — which baked the old hyper-parameters in
+        and would replay the first step on stale bf16 copies — is dropped and re-captured on the next step."""
+        if model_sd is not None:
+            self.model.load_state_dict(model_sd)
+        if optimizer_sd is not None:
+            self.optimizer.load_state_dict(optimizer_sd)
+        if isinstance(self.optimizer, FlatAdamW):
+            self.optimizer.refresh_shadow()
+        self._graph = self._graph2 = None
 
     @torch.no_grad()
     def predict(self, inputs):

@@ -267,12 +267,19 @@ def test_attention_fwd_bwd(B, N, H):
     ws = torch.empty(B * H * N, device=DEV)
     ops.attention_bwd(qkv, o, dO, lse, ws, dqkv, B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5)
     inner = H * hd
+    # N = 1: softmax over one key has dS = 0 exactly, so dq = dk = 0 in exact arithmetic while the kernel leaves the
+    # bf16 round-off of p (dP - delta); errors are therefore measured against the scale of the whole gradient
+    floor = 1e-3 * gref.abs().max().item()
+
+    def err(a, b):
+        return ((a.double() - b.double()).abs().max() / max(b.abs().max().item(), floor)).item()
+
     for nm, sl in (("dq", slice(0, inner)), ("dk", slice(inner, 2 * inner)), ("dv", slice(2 * inner, 3 * inner))):
-        assert rel_err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
+        assert err(dqkv[:, sl], gref[:, sl]) < 2e-2, nm
     # token 0 (handled outside the tensor-core tiles, as a query and as a key) and the last token, on their own
     for tok in (0, N - 1):
         assert rel_err(o.view(B, N, inner)[:, tok], oref.view(B, N, inner)[:, tok]) < 1e-2, tok
-        assert rel_err(dqkv.view(B, N, 3 * inner)[:, tok], gref.view(B, N, 3 * inner)[:, tok]) < 2e-2, tok
+        assert err(dqkv.view(B, N, 3 * inner)[:, tok], gref.view(B, N, 3 * inner)[:, tok]) < 2e-2, tok
 
 
 @pytest.mark.parametrize("B,N,H", [(3, 385, 8), (2, 64, 2), (2, 9, 1), (1, 1729, 2), (2, 1, 1)])

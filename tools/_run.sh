@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_gputests_a.log 2>&1; tail -n 3 gpurun_out/r2_gputests_a.log
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_a.log 2>&1; tail -n 1 gpurun_out/r2_bench_a.log | cut -c1-1500
-timeout 200 python tools/step_profile.py --out gpurun_out/r2_step_profile_a.md > gpurun_out/r2_step_profile_a.log 2>&1; tail -n 3 gpurun_out/r2_step_profile_a.log | cut -c1-200
-timeout 200 python bench.py --impl torch_gpu --steps 10 --warmup 3 > gpurun_out/r2_torchgpu_a.log 2>&1; tail -n 1 gpurun_out/r2_torchgpu_a.log | cut -c1-900
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2_gputests_b.log 2>&1; tail -n 12 gpurun_out/r2_gputests_b.log
+export NEUROVIT_LIB=$PWD/neurovit_b200/libneurovit_b200_prof.so
+timeout 100 python tools/attn_phases.py > gpurun_out/r2_phases_p0.log 2>&1; cat gpurun_out/r2_phases_p0.log | tail -20
+ATTN_DROPOUT=0.1 timeout 100 python tools/attn_phases.py > gpurun_out/r2_phases_p01.log 2>&1; cat gpurun_out/r2_phases_p01.log | tail -20
