@@ -23,6 +23,10 @@ F32 = torch.float32
 NUM_SMS = 148
 
 _VALID_MODES = ("bf16", "fp32")
+# A/B switches for the fusion study (tools/fusion_ab.sh): each REMOVES a kernel from the step to bound what fusing it
+# into its neighbour could gain at most. The step then computes wrong values; never set outside that measurement.
+AB_FLAGS = set(f for f in os.environ.get("NEUROVIT_AB", "").split(",") if f)
+AB_STATE = {}
 HEAD_FUSED_MAX_CLASSES = 256  # HEAD_T of csrc/misc.cu: the one-CTA-per-sample head kernels hold the logits in a block
 
 # dropout sites of one block (vit_3d.py:21,23,39,45; emb :100,119): distinct Philox streams under one seed
@@ -375,6 +379,11 @@ class Engine:
         y = torch.empty(M, D, device=x.device, dtype=out_dtype or self.act)
         mean = torch.empty(M, device=x.device, dtype=F32)
         rstd = torch.empty(M, device=x.device, dtype=F32)
+        if "skip_ln" in AB_FLAGS and M >= 1024:   # measurement only (tools/fusion_ab.sh): WRONG numerics by design
+            if not AB_STATE.get(("ln", M, D)):
+                AB_STATE[("ln", M, D)] = True
+                y.zero_(); mean.zero_(); rstd.fill_(1.0)
+            return y, mean, rstd
         ops.layernorm_fwd(x, weight.detach(), bias.detach(), y, M=M, D=D, mean=mean, rstd=rstd, eps=eps)
         return y, mean, rstd
 
@@ -842,7 +851,12 @@ class PatchEmbedFn(torch.autograd.Function):
         patches = torch.empty(B * n, Kp, device=dev, dtype=eng.act)
         mean1 = torch.empty(B * n, device=dev, dtype=F32)
         rstd1 = torch.empty(B * n, device=dev, dtype=F32)
-        ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
+        if "skip_gather" in AB_FLAGS:   # measurement only: the patch GEMM then reads whatever the buffer holds
+            patches.zero_() if not AB_STATE.get("gather") else None
+            AB_STATE["gather"] = True
+            mean1.zero_(); rstd1.fill_(1.0)
+        else:
+            ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
         if mode == "bf16":
             e, _ = eng.linear(patches, lin_w, bias=lin_b, out_dtype=F32, pad_k=Kp)
         else:

@@ -88,7 +88,8 @@ class FlatGradBuckets:
         self.seen = [set() for _ in self.buckets]   # parameters of each bucket whose gradient has landed this step
         self.fired = [False] * len(self.buckets)
         self.handles = []
-        self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params] \
+        self._echo = {}
+        self.hooks = [p.register_post_accumulate_grad_hook(self._on_hook) for p in self.params] \
             if self.world > 1 else []
         if self.world > 1:
             self.broadcast_from_rank0()
@@ -105,9 +106,20 @@ class FlatGradBuckets:
                     dist.broadcast(p.data, src=src, group=self.group)
 
     def sink_notify(self, key):
-        """A backward kernel accumulated this parameter's gradient in place (no autograd hook will fire)."""
+        """A backward kernel accumulated this parameter's gradient in place. Autograd still runs the parameter's
+        AccumulateGrad node afterwards (with an undefined gradient: the Function returned None) and with it the
+        post-accumulate hook — that echo carries no new gradient and is swallowed in _on_hook."""
         if self.world > 1:
-            self._on_grad(self._by_key[key])
+            p = self._by_key[key]
+            self._echo[id(p)] = self._echo.get(id(p), 0) + 1
+            self._on_grad(p)
+
+    def _on_hook(self, p):
+        n = self._echo.get(id(p), 0)
+        if n > 0:
+            self._echo[id(p)] = n - 1
+            return
+        self._on_grad(p)
 
     defer = False  # True: no all-reduce is launched from the backward thread; finish() reduces the whole buffer
 
@@ -148,6 +160,7 @@ class FlatGradBuckets:
             sset.clear()
         self.fired = [False] * len(self.buckets)
         self.handles = []
+        self._echo = {}
 
     def finish(self):
         """After backward: wait for the in-flight bucket all-reduces (the current stream waits, not the host)."""
@@ -288,7 +301,8 @@ class DataParallelTrainer:
             self.buckets.defer = True
         if self.use_graph and not isinstance(optimizer, FlatAdamW):
             raise ValueError("graph=True needs the built-in FlatAdamW optimizer (CUDA parameters, optimizer=None)")
-        self._graph = self._graph2 = None
+        self._graph = self._graph2 = self._graph_alt = None
+        self._flip = False
         self._cuda = plist[0].is_cuda
 
     def _fwd_bwd(self, inputs, labels):
@@ -332,9 +346,21 @@ class DataParallelTrainer:
         n0 = _lib.LAUNCHES.count
         self._graph = torch.cuda.CUDAGraph()
         if not self._two_graphs:
-            with torch.cuda.graph(self._graph, capture_error_mode="thread_local" if self.buckets.world > 1 else "global"):
+            mode = "thread_local" if self.buckets.world > 1 else "global"
+            with torch.cuda.graph(self._graph, capture_error_mode=mode):
                 self._sloss = self._eager_step(self._sx, self._sy)
             self._graph2 = None
+            # The same executable graph cannot overlap its own previous launch: the relaunch of a ~200-node graph
+            # leaves the GPU idle between replays. A second capture of the identical step (same static inputs and
+            # persistent buffers, its own activations from the same pool) lets consecutive steps alternate between two
+            # executables, so step i+1's launch is prepared while step i runs.
+            self._graph_alt = None
+            if os.environ.get("NEUROVIT_GRAPH_PINGPONG", "1") == "1":
+                self._graph_alt = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_alt, pool=self._graph.pool(), capture_error_mode=mode):
+                    self._sloss_alt = self._eager_step(self._sx, self._sy)
+                n_per = (_lib.LAUNCHES.count - n0) // 2
+                _lib.LAUNCHES.count = n0 + n_per
         else:
             # several ranks: NCCL stays OUT of the capture. Graph 1 = forward + backward into the flat gradient
             # buffer, then ONE eager all-reduce of that buffer, then graph 2 = optimizer + epoch advance.
@@ -364,13 +390,24 @@ class DataParallelTrainer:
             raise ValueError(f"graph=True needs static shapes: captured {tuple(self._sx.shape)}, got {tuple(inputs.shape)}")
         self._sx.copy_(inputs, non_blocking=True)
         self._sy.copy_(labels, non_blocking=True)
-        self._graph.replay()
+        loss = self._sloss
+        if getattr(self, "_graph_alt", None) is not None and self._flip:
+            self._graph_alt.replay()
+            loss = self._sloss_alt
+        else:
+            self._graph.replay()
+        self._flip = not self._flip
         if self._graph2 is not None:
             self.buckets.finish()   # deferred mode: one all-reduce (AVG) of the whole flat gradient buffer
             self._graph2.replay()
         from . import _lib
         _lib.LAUNCHES.count += self._graph_launches
-        return self._sloss
+        return loss
+
+    def reset_graph(self):
+        """Drop the captured step (new batch shape, changed hyper-parameters): the next step() captures again."""
+        self._graph = self._graph2 = self._graph_alt = None
+        self._flip = False
 
     def load_state_dict(self, model_sd=None, optimizer_sd=None):
         """Load a checkpoint into a live trainer: parameters go into the flat fp32 buffer (p.data are views of it),
@@ -382,7 +419,7 @@ class DataParallelTrainer:
             self.optimizer.load_state_dict(optimizer_sd)
         if isinstance(self.optimizer, FlatAdamW):
             self.optimizer.refresh_shadow()
-        self._graph = self._graph2 = None
+        self.reset_graph()
 
     @torch.no_grad()
     def predict(self, inputs):

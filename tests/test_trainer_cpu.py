@@ -33,6 +33,10 @@ def _worker(rank, world, port, q, defer=False):
         X = torch.randn(8, 12)
         Y = torch.randint(0, 2, (8,))
         m = _model()
+        if rank != 0:   # replicas that start from DIFFERENT weights: the trainer must broadcast rank 0's
+            with torch.no_grad():
+                for p in m.parameters():
+                    p.add_(torch.randn_like(p))
         tr = DataParallelTrainer(m, optimizer=torch.optim.SGD(m.parameters(), lr=0.0), bucket_mb=0)
         assert len(tr.buckets.buckets) == len(list(m.parameters()))  # bucket_mb=0: one bucket per parameter
         tr.buckets.defer = defer  # True: what the graph-captured multi-rank step does — ONE all-reduce after backward
@@ -76,6 +80,24 @@ def test_dp_step_world2_gloo_matches_full_batch(defer):
         for g, f in zip(grads, full):
             assert abs(g - f).max() < 1e-6, "averaged shard gradients must equal the full-batch gradients"
     assert abs(sum(r[1] for r in res) / world - float(torch.nn.functional.cross_entropy(_model()(X), Y))) < 1e-6
+
+
+def test_bucket_countdown_rejects_a_second_report():
+    """A parameter that reports twice in one step (shared weights / two forwards before one backward) must not
+    release its bucket early: the set-based countdown raises once the bucket has already been reduced."""
+    m = _model()
+    b = FlatGradBuckets(list(m.parameters()), bucket_bytes=0)
+    p0 = b.params[0]
+    b.world = 2                      # pretend: the countdown is only live with several ranks
+    fired = []
+    b._reduce_bucket = lambda i: (fired.append(i), b.fired.__setitem__(i, True))
+    b._on_grad(p0)
+    assert fired == [b.bucket_of[p0]]
+    with pytest.raises(RuntimeError):
+        b._on_grad(p0)
+    b.zero()
+    b._on_grad(p0)                   # a new step starts clean
+    assert fired == [b.bucket_of[p0]] * 2
 
 
 def test_shard_batch_and_buckets_single_process():

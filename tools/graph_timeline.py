@@ -1,0 +1,111 @@
+"""Timeline of the REPLAYED training-step graph (CUPTI activity records through torch.profiler): per-kernel time,
+the idle gaps between consecutive kernels on the main stream, and how much of the side-stream work (dropout bit
+generation, NCCL) runs under main-stream kernels. Answers "where does step time minus kernel time go".
+Usage: python tools/graph_timeline.py [--steps 3] [--dropout 0.1] [--out FILE]"""
+import argparse
+import collections
+import json
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from neurovit_b200.trainer import DataParallelTrainer  # noqa: E402
+from neurovit_b200.vit_3d import ViT  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--config", default="cfgA")
+ap.add_argument("--dropout", type=float, default=bench.DROPOUT)
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+bench.DROPOUT = args.dropout
+cfg = bench.CONFIGS[args.config]
+dev = torch.device("cuda", 0)
+torch.manual_seed(42)
+
+
+class Enc(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.vit3d = ViT(**bench.vit_ctor(cfg))
+
+    def forward(self, x):
+        return self.vit3d(x.permute(0, 3, 1, 2).unsqueeze(1))
+
+
+enc = Enc().to(dev).train()
+tr = DataParallelTrainer(enc, lr=1e-4, weight_decay=0.01, graph=True)
+H, W, D = cfg["vol"]
+xs = [torch.randn(args.batch, H, W, D, device=dev) for _ in range(3)]
+ys = [torch.randint(0, 2, (args.batch,), device=dev) for _ in range(3)]
+for i in range(6):
+    tr.step(xs[i % 3], ys[i % 3])
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(10):
+    tr.step(xs[i % 3], ys[i % 3])
+e1.record()
+torch.cuda.synchronize()
+plain_ms = e0.elapsed_time(e1) / 10
+
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for i in range(args.steps):
+        tr.step(xs[i % 3], ys[i % 3])
+    torch.cuda.synchronize()
+with tempfile.TemporaryDirectory() as tmp:
+    path = os.path.join(tmp, "trace.json")
+    prof.export_chrome_trace(path)
+    trace = json.load(open(path))
+ks = [e for e in trace["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e]
+ks.sort(key=lambda e: e["ts"])
+by_stream = collections.Counter(e["args"].get("stream") for e in ks)
+main = by_stream.most_common(1)[0][0]
+mk = [e for e in ks if e["args"].get("stream") == main]
+sk = [e for e in ks if e["args"].get("stream") != main]
+t_first, t_last = ks[0]["ts"], max(e["ts"] + e["dur"] for e in ks)
+span = (t_last - t_first) / args.steps
+gaps = []
+for a, b in zip(mk, mk[1:]):
+    g = b["ts"] - (a["ts"] + a["dur"])
+    gaps.append((g, a["name"][:60], b["name"][:60]))
+step_gap = sorted(gaps, key=lambda x: -x[0])[:args.steps - 1]   # the gaps between replays themselves
+inner = [g for g in gaps if g not in step_gap]
+pos = [g for g in inner if g[0] > 0]
+lines = [f"un-profiled graph replay: {plain_ms:.3f} ms/step; profiled span {span / 1e3:.3f} ms/step",
+         f"main stream {main}: {len(mk) / args.steps:.0f} kernels/step, kernel time {sum(e['dur'] for e in mk) / args.steps / 1e3:.3f} ms/step, "
+         f"positive gaps {sum(g[0] for g in pos) / args.steps / 1e3:.3f} ms/step over {len(pos) / args.steps:.0f} boundaries "
+         f"(mean {sum(g[0] for g in pos) / max(len(pos), 1):.2f} us); overlapping (negative) {sum(g[0] for g in inner if g[0] <= 0) / args.steps / 1e3:.3f} ms",
+         f"side streams: {len(sk) / args.steps:.0f} kernels/step, {sum(e['dur'] for e in sk) / args.steps / 1e3:.3f} ms/step"]
+lines.append("largest gaps (us): " + "; ".join(f"{g:.0f} [{a[:28]} -> {b[:28]}]" for g, a, b in sorted(gaps, key=lambda x: -x[0])[:6]))
+# gap by following-kernel name
+bynext = collections.defaultdict(lambda: [0.0, 0])
+for g, a, b in inner:
+    bynext[b][0] += g
+    bynext[b][1] += 1
+lines.append("| gap before kernel | count/step | total us/step | mean us |")
+lines.append("|---|---|---|---|")
+for k, (t, n) in sorted(bynext.items(), key=lambda kv: -kv[1][0])[:25]:
+    lines.append(f"| `{k}` | {n / args.steps:.1f} | {t / args.steps:.1f} | {t / n:.2f} |")
+# per-kernel durations in the replay
+tot = collections.defaultdict(lambda: [0.0, 0])
+for e in ks:
+    tot[e["name"][:90]][0] += e["dur"]
+    tot[e["name"][:90]][1] += 1
+lines.append("")
+lines.append("| kernel (graph replay) | launches/step | us/step | avg us |")
+lines.append("|---|---|---|---|")
+for k, (t, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:40]:
+    lines.append(f"| `{k}` | {n / args.steps:.1f} | {t / args.steps:.1f} | {t / n:.1f} |")
+text = "\n".join(lines)
+print(text)
+if args.out:
+    open(args.out, "w").write(text + "\n")
