@@ -312,7 +312,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(
 
 // One 32-key chunk of one query row: raw scores (registers) -> probabilities, packed as 16 bf16x2 words, and
 // the chunk's row-sum. FULL = all 32 keys valid (branch-free); otherwise keys >= nvalid (chunk-local) give 0.
-template <bool FULL, bool DROPOUT>
+template <bool FULL, bool DROPOUT, bool READY>
 __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float cs, float m_used, int nvalid,
                                                  const Common& c, uint64_t mrow, int key0, bool row_ok,
                                                  uint32_t (&w)[16], uint32_t km_ready = 0) {
@@ -329,7 +329,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     rs0 += e[0] + e[4]; rs1 += e[1] + e[5]; rs2 += e[2] + e[6]; rs3 += e[3] + e[7];
     if (DROPOUT) {
       uint32_t km;
-      if (c.mask_ready) {
+      if (READY) {
         km = (km_ready >> (8 * g8)) & 0xFFu;  // drawn ahead (nv_dropout_bits), fetched before the barrier waits
       } else {
         km = nv_keep_bits8(nv_seed(c.seed, c.epoch), mrow * (uint64_t)(c.mask_words * 4) + (uint64_t)((key0 >> 3) + g8), 0u,
@@ -344,7 +344,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
     w[g8 * 4 + 2] = pack_bf16x2(e[4], e[5]);
     w[g8 * 4 + 3] = pack_bf16x2(e[6], e[7]);
   }
-  if (DROPOUT && row_ok && !c.mask_ready) c.mask[mrow * c.mask_words + (key0 >> 5)] = km32;  // one word per 32-key chunk
+  if (DROPOUT && !READY && row_ok) c.mask[mrow * c.mask_words + (key0 >> 5)] = km32;  // one word per 32-key chunk
   return (rs0 + rs1) + (rs2 + rs3);
 }
 __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
@@ -483,7 +483,10 @@ __device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int
   }
 }
 
-template <bool DROPOUT>
+// READY: the keep bits were drawn ahead of time (nv_dropout_bits, the training step's path); the inline Philox draw is
+// then not compiled into the kernel at all — the hot loop of the two-path kernel missed the instruction cache in
+// 13 % of its stall samples (profiles/r02_summary.md).
+template <bool DROPOUT, bool READY>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const FwdParams p) {
@@ -628,7 +631,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const bool full = nvalid == FWD_KB;
       const uint32_t tSj = tS + lane_base + (uint32_t)((j & 1) * FWD_KB);
       uint32_t kmw[3] = {0u, 0u, 0u};  // pre-drawn dropout keep words of this row's block
-      if (DROPOUT && p.c.mask_ready) {
+      if (DROPOUT && READY) {
         const uint32_t* mp = p.c.mask + mrow * p.c.mask_words + (key0 >> 5);
         kmw[0] = __ldg(mp);
         if (nvalid > 32) kmw[1] = __ldg(mp + 1);
@@ -663,8 +666,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const bool row_ok = qrow < n;
       uint32_t w[16];
       float rs;
-      if (full) rs = fwd_chunk_probs<true, DROPOUT>(c0, cs, m_used, 32, p.c, mrow, key0, row_ok, w, kmw[0]);
-      else      rs = fwd_chunk_probs<false, DROPOUT>(c0, cs, m_used, nvalid, p.c, mrow, key0, row_ok, w, kmw[0]);
+      if (full) rs = fwd_chunk_probs<true, DROPOUT, READY>(c0, cs, m_used, 32, p.c, mrow, key0, row_ok, w, kmw[0]);
+      else      rs = fwd_chunk_probs<false, DROPOUT, READY>(c0, cs, m_used, nvalid, p.c, mrow, key0, row_ok, w, kmw[0]);
       PROF_MARK(3);
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
@@ -673,17 +676,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       PROF_MARK(4);
       store_p_chunk(sP_u32, row, 0, w);
       if (full) {
-        rs += fwd_chunk_probs<true, DROPOUT>(c1, cs, m_used, 32, p.c, mrow, key0 + 32, row_ok, w, kmw[1]);
+        rs += fwd_chunk_probs<true, DROPOUT, READY>(c1, cs, m_used, 32, p.c, mrow, key0 + 32, row_ok, w, kmw[1]);
         store_p_chunk(sP_u32, row, 1, w);
-        rs += fwd_chunk_probs<true, DROPOUT>(c2, cs, m_used, 32, p.c, mrow, key0 + 64, row_ok, w, kmw[2]);
+        rs += fwd_chunk_probs<true, DROPOUT, READY>(c2, cs, m_used, 32, p.c, mrow, key0 + 64, row_ok, w, kmw[2]);
         store_p_chunk(sP_u32, row, 2, w);
       } else {
         if (nvalid > 32) {
-          rs += fwd_chunk_probs<false, DROPOUT>(c1, cs, m_used, nvalid - 32, p.c, mrow, key0 + 32, row_ok, w, kmw[1]);
+          rs += fwd_chunk_probs<false, DROPOUT, READY>(c1, cs, m_used, nvalid - 32, p.c, mrow, key0 + 32, row_ok, w, kmw[1]);
           store_p_chunk(sP_u32, row, 1, w);
         }
         if (nvalid > 64) {
-          rs += fwd_chunk_probs<false, DROPOUT>(c2, cs, m_used, nvalid - 64, p.c, mrow, key0 + 64, row_ok, w, kmw[2]);
+          rs += fwd_chunk_probs<false, DROPOUT, READY>(c2, cs, m_used, nvalid - 64, p.c, mrow, key0 + 64, row_ok, w, kmw[2]);
           store_p_chunk(sP_u32, row, 2, w);
         }
       }
@@ -717,7 +720,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       if (DROPOUT) {
         const int pos = N - 1;
         uint32_t keep;
-        if (p.c.mask_ready) {
+        if (READY) {
           keep = (__ldg(p.c.mask + mrow * p.c.mask_words + (pos >> 5)) >> (pos & 31)) & 1u;
         } else {
           const uint32_t byte = nv_keep_bits8(nv_seed(p.c.seed, p.c.epoch),
@@ -1166,7 +1169,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 // backward, dK / dV: CTA = 128 keys (TMEM lane = key); loop over 64-query blocks
 // =====================================================================================================
 constexpr int DKV_SMEM_TILES = 2 * SLAB /*K, V*/ + 2 * 2 * BOX /*Q_i, dO_i x 2 stages*/ + 2 * SLAB /*P^T, dS^T*/;
-constexpr int DKV_SMEM = DKV_SMEM_TILES + 128 + 4 * 768 /*per-warp lse/delta/mask staging*/ + 1024;
+constexpr int DKV_SMEM = DKV_SMEM_TILES + 128 + 4 * 768 /*per-warp lse/delta/mask staging*/ + 4 * 256 /*per-warp q_0 / dO_0*/ + 1024;
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
@@ -1289,6 +1292,8 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     PROF_DECL
     // per-query statistics of a block: fetched one block ahead into registers (the global-load latency hides
     // behind the previous block's exponentials), then staged in shared memory and read back as broadcasts
+    // The loaded values are NOT touched here (no scaling, no select): any arithmetic on them would park the thread on
+    // the load right away and the one-block-ahead prefetch would hide nothing (it used to: 1.8 k cycles per block).
     float st_l[2], st_d[2];
     uint32_t st_m[2] = {0u, 0u};
     auto fetch_stats = [&](int blk) {
@@ -1296,13 +1301,24 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       for (int t = 0; t < 2; ++t) {
         const int q = blk * BWD_CB + t * 32 + lane;   // tile-local query index; token = q + 1
         const int qc = min(q + 1, N - 1);
-        // padded queries: lse = +inf makes P exactly 0 (their dO / Q rows are zero-filled anyway)
-        st_l[t] = q < n ? __ldg(lse_bh + qc) * LOG2E : INFINITY;
+        st_l[t] = __ldg(lse_bh + qc);
         st_d[t] = p.delta[((int64_t)b * p.c.H + h) * N + qc];  // written by the dQ grid (plain load: not read-only data)
         if (dropout) st_m[t] = p.c.mask[(mbase + qc) * p.c.mask_words + ((k0 + warp * 32) >> 5)];
       }
     };
     const uint32_t stats_u32 = smem_u32(stats), mwords_u32 = smem_u32(mwords);
+    // q and dO of token 0 (the query that stays outside the tiles) are needed after the loop: fetched now, straight
+    // into this warp's shared-memory scratch by cp.async (no registers held, no latency left at the point of use)
+    const uint32_t x0_u32 = smem_u32(smem + DKV_SMEM_TILES + 128 + 4 * 768) + (uint32_t)warp * 256u;
+    if (lane < 16) {
+      const bf16* src = (lane < 8 ? p.c.q + (int64_t)b * p.c.qkv_bs : p.dO + (int64_t)b * p.o_bs) + h * HD + 8 * (lane & 7);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(x0_u32 + (uint32_t)lane * 16u), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int64_t stat0 = ((int64_t)b * p.c.H + h) * N;
+    const float lse_0 = __ldg(p.lse + stat0), dl_0 = p.delta[stat0];
+    uint32_t kw_0 = 0xFFFFFFFFu;
+    if (dropout) kw_0 = __ldg(p.c.mask + stat0 * p.c.mask_words + (min(krow, n - 1) >> 5));
     fetch_stats(0);
     for (int i = 0; i < nblk; ++i) {
       const int qb = i * BWD_CB;
@@ -1311,6 +1327,8 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       __syncwarp();
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
+        // padded queries: lse = +inf makes P exactly 0 (their dO / Q rows are zero-filled anyway)
+        st_l[t] = (qb + t * 32 + lane) < n ? st_l[t] * LOG2E : INFINITY;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(stats_u32 + (uint32_t)(t * 32 + lane) * 4), "f"(st_l[t]) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(stats_u32 + (uint32_t)(64 + t * 32 + lane) * 4), "f"(st_d[t]) : "memory");
         if (dropout)
@@ -1381,12 +1399,17 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     mbar_wait(kv_full, 0);  // long since complete: orders this thread's reads of the TMA-written K / V tiles
     Vec64 q0v, do0;   // q and dO of token 0: used for the scores here and for the rank-1 terms below
     {
-      const int64_t stat0 = ((int64_t)b * p.c.H + h) * N;
-      load_vec64(q0v, p.c.q + (int64_t)b * p.c.qkv_bs + h * HD);
-      load_vec64(do0, p.dO + (int64_t)b * p.o_bs + h * HD);
-      uint32_t kw = 0xFFFFFFFFu;
-      if (dropout) kw = __ldg(p.c.mask + stat0 * p.c.mask_words + (min(krow, n - 1) >> 5));
-      const float lse2_0 = __ldg(p.lse + stat0) * LOG2E, dl_0 = p.delta[stat0];
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0v.c[i].x), "=r"(q0v.c[i].y), "=r"(q0v.c[i].z), "=r"(q0v.c[i].w)
+                     : "r"(x0_u32 + (uint32_t)i * 16u));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(do0.c[i].x), "=r"(do0.c[i].y), "=r"(do0.c[i].z), "=r"(do0.c[i].w)
+                     : "r"(x0_u32 + 128u + (uint32_t)i * 16u));
+      }
+      const uint32_t kw = kw_0;
+      const float lse2_0 = lse_0 * LOG2E;
       const float p_x = ex2(fmaf(row_dot(smem_u32(sK), row, q0v), cs, -lse2_0));
       const float dp_x = row_dot(smem_u32(sV), row, do0);
       const bool keep = (kw >> (krow & 31)) & 1u;
@@ -1620,14 +1643,16 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
   static uint64_t attr_done = 0;  // bit per device
   if (nv_first_on_device(&attr_done)) {
-    if ((s = set_smem(attn_tc_fwd_kernel<false>, FWD_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_fwd_kernel<true>, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<false, false>, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<true, false>, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<true, true>, FWD_SMEM)) != NV_OK) return s;
   }
   unsigned ncta;
   if ((s = tile_grid(p.c, B, &ncta)) != NV_OK) return s;
   dim3 grid(ncta);
-  if (p.c.drop_thr != 0) attn_tc_fwd_kernel<true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
-  else attn_tc_fwd_kernel<false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  if (p.c.drop_thr != 0 && p.c.mask_ready) attn_tc_fwd_kernel<true, true><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  else if (p.c.drop_thr != 0) attn_tc_fwd_kernel<true, false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
+  else attn_tc_fwd_kernel<false, false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
   NV_LAUNCH_CHECK("attn_tc_fwd_kernel");
   return dbg_sync("fwd", stream);
 }

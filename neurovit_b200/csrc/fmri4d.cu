@@ -40,22 +40,39 @@ fmri_deinterleave_kernel(const float* __restrict__ x, float* __restrict__ y, int
   for (int t0 = 0; t0 < T; t0 += FM_TC) {
     const int tc = min(FM_TC, T - t0);
     const int pitch = tc | 1;  // odd: the transposed reads below hit 32 different banks
-    {
-      // consecutive threads read consecutive addresses (when tc == T the CTA's whole source run is contiguous) and
-      // write consecutive shared-memory words: coalesced and conflict-free without vector accesses
+    if (tc == T && (T & 3) == 0 && ns == FM_S) {
+      // the CTA's whole source run [s0 T, (s0 + FM_S) T) is contiguous and 16-byte aligned (s0 is a multiple of 64):
+      // 16-byte loads, (row, column) advanced incrementally instead of divided out per element
+      const float4* src = reinterpret_cast<const float4*>(xb + s0 * T);
+      const int nvec = FM_S * T / 4;
+      int e = 4 * threadIdx.x, r = e / T, c = e - r * T;   // T % 4 == 0: a vector never straddles two rows
+      for (int i = threadIdx.x; i < nvec; i += FM_THREADS) {
+        const float4 v = __ldg(src + i);
+        float* d = tile + r * pitch + c;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        c += 4 * FM_THREADS;
+        while (c >= T) { c -= T; ++r; }
+      }
+    } else {
+      // ragged strip / T not a multiple of 4 / chunked T: element loads, still coalesced along t
       const int nel = ns * tc;
+      int r = threadIdx.x / tc, c = threadIdx.x - r * tc;
       for (int i = threadIdx.x; i < nel; i += FM_THREADS) {
-        const int s = i / tc, t = i - s * tc;
-        tile[s * pitch + t] = __ldg(xb + (s0 + s) * T + t0 + t);
+        tile[r * pitch + c] = __ldg(xb + (s0 + r) * T + t0 + c);
+        c += FM_THREADS;
+        while (c >= tc) { c -= tc; ++r; }
       }
     }
     __syncthreads();
     const int sl = threadIdx.x & (FM_S - 1);
-    for (int t = threadIdx.x / FM_S; t < tc; t += FM_THREADS / FM_S) {
-      if (sl < ns) {
-        float v = tile[sl * pitch + t];
+    if (sl < ns) {
+      const float* tp = tile + sl * pitch;
+      float* yp = yb + (int64_t)(t0 + threadIdx.x / FM_S) * S + s0 + sl;
+      const int64_t ystep = (int64_t)(FM_THREADS / FM_S) * S;
+      for (int t = threadIdx.x / FM_S; t < tc; t += FM_THREADS / FM_S, yp += ystep) {
+        float v = tp[t];
         if (zs) v = (float)(((double)v - mean) * inv);
-        yb[(int64_t)(t0 + t) * S + s0 + sl] = v;
+        *yp = v;
       }
     }
     __syncthreads();

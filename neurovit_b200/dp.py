@@ -38,7 +38,7 @@ class NcclComm:
     # CTAs NCCL may use per collective (env NEUROVIT_NCCL_MAX_CTAS; NCCL_MAX_CTAS wins if the user set it): the
     # all-reduce runs UNDER backward, where every SM it takes is taken from the persistent GEMMs, and NVSwitch
     # bandwidth is reached with few CTAs
-    MAX_CTAS = int(os.environ.get("NCCL_MAX_CTAS", os.environ.get("NEUROVIT_NCCL_MAX_CTAS", "8")))
+    MAX_CTAS = int(os.environ.get("NCCL_MAX_CTAS", os.environ.get("NEUROVIT_NCCL_MAX_CTAS", "4")))
 
     def __init__(self, group=None):
         if not (dist.is_available() and dist.is_initialized()):

@@ -209,6 +209,23 @@ class GradStash:
 
 _STASH = GradStash()
 
+_SPARSE = {}
+
+
+def sparse_grad_zeros(slot, shape, dtype, device):
+    """A cached all-zero tensor for a gradient that is non-zero in token 0 of every sample only (cls-pooled head and
+    the token-wise block under it): the kernels overwrite the token-0 rows through raw pointers every step and
+    nothing else is ever written, so the 100 MB + 50 MB zero fills per step are paid once. Any torch-side in-place
+    write (a user hook, say) bumps the version counter and the buffer is cleared again."""
+    key = (slot, tuple(shape), dtype, str(device))
+    e = _SPARSE.get(key)
+    if e is not None and e[0]._version == e[1]:
+        return e[0]
+    t = torch.zeros(shape, device=device, dtype=dtype)
+    _SPARSE[key] = (t, t._version)
+    return t
+
+
 
 # ------------------------------------------------------------------------------- gradient sinks
 class GradSinks:
@@ -752,8 +769,8 @@ class FFBlockFn(torch.autograd.Function):
             dW2 = eng.wgrad(dy_act, _cls_rows(g, B, N), acc=GradAcc(w2, mode))
             da = eng.dgrad(dU, w1, out_dtype=eng.act)
             dW1 = eng.wgrad(dU, _cls_rows(a, B, N), acc=GradAcc(w1, mode))
-            dx = torch.zeros(B * N, D, device=dy.device, dtype=F32)
-            dxb = torch.zeros(B * N, D, device=dy.device, dtype=BF16) if mode == "bf16" else None
+            dx = sparse_grad_zeros("ff", (B * N, D), F32, dy.device)
+            dxb = sparse_grad_zeros("ff", (B * N, D), BF16, dy.device) if mode == "bf16" else None
             acc_g, acc_b = GradAcc(ln_w, mode), GradAcc(ln_b, mode)
             cs2 = torch.zeros(D, device=dy.device, dtype=F32)
             side = eng.side_drop_for(prev, seed, B, D)
@@ -951,8 +968,8 @@ class HeadFn(torch.autograd.Function):
         if fused:
             acc_w, acc_b = GradAcc(w, mode), torch.zeros(C, device=dev, dtype=F32)
             acc_g, acc_be = torch.zeros(D, device=dev, dtype=F32), torch.zeros(D, device=dev, dtype=F32)
-            dx = torch.zeros(B, N, D, device=dev, dtype=F32)            # cls pool: only token 0 gets gradient
-            dxb = torch.zeros(B, N, D, device=dev, dtype=BF16) if mode == "bf16" else None
+            dx = sparse_grad_zeros("head", (B, N, D), F32, dev)         # cls pool: only token 0 gets gradient
+            dxb = sparse_grad_zeros("head", (B, N, D), BF16, dev) if mode == "bf16" else None
             ops.head_bwd(dl, x, N * D, y, mean, rstd, ln_w.detach(), w.detach().float().contiguous(), dx, N * D, dxb,
                          N * D, acc_w.buf, acc_b, acc_g, acc_be, B, D, C)
             cs = torch.zeros(D, device=dev, dtype=F32)   # column sums of dx = sum of the cls rows (bias gradient of
@@ -965,8 +982,11 @@ class HeadFn(torch.autograd.Function):
         dy = ops.linear_f32(dl, w.detach(), w_kn=True)              # [B, D]
         dg = torch.zeros(D, device=dev, dtype=F32)
         dbeta = torch.zeros(D, device=dev, dtype=F32)
-        dx = torch.zeros(B, N, D, device=dev, dtype=F32)            # cls pool: only token 0 gets gradient
-        dxb = torch.zeros(B, N, D, device=dev, dtype=BF16) if mode == "bf16" else None
+        sparse = pool != "mean"
+        dx = sparse_grad_zeros("head", (B, N, D), F32, dev) if sparse else torch.zeros(B, N, D, device=dev, dtype=F32)
+        dxb = None
+        if mode == "bf16":
+            dxb = sparse_grad_zeros("head", (B, N, D), BF16, dev) if sparse else torch.zeros(B, N, D, device=dev, dtype=BF16)
         if pool == "mean":
             dpooled = torch.empty(B, D, device=dev, dtype=F32)
             ops.layernorm_bwd(dy, pooled, mean, rstd, ln_w.detach(), M=B, D=D, dx=dpooled, dgamma=dg, dbeta=dbeta)

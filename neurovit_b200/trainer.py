@@ -275,8 +275,6 @@ class DataParallelTrainer:
         if world > 1 and plist[0].is_cuda and os.environ.get("NEUROVIT_DP_NCCL", "own") != "torch":
             from . import dp, ops
             comm = dp.NcclComm(group)
-            # NCCL's CTAs need SMs of their own while they overlap backward: the persistent kernels leave them free
-            ops.set_sm_reserve(int(os.environ.get("NEUROVIT_SM_RESERVE", str(dp.NcclComm.MAX_CTAS))))
         self.buckets = FlatGradBuckets(plist, bucket_mb << 20, group, flatten_params=own_adamw, comm=comm)
         if comm is not None:
             comm.register(self.buckets.flat)
@@ -304,13 +302,27 @@ class DataParallelTrainer:
         self._graph = self._graph2 = self._graph_alt = None
         self._flip = False
         self._cuda = plist[0].is_cuda
+        # NCCL's CTAs need SMs of their own while the bucket all-reduces run under backward: the persistent kernels
+        # (GEMM, LayerNorm backward) launched during backward leave that many SMs free — a persistent grid that asked
+        # for every SM would have some of its CTAs queued behind the NCCL kernel for a whole extra wave.
+        self._sm_reserve = 0
+        if comm is not None and not self.buckets.defer:
+            from . import dp
+            self._sm_reserve = int(os.environ.get("NEUROVIT_SM_RESERVE", str(dp.NcclComm.MAX_CTAS)))
 
     def _fwd_bwd(self, inputs, labels):
         self.buckets.zero()
         out = self.model(inputs)
         loss = self.criterion(out, labels)
-        with SINKS.active(self.buckets.sink_views, self.buckets.sink_notify):
-            loss.backward()
+        if self._sm_reserve:
+            from . import ops
+            ops.set_sm_reserve(self._sm_reserve)
+        try:
+            with SINKS.active(self.buckets.sink_views, self.buckets.sink_notify):
+                loss.backward()
+        finally:
+            if self._sm_reserve:
+                ops.set_sm_reserve(0)
         return loss
 
     def _update(self):
@@ -403,6 +415,15 @@ class DataParallelTrainer:
         from . import _lib
         _lib.LAUNCHES.count += self._graph_launches
         return loss
+
+    def close(self):
+        """Release the captured graphs BEFORE the communicator: NCCL keeps a reference per captured collective and
+        ncclCommDestroy waits for them."""
+        self.reset_graph()
+        self._sloss = self._sloss_alt = None
+        if self._cuda:
+            torch.cuda.synchronize()
+        self.buckets.close()
 
     def reset_graph(self):
         """Drop the captured step (new batch shape, changed hyper-parameters): the next step() captures again."""

@@ -35,6 +35,7 @@ def main():
     dist.broadcast(ref0, src=0)
     assert torch.equal(flat, ref0), "parameters differ between ranks after DataParallelTrainer construction"
     assert len(tr.buckets.buckets) >= 3, "want several buckets in flight"
+    print(f"rank {rank}: replicas identical, {len(tr.buckets.buckets)} buckets", flush=True)
     # (2) N-rank averaged gradients == single-process full-batch gradients
     g = torch.Generator().manual_seed(5)
     per = 6
@@ -50,17 +51,18 @@ def main():
         torch.cuda.synchronize()
         worst = max(rel(p.grad, want[k]) for k, p in model.named_parameters())
         assert worst < 2e-3, f"rank {rank} step {it}: averaged gradient differs from the full-batch gradient ({worst:.2e})"
+        print(f"rank {rank}: step {it} ok ({worst:.1e})", flush=True)
     # every rank holds the same reduced buffer
     red = tr.buckets.flat.clone()
     dist.broadcast(red, src=0)
     assert rel(tr.buckets.flat, red) < 1e-6, "reduced gradient buffers differ between ranks"
     # (3) lr > 0: parameters stay in lock-step over several steps
-    tr2 = None
     tr.optimizer.lr = 1e-3
     tr.reset_graph()                       # hyper-parameters are baked into a captured graph: re-capture
     for it in range(3):
         tr.step(shard_batch(X, rank, world), shard_batch(Y, rank, world))
     torch.cuda.synchronize()
+    print(f"rank {rank}: optimizer steps done", flush=True)
     cur = tr.buckets.flat_params.clone()
     dist.broadcast(cur, src=0)
     assert torch.equal(tr.buckets.flat_params, cur), "parameters diverged between ranks after optimizer steps"
@@ -69,7 +71,8 @@ def main():
     if rank == 0:
         mode = f"graph={int(tr.use_graph)} two_graphs={int(tr._two_graphs)} own_nccl={int(tr.buckets.comm is not None)}"
         print(f"DP_OK {mode} buckets={len(tr.buckets.buckets)} losses={losses}", flush=True)
-    tr.buckets.close()
+    print(f"rank {rank}: closing", flush=True)
+    tr.close()
     dist.destroy_process_group()
 
 

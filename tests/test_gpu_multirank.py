@@ -26,6 +26,10 @@ def test_two_rank_gradients_match_full_batch(env, expect):
     port = 29500 + (os.getpid() % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_dp_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, **env})
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env={**os.environ, **env})
+    except subprocess.TimeoutExpired as e:
+        out = (e.stdout or b"").decode("utf-8", "replace")[-3000:] + (e.stderr or b"").decode("utf-8", "replace")[-3000:]
+        raise AssertionError("2-rank worker timed out; output so far:\n" + out)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DP_OK " + expect in r.stdout, r.stdout[-2000:]
