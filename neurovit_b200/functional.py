@@ -209,6 +209,42 @@ class GradStash:
 
 _STASH = GradStash()
 
+class _ZeroArena:
+    """Small fp32 accumulators (column sums, LayerNorm / bias gradients: a few KB each, ~20 per backward) carved out of
+    one zero-filled chunk instead of one fill kernel each. A region is handed out once and never reused, so it is
+    always freshly zero; a chunk is abandoned at a step boundary (reset) and whenever the stream's capture state
+    differs from the one it was filled under — a CUDA graph must contain the fill of every accumulator it uses."""
+    CHUNK = 1 << 16   # floats (256 KB)
+
+    def __init__(self):
+        self._cur = {}
+
+    def reset(self):
+        self._cur.clear()
+
+    def take(self, n, device):
+        n = int(n)
+        pad = (n + 31) // 32 * 32   # 128-byte slots: the kernels add 16-byte vectors into them
+        if pad > self.CHUNK // 4:
+            return torch.zeros(n, device=device, dtype=F32)
+        capturing = torch.cuda.is_current_stream_capturing() if torch.device(device).type == "cuda" else False
+        key = str(device)
+        cur = self._cur.get(key)
+        if cur is None or cur[2] != capturing or cur[1] + pad > self.CHUNK:
+            cur = [torch.zeros(self.CHUNK, device=device, dtype=F32), 0, capturing]
+            self._cur[key] = cur
+        off = cur[1]
+        cur[1] = off + pad
+        return cur[0][off:off + n]
+
+
+ZEROS = _ZeroArena()
+
+
+def zeros_f32(n, device):
+    return ZEROS.take(n, device)
+
+
 _SPARSE = {}
 
 
@@ -343,7 +379,7 @@ class Engine:
         out = torch.empty(M, K_in, device=dy.device, dtype=out_dtype)
         cs = None
         if want_colsum:
-            cs = colsum_acc.buf if colsum_acc is not None else torch.zeros(K_in, device=dy.device, dtype=F32)
+            cs = colsum_acc.buf if colsum_acc is not None else zeros_f32(K_in, dy.device)
         if drop is not None and drop[0] <= 0:
             drop = None
         if self.mode == "bf16":
@@ -387,7 +423,7 @@ class Engine:
     def bias_grad(self, dy, colsum=None):
         if colsum is not None:
             return colsum
-        out = torch.zeros(dy.shape[1], device=dy.device, dtype=F32)
+        out = zeros_f32(dy.shape[1], dy.device)
         ops.colsum(dy, out)
         return out
 
@@ -397,9 +433,13 @@ class Engine:
         mean = torch.empty(M, device=x.device, dtype=F32)
         rstd = torch.empty(M, device=x.device, dtype=F32)
         if "skip_ln" in AB_FLAGS and M >= 1024:   # measurement only (tools/fusion_ab.sh): WRONG numerics by design
-            if not AB_STATE.get(("ln", M, D)):
-                AB_STATE[("ln", M, D)] = True
-                y.zero_(); mean.zero_(); rstd.fill_(1.0)
+            # the first call's real output is handed out again afterwards: realistic values matter — with an all-zero
+            # operand the GEMMs draw so much less power that the whole step runs 17 % faster (profiles/r02_summary.md)
+            hit = AB_STATE.get(("ln", M, D, y.dtype))
+            if hit is not None:
+                return hit
+            ops.layernorm_fwd(x, weight.detach(), bias.detach(), y, M=M, D=D, mean=mean, rstd=rstd, eps=eps)
+            AB_STATE[("ln", M, D, y.dtype)] = (y, mean, rstd)
             return y, mean, rstd
         ops.layernorm_fwd(x, weight.detach(), bias.detach(), y, M=M, D=D, mean=mean, rstd=rstd, eps=eps)
         return y, mean, rstd
@@ -416,7 +456,7 @@ class Engine:
         if acc_g is not None and acc_b is not None:
             dg, db = acc_g.buf, acc_b.buf
             if want_colsum:
-                cs = torch.zeros(D, device=dev, dtype=F32)
+                cs = zeros_f32(D, dev)
         else:
             acc_g = acc_b = None
             z = torch.zeros(3 if want_colsum else 2, D, device=dev, dtype=F32)  # one fill for all accumulators
@@ -445,7 +485,7 @@ class Engine:
         sums (the bias gradient). dy fp32 [M, N]."""
         M, N = dy.shape
         out = torch.empty(M, N, device=dy.device, dtype=self.act)
-        cs = torch.zeros(N, device=dy.device, dtype=F32)
+        cs = zeros_f32(N, dy.device)
         ops.dropout(dy, p=drop[0], seed=drop[1], stream=drop[2], colsum=cs,
                     out_f32=out if self.act == F32 else None, out_bf16=out if self.act == BF16 else None)
         return out, cs
@@ -608,7 +648,7 @@ def _cls_branch_grad(eng, dy2, B, N, drop):
     The dropout mask of that site is indexed with the ORIGINAL row (row_mul = N)."""
     D = dy2.shape[1]
     out = torch.empty(B, D, device=dy2.device, dtype=eng.act)
-    cs = torch.zeros(D, device=dy2.device, dtype=F32)
+    cs = zeros_f32(D, dy2.device)
     p, seed, stream = drop
     ops.dropout(_cls_rows(dy2, B, N), p=max(p, 0.0), seed=seed, stream=stream, colsum=cs, row_mul=N,
                 out_f32=out if eng.act == F32 else None, out_bf16=out if eng.act == BF16 else None)
@@ -772,7 +812,7 @@ class FFBlockFn(torch.autograd.Function):
             dx = sparse_grad_zeros("ff", (B * N, D), F32, dy.device)
             dxb = sparse_grad_zeros("ff", (B * N, D), BF16, dy.device) if mode == "bf16" else None
             acc_g, acc_b = GradAcc(ln_w, mode), GradAcc(ln_b, mode)
-            cs2 = torch.zeros(D, device=dy.device, dtype=F32)
+            cs2 = zeros_f32(D, dy.device)
             side = eng.side_drop_for(prev, seed, B, D)
             ops.layernorm_bwd(da, x2, mean.view(B, N)[:, 0].contiguous(), rstd.view(B, N)[:, 0].contiguous(),
                               ln_w.detach(), M=B, D=D, xmap=(1, N, 0), dres=dy2, ld_dres=N * D, dx=dx, dxmap=(1, N, 0),
@@ -868,10 +908,11 @@ class PatchEmbedFn(torch.autograd.Function):
         patches = torch.empty(B * n, Kp, device=dev, dtype=eng.act)
         mean1 = torch.empty(B * n, device=dev, dtype=F32)
         rstd1 = torch.empty(B * n, device=dev, dtype=F32)
-        if "skip_gather" in AB_FLAGS:   # measurement only: the patch GEMM then reads whatever the buffer holds
-            patches.zero_() if not AB_STATE.get("gather") else None
-            AB_STATE["gather"] = True
-            mean1.zero_(); rstd1.fill_(1.0)
+        if "skip_gather" in AB_FLAGS and AB_STATE.get(("gather", B, n, Kp)) is not None:
+            patches, mean1, rstd1 = AB_STATE[("gather", B, n, Kp)]   # measurement only: the first call's real patches again
+        elif "skip_gather" in AB_FLAGS:
+            ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
+            AB_STATE[("gather", B, n, Kp)] = (patches, mean1, rstd1)
         else:
             ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
         if mode == "bf16":
@@ -919,8 +960,8 @@ class PatchEmbedFn(torch.autograd.Function):
             dlin_w = eng.wgrad(de_act, patches[:, :P])
             dP = torch.empty(B * n, Kp, device=dev, dtype=F32)
             ops.linear_f32(de, lin_w.detach(), w_kn=True, out=dP[:, :P])
-        dg1 = torch.zeros(P, device=dev, dtype=F32)
-        db1 = torch.zeros(P, device=dev, dtype=F32)
+        dg1 = zeros_f32(P, dev)
+        db1 = zeros_f32(P, dev)
         ops.patch_ln_param_grad(video, patch, dP, mean1, rstd1, dg1, db1)
         return None, dg1, db1, dlin_w, dlin_b, dg2, db2, dcls, dpos, None, None, None
 
@@ -966,22 +1007,22 @@ class HeadFn(torch.autograd.Function):
         dev = x.device
         dl = dlogits.float().contiguous()
         if fused:
-            acc_w, acc_b = GradAcc(w, mode), torch.zeros(C, device=dev, dtype=F32)
-            acc_g, acc_be = torch.zeros(D, device=dev, dtype=F32), torch.zeros(D, device=dev, dtype=F32)
+            acc_w, acc_b = GradAcc(w, mode), zeros_f32(C, dev)
+            acc_g, acc_be = zeros_f32(D, dev), zeros_f32(D, dev)
             dx = sparse_grad_zeros("head", (B, N, D), F32, dev)         # cls pool: only token 0 gets gradient
             dxb = sparse_grad_zeros("head", (B, N, D), BF16, dev) if mode == "bf16" else None
             ops.head_bwd(dl, x, N * D, y, mean, rstd, ln_w.detach(), w.detach().float().contiguous(), dx, N * D, dxb,
                          N * D, acc_w.buf, acc_b, acc_g, acc_be, B, D, C)
-            cs = torch.zeros(D, device=dev, dtype=F32)   # column sums of dx = sum of the cls rows (bias gradient of
+            cs = zeros_f32(D, dev)   # column sums of dx = sum of the cls rows (bias gradient of
             ops.batch_sum(dx, N * D, cs, B, D)           # the last block's down projection): no 100 MB colsum pass
             _STASH.put(dx, dxb, cs, cls_only=True)
             return dx, acc_g, acc_be, acc_w.result(), acc_b, None, None, None
         dw = ops.linear_f32(dl, y, x_km=True, w_kn=True)            # [C, D] = dl^T y
-        db = torch.zeros(C, device=dev, dtype=F32)
+        db = zeros_f32(C, dev)
         ops.colsum(dl, db)
         dy = ops.linear_f32(dl, w.detach(), w_kn=True)              # [B, D]
-        dg = torch.zeros(D, device=dev, dtype=F32)
-        dbeta = torch.zeros(D, device=dev, dtype=F32)
+        dg = zeros_f32(D, dev)
+        dbeta = zeros_f32(D, dev)
         sparse = pool != "mean"
         dx = sparse_grad_zeros("head", (B, N, D), F32, dev) if sparse else torch.zeros(B, N, D, device=dev, dtype=F32)
         dxb = None
@@ -994,7 +1035,7 @@ class HeadFn(torch.autograd.Function):
         else:
             ops.layernorm_bwd(dy, x, mean, rstd, ln_w.detach(), M=B, D=D, ld_x=N * D, dx=dx, ld_dx=N * D,
                               dx_bf16=dxb, ld_dxb=N * D, dgamma=dg, dbeta=dbeta)
-            cs = torch.zeros(D, device=dev, dtype=F32)
+            cs = zeros_f32(D, dev)
             ops.batch_sum(dx, N * D, cs, B, D)
             _STASH.put(dx, dxb, cs, cls_only=True)   # same contract as the fused cls head: zero outside token 0
             return dx, dg, dbeta, dw, db, None, None, None
@@ -1103,7 +1144,7 @@ class TemporalSeqFn(torch.autograd.Function):
         F = params[4].shape[0]
         x = x.float().contiguous()
         dev = x.device
-        ident = [torch.eye(2, device=dev, dtype=F32), torch.zeros(2, device=dev, dtype=F32)]  # unused head slot
+        ident = [torch.eye(2, device=dev, dtype=F32), zeros_f32(2, dev)]  # unused head slot
         packed = pack_temporal_params(list(params) + ident)
         seq = torch.empty(B, T, 2, device=dev, dtype=F32)
         saved = torch.empty(B, T * 4, device=dev, dtype=F32)
@@ -1152,6 +1193,6 @@ class SmallLinearFn(torch.autograd.Function):
         dw = ops.linear_f32(dy2, x2, x_km=True, w_kn=True)
         db = None
         if ctx.has_bias:
-            db = torch.zeros(w.shape[0], device=dy.device, dtype=F32)
+            db = zeros_f32(w.shape[0], dy.device)
             ops.colsum(dy2, db)
         return dx, dw, db

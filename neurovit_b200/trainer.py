@@ -311,6 +311,9 @@ class DataParallelTrainer:
             self._sm_reserve = int(os.environ.get("NEUROVIT_SM_RESERVE", str(dp.NcclComm.MAX_CTAS)))
 
     def _fwd_bwd(self, inputs, labels):
+        if self._cuda:
+            from .functional import ZEROS
+            ZEROS.reset()   # accumulators of this step come from chunks filled inside this step (or this capture)
         self.buckets.zero()
         out = self.model(inputs)
         loss = self.criterion(out, labels)

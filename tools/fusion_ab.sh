@@ -5,9 +5,14 @@
 #   skip_gather  no patch_gather_ln kernel (gather + LN fused into the patch GEMM's operand staging at zero cost)
 # Usage (GPU box): bash tools/fusion_ab.sh > gpurun_out/fusion_ab.txt
 cd ${GRAFT_REPO_ROOT:-.}
+cat > /tmp/_ab_line.py <<'PY'
+import json, sys
+d = json.loads(sys.stdin.read())
+print(f"{d['ms_per_step']:.3f} ms/step  {d['value']:.0f} vol/s  sm {d['clocks']['sm_mhz']} MHz {d['clocks']['reasons']}")
+PY
 for rep in 1 2; do
 for ab in "" skip_ln skip_gather skip_ln,skip_gather; do
   line=$(NEUROVIT_AB=$ab timeout 300 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --no-kernel-events --no-secondary 2>/dev/null | tail -n 1)
-  echo "AB='${ab}' rep $rep: $(echo "$line" | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(f"{d[\"ms_per_step\"]:.3f} ms/step  {d[\"value\"]:.0f} vol/s  sm {d[\"clocks\"][\"sm_mhz\"]} MHz {d[\"clocks\"][\"reasons\"]}")')"
+  echo "AB='${ab}' rep $rep: $(echo "$line" | python /tmp/_ab_line.py)"
 done
 done
