@@ -235,7 +235,9 @@ int nv_fmri_deinterleave(const float* x, float* y, int B, int64_t S, int T, void
  *   nv_dp_load(path)            dlopen NCCL (path NULL/"" = "libnccl.so.2"); 4 (not initialised) if unavailable
  *   nv_dp_nccl_version()        NCCL version code (22809 = 2.28.9), 0 when not loaded   [returns the value]
  *   nv_dp_unique_id(out128)     rank 0: 128-byte id (HOST pointer) to hand to every rank
- *   nv_dp_init(uid128, r, w)    collective: create the communicator of rank r of w on the current device
+ *   nv_dp_init(uid128, r, w, c) collective: create the communicator of rank r of w on the current device; c > 0 caps
+ *                               the CTAs of its collectives (ncclConfig_t.maxCTAs: per communicator, unlike NCCL_MAX_CTAS,
+ *                               which NCCL reads once per process)
  *   nv_dp_register(buf, bytes)  register a long-lived DEVICE buffer (the flat gradient buffer): zero-copy / NVLS
  *   nv_dp_allreduce_bucket      in place over `count` elements; dtype 0 = fp32, 1 = bf16; op 0 = sum, 1 = average
  *   nv_dp_world(rank*, world*)  HOST int pointers
@@ -246,7 +248,7 @@ int nv_dp_load(const char* path);
 int nv_set_sm_reserve(int n);
 int nv_dp_nccl_version(void);
 int nv_dp_unique_id(void* out128);
-int nv_dp_init(const void* uid128, int rank, int world);
+int nv_dp_init(const void* uid128, int rank, int world, int max_ctas);
 int nv_dp_register(void* buf, int64_t bytes);
 int nv_dp_allreduce_bucket(void* buf, int64_t count, int dtype, int op, void* stream);
 int nv_dp_world(int* rank, int* world);

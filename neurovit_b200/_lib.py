@@ -60,7 +60,7 @@ SIGNATURES = {
     "nv_dp_load": [_p],
     "nv_dp_nccl_version": [],
     "nv_dp_unique_id": [_p],
-    "nv_dp_init": [_p, _i, _i],
+    "nv_dp_init": [_p, _i, _i, _i],
     "nv_dp_register": [_p, _l],
     "nv_dp_allreduce_bucket": [_p, _l, _i, _i, _p],
     "nv_dp_world": [_p, _p],

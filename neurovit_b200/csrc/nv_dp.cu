@@ -19,12 +19,27 @@ namespace {
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef void* ncclComm_p;
 typedef int ncclResult;  // 0 = ncclSuccess
+// ncclConfig_t as NCCL 2.17 declared it; newer libraries accept it (they look at .version and default the fields
+// added later). Per-communicator settings: unlike the NCCL_* environment variables, which the library reads once per
+// process — PyTorch's own communicator has usually done that already — these cannot be pre-empted.
+struct ncclConfig_v21700 {
+  size_t size;
+  unsigned int magic;
+  unsigned int version;
+  int blocking;
+  int cgaClusterSize;
+  int minCTAs;
+  int maxCTAs;
+  const char* netName;
+};
+constexpr int NCCL_UNDEF_INT = -2147483647 - 1;
 enum { NCCL_SUM = 0, NCCL_AVG = 4, NCCL_FLOAT32 = 7, NCCL_BFLOAT16 = 9 };
 
 struct NcclApi {
   void* lib = nullptr;
   ncclResult (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
   ncclResult (*CommInitRank)(ncclComm_p*, int, ncclUniqueId_t, int) = nullptr;
+  ncclResult (*CommInitRankConfig)(ncclComm_p*, int, ncclUniqueId_t, int, void*) = nullptr;
   ncclResult (*CommDestroy)(ncclComm_p) = nullptr;
   ncclResult (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_p, cudaStream_t) = nullptr;
   ncclResult (*CommRegister)(ncclComm_p, void*, size_t, void**) = nullptr;
@@ -77,6 +92,7 @@ int nv_dp_load(const char* path) {
     nv_set_error("nv_dp_load: NCCL library lacks a required symbol");
     return NV_ERR_NOT_INIT;
   }
+  sym(lib, "ncclCommInitRankConfig", a.CommInitRankConfig);   // optional (NCCL >= 2.14; maxCTAs since 2.17)
   sym(lib, "ncclCommRegister", a.CommRegister);      // optional (NCCL >= 2.19)
   sym(lib, "ncclCommDeregister", a.CommDeregister);
   g_api = a;
@@ -102,7 +118,9 @@ int nv_dp_unique_id(void* out128) {
 }
 
 // Create this process's communicator on the CURRENT device (collective: every rank calls it). One per device.
-int nv_dp_init(const void* uid128, int rank, int world) {
+// max_ctas > 0: the communicator's collectives use at most that many CTAs (ncclConfig_t.maxCTAs) — the all-reduce
+// runs under backward, where every SM it takes is taken from the persistent GEMMs.
+int nv_dp_init(const void* uid128, int rank, int world, int max_ctas) {
   NV_REQUIRE(uid128 != nullptr && world >= 1 && rank >= 0 && rank < world, "nv_dp_init: bad rank %d / world %d", rank, world);
   if (g_api.lib == nullptr) { nv_set_error("nv_dp: NCCL not loaded (nv_dp_load)"); return NV_ERR_NOT_INIT; }
   const int d = cur_dev();
@@ -111,8 +129,23 @@ int nv_dp_init(const void* uid128, int rank, int world) {
   ncclUniqueId_t id;
   memcpy(id.internal, uid128, 128);
   ncclComm_p comm = nullptr;
-  ncclResult r = g_api.CommInitRank(&comm, world, id, rank);
-  if (r != 0) return nccl_fail(r, "ncclCommInitRank");
+  ncclResult r;
+  int ver = 0;
+  if (max_ctas > 0 && g_api.CommInitRankConfig != nullptr && g_api.GetVersion(&ver) == 0 && ver >= 21700) {
+    ncclConfig_v21700 cfg;
+    cfg.size = sizeof(cfg); cfg.magic = 0xcafebeef; cfg.version = 21700;
+    cfg.blocking = NCCL_UNDEF_INT; cfg.cgaClusterSize = NCCL_UNDEF_INT; cfg.minCTAs = NCCL_UNDEF_INT;
+    cfg.maxCTAs = max_ctas; cfg.netName = nullptr;
+    r = g_api.CommInitRankConfig(&comm, world, id, rank, &cfg);
+    if (r != 0) {   // argument validation fails identically (and immediately) on every rank: plain init instead
+      comm = nullptr;
+      r = g_api.CommInitRank(&comm, world, id, rank);
+      if (r != 0) return nccl_fail(r, "ncclCommInitRank (after ncclCommInitRankConfig was rejected)");
+    }
+  } else {
+    r = g_api.CommInitRank(&comm, world, id, rank);
+    if (r != 0) return nccl_fail(r, "ncclCommInitRank");
+  }
   g_comm[d].comm = comm; g_comm[d].rank = rank; g_comm[d].world = world; g_comm[d].nreg = 0;
   return NV_OK;
 }

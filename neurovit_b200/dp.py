@@ -35,17 +35,16 @@ def _find_nccl() -> str:
 class NcclComm:
     """`NcclComm(group)` creates the library's communicator for this rank on the current CUDA device."""
 
-    # CTAs NCCL may use per collective (env NEUROVIT_NCCL_MAX_CTAS; NCCL_MAX_CTAS wins if the user set it): the
-    # all-reduce runs UNDER backward, where every SM it takes is taken from the persistent GEMMs, and NVSwitch
-    # bandwidth is reached with few CTAs
-    MAX_CTAS = int(os.environ.get("NCCL_MAX_CTAS", os.environ.get("NEUROVIT_NCCL_MAX_CTAS", "4")))
+    # CTAs this communicator's collectives may use (env NEUROVIT_NCCL_MAX_CTAS; ncclConfig_t.maxCTAs — NOT the
+    # NCCL_MAX_CTAS environment variable, which NCCL reads once per process and PyTorch's own communicator has usually
+    # consumed already): the all-reduce runs UNDER backward, where every SM it takes is taken from the persistent GEMMs
+    MAX_CTAS = int(os.environ.get("NEUROVIT_NCCL_MAX_CTAS", "4"))
 
     def __init__(self, group=None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("NcclComm needs an initialised torch.distributed process group to exchange the NCCL id")
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        os.environ.setdefault("NCCL_MAX_CTAS", str(self.MAX_CTAS))
         path = _find_nccl()
         _lib.call("nv_dp_load", ctypes.c_char_p(path.encode()) if path else None)
         uid = ctypes.create_string_buffer(128)
@@ -54,7 +53,7 @@ class NcclComm:
         box = [bytes(uid.raw)]
         dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self._uid = ctypes.create_string_buffer(box[0], 128)
-        _lib.call("nv_dp_init", self._uid, self.rank, self.world)
+        _lib.call("nv_dp_init", self._uid, self.rank, self.world, self.MAX_CTAS)
         self.version = _lib.load().nv_dp_nccl_version()
         self._alive = True
 
