@@ -96,3 +96,37 @@ def test_neuroencoder_rejects_an_unknown_training_dim(tmp_path):
     m.config["TRAINING_DIM"] = 5
     with pytest.raises(ValueError, match="TRAINING_DIM must be 3 or 4"):
         m(torch.zeros(1, 16, 16, 16))
+
+
+def test_zero_arena_hands_out_disjoint_aligned_regions():
+    """functional.ZEROS: small fp32 accumulators carved from one zero-filled chunk — every region handed out once,
+    128-byte slots, a fresh chunk after reset() and when the request does not fit."""
+    from neurovit_b200 import functional as Fn
+    Fn.ZEROS.reset()
+    a = Fn.zeros_f32(10, "cpu")
+    b = Fn.zeros_f32(1024, "cpu")
+    c = Fn.zeros_f32(3, "cpu")
+    assert a.shape == (10,) and b.shape == (1024,) and c.shape == (3,)
+    assert float(a.abs().sum() + b.abs().sum() + c.abs().sum()) == 0.0
+    assert b.data_ptr() - a.data_ptr() == 128 and c.data_ptr() - b.data_ptr() == 4096   # 32-float slots, in order
+    a.fill_(1.0)
+    b.fill_(2.0)
+    assert float(c.sum()) == 0.0 and float(Fn.zeros_f32(10, "cpu").sum()) == 0.0          # neighbours untouched
+    big = Fn.zeros_f32(Fn.ZEROS.CHUNK, "cpu")                                             # larger than a chunk share: own tensor
+    assert big.numel() == Fn.ZEROS.CHUNK and float(big.sum()) == 0.0
+    Fn.ZEROS.reset()
+    d = Fn.zeros_f32(10, "cpu")
+    assert d.data_ptr() != a.data_ptr() and float(d.sum()) == 0.0                         # a new chunk after a step boundary
+    # exhaust a chunk: the next request starts a new one instead of wrapping around
+    n = Fn.ZEROS.CHUNK // 4
+    ptrs = {Fn.zeros_f32(n, "cpu").data_ptr() for _ in range(6)}
+    assert len(ptrs) == 6
+
+
+def test_sparse_grad_zeros_is_cached_and_recleared_after_an_in_place_write():
+    from neurovit_b200 import functional as Fn
+    t = Fn.sparse_grad_zeros("test", (4, 3, 8), torch.float32, "cpu")
+    assert Fn.sparse_grad_zeros("test", (4, 3, 8), torch.float32, "cpu") is t           # same buffer, no new fill
+    t.add_(1.0)                                                                           # a torch-side write bumps the version
+    u = Fn.sparse_grad_zeros("test", (4, 3, 8), torch.float32, "cpu")
+    assert u is not t and float(u.abs().sum()) == 0.0
