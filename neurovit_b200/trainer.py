@@ -272,7 +272,15 @@ class DataParallelTrainer:
         own_adamw = optimizer is None and plist[0].is_cuda and os.environ.get("NEUROVIT_TORCH_ADAMW") != "1"
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         comm = None
-        if world > 1 and plist[0].is_cuda and os.environ.get("NEUROVIT_DP_NCCL", "own") != "torch":
+        # Which all-reduce: "own" = the library's communicator, buckets reduced under backward inside the step's graph;
+        # "torch" = torch.distributed, one all-reduce of the whole buffer between two graphs. Measured (profiles/
+        # r02_summary.md §6): at 2 ranks the overlapped path wins (9.34 vs 9.45 ms/step); at 8 ranks NCCL confined to the
+        # few CTAs that backward can spare is too slow to finish inside backward and the exposed full-speed all-reduce
+        # wins (9.54 vs 9.87). "auto" (default) picks accordingly.
+        which = os.environ.get("NEUROVIT_DP_NCCL", "auto")
+        if which == "auto":
+            which = "own" if world == 2 else "torch"
+        if world > 1 and plist[0].is_cuda and which == "own":
             from . import dp, ops
             comm = dp.NcclComm(group)
         self.buckets = FlatGradBuckets(plist, bucket_mb << 20, group, flatten_params=own_adamw, comm=comm)

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("env,expect", [
-    ({}, "graph=1 two_graphs=0 own_nccl=1"),                                   # the benchmarked path: NCCL inside ONE graph
+    ({}, "graph=1 two_graphs=0 own_nccl=1"),                                   # the default at 2 ranks: NCCL inside ONE graph
     ({"DP_TEST_GRAPH": "0"}, "graph=0 two_graphs=0 own_nccl=1"),                # eager, bucketed, own communicator
     ({"NEUROVIT_DP_NCCL": "torch"}, "graph=1 two_graphs=1 own_nccl=0"),         # torch.distributed: two graphs + one all-reduce
     ({"NEUROVIT_DP_NCCL": "torch", "DP_TEST_GRAPH": "0"}, "graph=0 two_graphs=0 own_nccl=0"),
