@@ -70,7 +70,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled every 50 ms during the timed region (a 20-step region is < 200 ms)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -79,7 +79,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()

@@ -459,3 +459,37 @@ def test_predrawn_and_inline_dropout_bits_give_identical_results():
     assert torch.equal(results[0][0], results[1][0])
     for k in results[0][1]:
         assert rel(results[0][1][k], results[1][1][k]) < 1e-4, k   # split-K / column-sum atomics reorder
+
+
+def test_trainer_load_state_dict_refreshes_bf16_copies_and_recaptures():
+    """A checkpoint loaded into a live graphed trainer (trainer.load_state_dict): the next step must run on the loaded
+    weights — bf16 operand copies re-cast, the captured graph dropped, optimizer hyper-parameters and moments
+    restored — i.e. continue exactly like a fresh trainer built from that checkpoint."""
+    import copy
+    from neurovit_b200.trainer import DataParallelTrainer
+    torch.manual_seed(51)
+    ctor = dict(image_size=16, image_patch_size=8, frames=16, frame_patch_size=8, num_classes=2, dim=128, depth=2,
+                heads=2, mlp_dim=256, channels=1, dim_head=64)
+    x = torch.randn(8, 1, 16, 16, 16, device=DEV)
+    y = torch.randint(0, 2, (8,), device=DEV)
+    # trainer A: two steps, then checkpoint
+    ma = ViT(**ctor).to(DEV)
+    ta = DataParallelTrainer(ma, lr=1e-3, graph=True)
+    for _ in range(2):
+        ta.step(x, y)
+    torch.cuda.synchronize()
+    model_sd = copy.deepcopy(ma.state_dict())
+    opt_sd = copy.deepcopy(ta.optimizer.state_dict())
+    la = ta.step(x, y).item()                      # what the third step gives from that checkpoint
+    # trainer B: different weights and hyper-parameters, already captured; then the checkpoint is loaded into it
+    torch.manual_seed(52)
+    mb = ViT(**ctor).to(DEV)
+    tb = DataParallelTrainer(mb, lr=5e-2, weight_decay=0.3, graph=True)
+    tb.step(x, y)
+    tb.load_state_dict(model_sd, opt_sd)
+    assert tb.optimizer.lr == 1e-3 and tb.optimizer.t == 2
+    lb = tb.step(x, y).item()
+    torch.cuda.synchronize()
+    assert abs(la - lb) < 2e-3, (la, lb)
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert (pa - pb).abs().max().item() < 1e-3 + 2e-3 * pa.abs().max().item(), k
