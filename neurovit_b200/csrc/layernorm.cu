@@ -297,6 +297,9 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
     }
   };
   fetch_stats(0);
+  // effective seed of the inline draw, read ONCE: inside the loop the multiply on the freshly loaded epoch stalled every
+  // iteration on a global load (ncu: IMAD ... 0x7f4a7c15 on long_sb) — even when the bits are pre-drawn and no seed is used
+  const uint64_t side_seed = (side_thr != 0 && side_bits == nullptr) ? nv_seed(side_seed_host, side_epoch) : 0ull;
   for (int it = 0; it < iters; ++it) {
     const int r0 = (it * gridDim.x + blockIdx.x) * LNP_ROWS;
     if (r0 >= M) break;  // uniform across the CTA
@@ -359,7 +362,6 @@ ln_bwd_pipe_kernel(const DyT* __restrict__ dy, int64_t ld_dy, RowMap dymap, cons
 #pragma unroll
     for (int k = 0; k < LNP_ROWS; ++k) keep4[k] = 0xFu;
     if (side_thr != 0) {
-      const uint64_t side_seed = nv_seed(side_seed_host, side_epoch);
       static_assert(LNP_ROWS == 2, "pair exchange below assumes two rows per iteration");
       const int rmine = min(r0 + (c & 1), M - 1);
       const uint64_t grp = ((uint64_t)dxmap(rmine) * D + 4 * (c & ~1)) >> 3;
