@@ -199,6 +199,10 @@ int nv_counter_add(float* counter, float inc, void* stream);
  * a training step captured in a CUDA graph ends with nv_rng_epoch_advance so each replay draws new masks even
  * though the host-drawn seeds are baked into the graph. Forward and backward of a step share the epoch. */
 int nv_rng_epoch_advance(void* stream);
+/* Current value of that counter, copied to *out_host (synchronises the stream). With it the keep bits of any site are
+ * a closed-form function of (seed, epoch, stream, element index): oracle/rng_oracle.py restates it in numpy and
+ * tests/test_gpu_kernels.py pins nv_dropout_bits / nv_dropout to it bit for bit. */
+int nv_rng_epoch_get(unsigned long long* out_host, void* stream);
 
 /* ---- 4D temporal head -------------------------------------------------------------------------------
  * replaces: TemporalTransformer (nn.TransformerEncoderLayer(d_model=2, nhead=2, batch_first=True),

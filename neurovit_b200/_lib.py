@@ -31,6 +31,7 @@ SIGNATURES = {
     "nv_adamw_flat": [_p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _p],
     "nv_counter_add": [_p, _f, _p],
     "nv_rng_epoch_advance": [_p],
+    "nv_rng_epoch_get": [_p, _p],
     "nv_dropout": [_p, _l, _p, _l, _p, _l, _p, _l, _p, _i, _i, _f, _l, _i, _i, _p],
     "nv_gemm_f32": [_i, _i, _i, _i, _i, _p, _l, _l, _l, _l, _p, _l, _l, _l, _l, _p, _l, _l, _l,
                     _p, _p, _l, _p, _l, _p, _l, _i, _i, _f, _p],
@@ -125,7 +126,7 @@ def require_device(device_index: int) -> None:
 
 class _LaunchCounter:
     """Counts the CUDA kernels launched through the C ABI (bench.py reports it as `gpu_launches`)."""
-    KERNELS_PER_CALL = {"nv_attention_bwd": 2, "nv_version": 0, "nv_device_check": 0, "nv_dp_load": 0, "nv_set_sm_reserve": 0,
+    KERNELS_PER_CALL = {"nv_attention_bwd": 2, "nv_version": 0, "nv_rng_epoch_get": 0, "nv_device_check": 0, "nv_dp_load": 0, "nv_set_sm_reserve": 0,
                         "nv_dp_nccl_version": 0, "nv_dp_unique_id": 0, "nv_dp_init": 0, "nv_dp_register": 0,
                         "nv_dp_world": 0, "nv_dp_destroy": 0}
 

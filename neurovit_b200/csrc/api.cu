@@ -24,6 +24,7 @@ int nv_adamw_flat_launch(float* p, const float* g, float* m, float* v, bf16* p_b
                          float beta2, float eps, float weight_decay, int step, const float* step_dev,
                          cudaStream_t stream);
 int nv_rng_epoch_advance_launch(cudaStream_t stream);
+int nv_rng_epoch_read(uint64_t* out, cudaStream_t stream);
 int nv_counter_add_launch(float* counter, float inc, cudaStream_t stream);
 int nv_dropout_launch(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32,
                       int64_t ld_f32, bf16* out_bf16, int64_t ld_bf16, float* colsum, int M, int N, float p,
@@ -130,6 +131,9 @@ int nv_adamw_flat(float* p, const float* g, float* m, float* v, void* p_bf16, in
                               ST(stream));
 }
 int nv_rng_epoch_advance(void* stream) { return nv_rng_epoch_advance_launch(ST(stream)); }
+int nv_rng_epoch_get(unsigned long long* out_host, void* stream) {
+  return nv_rng_epoch_read(reinterpret_cast<uint64_t*>(out_host), ST(stream));
+}
 int nv_counter_add(float* counter, float inc, void* stream) { return nv_counter_add_launch(counter, inc, ST(stream)); }
 
 int nv_dropout(const float* in, int64_t ld_in, const float* residual, int64_t ld_res, float* out_f32, int64_t ld_f32,

@@ -243,10 +243,7 @@ __global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t n_words,
                                     uint32_t stream_id, const uint64_t* epoch) {
   const uint64_t seed = nv_seed(seed_host, epoch);
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v |= nv_keep_bits8(seed, (uint64_t)(4 * w + k), stream_id, thr) << (8 * k);
-    out[w] = v;
+    out[w] = nv_keep_bits32(seed, (uint64_t)w, stream_id, thr);   // = four nv_keep_bits8 groups, one per byte
   }
 }
 

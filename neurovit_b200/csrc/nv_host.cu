@@ -128,6 +128,15 @@ int nv_rng_epoch_advance_launch(cudaStream_t stream) {
   return NV_OK;
 }
 
+int nv_rng_epoch_read(uint64_t* out, cudaStream_t stream) {
+  NV_REQUIRE(out != nullptr, "rng epoch: null output");
+  const uint64_t* e = nv_rng_epoch_dev();
+  NV_REQUIRE(e != nullptr, "rng epoch: allocation failed");
+  NV_CUDA(cudaMemcpyAsync(out, e, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  NV_CUDA(cudaStreamSynchronize(stream));
+  return NV_OK;
+}
+
 int nv_counter_add_launch(float* counter, float inc, cudaStream_t stream) {
   NV_REQUIRE(counter != nullptr, "counter_add: null pointer");
   counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);

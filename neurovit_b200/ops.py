@@ -146,6 +146,14 @@ def adamw_flat(p, g, m, v, p_bf16, *, lr, beta1, beta2, eps, weight_decay, step,
               float(beta2), float(eps), float(weight_decay), int(step), _ptr(step_dev), _stream())
 
 
+def rng_epoch() -> int:
+    """The device-side dropout epoch right now (synchronises the current stream): with (seed, epoch, site stream,
+    element index) every keep bit is a closed form — oracle/rng_oracle.py."""
+    out = ctypes.c_ulonglong(0)
+    _lib.call("nv_rng_epoch_get", ctypes.byref(out), _stream())
+    return int(out.value)
+
+
 def dropout(x, *, p, seed, stream, residual=None, out_f32=None, out_bf16=None, colsum=None, row_mul=1):
     """v = x * keep / (1 - p) with the (seed, stream, row * N + col) mask of the GEMM epilogues; out = v (+ residual);
     colsum += column sums of v. x: fp32 [M, N] (unit inner stride), N % 8 == 0."""

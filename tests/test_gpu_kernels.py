@@ -551,6 +551,38 @@ def test_dropout_kernel_mask_statistics_and_determinism():
     assert torch.equal(out, x) and rel_err(cs, x.double().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("p", [0.1, 0.25, 0.5, 0.9])
+def test_keep_bits_match_the_numpy_contract_bit_for_bit(p):
+    """Integer work, pinned bit-exact: nv_dropout_bits (four Philox calls per 32-bit word, byte-transposed, bit-sliced
+    compare) and the inline draw of nv_dropout (one call per 8 elements) both equal oracle/rng_oracle.py, which states
+    the contract on explicitly assembled 16-bit uniforms (generator pinned to Random123's known-answer vectors in
+    tests/test_oracle.py)."""
+    import numpy as np
+    from oracle import rng_oracle as R
+    seed, stream = 0x1F2E3D4C5B6A7988 >> 2, 7
+    epoch = ops.rng_epoch()
+    n_groups = 4 * 5003                                  # ragged against the kernel's grid stride
+    bits = torch.zeros(n_groups, device=DEV, dtype=torch.uint8)
+    ops.dropout_bits(bits, p=p, seed=seed, stream=stream)
+    want = R.dropout_bits(n_groups, p, seed, stream, epoch=epoch)
+    assert np.array_equal(bits.cpu().numpy(), want)
+    # element-indexed site drawn inline, incl. the row multiplier of the cls-row paths (index = row * row_mul * N + col)
+    M, N = 37, 264
+    ones = torch.ones(M, N, device=DEV)
+    for row_mul in (1, 5):
+        out = torch.empty_like(ones)
+        ops.dropout(ones, p=p, seed=seed, stream=stream, out_f32=out, row_mul=row_mul)
+        keep = (out != 0).cpu().numpy()
+        assert np.array_equal(keep, R.keep_mask(M, N, p, seed, stream, epoch=epoch, row_mul=row_mul))
+        ks = np.float32(65536.0) / np.float32(65536 - R.threshold(p))   # nv_dropout_keep_scale, in fp32
+        assert np.array_equal(out.cpu().numpy(), np.where(keep, ks, np.float32(0)))
+    # the epoch enters the seed: advance it and the same site draws the oracle's next-epoch bits
+    ops.rng_epoch_advance()
+    assert ops.rng_epoch() == epoch + 1
+    ops.dropout_bits(bits, p=p, seed=seed, stream=stream)
+    assert np.array_equal(bits.cpu().numpy(), R.dropout_bits(n_groups, p, seed, stream, epoch=epoch + 1))
+
+
 def test_gemm_epilogue_dropout_matches_elementwise_mask():
     """The three GEMM epilogues draw the same (seed, stream, row * N + col) mask as nv_dropout."""
     torch.manual_seed(12)

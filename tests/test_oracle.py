@@ -112,3 +112,61 @@ def test_neuroencoder_4d_oracle(tmp_path):
         # any two fp32 evaluation orders. Well-conditioned gradients are held to 1e-3.
         tol = 1e-3 if ("norm2" in k or "projection_head" in k) else 0.2
         assert rel(gr, g["grad." + k]) < tol, k
+
+
+# ---------------------------------------------------------------------------- dropout keep-bit contract (rng_oracle)
+from oracle import rng_oracle as R  # noqa: E402
+
+# Random123 (D. E. Shaw Research) examples/kat_vectors, lines "philox4x32 <rounds> <ctr x4> <key x2> <expected x4>"
+PHILOX_KAT = [
+    (7, [0, 0, 0, 0], [0, 0], [0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48]),
+    (10, [0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+    (10, [0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+    (10, [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+     [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+]
+
+
+@pytest.mark.parametrize("rounds,ctr,key,want", PHILOX_KAT)
+def test_philox_known_answer_vectors(rounds, ctr, key, want):
+    assert R.philox4x32_raw(ctr, key, rounds) == want
+
+
+def test_philox_vectorised_matches_scalar():
+    rng = np.random.default_rng(3)
+    seed = int(rng.integers(0, 1 << 62))
+    idx = np.concatenate([np.arange(5, dtype=np.uint64), rng.integers(0, 1 << 40, 20).astype(np.uint64),
+                          np.array([(1 << 32) - 1, 1 << 32, (1 << 45) + 7], dtype=np.uint64)])
+    got = np.stack(R.philox4x32(seed, idx, 5), axis=1)
+    for row, i in zip(got, idx):
+        assert row.tolist() == R.philox_scalar(seed, int(i), 5)
+
+
+@pytest.mark.parametrize("thr", [0, 1, 255, 256, 6554, 0x8000, 0xFFFE, 0xFFFF])
+def test_bitsliced_compare_equals_explicit_uniform_compare(thr):
+    """The kernels evaluate u_j >= thr plane by plane (nv_keep_bits8); the contract is stated on explicit uniforms."""
+    seed, stream = 0x1234_5678_9ABC_DEF0, 3
+    groups = np.arange(300, dtype=np.uint64)
+    want = R.keep_bits8(seed, groups, stream, thr)
+    words = np.stack(R.philox4x32(seed, groups, stream), axis=1)
+    got = [R.bitsliced_keep_bits8([int(v) for v in w], thr) for w in words]
+    assert got == want.tolist()
+    if thr == 0:
+        assert all(b == 0xFF for b in got)
+
+
+def test_keep_rate_and_independence_of_lanes():
+    thr = R.threshold(0.1)
+    assert thr == 6554 and abs(R.keep_scale(thr) - 65536 / (65536 - 6554)) < 1e-12
+    bits = R.dropout_bits(1 << 17, 0.1, seed=42, stream=1)
+    lanes = ((bits[:, None] >> np.arange(8, dtype=np.uint8)[None, :]) & 1).astype(np.float64)   # [groups, 8]
+    n = lanes.size
+    p_keep = 1 - thr / 65536
+    assert abs(lanes.mean() - p_keep) < 4 * np.sqrt(p_keep * (1 - p_keep) / n)
+    # every lane has the right marginal, and neighbouring lanes of a call are uncorrelated
+    per_lane = lanes.mean(axis=0)
+    assert np.all(np.abs(per_lane - p_keep) < 5 * np.sqrt(p_keep * (1 - p_keep) / lanes.shape[0]))
+    c = np.corrcoef(lanes.T)
+    assert np.abs(c - np.eye(8)).max() < 5 / np.sqrt(lanes.shape[0])
+    # the epoch moves the seed: same site, next step, different bits
+    assert not np.array_equal(bits[:64], R.dropout_bits(64, 0.1, seed=42, stream=1, epoch=1))
