@@ -55,13 +55,18 @@ def _deps_mtime() -> float:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link the shared library. Returns its path.
     NV_PROFILE=1 / NV_DEBUG_PROGRESS=1 build an instrumented variant next to the product library
-    (libneurovit_b200_prof.so, objects under build/prof/); load it with NEUROVIT_LIB=<path>."""
+    (libneurovit_b200_prof.so, objects under build/prof/); NV_VARIANT=<name> NV_DEFINES="-D..." builds an A/B variant
+    (libneurovit_b200_<name>.so). Load either with NEUROVIT_LIB=<path>."""
     nvcc = _nvcc()
     hdr_mtime = _deps_mtime()
     extra = ["-DNV_PROFILE"] if os.environ.get("NV_PROFILE") == "1" else []  # in-kernel phase clocks (tools/attn_phases.py)
     if os.environ.get("NV_DEBUG_PROGRESS") == "1":  # progress markers into a host-mapped buffer
         extra.append("-DNV_DEBUG_PROGRESS")
     build_dir, lib_path = (os.path.join(BUILD_DIR, "prof"), LIB_PATH.replace(".so", "_prof.so")) if extra else (BUILD_DIR, LIB_PATH)
+    variant = os.environ.get("NV_VARIANT")   # A/B builds: NV_VARIANT=g1 NV_DEFINES="-DNV_SIMT_GROUPS=1" -> libneurovit_b200_g1.so
+    if variant:
+        extra += os.environ.get("NV_DEFINES", "").split()
+        build_dir, lib_path = os.path.join(BUILD_DIR, variant), LIB_PATH.replace(".so", f"_{variant}.so")
     os.makedirs(build_dir, exist_ok=True)
     jobs = []
     objs = []

@@ -214,7 +214,10 @@ __device__ __forceinline__ void unpack8(const uint4& x, float (&f)[8]) {
 // half an SM's shared memory and registers. Two lanes per token (32 dims each: one shuffle per dot product, 64 FMAs
 // per 64 unpacks) and three pairs per CTA keep them few and short enough to run in the slots the last partial wave
 // of tile CTAs leaves idle (cfgA: 171 CTAs for 240 idle slots).
-constexpr int SIMT_GROUPS = 3;
+#ifndef NV_SIMT_GROUPS
+#define NV_SIMT_GROUPS 3
+#endif
+constexpr int SIMT_GROUPS = NV_SIMT_GROUPS;
 constexpr int SIMT_GTHREADS = NTHREADS / SIMT_GROUPS;   // 64 threads per pair
 constexpr int SIMT_LPT = 2;                             // lanes per token
 constexpr int SIMT_DPL = HD / SIMT_LPT;                 // dims per lane (32 = four 16-byte loads)
@@ -1165,12 +1168,274 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   }
 }
 
+// dQ, second schedule (the default; NV_ATTN_DQ=1 selects the first): S double-buffered in TMEM (2 x 64 columns + dP 64 +
+// dQ 64 = the CTA's 256) and issued two key blocks ahead through a three-stage K/V ring, dP issued one block ahead. In
+// the first schedule the row warps waited 1.1-1.4 k cycles per 64-key block for the round trip rows -> MMA warp -> S,
+// dP -> commit -> rows (as long as their own arithmetic); here S is already there and the dP round trip runs under the
+// block's exponentials.
+constexpr int DQ2_STAGES = 3;
+constexpr int DQ2_SMEM_TILES = 2 * SLAB /*Q, dO*/ + DQ2_STAGES * 2 * BOX /*K,V ring*/ + SLAB /*dS*/;
+constexpr int DQ2_SMEM = DQ2_SMEM_TILES + 256 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                      const __grid_constant__ CUtensorMap to, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + SLAB;
+  uint8_t* sKV = smem + 2 * SLAB;            // stage s (of DQ2_STAGES): K at s*2*BOX, V at s*2*BOX + BOX
+  uint8_t* sdS = smem + 2 * SLAB + DQ2_STAGES * 2 * BOX;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ2_SMEM_TILES);
+  uint64_t* qd_full = bars;         // 1
+  uint64_t* kv_full = bars + 1;     // 3
+  uint64_t* kv_empty = bars + 4;    // 3
+  uint64_t* s_full = bars + 7;      // 2  S is double-buffered in TMEM
+  uint64_t* dp_full = bars + 9;     // 1
+  uint64_t* ds_ready = bars + 10;   // 1
+  uint64_t* ds_free = bars + 11;    // 1  (also "dQ accumulated" after the last block)
+  uint64_t* o_full = bars + 12;     // 1  the O tile, parked in the dS slab until the rows have taken delta from it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.c.N;
+  const int n = N - 1;  // tokens 1 .. n are tiled; tile-local index r <-> token r + 1
+  const CtaRole role = cta_role((n + BQ - 1) / BQ, p.c.H, p.c.ntile_ctas);
+  const int b = role.b, h = role.h, q0 = role.tile * BQ;
+  if (role.simt) {  // query token 0 (delta, dQ), SIMT
+    PROF_DECL
+    bwd_cls_query_dq(p, reinterpret_cast<float*>(smem), role.tile);
+    PROF_MARK(0);
+#ifdef NV_PROFILE
+    if (role.tile == 14 && threadIdx.x == 0) PROF_DUMP(13);
+#endif
+    return;
+  }
+  const int nblk = (n + BWD_CB - 1) / BWD_CB;
+  const int nactive = (min(BQ, n - q0) + 31) >> 5;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); tma_prefetch_desc(&to);
+    mbar_init(qd_full, 1);
+    for (int i = 0; i < DQ2_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_ready, 32 * nactive);
+    mbar_init(ds_free, 1);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base /* two buffers: +0, +64 */, tdP = tmem_base + 128, tdQ = tmem_base + 192;
+
+  if (warp == TMA_WARP) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(qd_full, 2 * SLAB);
+      load_rows(sQ, &tq, qd_full, h * HD, 1 + q0, b, 2);
+      load_rows(sdO, &tdo, qd_full, h * HD, 1 + q0, b, 2);
+      // O rows of the tile -> the dS slab (free until the first dS is written): each row thread reads delta = dO . O
+      // from its own row and only then overwrites that row with dS, so no other synchronisation is needed
+      mbar_arrive_expect_tx(o_full, SLAB);
+      load_rows(sdS, &to, o_full, h * HD, 1 + q0, b, 2);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j % DQ2_STAGES;
+      mbar_wait(&kv_empty[s], ((j / DQ2_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[s], 2 * BOX);
+        load_rows(sKV + s * 2 * BOX, &tk, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
+        load_rows(sKV + s * 2 * BOX + BOX, &tv, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
+      }
+      __syncwarp();
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 0, 1);
+    const uint64_t q_desc = kmajor_desc(sQ), do_desc = kmajor_desc(sdO);
+    auto cols16 = [&](int j) { return (min(BWD_CB, n - j * BWD_CB) + 15) & ~15; };
+    auto kv_stage = [&](int j) { return sKV + (j % DQ2_STAGES) * 2 * BOX; };
+    auto kv_wait = [&](int j) { mbar_wait(&kv_full[j % DQ2_STAGES], (j / DQ2_STAGES) & 1); };
+    auto issue_s = [&](int j) {    // S_j = Q K_j^T into S buffer j & 1
+      mma_k64(tS + (uint32_t)((j & 1) * BWD_CB), q_desc, kmajor_desc(kv_stage(j)), umma_idesc_bf16(128, cols16(j), 0, 0));
+      umma_commit(&s_full[j & 1]);
+    };
+    auto issue_dp = [&](int j) {   // dP_j = dO V_j^T (single buffer)
+      mma_k64(tdP, do_desc, kmajor_desc(kv_stage(j) + BOX), umma_idesc_bf16(128, cols16(j), 0, 0));
+      umma_commit(dp_full);
+    };
+    // Schedule: S runs TWO blocks ahead of the rows (its buffer pair frees one when the rows have read it), dP one block
+    // ahead, right behind the rows' arrival; the rows find S_j waiting and spend the dP round trip on their exponentials.
+    mbar_wait(qd_full, 0);
+    kv_wait(0);
+    tc_fence_after();
+    if (elect_one()) { issue_s(0); issue_dp(0); }
+    __syncwarp();
+    if (nblk > 1) {
+      kv_wait(1);
+      tc_fence_after();
+      if (elect_one()) issue_s(1);
+      __syncwarp();
+    }
+    for (int j = 0; j < nblk; ++j) {
+      if (j + 2 < nblk) kv_wait(j + 2);      // K/V of the block whose scores are issued below (stage freed by dQ_{j-1})
+      mbar_wait(ds_ready, j & 1);            // rows: S_j and dP_j consumed, dS_j in shared memory
+      tc_fence_after();
+      if (elect_one()) {
+        if (j + 1 < nblk) issue_dp(j + 1);   // its K/V stage was waited for when S_{j+1} was issued
+        mma_rows(tdQ, sdS, kv_stage(j), idesc_dq, cols16(j) >> 4, j > 0);  // dQ += dS K_j
+        umma_commit(&kv_empty[j % DQ2_STAGES]);
+        umma_commit(ds_free);
+        if (j + 2 < nblk) issue_s(j + 2);
+      }
+      __syncwarp();
+    }
+  } else if (warp < nactive) {
+    const int row = warp * 32 + lane;
+    const int qrow = q0 + row;               // tile-local query index; token = qrow + 1
+    const int token = min(qrow + 1, N - 1);
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t sdS_u32 = smem_u32(sdS);
+    const float cs = p.c.scale * LOG2E;
+    const bool dropout = p.c.drop_thr != 0;
+    const int64_t stat = ((int64_t)b * p.c.H + h) * N + token;
+    const uint64_t mrow = (uint64_t)stat;
+    const float lse2 = p.lse[stat] * LOG2E;
+    // prologue on this row's Q / dO in shared memory: delta_i = dO_i . O_i (also published for the dK/dV kernel)
+    // and the dS of key token 0, which stays outside the tiles
+    PROF_DECL
+    float dl, ds_x;
+    {
+      Vec64 v0, k0;   // in flight while the Q / dO / O tiles land
+      load_vec64(v0, p.c.v + (int64_t)b * p.c.qkv_bs + h * HD);
+      load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);
+      uint32_t kw = 0xFFFFFFFFu;
+      if (dropout) kw = __ldg(p.c.mask + mrow * p.c.mask_words + ((N - 1) >> 5));
+      mbar_wait(qd_full, 0);
+      mbar_wait(o_full, 0);
+      dl = row_dot2(smem_u32(sdO), sdS_u32, row);
+      if (qrow < n) p.delta[stat] = dl;
+      const float dp_x = row_dot(smem_u32(sdO), row, v0);
+      const float p_x = ex2(fmaf(row_dot(smem_u32(sQ), row, k0), cs, -lse2));
+      const bool keep = (kw >> ((N - 1) & 31)) & 1u;
+      ds_x = p_x * ((keep ? dp_x * p.c.keep_scale : 0.f) - dl);
+    }
+    PROF_MARK(8);
+    for (int j = 0; j < nblk; ++j) {
+      const int key0 = j * BWD_CB;           // tile-local key index == mask bit position
+      const int nch = (min(BWD_CB, n - key0) + 31) >> 5;
+      uint32_t kmw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // dropout keep words of the block, fetched before the waits
+      if (dropout) {
+        kmw[0] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5));
+        if (nch > 1) kmw[1] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5) + 1);
+      }
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);   // issued two blocks ago: normally complete
+      tc_fence_after();
+      PROF_MARK(j == 0 ? 0 : 1);
+      // probabilities of the whole block first (they need S only): the dP MMA issued at this row's last arrival
+      // completes underneath
+      float pe[2 * 32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < nch) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tS + lane_base + (uint32_t)((j & 1) * BWD_CB + c * 32), sv);
+          tmem_ld_wait();
+          // keys >= N: K rows are zero-filled, so whatever finite dS lands there multiplies zeros in dS K
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pe[c * 32 + i] = ex2(fmaf(__uint_as_float(sv[i]), cs, -lse2));
+        }
+      }
+      PROF_MARK(2);
+      mbar_wait(dp_full, j & 1);
+      tc_fence_after();
+      PROF_MARK(6);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c < nch) {
+          uint32_t dv[32];
+          tmem_ld_32x32(tdP + lane_base + c * 32, dv);
+          tmem_ld_wait();
+          float ds[32];
+          if (dropout) {
+            const uint32_t km = kmw[c];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              ds[i] = pe[c * 32 + i] * (((km >> i) & 1u ? __uint_as_float(dv[i]) * p.c.keep_scale : 0.f) - dl);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ds[i] = pe[c * 32 + i] * (__uint_as_float(dv[i]) - dl);
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
+          if (c == 0 && j > 0) {   // dS tile consumed by the previous dQ MMA (issued a whole block ago)
+            mbar_wait(ds_free, (j - 1) & 1);
+            tc_fence_after();
+          }
+          store_operand_chunk(sdS_u32, row, c, w);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(ds_ready);
+      PROF_MARK(3);
+    }
+    Vec64 k0;
+    load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);   // in flight under the last dQ MMA
+    mbar_wait(ds_free, (nblk - 1) & 1);  // last dQ MMA retired
+    tc_fence_after();
+    PROF_MARK(4);
+    {  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows store
+      bf16* dst = p.dq + (int64_t)b * p.d_bs + (int64_t)token * p.d_rs + h * HD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tdQ + lane_base + c * 32, v);
+        tmem_ld_wait();
+        axpy_half(v, ds_x, k0, c);   // + dS_{i,0} k_0
+        if (qrow < n) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 t;
+            t.x = pack_bf16x2(__uint_as_float(v[8 * i]) * p.c.scale, __uint_as_float(v[8 * i + 1]) * p.c.scale);
+            t.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * p.c.scale, __uint_as_float(v[8 * i + 3]) * p.c.scale);
+            t.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * p.c.scale, __uint_as_float(v[8 * i + 5]) * p.c.scale);
+            t.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * p.c.scale, __uint_as_float(v[8 * i + 7]) * p.c.scale);
+            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = t;
+          }
+        }
+      }
+    }
+    PROF_MARK(5);
+#ifdef NV_PROFILE
+    if (role.tile == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
+      PROF_DUMP(4 + (b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // =====================================================================================================
 // backward, dK / dV: CTA = 128 keys (TMEM lane = key); loop over 64-query blocks
 // =====================================================================================================
 constexpr int DKV_SMEM_TILES = 2 * SLAB /*K, V*/ + 2 * 2 * BOX /*Q_i, dO_i x 2 stages*/ + 2 * SLAB /*P^T, dS^T*/;
 constexpr int DKV_SMEM = DKV_SMEM_TILES + 128 + 4 * 768 /*per-warp lse/delta/mask staging*/ + 4 * 256 /*per-warp q_0 / dO_0*/ + 1024;
 
+// SCORES_FIRST: when a block's P^T / dS^T are ready the MMA warp issues the NEXT block's S^T / dP^T before this block's
+// dV / dK accumulation (the rows wait for 8 MMAs instead of 16), and the rows take the "operand tiles free" barrier only
+// right before their first store.
+template <bool SCORES_FIRST>
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                        const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
@@ -1259,9 +1524,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     __syncwarp();
     for (int i = 0; i < nblk; ++i) {
       const int s = i & 1;
+      if (SCORES_FIRST && i + 1 < nblk) mbar_wait(&qd_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
       mbar_wait(pds_ready, i & 1);
       tc_fence_after();
       if (elect_one()) {
+        if (SCORES_FIRST && i + 1 < nblk) issue_scores(i + 1);
         const uint8_t* qt = sQD + s * 2 * BOX;
         mma_rows(tdV, sPT, qt + BOX, idesc_acc, cols16(i) >> 4, i > 0);  // dV += P^T  dO_i
         mma_rows(tdK, sdST, qt, idesc_acc, cols16(i) >> 4, i > 0);       // dK += dS^T Q_i
@@ -1269,7 +1536,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         umma_commit(pds_free);
       }
       __syncwarp();
-      if (i + 1 < nblk) {
+      if (!SCORES_FIRST && i + 1 < nblk) {
         mbar_wait(&qd_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
         tc_fence_after();
         if (elect_one()) issue_scores(i + 1);
@@ -1340,7 +1607,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       PROF_MARK(1);
-      if (i > 0) mbar_wait(pds_free, (i - 1) & 1);  // P^T / dS^T tiles consumed by the previous dV / dK MMAs
+      if (!SCORES_FIRST && i > 0) mbar_wait(pds_free, (i - 1) & 1);  // P^T / dS^T tiles consumed by the previous dV / dK MMAs
       PROF_MARK(2);
       for (int c = 0; c < nch; ++c) {
         uint32_t sv[32], dv[32];
@@ -1383,6 +1650,10 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         uint32_t w[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(pt[2 * e], pt[2 * e + 1]);
+        if (SCORES_FIRST && c == 0 && i > 0) {   // the previous dV / dK MMAs (issued behind this block's scores) are done
+          mbar_wait(pds_free, (i - 1) & 1);
+          tc_fence_after();
+        }
         store_operand_chunk(sPT_u32, row, c, w);
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(ds[2 * e], ds[2 * e + 1]);
@@ -1688,17 +1959,27 @@ int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   static uint64_t attr_done = 0;  // bit per device
   if (nv_first_on_device(&attr_done)) {
     if ((s = set_smem(attn_tc_bwd_dq_kernel, DQ_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_bwd_dkv_kernel, DKV_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_bwd_dq2_kernel, DQ2_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_bwd_dkv_kernel<false>, DKV_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_bwd_dkv_kernel<true>, DKV_SMEM)) != NV_OK) return s;
   }
   // dQ first (it also writes delta, which the dK/dV grid reads); the last x-slot of each grid is the SIMT CTA
   unsigned ncta;
   if ((s = tile_grid(p.c, B, &ncta)) != NV_OK) return s;
   dim3 grid(ncta);
   static const char* only = getenv("NV_ATTN_ONLY");   // timing experiments: launch one of the two kernels only
-  if (!only || !strcmp(only, "dq")) attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
+  static const char* dq_sched = getenv("NV_ATTN_DQ");   // "1": the first dQ schedule (single S buffer, two K/V stages)
+  if (!only || !strcmp(only, "dq")) {
+    if (dq_sched && dq_sched[0] == '1') attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
+    else attn_tc_bwd_dq2_kernel<<<grid, NTHREADS, DQ2_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
+  }
   NV_LAUNCH_CHECK("attn_tc_bwd_dq_kernel");
   { int ds = dbg_sync("dq", stream); if (ds != NV_OK) return ds; }
-  if (!only || !strcmp(only, "dkv")) attn_tc_bwd_dkv_kernel<<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  static const char* dkv_sched = getenv("NV_ATTN_DKV");   // "1": accumulate dV / dK before issuing the next block's scores
+  if (!only || !strcmp(only, "dkv")) {
+    if (dkv_sched && dkv_sched[0] == '1') attn_tc_bwd_dkv_kernel<false><<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+    else attn_tc_bwd_dkv_kernel<true><<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  }
   NV_LAUNCH_CHECK("attn_tc_bwd_dkv_kernel");
   return dbg_sync("dkv", stream);
 }

@@ -74,6 +74,9 @@ class MaskGen:
         self._parked = collections.OrderedDict()
         # which sites are drawn ahead: "attn" (the flash kernel's mask), "gemm" (epilogue / LayerNorm side-car sites)
         self.sites = set(filter(None, os.environ.get("NEUROVIT_MASKGEN", "attn,gemm").split(",")))
+        # "after": the draw is enqueued BEHIND the GEMM it should run under (its stream forks from a point before that
+        # GEMM), so the GEMM's persistent CTAs are placed first and the generator's CTAs fill the registers they leave
+        self.after = os.environ.get("NEUROVIT_BITS_ORDER", "before") == "after"
 
     def _stream(self, dev):
         s = self._side.get(dev)
@@ -81,14 +84,24 @@ class MaskGen:
             s = self._side[dev] = torch.cuda.Stream(device=dev)
         return s
 
-    def draw(self, n_bytes, p, seed, stream_id, device, site="gemm"):
+    def fork(self, device):
+        """An event at the current point of the current stream: draws given it start no earlier than this point even
+        when they are enqueued later (order "after")."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        return ev
+
+    def draw(self, n_bytes, p, seed, stream_id, device, site="gemm", fork=None):
         """(uint8 buffer of ceil4(n_bytes), event to wait for) or None when that site kind is drawn inline / p == 0."""
         if site not in self.sites or p <= 0:
             return None
         buf = torch.empty((n_bytes + 3) // 4 * 4, dtype=torch.uint8, device=device)
         cur = torch.cuda.current_stream(device)
         side = self._stream(device)
-        side.wait_stream(cur)
+        if fork is not None:
+            side.wait_event(fork)
+        else:
+            side.wait_stream(cur)
         with torch.cuda.stream(side):
             ops.dropout_bits(buf, p=p, seed=seed, stream=stream_id)
             ev = torch.cuda.Event()
@@ -521,10 +534,18 @@ class Engine:
         D_out = w_out.shape[0] if w_out is not None else inner
         mask_words = (N + 31) // 32
         bits_attn = bits_out = None
-        if self.mode == "bf16":  # keep bits of this block's sites, drawn on the side stream under the QKV GEMM
-            bits_attn = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn")
-            bits_out = MASKS.draw(M * D_out // 8, p_out, seed, sbase + DROP_OUT, dev) if D_out % 8 == 0 else None
+
+        def draw_bits(fork=None):  # keep bits of this block's sites, drawn on the side stream under the QKV GEMM
+            ba = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn", fork=fork)
+            bo = MASKS.draw(M * D_out // 8, p_out, seed, sbase + DROP_OUT, dev, fork=fork) if D_out % 8 == 0 else None
+            return ba, bo
+
+        if self.mode == "bf16" and not MASKS.after:
+            bits_attn, bits_out = draw_bits()
+        fork = MASKS.fork(dev) if self.mode == "bf16" and MASKS.after and (p_attn > 0 or p_out > 0) else None
         qkv, _ = self.linear(a, w_qkv)
+        if fork is not None:
+            bits_attn, bits_out = draw_bits(fork)
         o = torch.empty(M, inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
             lse = torch.empty(B, heads, N, device=dev, dtype=F32)
@@ -617,9 +638,13 @@ class Engine:
         bits_gelu = bits_down = None
         if self.mode == "bf16":  # drawn on the side stream under the up-projection GEMM
             bits_gelu = MASKS.draw(M * Fh // 8, p_gelu, seed, sbase + DROP_GELU, dev) if Fh % 8 == 0 else None
-            bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
+            if not MASKS.after:
+                bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
         bg = MASKS.ready(bits_gelu)
+        fork = MASKS.fork(dev) if self.mode == "bf16" and MASKS.after and p_down > 0 and D_out % 8 == 0 else None
         g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU, bg))
+        if fork is not None:
+            bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev, fork=fork)
         y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32,
                            drop=(p_down, seed, sbase + DROP_DOWN, MASKS.ready(bits_down)))
         MASKS.park((seed, sbase + DROP_DOWN), bits_down)
