@@ -140,6 +140,14 @@ int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_ba
                      void* o, int64_t o_batch_stride, int64_t o_row_stride, float* lse,
                      int B, int N, int H, int head_dim, float scale, float dropout_p, int64_t seed,
                      void* drop_mask, int drop_mask_ready, void* stream);
+/* Forward for the cls query only: with pool='cls' (vit_3d.py:123) the LAST block's attention output is used at token 0
+ * alone, so that block computes one query row per (batch, head) — the same SIMT code, dropout bits and arithmetic that
+ * serve token 0 inside nv_attention_fwd. o_cls row b (H*64 bf16) is written at o_cls + b*o_batch_stride; lse and
+ * drop_mask keep nv_attention_fwd's layouts ([B,H,N] and [B*H, N, ceil(N/32)]) with only the token-0 entries / rows
+ * written (drop_mask_ready = 1: read instead). Pairs with nv_attention_cls_bwd. */
+int nv_attention_cls_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                         void* o_cls, int64_t o_batch_stride, float* lse, int B, int N, int H, int head_dim, float scale,
+                         float dropout_p, int64_t seed, void* drop_mask, int drop_mask_ready, void* stream);
 /* Backward when only the cls query (token 0 of every sample) carries gradient (last block, pool='cls'):
  * dO_cls [B, H*64] holds that row's dO (batch stride dO_batch_stride), o's token-0 rows are read at o + b*o_batch_stride.
  * Writes dq (zero except token 0), dk, dv for every token: O(N d) per (batch, head). */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "nv_attention_fwd": [_p, _p, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _l, _p, _i, _p],
     "nv_attention_bwd": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _p, _p, _p, _p, _l, _l,
                          _i, _i, _i, _i, _f, _f, _p, _p],
+    "nv_attention_cls_fwd": [_p, _p, _p, _l, _l, _p, _l, _p, _i, _i, _i, _i, _f, _f, _l, _p, _i, _p],
     "nv_attention_cls_bwd": [_p, _p, _p, _l, _l, _p, _l, _p, _l, _p, _p, _p, _p, _l, _l, _i, _i, _i, _i, _f, _f, _p, _p],
     "nv_softmax_fwd": [_p, _l, _i, _p],
     "nv_softmax_bwd": [_p, _p, _l, _i, _p],

@@ -59,6 +59,9 @@ int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
                           const bf16* dO, int64_t o_bs, int64_t o_rs, const float* lse, float* delta_ws, bf16* dq,
                           bf16* dk, bf16* dv, int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim,
                           float scale, float dropout_p, const uint32_t* drop_mask, cudaStream_t stream);
+int nv_attn_cls_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
+                           int64_t o_bs, float* lse, int B, int N, int H, int head_dim, float scale, float dropout_p,
+                           uint64_t seed, uint32_t* drop_mask, int mask_ready, cudaStream_t stream);
 int nv_attn_cls_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
                            int64_t o_bs, const bf16* dO_cls, int64_t do_bs, const float* lse, bf16* dq, bf16* dk, bf16* dv,
                            int64_t d_bs, int64_t d_rs, int B, int N, int H, int head_dim, float scale, float dropout_p,
@@ -197,6 +200,14 @@ int nv_attention_fwd(const void* q, const void* k, const void* v, int64_t qkv_ba
   return nv_attn_tc_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
                                (bf16*)o, o_batch_stride, o_row_stride, lse, B, N, H, head_dim, scale, dropout_p,
                                (uint64_t)seed, (uint32_t*)drop_mask, drop_mask_ready, ST(stream));
+}
+
+int nv_attention_cls_fwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,
+                         void* o_cls, int64_t o_batch_stride, float* lse, int B, int N, int H, int head_dim, float scale,
+                         float dropout_p, int64_t seed, void* drop_mask, int drop_mask_ready, void* stream) {
+  return nv_attn_cls_fwd_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, qkv_batch_stride, qkv_row_stride,
+                                (bf16*)o_cls, o_batch_stride, lse, B, N, H, head_dim, scale, dropout_p, (uint64_t)seed,
+                                (uint32_t*)drop_mask, drop_mask_ready, ST(stream));
 }
 
 int nv_attention_bwd(const void* q, const void* k, const void* v, int64_t qkv_batch_stride, int64_t qkv_row_stride,

@@ -32,10 +32,14 @@
 //         maximum exceeds it by 2^8), P -> smem, O += P V_j accumulates in TMEM across blocks (rescaled in place
 //         on the rare raises).
 //   dQ  : prologue: delta_i = dO_i . O_i (written for the dK/dV kernel), the extra key's dS; per key block j
-//         (64 keys): S = Q K_j^T, dP = dO V_j^T -> TMEM; dS = P o (dP - delta) -> smem; dQ += dS K_j in TMEM.
-//   dKV : per query block i (64 queries): S^T = K Q_i^T, dP^T = V dO_i^T -> TMEM (lane = key);
-//         P^T, dS^T -> smem; dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM; epilogue adds the cls query's
-//         rank-1 term.
+//         (64 keys): S = Q K_j^T (double-buffered, issued two blocks ahead through a 3-stage K/V ring), dP = dO V_j^T
+//         (one block ahead) -> TMEM; the rows take all of the block's exponentials first, then dP:
+//         dS = P o (dP - delta) -> smem; dQ += dS K_j in TMEM.
+//   dKV : per query block i (64 queries): S^T = K Q_i^T, dP^T = V dO_i^T -> TMEM (lane = key), issued BEFORE the
+//         previous block's accumulation; P^T, dS^T -> smem; dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM; epilogue
+//         adds the cls query's rank-1 term.
+//   cls-only forward (nv_attention_cls_fwd): the SIMT CTAs alone — the last block under a cls-pooled head needs the
+//         attention output of token 0 only.
 #include "nv_common.cuh"
 #include "nv_rng.cuh"
 #include <cstdlib>
@@ -209,16 +213,19 @@ __device__ __forceinline__ void unpack8(const uint4& x, float (&f)[8]) {
     f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
   }
 }
-// A SIMT CTA serves SIMT_GROUPS (batch, head) pairs at once, two warps each. These CTAs are instruction-bound (bf16
-// unpacking and the dot-product shuffles, not the loads), and what they cost is the slot-time they hold — a slot is
-// half an SM's shared memory and registers. Two lanes per token (32 dims each: one shuffle per dot product, 64 FMAs
-// per 64 unpacks) and three pairs per CTA keep them few and short enough to run in the slots the last partial wave
-// of tile CTAs leaves idle (cfgA: 171 CTAs for 240 idle slots).
+// A SIMT CTA serves SIMT_GROUPS (batch, head) pairs at once, NTHREADS / SIMT_GROUPS threads each. These CTAs are
+// instruction-bound (bf16 unpacking and the dot-product shuffles, not the loads), and what they cost is the slot-time
+// they hold — a slot is half an SM's shared memory and registers — at the END of the grid, where they fill the slots the
+// last partial wave of tile CTAs leaves idle. Two lanes per token (32 dims each: one shuffle per dot product, 64 FMAs per
+// 64 unpacks). Pairs per CTA, measured (B=64, N=385, dropout 0.1, fwd / bwd us per layer; N=1729, B=16 in brackets):
+// 3 pairs 84.0 / 248.9 (211 / 695), 2 pairs 81.9 / 244.7 (198 / 658), 1 pair 88.1 / 255.0 (186 / 619): with three the
+// SIMT CTAs outlast the tile CTAs they run beside (25-50 k cycles against 16-27 k), with one there are more of them than
+// idle slots at N=385. Two is the default; -DNV_SIMT_GROUPS=n rebuilds with another count.
 #ifndef NV_SIMT_GROUPS
-#define NV_SIMT_GROUPS 3
+#define NV_SIMT_GROUPS 2
 #endif
 constexpr int SIMT_GROUPS = NV_SIMT_GROUPS;
-constexpr int SIMT_GTHREADS = NTHREADS / SIMT_GROUPS;   // 64 threads per pair
+constexpr int SIMT_GTHREADS = NTHREADS / SIMT_GROUPS;   // threads per pair
 constexpr int SIMT_LPT = 2;                             // lanes per token
 constexpr int SIMT_DPL = HD / SIMT_LPT;                 // dims per lane (32 = four 16-byte loads)
 constexpr int SIMT_SLOTS = SIMT_GTHREADS / SIMT_LPT;    // tokens processed per pass by one pair's threads
@@ -945,8 +952,14 @@ __device__ __forceinline__ void bwd_extra_key_dkv(const BwdParams& p, float* sm,
   }
 }
 constexpr int BWD_CB = 64;  // columns per block (keys in dQ, queries in dKV)
-constexpr int DQ_SMEM_TILES = 2 * SLAB /*Q, dO*/ + 2 * 2 * BOX /*K,V x 2 stages*/ + SLAB /*dS*/;
-constexpr int DQ_SMEM = DQ_SMEM_TILES + 128 + 1024;
+// S is double-buffered in TMEM (2 x 64 columns + dP 64 + dQ 64 = the CTA's 256) and issued two key blocks ahead through
+// a three-stage K/V ring; dP is issued one block ahead. With a single S buffer (round 1 / early round 2) the row warps
+// waited 1.1-1.4 k cycles per 64-key block for the round trip rows -> MMA warp -> S, dP -> commit -> rows — as long as
+// their own arithmetic; now S is already there and the dP round trip runs under the block's exponentials
+// (118.8 -> 108.5 us per layer at B=64, N=385, dropout 0.1; profiles/r02_summary.md §4).
+constexpr int DQ_STAGES = 3;
+constexpr int DQ_SMEM_TILES = 2 * SLAB /*Q, dO*/ + DQ_STAGES * 2 * BOX /*K,V ring*/ + SLAB /*dS*/;
+constexpr int DQ_SMEM = DQ_SMEM_TILES + 256 + 1024;
 
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
@@ -956,238 +969,9 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + SLAB;
-  uint8_t* sKV = smem + 2 * SLAB;            // stage s: K at s*2*BOX, V at s*2*BOX + BOX
-  uint8_t* sdS = smem + 2 * SLAB + 4 * BOX;
+  uint8_t* sKV = smem + 2 * SLAB;            // stage s (of DQ_STAGES): K at s*2*BOX, V at s*2*BOX + BOX
+  uint8_t* sdS = smem + 2 * SLAB + DQ_STAGES * 2 * BOX;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_SMEM_TILES);
-  uint64_t* qd_full = bars;         // 1
-  uint64_t* kv_full = bars + 1;     // 2
-  uint64_t* kv_empty = bars + 3;    // 2
-  uint64_t* s_full = bars + 5;      // 1
-  uint64_t* ds_ready = bars + 6;    // 1
-  uint64_t* ds_free = bars + 7;     // 1  (also "dQ accumulated" after the last block)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  uint64_t* o_full = bars + 9;      // 1  the O tile, parked in the dS slab until the rows have taken delta from it
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = p.c.N;
-  const int n = N - 1;  // tokens 1 .. n are tiled; tile-local index r <-> token r + 1
-  const CtaRole role = cta_role((n + BQ - 1) / BQ, p.c.H, p.c.ntile_ctas);
-  const int b = role.b, h = role.h, q0 = role.tile * BQ;
-  if (role.simt) {  // query token 0 (delta, dQ), SIMT
-    PROF_DECL
-    bwd_cls_query_dq(p, reinterpret_cast<float*>(smem), role.tile);
-    PROF_MARK(0);
-#ifdef NV_PROFILE
-    if (role.tile == 14 && threadIdx.x == 0) PROF_DUMP(13);
-#endif
-    return;
-  }
-  const int nblk = (n + BWD_CB - 1) / BWD_CB;
-  const int nactive = (min(BQ, n - q0) + 31) >> 5;
-
-  if (warp == TMA_WARP && lane == 0) {
-    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); tma_prefetch_desc(&to);
-    mbar_init(qd_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(ds_ready, 32 * nactive);
-    mbar_init(ds_free, 1);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tdP = tmem_base + 64, tdQ = tmem_base + 128;
-
-  if (warp == TMA_WARP) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(qd_full, 2 * SLAB);
-      load_rows(sQ, &tq, qd_full, h * HD, 1 + q0, b, 2);
-      load_rows(sdO, &tdo, qd_full, h * HD, 1 + q0, b, 2);
-      // O rows of the tile -> the dS slab (free until the first dS is written): each row thread reads delta = dO . O
-      // from its own row and only then overwrites that row with dS, so no other synchronisation is needed
-      mbar_arrive_expect_tx(o_full, SLAB);
-      load_rows(sdS, &to, o_full, h * HD, 1 + q0, b, 2);
-    }
-    __syncwarp();
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&kv_full[s], 2 * BOX);
-        load_rows(sKV + s * 2 * BOX, &tk, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
-        load_rows(sKV + s * 2 * BOX + BOX, &tv, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
-      }
-      __syncwarp();
-    }
-  } else if (warp == MMA_WARP) {
-    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 0, 1);
-    const uint64_t q_desc = kmajor_desc(sQ), do_desc = kmajor_desc(sdO);
-    auto cols16 = [&](int j) { return (min(BWD_CB, n - j * BWD_CB) + 15) & ~15; };
-    auto issue_scores = [&](int j) {
-      const uint8_t* kt = sKV + (j & 1) * 2 * BOX;
-      const uint32_t idesc = umma_idesc_bf16(128, cols16(j), 0, 0);
-      mma_k64(tS, q_desc, kmajor_desc(kt), idesc);         // S  = Q  K_j^T
-      mma_k64(tdP, do_desc, kmajor_desc(kt + BOX), idesc);  // dP = dO V_j^T
-      umma_commit(s_full);
-    };
-    mbar_wait(qd_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) issue_scores(0);
-    __syncwarp();
-    for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      mbar_wait(ds_ready, j & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        mma_rows(tdQ, sdS, sKV + s * 2 * BOX, idesc_dq, cols16(j) >> 4, j > 0);  // dQ += dS K_j
-        umma_commit(&kv_empty[s]);
-        umma_commit(ds_free);
-      }
-      __syncwarp();
-      if (j + 1 < nblk) {
-        mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) issue_scores(j + 1);
-        __syncwarp();
-      }
-    }
-  } else if (warp < nactive) {
-    const int row = warp * 32 + lane;
-    const int qrow = q0 + row;               // tile-local query index; token = qrow + 1
-    const int token = min(qrow + 1, N - 1);
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const uint32_t sdS_u32 = smem_u32(sdS);
-    const float cs = p.c.scale * LOG2E;
-    const bool dropout = p.c.drop_thr != 0;
-    const int64_t stat = ((int64_t)b * p.c.H + h) * N + token;
-    const uint64_t mrow = (uint64_t)stat;
-    const float lse2 = p.lse[stat] * LOG2E;
-    // prologue on this row's Q / dO in shared memory: delta_i = dO_i . O_i (also published for the dK/dV kernel)
-    // and the dS of key token 0, which stays outside the tiles
-    PROF_DECL
-    float dl, ds_x;
-    {
-      Vec64 v0, k0;   // in flight while the Q / dO / O tiles land
-      load_vec64(v0, p.c.v + (int64_t)b * p.c.qkv_bs + h * HD);
-      load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);
-      uint32_t kw = 0xFFFFFFFFu;
-      if (dropout) kw = __ldg(p.c.mask + mrow * p.c.mask_words + ((N - 1) >> 5));
-      mbar_wait(qd_full, 0);
-      mbar_wait(o_full, 0);
-      dl = row_dot2(smem_u32(sdO), sdS_u32, row);
-      if (qrow < n) p.delta[stat] = dl;
-      const float dp_x = row_dot(smem_u32(sdO), row, v0);
-      const float p_x = ex2(fmaf(row_dot(smem_u32(sQ), row, k0), cs, -lse2));
-      const bool keep = (kw >> ((N - 1) & 31)) & 1u;
-      ds_x = p_x * ((keep ? dp_x * p.c.keep_scale : 0.f) - dl);
-    }
-    PROF_MARK(8);
-    for (int j = 0; j < nblk; ++j) {
-      const int key0 = j * BWD_CB;           // tile-local key index == mask bit position
-      const int nch = (min(BWD_CB, n - key0) + 31) >> 5;
-      uint32_t kmw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};  // dropout keep words of the block, fetched before the waits
-      if (dropout) {
-        kmw[0] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5));
-        if (nch > 1) kmw[1] = __ldg(p.c.mask + mrow * p.c.mask_words + (key0 >> 5) + 1);
-      }
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      PROF_MARK(j == 0 ? 0 : 1);
-      if (j > 0) mbar_wait(ds_free, (j - 1) & 1);  // dS tile consumed by the previous dQ MMA
-      PROF_MARK(2);
-      for (int c = 0; c < nch; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tS + lane_base + c * 32, sv);
-        tmem_ld_32x32(tdP + lane_base + c * 32, dv);
-        tmem_ld_wait();
-        float ds[32];
-        // keys >= N: K rows are zero-filled, so whatever finite dS lands there multiplies zeros in dS K
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ds[i] = ex2(fmaf(__uint_as_float(sv[i]), cs, -lse2));
-        if (dropout) {
-          const uint32_t km = kmw[c];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) ds[i] *= ((km >> i) & 1u ? __uint_as_float(dv[i]) * p.c.keep_scale : 0.f) - dl;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) ds[i] *= __uint_as_float(dv[i]) - dl;
-        }
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(ds[2 * i], ds[2 * i + 1]);
-        store_operand_chunk(sdS_u32, row, c, w);
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(ds_ready);
-      PROF_MARK(3);
-    }
-    Vec64 k0;
-    load_vec64(k0, p.c.k + (int64_t)b * p.c.qkv_bs + h * HD);   // in flight under the last dQ MMA
-    mbar_wait(ds_free, (nblk - 1) & 1);  // last dQ MMA retired
-    tc_fence_after();
-    PROF_MARK(4);
-    {  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only valid rows store
-      bf16* dst = p.dq + (int64_t)b * p.d_bs + (int64_t)token * p.d_rs + h * HD;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tdQ + lane_base + c * 32, v);
-        tmem_ld_wait();
-        axpy_half(v, ds_x, k0, c);   // + dS_{i,0} k_0
-        if (qrow < n) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 t;
-            t.x = pack_bf16x2(__uint_as_float(v[8 * i]) * p.c.scale, __uint_as_float(v[8 * i + 1]) * p.c.scale);
-            t.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) * p.c.scale, __uint_as_float(v[8 * i + 3]) * p.c.scale);
-            t.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) * p.c.scale, __uint_as_float(v[8 * i + 5]) * p.c.scale);
-            t.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) * p.c.scale, __uint_as_float(v[8 * i + 7]) * p.c.scale);
-            *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = t;
-          }
-        }
-      }
-    }
-    PROF_MARK(5);
-#ifdef NV_PROFILE
-    if (role.tile == 1 && h == 3 && (b == 5 || b == 40) && (threadIdx.x == 0 || threadIdx.x == 70))
-      PROF_DUMP(4 + (b == 40 ? 2 : 0) + (threadIdx.x == 70 ? 1 : 0));
-#endif
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// dQ, second schedule (the default; NV_ATTN_DQ=1 selects the first): S double-buffered in TMEM (2 x 64 columns + dP 64 +
-// dQ 64 = the CTA's 256) and issued two key blocks ahead through a three-stage K/V ring, dP issued one block ahead. In
-// the first schedule the row warps waited 1.1-1.4 k cycles per 64-key block for the round trip rows -> MMA warp -> S,
-// dP -> commit -> rows (as long as their own arithmetic); here S is already there and the dP round trip runs under the
-// block's exponentials.
-constexpr int DQ2_STAGES = 3;
-constexpr int DQ2_SMEM_TILES = 2 * SLAB /*Q, dO*/ + DQ2_STAGES * 2 * BOX /*K,V ring*/ + SLAB /*dS*/;
-constexpr int DQ2_SMEM = DQ2_SMEM_TILES + 256 + 1024;
-
-__global__ void __launch_bounds__(NTHREADS, 2)
-attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
-                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
-                      const __grid_constant__ CUtensorMap to, const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sdO = smem + SLAB;
-  uint8_t* sKV = smem + 2 * SLAB;            // stage s (of DQ2_STAGES): K at s*2*BOX, V at s*2*BOX + BOX
-  uint8_t* sdS = smem + 2 * SLAB + DQ2_STAGES * 2 * BOX;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ2_SMEM_TILES);
   uint64_t* qd_full = bars;         // 1
   uint64_t* kv_full = bars + 1;     // 3
   uint64_t* kv_empty = bars + 4;    // 3
@@ -1218,7 +1002,7 @@ attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
   if (warp == TMA_WARP && lane == 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo); tma_prefetch_desc(&to);
     mbar_init(qd_full, 1);
-    for (int i = 0; i < DQ2_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < DQ_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
     mbar_init(dp_full, 1);
     mbar_init(ds_ready, 32 * nactive);
@@ -1245,8 +1029,8 @@ attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     }
     __syncwarp();
     for (int j = 0; j < nblk; ++j) {
-      const int s = j % DQ2_STAGES;
-      mbar_wait(&kv_empty[s], ((j / DQ2_STAGES) & 1) ^ 1);
+      const int s = j % DQ_STAGES;
+      mbar_wait(&kv_empty[s], ((j / DQ_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[s], 2 * BOX);
         load_rows(sKV + s * 2 * BOX, &tk, &kv_full[s], h * HD, 1 + j * BWD_CB, b, 1);
@@ -1258,8 +1042,8 @@ attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     constexpr uint32_t idesc_dq = umma_idesc_bf16(128, HD, 0, 1);
     const uint64_t q_desc = kmajor_desc(sQ), do_desc = kmajor_desc(sdO);
     auto cols16 = [&](int j) { return (min(BWD_CB, n - j * BWD_CB) + 15) & ~15; };
-    auto kv_stage = [&](int j) { return sKV + (j % DQ2_STAGES) * 2 * BOX; };
-    auto kv_wait = [&](int j) { mbar_wait(&kv_full[j % DQ2_STAGES], (j / DQ2_STAGES) & 1); };
+    auto kv_stage = [&](int j) { return sKV + (j % DQ_STAGES) * 2 * BOX; };
+    auto kv_wait = [&](int j) { mbar_wait(&kv_full[j % DQ_STAGES], (j / DQ_STAGES) & 1); };
     auto issue_s = [&](int j) {    // S_j = Q K_j^T into S buffer j & 1
       mma_k64(tS + (uint32_t)((j & 1) * BWD_CB), q_desc, kmajor_desc(kv_stage(j)), umma_idesc_bf16(128, cols16(j), 0, 0));
       umma_commit(&s_full[j & 1]);
@@ -1288,7 +1072,7 @@ attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       if (elect_one()) {
         if (j + 1 < nblk) issue_dp(j + 1);   // its K/V stage was waited for when S_{j+1} was issued
         mma_rows(tdQ, sdS, kv_stage(j), idesc_dq, cols16(j) >> 4, j > 0);  // dQ += dS K_j
-        umma_commit(&kv_empty[j % DQ2_STAGES]);
+        umma_commit(&kv_empty[j % DQ_STAGES]);
         umma_commit(ds_free);
         if (j + 2 < nblk) issue_s(j + 2);
       }
@@ -1432,10 +1216,9 @@ attn_tc_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
 constexpr int DKV_SMEM_TILES = 2 * SLAB /*K, V*/ + 2 * 2 * BOX /*Q_i, dO_i x 2 stages*/ + 2 * SLAB /*P^T, dS^T*/;
 constexpr int DKV_SMEM = DKV_SMEM_TILES + 128 + 4 * 768 /*per-warp lse/delta/mask staging*/ + 4 * 256 /*per-warp q_0 / dO_0*/ + 1024;
 
-// SCORES_FIRST: when a block's P^T / dS^T are ready the MMA warp issues the NEXT block's S^T / dP^T before this block's
-// dV / dK accumulation (the rows wait for 8 MMAs instead of 16), and the rows take the "operand tiles free" barrier only
-// right before their first store.
-template <bool SCORES_FIRST>
+// When a block's P^T / dS^T are ready the MMA warp issues the NEXT block's S^T / dP^T before this block's dV / dK
+// accumulation (the rows wait for 8 MMAs instead of 16), and the rows take the "operand tiles free" barrier only right
+// before their first store.
 __global__ void __launch_bounds__(NTHREADS, 2)
 attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                        const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
@@ -1524,11 +1307,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
     __syncwarp();
     for (int i = 0; i < nblk; ++i) {
       const int s = i & 1;
-      if (SCORES_FIRST && i + 1 < nblk) mbar_wait(&qd_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+      if (i + 1 < nblk) mbar_wait(&qd_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
       mbar_wait(pds_ready, i & 1);
       tc_fence_after();
       if (elect_one()) {
-        if (SCORES_FIRST && i + 1 < nblk) issue_scores(i + 1);
+        if (i + 1 < nblk) issue_scores(i + 1);
         const uint8_t* qt = sQD + s * 2 * BOX;
         mma_rows(tdV, sPT, qt + BOX, idesc_acc, cols16(i) >> 4, i > 0);  // dV += P^T  dO_i
         mma_rows(tdK, sdST, qt, idesc_acc, cols16(i) >> 4, i > 0);       // dK += dS^T Q_i
@@ -1536,12 +1319,6 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         umma_commit(pds_free);
       }
       __syncwarp();
-      if (!SCORES_FIRST && i + 1 < nblk) {
-        mbar_wait(&qd_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-        tc_fence_after();
-        if (elect_one()) issue_scores(i + 1);
-        __syncwarp();
-      }
     }
   } else if (warp < nactive) {
     const int row = warp * 32 + lane;
@@ -1607,7 +1384,6 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
       mbar_wait(s_full, i & 1);
       tc_fence_after();
       PROF_MARK(1);
-      if (!SCORES_FIRST && i > 0) mbar_wait(pds_free, (i - 1) & 1);  // P^T / dS^T tiles consumed by the previous dV / dK MMAs
       PROF_MARK(2);
       for (int c = 0; c < nch; ++c) {
         uint32_t sv[32], dv[32];
@@ -1650,7 +1426,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_cons
         uint32_t w[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(pt[2 * e], pt[2 * e + 1]);
-        if (SCORES_FIRST && c == 0 && i > 0) {   // the previous dV / dK MMAs (issued behind this block's scores) are done
+        if (c == 0 && i > 0) {   // the previous dV / dK MMAs (issued behind this block's scores) are done
           mbar_wait(pds_free, (i - 1) & 1);
           tc_fence_after();
         }
@@ -1891,6 +1667,17 @@ int set_smem(K kern, int bytes) {
   return NV_OK;
 }
 
+int fwd_attrs_once() {
+  static uint64_t attr_done = 0;  // bit per device
+  int s;
+  if (nv_first_on_device(&attr_done)) {
+    if ((s = set_smem(attn_tc_fwd_kernel<false, false>, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<true, false>, FWD_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_fwd_kernel<true, true>, FWD_SMEM)) != NV_OK) return s;
+  }
+  return NV_OK;
+}
+
 }  // namespace
 
 int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
@@ -1912,12 +1699,7 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   FwdParams p;
   if ((s = fill_common(p.c, q, k, v, qkv_bs, qkv_rs, N, H, scale, dropout_p, seed, drop_mask, mask_ready)) != NV_OK) return s;
   p.o = o; p.o_bs = o_bs; p.o_rs = o_rs; p.lse = lse;
-  static uint64_t attr_done = 0;  // bit per device
-  if (nv_first_on_device(&attr_done)) {
-    if ((s = set_smem(attn_tc_fwd_kernel<false, false>, FWD_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_fwd_kernel<true, false>, FWD_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_fwd_kernel<true, true>, FWD_SMEM)) != NV_OK) return s;
-  }
+  if ((s = fwd_attrs_once()) != NV_OK) return s;
   unsigned ncta;
   if ((s = tile_grid(p.c, B, &ncta)) != NV_OK) return s;
   dim3 grid(ncta);
@@ -1926,6 +1708,36 @@ int nv_attn_tc_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   else attn_tc_fwd_kernel<false, false><<<grid, NTHREADS, FWD_SMEM, stream>>>(tq, tk, tv, p);
   NV_LAUNCH_CHECK("attn_tc_fwd_kernel");
   return dbg_sync("fwd", stream);
+}
+
+// Forward for the cls query only (token 0 of every sample): the last block under a cls-pooled head (vit_3d.py:123)
+// uses nothing else of its attention output. Launches the forward kernel with zero tile CTAs, i.e. only the SIMT CTAs
+// that serve token 0 in the full forward: same arithmetic, same dropout bits (row (b*H+h, token 0) of drop_mask is
+// drawn inline and written, or read when mask_ready), o row b written at o + b*o_bs, lse at lse[(b*H+h)*N].
+int nv_attn_cls_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, bf16* o,
+                           int64_t o_bs, float* lse, int B, int N, int H, int head_dim, float scale, float dropout_p,
+                           uint64_t seed, uint32_t* drop_mask, int mask_ready, cudaStream_t stream) {
+  NV_REQUIRE(head_dim == HD, "attention: head_dim %d unsupported by the bf16 flash kernel (needs 64)", head_dim);
+  NV_REQUIRE(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "attention: bad sizes B=%d N=%d H=%d", B, N, H);
+  if (B == 0) return NV_OK;
+  int s;
+  if ((s = check_args(q, qkv_bs, qkv_rs, "q")) != NV_OK) return s;
+  if ((s = check_args(k, qkv_bs, qkv_rs, "k")) != NV_OK) return s;
+  if ((s = check_args(v, qkv_bs, qkv_rs, "v")) != NV_OK) return s;
+  NV_REQUIRE(o != nullptr && lse != nullptr, "attention: o / lse is null");
+  FwdParams p;
+  if ((s = fill_common(p.c, q, k, v, qkv_bs, qkv_rs, N, H, scale, dropout_p, seed, drop_mask, mask_ready)) != NV_OK) return s;
+  p.o = o; p.o_bs = o_bs; p.o_rs = 0; p.lse = lse;
+  if ((s = fwd_attrs_once()) != NV_OK) return s;
+  p.c.B = B;
+  p.c.ntile_ctas = 0;   // every CTA takes the SIMT role (cta_role)
+  const dim3 grid((unsigned)(((int64_t)H * B + SIMT_GROUPS - 1) / SIMT_GROUPS));
+  CUtensorMap none;     // the SIMT role returns before any tensor map is touched
+  memset(&none, 0, sizeof(none));
+  if (p.c.drop_thr != 0) attn_tc_fwd_kernel<true, false><<<grid, NTHREADS, FWD_SMEM, stream>>>(none, none, none, p);
+  else attn_tc_fwd_kernel<false, false><<<grid, NTHREADS, FWD_SMEM, stream>>>(none, none, none, p);
+  NV_LAUNCH_CHECK("attn_tc_fwd_kernel (cls only)");
+  return dbg_sync("fwd cls", stream);
 }
 
 int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t qkv_bs, int64_t qkv_rs, const bf16* o,
@@ -1959,27 +1771,17 @@ int nv_attn_tc_bwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t q
   static uint64_t attr_done = 0;  // bit per device
   if (nv_first_on_device(&attr_done)) {
     if ((s = set_smem(attn_tc_bwd_dq_kernel, DQ_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_bwd_dq2_kernel, DQ2_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_bwd_dkv_kernel<false>, DKV_SMEM)) != NV_OK) return s;
-    if ((s = set_smem(attn_tc_bwd_dkv_kernel<true>, DKV_SMEM)) != NV_OK) return s;
+    if ((s = set_smem(attn_tc_bwd_dkv_kernel, DKV_SMEM)) != NV_OK) return s;
   }
   // dQ first (it also writes delta, which the dK/dV grid reads); the last x-slot of each grid is the SIMT CTA
   unsigned ncta;
   if ((s = tile_grid(p.c, B, &ncta)) != NV_OK) return s;
   dim3 grid(ncta);
   static const char* only = getenv("NV_ATTN_ONLY");   // timing experiments: launch one of the two kernels only
-  static const char* dq_sched = getenv("NV_ATTN_DQ");   // "1": the first dQ schedule (single S buffer, two K/V stages)
-  if (!only || !strcmp(only, "dq")) {
-    if (dq_sched && dq_sched[0] == '1') attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
-    else attn_tc_bwd_dq2_kernel<<<grid, NTHREADS, DQ2_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
-  }
+  if (!only || !strcmp(only, "dq")) attn_tc_bwd_dq_kernel<<<grid, NTHREADS, DQ_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
   NV_LAUNCH_CHECK("attn_tc_bwd_dq_kernel");
   { int ds = dbg_sync("dq", stream); if (ds != NV_OK) return ds; }
-  static const char* dkv_sched = getenv("NV_ATTN_DKV");   // "1": accumulate dV / dK before issuing the next block's scores
-  if (!only || !strcmp(only, "dkv")) {
-    if (dkv_sched && dkv_sched[0] == '1') attn_tc_bwd_dkv_kernel<false><<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
-    else attn_tc_bwd_dkv_kernel<true><<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
-  }
+  if (!only || !strcmp(only, "dkv")) attn_tc_bwd_dkv_kernel<<<grid, NTHREADS, DKV_SMEM, stream>>>(tq, tk, tv, tdo, p);
   NV_LAUNCH_CHECK("attn_tc_bwd_dkv_kernel");
   return dbg_sync("dkv", stream);
 }

@@ -27,6 +27,10 @@ _VALID_MODES = ("bf16", "fp32")
 # into its neighbour could gain at most. The step then computes wrong values; never set outside that measurement.
 AB_FLAGS = set(f for f in os.environ.get("NEUROVIT_AB", "").split(",") if f)
 AB_STATE = {}
+# With pool='cls' only token 0 of the LAST block's output is used (vit_3d.py:123): that block then runs its attention
+# for one query row per (batch, head) and its out-projection / FeedForward on B rows (AttnBlockClsFn, FFBlockClsFn).
+# NEUROVIT_CLS_LAST=0 keeps the dense last block (A/B and the equivalence test).
+CLS_LAST = os.environ.get("NEUROVIT_CLS_LAST", "1") == "1"
 HEAD_FUSED_MAX_CLASSES = 256  # HEAD_T of csrc/misc.cu: the one-CTA-per-sample head kernels hold the logits in a block
 
 # dropout sites of one block (vit_3d.py:21,23,39,45; emb :100,119): distinct Philox streams under one seed
@@ -74,9 +78,6 @@ class MaskGen:
         self._parked = collections.OrderedDict()
         # which sites are drawn ahead: "attn" (the flash kernel's mask), "gemm" (epilogue / LayerNorm side-car sites)
         self.sites = set(filter(None, os.environ.get("NEUROVIT_MASKGEN", "attn,gemm").split(",")))
-        # "after": the draw is enqueued BEHIND the GEMM it should run under (its stream forks from a point before that
-        # GEMM), so the GEMM's persistent CTAs are placed first and the generator's CTAs fill the registers they leave
-        self.after = os.environ.get("NEUROVIT_BITS_ORDER", "before") == "after"
 
     def _stream(self, dev):
         s = self._side.get(dev)
@@ -84,24 +85,14 @@ class MaskGen:
             s = self._side[dev] = torch.cuda.Stream(device=dev)
         return s
 
-    def fork(self, device):
-        """An event at the current point of the current stream: draws given it start no earlier than this point even
-        when they are enqueued later (order "after")."""
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(device))
-        return ev
-
-    def draw(self, n_bytes, p, seed, stream_id, device, site="gemm", fork=None):
+    def draw(self, n_bytes, p, seed, stream_id, device, site="gemm"):
         """(uint8 buffer of ceil4(n_bytes), event to wait for) or None when that site kind is drawn inline / p == 0."""
         if site not in self.sites or p <= 0:
             return None
         buf = torch.empty((n_bytes + 3) // 4 * 4, dtype=torch.uint8, device=device)
         cur = torch.cuda.current_stream(device)
         side = self._stream(device)
-        if fork is not None:
-            side.wait_event(fork)
-        else:
-            side.wait_stream(cur)
+        side.wait_stream(cur)
         with torch.cuda.stream(side):
             ops.dropout_bits(buf, p=p, seed=seed, stream=stream_id)
             ev = torch.cuda.Event()
@@ -534,18 +525,12 @@ class Engine:
         D_out = w_out.shape[0] if w_out is not None else inner
         mask_words = (N + 31) // 32
         bits_attn = bits_out = None
-
-        def draw_bits(fork=None):  # keep bits of this block's sites, drawn on the side stream under the QKV GEMM
-            ba = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn", fork=fork)
-            bo = MASKS.draw(M * D_out // 8, p_out, seed, sbase + DROP_OUT, dev, fork=fork) if D_out % 8 == 0 else None
-            return ba, bo
-
-        if self.mode == "bf16" and not MASKS.after:
-            bits_attn, bits_out = draw_bits()
-        fork = MASKS.fork(dev) if self.mode == "bf16" and MASKS.after and (p_attn > 0 or p_out > 0) else None
+        if self.mode == "bf16":  # keep bits of this block's sites, drawn on the side stream ahead of the QKV GEMM
+            # (enqueueing the draw BEHIND the GEMM, so that its CTAs fill the registers the persistent GEMM CTAs leave,
+            # was measured slower: 8.85 against 8.74 ms/step — the generator then slows the GEMM by more than its own time)
+            bits_attn = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn")
+            bits_out = MASKS.draw(M * D_out // 8, p_out, seed, sbase + DROP_OUT, dev) if D_out % 8 == 0 else None
         qkv, _ = self.linear(a, w_qkv)
-        if fork is not None:
-            bits_attn, bits_out = draw_bits(fork)
         o = torch.empty(M, inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
             lse = torch.empty(B, heads, N, device=dev, dtype=F32)
@@ -632,19 +617,62 @@ class Engine:
         dWqkv = self.wgrad(dqkv, a, acc=GradAcc(w_qkv, self.mode))
         return da, dWqkv, dWo, dbo
 
+    # -- attention core of the last block under a cls-pooled head ------------------------------------
+    def attn_cls_fwd(self, a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn=0.0, p_out=0.0, seed=0, sbase=0):
+        """a = LN(x) [B*N, D] bf16 — every token is a key / value; only the cls query is evaluated. Returns
+        y_cls [B, D] fp32 = x[:, 0] + dropout(to_out(attention(a)[:, 0])) and the saved tensors. Every dropout mask is
+        the dense block's (element index of the ORIGINAL row b*N, same seeds and streams), so y_cls equals the token-0
+        rows of attn_core_fwd. vit_3d.py:50-60,73,123."""
+        M = a.shape[0]
+        inner = heads * dim_head
+        scale = dim_head ** -0.5
+        dev = a.device
+        qkv, _ = self.linear(a, w_qkv)
+        o_cls = torch.empty(B, inner, device=dev, dtype=BF16)
+        lse = torch.empty(B, heads, N, device=dev, dtype=F32)          # token-0 entries written
+        mask, ready = None, False
+        if p_attn > 0:
+            mask = torch.empty(B * heads, N, (N + 31) // 32, device=dev, dtype=torch.int32)   # token-0 rows written
+            if DROPOUT_TRACE.record is not None:   # a test replays the whole mask into the oracle: draw all of it (same bits)
+                ops.dropout_bits(mask, p=p_attn, seed=seed + sbase + DROP_ATTN, stream=0)
+                ready = True
+        ops.attention_cls_fwd(qkv, o_cls, lse, B=B, N=N, H=heads, head_dim=dim_head, scale=scale, dropout_p=p_attn,
+                              seed=seed + sbase + DROP_ATTN, drop_mask=mask, mask_ready=ready)
+        _trace("attn", p_attn, seed, sbase + DROP_ATTN, mask)
+        x_cls = x2.view(B, N, -1)[:, 0, :]                              # strided [B, D] view of the residual rows
+        y, _ = self.linear(o_cls, w_out, bias=b_out, residual=x_cls, out_dtype=F32,
+                           drop=(p_out, seed, sbase + DROP_OUT, None, N))
+        _trace("out", p_out, seed, sbase + DROP_OUT, (M, w_out.shape[0]))
+        return y, (qkv, o_cls, lse, mask)
+
+    def attn_cls_bwd(self, dy_c, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=None, p_attn=0.0, p_out=0.0,
+                     seed=0, sbase=0):
+        """dy_c [B, D] fp32 = gradient of y_cls. Returns da [B*N, D], dWqkv, dWo, dbo."""
+        qkv, o_cls, lse, mask = saved
+        M, inner = a.shape[0], heads * dim_head
+        dev = a.device
+        D_out = w_out.shape[0]
+        dy_act = torch.empty(B, D_out, device=dev, dtype=self.act)
+        dbo = zeros_f32(D_out, dev)
+        ops.dropout(dy_c, p=max(p_out, 0.0), seed=seed, stream=sbase + DROP_OUT, colsum=dbo, row_mul=N, out_bf16=dy_act)
+        dO_c = self.dgrad(dy_act, w_out)                                # [B, inner]: dO of the cls query
+        dWo = self.wgrad(dy_act, o_cls, acc=GradAcc(w_out, self.mode))
+        dqkv = torch.empty(M, 3 * inner, device=dev, dtype=self.act)
+        ops.attention_cls_bwd(qkv, o_cls, dO_c, lse, dqkv, B=B, N=N, H=heads, head_dim=dim_head, scale=dim_head ** -0.5,
+                              dropout_p=p_attn if mask is not None else 0.0, drop_mask=mask, o_bs=o_cls.stride(0))
+        da = self.dgrad(dqkv, w_qkv, out_dtype=da_dtype or F32)
+        dWqkv = self.wgrad(dqkv, a, acc=GradAcc(w_qkv, self.mode))
+        return da, dWqkv, dWo, dbo
+
     # -- feed-forward core -------------------------------------------------------------------------
     def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0, sbase=0):
         M, Fh, D_out, dev = a.shape[0], w1.shape[0], w2.shape[0], a.device
         bits_gelu = bits_down = None
         if self.mode == "bf16":  # drawn on the side stream under the up-projection GEMM
             bits_gelu = MASKS.draw(M * Fh // 8, p_gelu, seed, sbase + DROP_GELU, dev) if Fh % 8 == 0 else None
-            if not MASKS.after:
-                bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
+            bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
         bg = MASKS.ready(bits_gelu)
-        fork = MASKS.fork(dev) if self.mode == "bf16" and MASKS.after and p_down > 0 and D_out % 8 == 0 else None
         g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU, bg))
-        if fork is not None:
-            bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev, fork=fork)
         y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32,
                            drop=(p_down, seed, sbase + DROP_DOWN, MASKS.ready(bits_down)))
         MASKS.park((seed, sbase + DROP_DOWN), bits_down)
@@ -771,6 +799,117 @@ class AttnBlockFn(torch.autograd.Function):
         dx = dx.view(B, N, -1)
         _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2, tag=side)
         return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None, None, None, None, None, None
+
+
+def _cls_residual_grad(dy_c, B, N, slot):
+    """Dense [B*N, D] fp32 gradient that is dy_c in the token-0 rows and zero elsewhere (x reaches a cls-only block's
+    output through token 0 alone): a cached zero buffer whose token-0 rows are overwritten through a raw pointer."""
+    D = dy_c.shape[1]
+    dres = sparse_grad_zeros(slot, (B * N, D), F32, dy_c.device)
+    ops.dropout(dy_c, p=0.0, seed=0, stream=0, out_f32=dres.view(B, N, D)[:, 0, :])   # p = 0: a strided copy
+    return dres
+
+
+class AttnBlockClsFn(torch.autograd.Function):
+    """Token 0 of x + to_out(attention(LN(x))) — the attention sub-block of the LAST layer under pool='cls'
+    (vit_3d.py:48-60,73,123): [B, N, D] -> [B, 1, D]. bf16 mode only."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w_qkv, w_out, b_out, heads, dim_head, eps, mode, p_attn=0.0, p_out=0.0, seed=0,
+                sbase=0, prev=None):
+        eng = engine(mode)
+        x2, B, N = _flat(x)
+        a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
+        y, saved = eng.attn_cls_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed, sbase)
+        ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved)
+        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase, prev)
+        return y.view(B, 1, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved = ctx.saved_tensors
+        B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase, prev = ctx.cfg
+        eng = engine(mode)
+        _STASH.take(dy)
+        dy_c = dy.reshape(B, -1).float().contiguous()
+        da, dWqkv, dWo, dbo = eng.attn_cls_bwd(dy_c, a, saved, w_qkv, w_out, B, N, heads, dim_head, da_dtype=eng.act,
+                                               p_attn=p_attn, p_out=p_out, seed=seed, sbase=sbase)
+        dres = _cls_residual_grad(dy_c, B, N, "attn_cls_res")
+        side = eng.side_drop_for(prev, seed, B * N, x2.shape[1])
+        dx, dxa, dg, db, cs2 = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dres, want_colsum=True,
+                                          acc_g=GradAcc(ln_w, mode), acc_b=GradAcc(ln_b, mode),
+                                          side_drop=None if side is None else (*side, eng.side_bits(side)))
+        dx = dx.view(B, N, -1)
+        _STASH.put(dx, dxa.view(B, N, -1) if mode == "bf16" else None, cs2, tag=side)
+        return dx, dg, db, dWqkv, dWo, dbo, None, None, None, None, None, None, None, None, None
+
+
+class AttnCoreClsFn(torch.autograd.Function):
+    """Same for a LayerNorm output `a` produced by the real module call (Grad-CAM hooks on Attention.norm of the last
+    layer, NeuroEncoder.py:47,70-82: they still see the whole [B, N, D] output and its gradient)."""
+
+    @staticmethod
+    def forward(ctx, a, x_res, w_qkv, w_out, b_out, heads, dim_head, mode, p_attn=0.0, p_out=0.0, seed=0, sbase=0):
+        eng = engine(mode)
+        a2, B, N = _flat(a)
+        x2, _, _ = _flat(x_res)
+        a_act = ops.cast_bf16(a2)
+        y, saved = eng.attn_cls_fwd(a_act, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed, sbase)
+        ctx.save_for_backward(a_act, w_qkv, w_out, *saved)
+        ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase)
+        return y.view(B, 1, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a_act, w_qkv, w_out, *saved = ctx.saved_tensors
+        B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase = ctx.cfg
+        eng = engine(mode)
+        _STASH.take(dy)
+        dy_c = dy.reshape(B, -1).float().contiguous()
+        da, dWqkv, dWo, dbo = eng.attn_cls_bwd(dy_c, a_act, saved, w_qkv, w_out, B, N, heads, dim_head,
+                                               p_attn=p_attn, p_out=p_out, seed=seed, sbase=sbase)
+        dres = torch.zeros(B, N, dy_c.shape[1], device=dy_c.device, dtype=F32)   # a fresh tensor: autograd sums it with da's
+        dres[:, 0, :] = dy_c                                                   # LayerNorm backward, possibly in place
+        return da.view(B, N, -1), dres, dWqkv, dWo, dbo, None, None, None, None, None, None, None
+
+
+class FFBlockClsFn(torch.autograd.Function):
+    """x_c + W2 gelu(W1 LN(x_c) + b1) + b2 on the cls rows [B, 1, D] of the last layer (the block is token-wise and only
+    token 0 of its output is used: vit_3d.py:14-26,74,123). n_tok = tokens per sample of the dense layout: the dropout
+    masks are indexed with the original row b * n_tok, i.e. they are the dense block's. bf16 mode only."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode, p_gelu=0.0, p_down=0.0, seed=0, sbase=0, n_tok=1):
+        eng = engine(mode)
+        B, D = x.shape[0], x.shape[-1]
+        x2 = x.reshape(B, D).float().contiguous()
+        a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
+        g, u = eng.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU, None, n_tok))
+        y, _ = eng.linear(g, w2, bias=b2, residual=x2, out_dtype=F32, drop=(p_down, seed, sbase + DROP_DOWN, None, n_tok))
+        _trace("gelu", p_gelu, seed, sbase + DROP_GELU, (B * n_tok, w1.shape[0]))
+        _trace("down", p_down, seed, sbase + DROP_DOWN, (B * n_tok, D))
+        ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, u, g)
+        ctx.cfg = (B, D, mode, p_gelu, p_down, seed, sbase, n_tok)
+        return y.view(B, 1, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, u, g = ctx.saved_tensors
+        B, D, mode, p_gelu, p_down, seed, sbase, n_tok = ctx.cfg
+        eng = engine(mode)
+        _STASH.take(dy)
+        dy_c = dy.reshape(B, D).float().contiguous()
+        dy_act = torch.empty(B, D, device=dy.device, dtype=eng.act)
+        db2 = zeros_f32(D, dy.device)
+        ops.dropout(dy_c, p=max(p_down, 0.0), seed=seed, stream=sbase + DROP_DOWN, colsum=db2, row_mul=n_tok, out_bf16=dy_act)
+        dU, db1 = eng.dgrad(dy_act, w2, gelu_u=u, want_colsum=True, colsum_acc=GradAcc(b1, mode),
+                            drop=(p_gelu, seed, sbase + DROP_GELU, None, n_tok))
+        dW2 = eng.wgrad(dy_act, g, acc=GradAcc(w2, mode))
+        da = eng.dgrad(dU, w1, out_dtype=eng.act)
+        dW1 = eng.wgrad(dU, a, acc=GradAcc(w1, mode))
+        dx, _, dg, db, _ = eng.ln_bwd(da, x2, mean, rstd, ln_w, dres=dy_c, acc_g=GradAcc(ln_w, mode),
+                                      acc_b=GradAcc(ln_b, mode))
+        return dx.view(B, 1, D), dg, db, dW1, db1, dW2, db2, None, None, None, None, None, None, None
 
 
 class AttnCoreFn(torch.autograd.Function):

@@ -312,14 +312,30 @@ def attention_fwd(qkv, o, lse, *, B, N, H, head_dim, scale, dropout_p=0.0, seed=
               _ptr(drop_mask), int(bool(mask_ready)), _stream())
 
 
-def attention_cls_bwd(qkv, o, dO_cls, lse, dqkv, *, B, N, H, head_dim, scale, dropout_p=0.0, drop_mask=None):
-    """Attention backward when only token 0 of every sample has gradient: dO_cls [B, H*hd] bf16 (contiguous rows)."""
+def attention_cls_fwd(qkv, o_cls, lse, *, B, N, H, head_dim, scale, dropout_p=0.0, seed=0, drop_mask=None,
+                      mask_ready=False):
+    """Attention forward for query token 0 only (last block under a cls-pooled head): o_cls [B, H*hd] bf16; lse [B,H,N]
+    and drop_mask [B*H, N, ceil(N/32)] keep the full layouts, only their token-0 entries / rows are written."""
+    _dev(qkv)
+    assert qkv.dtype == BF16 and o_cls.dtype == BF16 and lse.dtype == F32
+    inner = H * head_dim
+    assert tuple(o_cls.shape) == (B, inner) and o_cls.stride(1) == 1 and tuple(lse.shape) == (B, H, N) and lse.is_contiguous()
+    rs = qkv.stride(0)
+    _lib.call("nv_attention_cls_fwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o_cls),
+              o_cls.stride(0), _ptr(lse), B, N, H, head_dim, float(scale), float(dropout_p), int(seed), _ptr(drop_mask),
+              int(bool(mask_ready)), _stream())
+
+
+def attention_cls_bwd(qkv, o, dO_cls, lse, dqkv, *, B, N, H, head_dim, scale, dropout_p=0.0, drop_mask=None, o_bs=None):
+    """Attention backward when only token 0 of every sample has gradient: dO_cls [B, H*hd] bf16 (contiguous rows).
+    o: the forward's output, [B*N, H*hd] (token-0 rows read at stride N) or, with o_bs given, any tensor whose sample b's
+    token-0 row starts at element b * o_bs (the compact [B, H*hd] of attention_cls_fwd: o_bs = its row stride)."""
     _dev(qkv)
     inner = H * head_dim
     rs, drs = qkv.stride(0), dqkv.stride(0)
     assert dO_cls.dtype == BF16 and dO_cls.stride(1) == 1 and tuple(dO_cls.shape) == (B, inner)
     _lib.call("nv_attention_cls_bwd", _off(qkv, 0), _off(qkv, inner), _off(qkv, 2 * inner), N * rs, rs, _ptr(o),
-              N * o.stride(0), _ptr(dO_cls), dO_cls.stride(0), _ptr(lse), _off(dqkv, 0), _off(dqkv, inner),
+              N * o.stride(0) if o_bs is None else int(o_bs), _ptr(dO_cls), dO_cls.stride(0), _ptr(lse), _off(dqkv, 0), _off(dqkv, inner),
               _off(dqkv, 2 * inner), N * drs, drs, B, N, H, head_dim, float(scale), float(dropout_p), _ptr(drop_mask),
               _stream())
 

@@ -118,6 +118,15 @@ class FeedForward(nn.Module, _PrecisionMixin):
                                  p_down, seed, sbase)
 
 
+    def forward_cls(self, x_c, n_tok, _drop):
+        """The residual block on the cls rows only, x_c [B, 1, D] (last layer under pool='cls'); masks are the dense
+        block's (rows indexed b * n_tok). _drop = (seed, stream base)."""
+        ln, l1, l2 = self.net[0], self.net[1], self.net[4]
+        p_gelu, p_down = self.drop_p()
+        return Fn.FFBlockClsFn.apply(x_c, ln.weight, ln.bias, l1.weight, l1.bias, l2.weight, l2.bias, ln.eps,
+                                     self.precision, p_gelu, p_down, _drop[0], _drop[1], n_tok)
+
+
 class Attention(nn.Module, _PrecisionMixin):
     def __init__(self, dim, heads=8, dim_head=64, dropout=0.):
         super().__init__()
@@ -167,6 +176,25 @@ class Attention(nn.Module, _PrecisionMixin):
                                    self.precision, p_attn, p_out, seed, sbase)
 
 
+    def forward_cls(self, x, _drop):
+        """Token 0 of attn(x) + x, [B, N, D] -> [B, 1, D] (last layer under pool='cls'). Hooks on .norm still see the
+        whole LayerNorm output and its gradient. _drop = (seed, stream base, prev)."""
+        w_out, b_out = self.to_out[0].weight, self.to_out[0].bias
+        p_attn, p_out = self.drop_p()
+        seed, sbase, prev = _drop
+        if not _has_hooks(self.norm):
+            return Fn.AttnBlockClsFn.apply(x, self.norm.weight, self.norm.bias, self.to_qkv.weight, w_out, b_out,
+                                           self.heads, self.dim_head, self.norm.eps, self.precision, p_attn, p_out,
+                                           seed, sbase, prev)
+        a = self.norm(x)
+        return Fn.AttnCoreClsFn.apply(a, x, self.to_qkv.weight, w_out, b_out, self.heads, self.dim_head,
+                                      self.precision, p_attn, p_out, seed, sbase)
+
+
+def _subtree_has_hooks(m: nn.Module, allow=()) -> bool:
+    return any(_has_hooks(c) for c in m.modules() if not any(c is a for a in allow))
+
+
 class Transformer(nn.Module):
     def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.):
         super().__init__()
@@ -177,12 +205,27 @@ class Transformer(nn.Module):
                 FeedForward(dim, mlp_dim, dropout=dropout)
             ]))
 
-    def forward(self, x):
+    def _cls_last_ok(self, x) -> bool:
+        """The last layer may run on the cls query / cls rows only: bf16 mode, a projecting attention, and no user hooks
+        inside it other than on Attention.norm (which still sees every token) — a hook elsewhere would observe [B, 1, D]."""
+        attn, ff = self.layers[-1]
+        return (Fn.CLS_LAST and x.dim() == 3 and x.shape[1] > 1 and attn.precision == "bf16" and ff.precision == "bf16"
+                and not isinstance(attn.to_out, nn.Identity) and attn.dim_head == 64
+                and not _subtree_has_hooks(attn, allow=(attn.norm,)) and not _subtree_has_hooks(ff))
+
+    def forward(self, x, _cls_last=False):
+        """_cls_last (set by ViT.forward when pool == 'cls'): the caller uses token 0 of the result only, so the last
+        layer is evaluated for that token alone and the result is [B, 1, D] (vit_3d.py:123 takes x[:, 0])."""
         # one dropout seed per forward; site streams = layer * 8 + {attn 0, to_out 1, gelu 2, down 3}
         drops = [(attn.drop_p(), ff.drop_p()) for attn, ff in self.layers]
         seed = Fn.draw_seed() if any(p > 0 for pair_ in drops for ps in pair_ for p in ps) else 0
         prev = None  # (p, stream) of the dropout site right before the residual add that produced x
+        cls_last = bool(_cls_last) and len(self.layers) > 0 and self._cls_last_ok(x)
         for i, (attn, ff) in enumerate(self.layers):
+            if cls_last and i == len(self.layers) - 1:
+                n_tok = x.shape[1]
+                x = attn.forward_cls(x, _drop=(seed, 8 * i, prev))
+                return ff.forward_cls(x, n_tok, _drop=(seed, 8 * i))
             # x = attn(x) + x ; x = ff(x) + x   (vit_3d.py:72-74) with the adds fused into the GEMM epilogues;
             # modules that carry user hooks keep the reference's unfused call shape so the hooks see attn(x)
             if _has_hooks(attn):
@@ -257,7 +300,7 @@ class ViT(nn.Module, _PrecisionMixin):
         p_emb = _p(self, self.dropout)
         if p_emb > 0:  # x = dropout(x), vit_3d.py:119
             x = Fn.DropoutFn.apply(x, p_emb, Fn.draw_seed(), Fn.DROP_EMB)
-        x = self.transformer(x)
+        x = self.transformer(x, _cls_last=self.pool == 'cls')   # pool == 'cls': [B, 1, D], token 0 of the last layer
         h = self.mlp_head
         x = self.to_latent(x)
         return Fn.HeadFn.apply(x, h[0].weight, h[0].bias, h[1].weight, h[1].bias, self.pool, h[0].eps,

@@ -316,6 +316,49 @@ def test_attention_cls_bwd_matches_full_backward(B, N, H, p_drop):
         assert rel_err(got, gref) < 2e-2
 
 
+@pytest.mark.parametrize("B,N,H", [(3, 385, 8), (5, 64, 2), (2, 9, 1), (1, 1729, 2), (2, 1, 1), (7, 129, 3)])
+@pytest.mark.parametrize("p_drop,predrawn", [(0.0, False), (0.25, False), (0.25, True)])
+def test_attention_cls_fwd_equals_token0_of_full_forward(B, N, H, p_drop, predrawn):
+    """nv_attention_cls_fwd (query token 0 only: the last block under pool='cls', vit_3d.py:123) is the full forward's
+    own token-0 code run alone: output row, lse entry and the mask row it draws are bit-identical, and it feeds
+    nv_attention_cls_bwd (compact o, batch stride given) to the same gradients."""
+    hd = 64
+    inner = H * hd
+    torch.manual_seed(23)
+    qkv = torch.randn(B * N, 3 * inner, device=DEV).to(torch.bfloat16)
+    kw = dict(B=B, N=N, H=H, head_dim=hd, scale=hd ** -0.5, dropout_p=p_drop)
+    words = (N + 31) // 32
+
+    def new_mask():
+        if p_drop == 0:
+            return None
+        m = torch.zeros(B * H, N, words, device=DEV, dtype=torch.int32)
+        if predrawn:
+            ops.dropout_bits(m, p=p_drop, seed=99, stream=0)
+        return m
+
+    o = torch.empty(B * N, inner, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, N, device=DEV)
+    mask = new_mask()
+    ops.attention_fwd(qkv, o, lse, seed=99, drop_mask=mask, mask_ready=predrawn, **kw)
+    o_cls = torch.full((B, inner), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lse_c = torch.full((B, H, N), float("nan"), device=DEV)
+    mask_c = new_mask()
+    ops.attention_cls_fwd(qkv, o_cls, lse_c, seed=99, drop_mask=mask_c, mask_ready=predrawn, **kw)
+    assert torch.equal(o_cls, o.view(B, N, inner)[:, 0])
+    assert torch.equal(lse_c[:, :, 0], lse[:, :, 0])
+    if mask is not None:
+        assert torch.equal(mask_c[:, 0], mask[:, 0])                       # the cls query's keep bits, drawn or read
+        if not predrawn and N > 1:
+            assert (mask_c[:, 1:] == 0).all()                              # nothing else is touched
+    dO_cls = torch.randn(B, inner, device=DEV).to(torch.bfloat16)
+    want = torch.full_like(qkv, float("nan"))
+    ops.attention_cls_bwd(qkv, o, dO_cls, lse, want, drop_mask=mask, **kw)
+    got = torch.full_like(qkv, float("nan"))
+    ops.attention_cls_bwd(qkv, o_cls, dO_cls, lse_c, got, drop_mask=mask_c, o_bs=o_cls.stride(0), **kw)
+    assert torch.equal(got, want)
+
+
 def _mask_bits_to_keys(mask, B, H, N):
     """Saved keep-bit words [B*H, N, ceil(N/32)] -> float keep mask [B, H, N(query), N(key)]. Bit position p of a row
     is key token p + 1 for p < N - 1 and key token 0 for p = N - 1 (csrc/attention_tc.cu: token 0 is handled outside
