@@ -5,10 +5,13 @@ fused kernel cannot replay that stream, so the library defines its 
 file states it in the plainest possible form, with no bit-slicing:
 
     effective seed  s = seed + epoch * 0x9E3779B97F4A7C15              (mod 2^64; nv_seed)
-    one group g of 8 consecutive elements  <-  Philox4x32-7(key = s, counter = (g, stream, 0x2B992DDF))
-    the call's 16 output bytes (little-endian over x, y, z, w) are 16 bit-planes of 8 lanes:
-        u_j = sum_q  bit_j(byte_q) << q          j = 0..7, q = 0..15        (a 16-bit uniform per element)
+    one PAIR of groups (2c, 2c + 1), 16 consecutive elements  <-  Philox4x32-7(key = s, counter = (c, stream, 0x2B992DDF))
+    the call's 16 output bytes (little-endian over x, y, z, w) are bit-planes of 8 lanes (lane j = bit j of a byte):
+    H0 = bytes 0..7, H1 = bytes 8..15, each one byte VALUE per lane (plane q of a half = bit q of that value);
+        u_j(group 2c + s) = 256 * H_s[j] + bitrev8(H_{1-s}[j])          j = 0..7   (a 16-bit uniform per element)
     element 8 g + j is KEPT iff u_j >= thr,  thr = round(p * 65536);  survivors are scaled by 65536 / (65536 - thr)
+(marginals exactly uniform; lane j of the two groups of a pair reuse each other's high byte as low byte — see the
+dependence note in nv_rng.cuh and test_keep_rate_and_independence_of_lanes.)
 
 The CUDA side evaluates "u_j >= thr" bit-sliced (one LOP3 per plane for all lanes of a register); here the uniforms
 are assembled explicitly. Pinned two ways: tests/test_oracle.py checks the generator against Random123's published known-answer vectors
@@ -67,15 +70,24 @@ def keep_scale(thr: int) -> float:
 
 
 def uniforms16(seed: int, groups, stream: int) -> np.ndarray:
-    """[len(groups), 8] uint32: the eight 16-bit uniforms of each Philox group (planes assembled explicitly)."""
-    x, y, z, w = philox4x32(seed, groups, stream)
-    u = np.zeros((len(x), 8), dtype=np.uint32)
+    """[len(groups), 8] uint32: the eight 16-bit uniforms of each group (byte values assembled explicitly)."""
+    groups = np.asarray(groups, dtype=np.uint64)
+    words = philox4x32(seed, groups >> np.uint64(1), stream)
+    byte = np.stack([(words[q >> 2] >> np.uint32(8 * (q & 3))) & np.uint32(0xFF) for q in range(16)], axis=1)  # [n, 16]
     lanes = np.arange(8, dtype=np.uint32)
-    for q in range(16):
-        word = (x, y, z, w)[q >> 2]
-        byte = (word >> np.uint32(8 * (q & 3))) & np.uint32(0xFF)
-        u |= ((byte[:, None] >> lanes[None, :]) & np.uint32(1)) << np.uint32(q)
-    return u
+
+    def lane_values(planes, reverse):   # planes [n, 8] (byte q = plane q) -> per-lane byte value [n, 8 lanes]
+        v = np.zeros((planes.shape[0], 8), dtype=np.uint32)
+        for q in range(8):
+            bit = (planes[:, q, None] >> lanes[None, :]) & np.uint32(1)
+            v |= bit << np.uint32(7 - q if reverse else q)
+        return v
+
+    odd = (groups & np.uint64(1)).astype(bool)[:, None]
+    h0, h1 = byte[:, :8], byte[:, 8:]
+    hi = np.where(odd, h1, h0)
+    lo = np.where(odd, h0, h1)
+    return (lane_values(hi, False) << np.uint32(8)) | lane_values(lo, True)
 
 
 def keep_bits8(seed: int, groups, stream: int, thr: int) -> np.ndarray:
@@ -118,12 +130,20 @@ def philox_scalar(seed: int, idx: int, stream: int, rounds: int = ROUNDS):
                           [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], rounds)
 
 
-def bitsliced_keep_bits8(words, thr: int) -> int:
-    """The CUDA evaluation order (nv_keep_bits8): least-significant plane first, lt <- t_q ? (lt | ~B) : (lt & ~B).
-    words: the call's four 32-bit outputs. Returned byte must equal the explicit compare — tests assert that."""
+def bitsliced_keep_bits8(words, thr: int, odd: bool = False) -> int:
+    """The CUDA evaluation order (nv_keep_bits8): least-significant plane first, lt <- t_q ? (lt | ~B) : (lt & ~B);
+    low planes = the other half's bytes last first, high planes = the group's own half. words: the call's four 32-bit
+    outputs. The returned byte must equal the explicit compare — tests assert that."""
+    hi = words[2:] if odd else words[:2]
+    lo = words[:2] if odd else words[2:]
     lt = 0
     for q in range(16):
-        B = (words[q >> 2] >> (8 * (q & 3))) & 0xFFFFFFFF
+        if q < 8:
+            b = 7 - q
+            B = (lo[b >> 2] >> (8 * (b & 3))) & 0xFFFFFFFF
+        else:
+            b = q - 8
+            B = (hi[b >> 2] >> (8 * (b & 3))) & 0xFFFFFFFF
         lt = (lt | ~B) if (thr >> q) & 1 else (lt & ~B)
         lt &= 0xFFFFFFFF
     return ~lt & 0xFF
