@@ -140,8 +140,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 //           1 = bias + exact-erf GELU forward (writes pre-activation and activation, bf16)
 //           2 = dgrad through GELU: acc * gelu'(u) (+ column sums)
 // erf is evaluated with Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution): one
-// MUFU.RCP + one MUFU.EX2 + 11 FMA-pipe instructions for gelu (13 + a sign copy for gelu'); gelu' reuses the same
-// exponential (exp(-u^2/2) is erf's exp(-x^2)).
+// MUFU.RCP + one MUFU.EX2 + 7 FMAs; gelu' reuses the same exponential (exp(-u^2/2) is erf's exp(-x^2)).
 // (MUFU.RCP / MUFU.EX2 are issued as the bare approx instructions: the IEEE-rounded intrinsics expand to
 // range checks with slow-path calls that break the instruction-level parallelism of the unrolled epilogue.)
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -154,29 +153,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// |erf(u / sqrt 2)| and exp(-u^2 / 2), constants folded so that nothing is computed on x = u / sqrt 2 itself:
-// t = 1 / (1 + p |x|) with p / sqrt 2 applied to |u|; poly(t) * t * exp = poly(t) * (t * exp); exp(-x^2) = 2^(-u^2 log2e / 2)
-__device__ __forceinline__ void erf_abs_parts(float u, float& erf_abs, float& expv) {
-  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(u), 1.0f));
+__device__ __forceinline__ void erf_parts(float u, float& erf_v, float& expv) {
+  const float x = u * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  expv = ex2_approx((u * u) * (-0.5f * 1.4426950408889634f));
-  erf_abs = fmaf(-poly, t * expv, 1.0f);
+  poly *= t;
+  expv = ex2_approx(-x * x * 1.4426950408889634f);  // exp(-x^2) = exp(-u^2/2)
+  erf_v = copysignf(fmaf(-poly, expv, 1.0f), x);
 }
-// gelu(u) = u/2 (1 + erf) = u/2 + |u/2| |erf|   (u and erf(u / sqrt 2) share their sign)
 __device__ __forceinline__ float gelu_fast(float u) {
   float e, ex;
-  erf_abs_parts(u, e, ex);
-  const float h = 0.5f * u;
-  return fmaf(fabsf(h), e, h);
+  erf_parts(u, e, ex);
+  return 0.5f * u * (1.0f + e);
 }
-// gelu'(u) = (1 + erf) / 2 + u phi(u),  phi(u) = exp(-u^2 / 2) / sqrt(2 pi)
 __device__ __forceinline__ float gelu_grad_fast(float u) {
   float e, ex;
-  erf_abs_parts(u, e, ex);
-  return fmaf(u * 0.39894228040143267794f, ex, fmaf(0.5f, copysignf(e, u), 0.5f));
+  erf_parts(u, e, ex);
+  return fmaf(u * 0.39894228040143267794f, ex, 0.5f * (1.0f + e));
 }
 
 struct EpiAux {  // global operands of one 32x32 chunk, prefetched one chunk ahead

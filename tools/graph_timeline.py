@@ -23,6 +23,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--config", default="cfgA")
 ap.add_argument("--dropout", type=float, default=bench.DROPOUT)
 ap.add_argument("--out", default=None)
+ap.add_argument("--dump", default=None, help="CSV of every kernel of the profiled steps: start us, duration us, stream, name")
 args = ap.parse_args()
 bench.DROPOUT = args.dropout
 cfg = bench.CONFIGS[args.config]
@@ -105,6 +106,25 @@ lines.append("| kernel (graph replay) | launches/step | us/step | avg us |")
 lines.append("|---|---|---|---|")
 for k, (t, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:40]:
     lines.append(f"| `{k}` | {n / args.steps:.1f} | {t / args.steps:.1f} | {t / n:.1f} |")
+# busy / idle / concurrency over the whole profiled span (all streams)
+ev = sorted([(e["ts"], 1) for e in ks] + [(e["ts"] + e["dur"], -1) for e in ks])
+busy = multi = 0.0
+depth, last = 0, ev[0][0]
+for t, d in ev:
+    if depth >= 1:
+        busy += t - last
+    if depth >= 2:
+        multi += t - last
+    depth += d
+    last = t
+ksum = sum(e["dur"] for e in ks)
+lines.insert(1, f"all streams: sum of kernel durations {ksum / args.steps / 1e3:.3f} ms/step, GPU busy (union) {busy / args.steps / 1e3:.3f}, "
+                f"two or more kernels resident {multi / args.steps / 1e3:.3f}, idle {(t_last - t_first - busy) / args.steps / 1e3:.3f} ms/step")
+if args.dump:   # every kernel / copy of the profiled span, times relative to the first one
+    with open(args.dump, "w") as f:
+        f.write("start_us,dur_us,stream,name\n")
+        for e in ks:
+            f.write(f"{e['ts'] - t_first:.1f},{e['dur']:.1f},{e['args'].get('stream')},\"{e['name'][:110]}\"\n")
 text = "\n".join(lines)
 print(text)
 if args.out:
