@@ -106,20 +106,34 @@ lines.append("| kernel (graph replay) | launches/step | us/step | avg us |")
 lines.append("|---|---|---|---|")
 for k, (t, n) in sorted(tot.items(), key=lambda kv: -kv[1][0])[:40]:
     lines.append(f"| `{k}` | {n / args.steps:.1f} | {t / args.steps:.1f} | {t / n:.1f} |")
-# busy / idle / concurrency over the whole profiled span (all streams)
-ev = sorted([(e["ts"], 1) for e in ks] + [(e["ts"] + e["dur"], -1) for e in ks])
-busy = multi = 0.0
-depth, last = 0, ev[0][0]
-for t, d in ev:
+# busy / idle / concurrency over the whole profiled span (all streams). Idle time next to the input copies (the only
+# memcpys of a step: they sit between two replays) is the step boundary — graph launch latency, and once per trace the
+# profiler's own start-up — and is reported apart from idle time inside a step.
+ev = sorted([(e["ts"], 1, e) for e in ks] + [(e["ts"] + e["dur"], -1, e) for e in ks], key=lambda t: (t[0], t[1]))
+busy = multi = idle_in = 0.0
+boundary = []
+depth, last, last_e = 0, ev[0][0], None
+for t, d, e in ev:
     if depth >= 1:
         busy += t - last
+    elif d == 1 and last_e is not None and t > last:
+        if "memcpy" in e.get("cat", "") or "memcpy" in last_e.get("cat", ""):
+            boundary.append(t - last)
+        else:
+            idle_in += t - last
     if depth >= 2:
         multi += t - last
     depth += d
     last = t
+    if d == -1:
+        last_e = e
 ksum = sum(e["dur"] for e in ks)
+boundary.sort()
+startup = boundary.pop() if boundary else 0.0   # the largest one is the profiler starting up under the first replay
 lines.insert(1, f"all streams: sum of kernel durations {ksum / args.steps / 1e3:.3f} ms/step, GPU busy (union) {busy / args.steps / 1e3:.3f}, "
-                f"two or more kernels resident {multi / args.steps / 1e3:.3f}, idle {(t_last - t_first - busy) / args.steps / 1e3:.3f} ms/step")
+                f"two or more kernels resident {multi / args.steps / 1e3:.3f}, idle inside a step {idle_in / args.steps / 1e3:.3f}, "
+                f"idle at a step boundary (input copies -> first kernel of the next replay) {sum(boundary) / max(args.steps - 1, 1) / 1e3:.3f} ms/step "
+                f"(+ {startup / 1e3:.2f} ms once: profiler start-up)")
 if args.dump:   # every kernel / copy of the profiled span, times relative to the first one
     with open(args.dump, "w") as f:
         f.write("start_us,dur_us,stream,name\n")
