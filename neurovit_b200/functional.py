@@ -78,6 +78,11 @@ class MaskGen:
         self._parked = collections.OrderedDict()
         # which sites are drawn ahead: "attn" (the flash kernel's mask), "gemm" (epilogue / LayerNorm side-car sites)
         self.sites = set(filter(None, os.environ.get("NEUROVIT_MASKGEN", "attn,gemm").split(",")))
+        # early: a block's draws are enqueued BEFORE its LayerNorm (not between the LayerNorm and the GEMM): the
+        # generator (integer pipe) and the LayerNorm (HBM) then run side by side instead of one after the other — the
+        # timeline of the replayed graph shows every other pair of kernels of a step serialised, because each fills the
+        # machine (profiles/r02_summary.md §7c)
+        self.early = os.environ.get("NEUROVIT_BITS_EARLY", "1") == "1"
 
     def _stream(self, dev):
         s = self._side.get(dev)
@@ -514,8 +519,25 @@ class Engine:
         return bf, cs
 
     # -- attention core (after the pre-norm) ------------------------------------------------------
+    def draw_attn_bits(self, B, N, heads, D_out, p_attn, p_out, seed, sbase, dev):
+        """Keep bits of an attention block's two sites (flash-kernel mask, to_out dropout), on the side stream."""
+        if self.mode != "bf16":
+            return None, None
+        mask_words = (N + 31) // 32
+        ba = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn")
+        bo = MASKS.draw(B * N * D_out // 8, p_out, seed, sbase + DROP_OUT, dev) if D_out % 8 == 0 else None
+        return ba, bo
+
+    def draw_ff_bits(self, M, Fh, D_out, p_gelu, p_down, seed, sbase, dev):
+        """Keep bits of a FeedForward block's two sites (after GELU, after the down projection)."""
+        if self.mode != "bf16":
+            return None, None
+        bg = MASKS.draw(M * Fh // 8, p_gelu, seed, sbase + DROP_GELU, dev) if Fh % 8 == 0 else None
+        bd = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
+        return bg, bd
+
     def attn_core_fwd(self, a, x_res, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn=0.0, p_out=0.0, seed=0,
-                      sbase=0):
+                      sbase=0, drawn=None):
         """a = LN(x) [M,D] in act dtype; returns x_res + to_out(attention(a)) (fp32) and the saved tensors.
         vit_3d.py:50-60,73."""
         M = a.shape[0]
@@ -524,12 +546,11 @@ class Engine:
         dev = a.device
         D_out = w_out.shape[0] if w_out is not None else inner
         mask_words = (N + 31) // 32
-        bits_attn = bits_out = None
-        if self.mode == "bf16":  # keep bits of this block's sites, drawn on the side stream ahead of the QKV GEMM
-            # (enqueueing the draw BEHIND the GEMM, so that its CTAs fill the registers the persistent GEMM CTAs leave,
-            # was measured slower: 8.85 against 8.74 ms/step — the generator then slows the GEMM by more than its own time)
-            bits_attn = MASKS.draw(B * heads * N * mask_words * 4, p_attn, seed + sbase + DROP_ATTN, 0, dev, site="attn")
-            bits_out = MASKS.draw(M * D_out // 8, p_out, seed, sbase + DROP_OUT, dev) if D_out % 8 == 0 else None
+        # keep bits of this block's sites: drawn by the caller ahead of the LayerNorm (`drawn`), or here ahead of the QKV
+        # GEMM. (Enqueueing the draw BEHIND the GEMM, so that its CTAs fill the registers the persistent GEMM CTAs leave,
+        # was measured slower: 8.85 against 8.74 ms/step — the generator then slows the GEMM by more than its own time.)
+        bits_attn, bits_out = drawn if drawn is not None else \
+            self.draw_attn_bits(B, N, heads, D_out, p_attn, p_out, seed, sbase, dev)
         qkv, _ = self.linear(a, w_qkv)
         o = torch.empty(M, inner, device=dev, dtype=self.act)
         if self.mode == "bf16":
@@ -665,12 +686,10 @@ class Engine:
         return da, dWqkv, dWo, dbo
 
     # -- feed-forward core -------------------------------------------------------------------------
-    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0, sbase=0):
+    def ff_core_fwd(self, a, x_res, w1, b1, w2, b2, p_gelu=0.0, p_down=0.0, seed=0, sbase=0, drawn=None):
         M, Fh, D_out, dev = a.shape[0], w1.shape[0], w2.shape[0], a.device
-        bits_gelu = bits_down = None
-        if self.mode == "bf16":  # drawn on the side stream under the up-projection GEMM
-            bits_gelu = MASKS.draw(M * Fh // 8, p_gelu, seed, sbase + DROP_GELU, dev) if Fh % 8 == 0 else None
-            bits_down = MASKS.draw(M * D_out // 8, p_down, seed, sbase + DROP_DOWN, dev) if D_out % 8 == 0 else None
+        bits_gelu, bits_down = drawn if drawn is not None else \
+            self.draw_ff_bits(M, Fh, D_out, p_gelu, p_down, seed, sbase, dev)
         bg = MASKS.ready(bits_gelu)
         g, u = self.linear(a, w1, bias=b1, gelu=True, drop=(p_gelu, seed, sbase + DROP_GELU, bg))
         y, _ = self.linear(g, w2, bias=b2, residual=x_res, out_dtype=F32,
@@ -764,8 +783,11 @@ class AttnBlockFn(torch.autograd.Function):
         shares one seed per forward); prev = (p, stream) of the dropout site that produced x, if any."""
         eng = engine(mode)
         x2, B, N = _flat(x)
+        drawn = eng.draw_attn_bits(B, N, heads, w_out.shape[0], p_attn, p_out, seed, sbase, x2.device) \
+            if MASKS.early and w_out is not None else None
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
-        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed, sbase)
+        y, saved = eng.attn_core_fwd(a, x2, w_qkv, w_out, b_out, B, N, heads, dim_head, p_attn, p_out, seed, sbase,
+                                     drawn=drawn)
         ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w_qkv, w_out, *saved)
         ctx.cfg = (B, N, heads, dim_head, mode, p_attn, p_out, seed, sbase, prev)
         return y.view(B, N, -1)
@@ -948,8 +970,10 @@ class FFBlockFn(torch.autograd.Function):
     def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, eps, mode, p_gelu=0.0, p_down=0.0, seed=0, sbase=0, prev=None):
         eng = engine(mode)
         x2, B, N = _flat(x)
+        drawn = eng.draw_ff_bits(x2.shape[0], w1.shape[0], w2.shape[0], p_gelu, p_down, seed, sbase, x2.device) \
+            if MASKS.early else None
         a, mean, rstd = eng.ln_fwd(x2, ln_w, ln_b, eps)
-        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2, p_gelu, p_down, seed, sbase)
+        y, saved = eng.ff_core_fwd(a, x2, w1, b1, w2, b2, p_gelu, p_down, seed, sbase, drawn=drawn)
         ctx.save_for_backward(x2, mean, rstd, a, ln_w, ln_b, w1, b1, w2, *saved)
         ctx.cfg = (B, N, mode, p_gelu, p_down, seed, sbase, prev)
         return y.view(B, N, -1)
