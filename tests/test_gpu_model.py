@@ -377,15 +377,15 @@ def test_vit_training_dropout_matches_oracle_with_replayed_masks(mode, batch):
 
 
 @pytest.mark.parametrize("p_drop", [0.0, 0.2])
-@pytest.mark.parametrize("hooked", [False, True])
-def test_cls_only_last_layer_equals_dense_last_layer(p_drop, hooked):
+@pytest.mark.parametrize("hooked,depth,batch", [(False, 2, 64), (True, 2, 64), (False, 1, 64), (False, 3, 3)])
+def test_cls_only_last_layer_equals_dense_last_layer(p_drop, hooked, depth, batch):
     """pool='cls' (vit_3d.py:123): the last layer evaluated for the cls query / cls rows only (AttnBlockClsFn,
     FFBlockClsFn; AttnCoreClsFn when Attention.norm of that layer carries hooks, as under NeuroEncoder) gives the dense
     layer's logits and gradients: same dropout masks (indexed by the original rows), same arithmetic per row. What a
     hook on that LayerNorm sees (all tokens, output and gradient) is the same too."""
     from neurovit_b200 import functional as Fn
     torch.manual_seed(5)
-    ctor = dict(image_size=16, image_patch_size=8, frames=24, frame_patch_size=8, num_classes=2, dim=128, depth=2,
+    ctor = dict(image_size=16, image_patch_size=8, frames=24, frame_patch_size=8, num_classes=2, dim=128, depth=depth,
                 heads=2, mlp_dim=256, channels=1, dim_head=64, dropout=p_drop, emb_dropout=p_drop / 2)
     m = ViT(**ctor).to(DEV).train()
     seen = {}
@@ -393,8 +393,8 @@ def test_cls_only_last_layer_equals_dense_last_layer(p_drop, hooked):
         norm = m.transformer.layers[-1][0].norm
         norm.register_forward_hook(lambda mod, inp, out: seen.__setitem__("act", out.detach().clone()))
         norm.register_full_backward_hook(lambda mod, gi, go: seen.__setitem__("grad", go[0].detach().clone()))
-    x = torch.randn(64, 1, 24, 16, 16, device=DEV)
-    y = torch.randint(0, 2, (64,), device=DEV)
+    x = torch.randn(batch, 1, 24, 16, 16, device=DEV)
+    y = torch.randint(0, 2, (batch,), device=DEV)
 
     def run(flag):
         Fn.CLS_LAST = flag
@@ -410,7 +410,7 @@ def test_cls_only_last_layer_equals_dense_last_layer(p_drop, hooked):
         got, want = run(True), run(False)
     finally:
         Fn.CLS_LAST = True
-    assert got[0].shape == want[0].shape == (64, 2)
+    assert got[0].shape == want[0].shape == (batch, 2)
     assert rel(got[0], want[0]) < 1e-5                      # same kernels per row; nothing but reduction order may differ
     for k in want[1]:
         assert rel(got[1][k], want[1][k]) < 2e-3, k         # split-K / column-sum atomics order, bf16 side-car rounding
