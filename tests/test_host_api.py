@@ -130,3 +130,39 @@ def test_sparse_grad_zeros_is_cached_and_recleared_after_an_in_place_write():
     t.add_(1.0)                                                                           # a torch-side write bumps the version
     u = Fn.sparse_grad_zeros("test", (4, 3, 8), torch.float32, "cpu")
     assert u is not t and float(u.abs().sum()) == 0.0
+
+
+def test_cls_only_last_layer_is_taken_only_when_nothing_could_observe_the_difference():
+    """Transformer._cls_last_ok (host logic, no device): with pool='cls' the last layer may run for token 0 alone only in
+    bf16 mode and only when no user hook sits inside it other than on Attention.norm (Grad-CAM, NeuroEncoder.py:47: that
+    LayerNorm still sees every token); a hook anywhere else would observe [B, 1, D] instead of [B, N, D]."""
+    from neurovit_b200 import functional as Fn
+    x = torch.zeros(2, 9, 64)
+    m = _vit()
+    tr = m.transformer
+    attn, ff = tr.layers[-1]
+    assert tr._cls_last_ok(x)
+    assert not tr._cls_last_ok(torch.zeros(2, 1, 64))             # a single token: nothing to skip
+    h = attn.norm.register_forward_hook(lambda *a: None)
+    assert tr._cls_last_ok(x)                                      # the Grad-CAM hook point is allowed
+    h.remove()
+    for mod in (attn, attn.to_qkv, attn.to_out[0], ff, ff.net[0], ff.net[4]):
+        h = mod.register_forward_hook(lambda *a: None)
+        assert not tr._cls_last_ok(x), type(mod).__name__
+        h.remove()
+        h = mod.register_full_backward_hook(lambda *a: None)
+        assert not tr._cls_last_ok(x), type(mod).__name__
+        h.remove()
+    assert tr._cls_last_ok(x)
+    hook_first = tr.layers[0][1].register_forward_hook(lambda *a: None)   # hooks in OTHER layers do not matter
+    assert tr._cls_last_ok(x)
+    hook_first.remove()
+    m.set_precision("fp32")
+    assert not tr._cls_last_ok(x)                                  # the verification mode keeps the dense layer
+    m.set_precision("bf16")
+    try:
+        Fn.CLS_LAST = False
+        assert not tr._cls_last_ok(x)
+    finally:
+        Fn.CLS_LAST = True
+    assert not _vit(pool="mean").pool == "cls"                     # ViT.forward asks for it with pool == 'cls' only
