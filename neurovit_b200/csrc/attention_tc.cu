@@ -347,7 +347,7 @@ __device__ __forceinline__ float fwd_chunk_probs(const uint32_t (&sv)[32], float
         km32 |= km << (8 * g8);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) e[i] = (km >> i) & 1u ? e[i] * c.keep_scale : 0.f;
+      for (int i = 0; i < 8; ++i) e[i] = (km >> i) & 1u ? e[i] : 0.f;   // 1 / (1 - p) is applied once, with 1 / l
     }
     w[g8 * 4 + 0] = pack_bf16x2(e[0], e[1]);
     w[g8 * 4 + 1] = pack_bf16x2(e[2], e[3]);
@@ -739,9 +739,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           // the word of position N-1 is written by the last key chunk unless that chunk ended on a word boundary
           if ((pos & 31) == 0 && qrow < n) p.c.mask[mrow * p.c.mask_words + (pos >> 5)] = byte;
         }
-        p_xd = keep ? p_x * p.c.keep_scale : 0.f;
+        p_xd = keep ? p_x : 0.f;
       }
-      const float inv = 1.0f / l_run;
+      // dropped probabilities went into P unscaled (one select per score instead of a multiply and a select): the
+      // survivors' 1 / (1 - p) rides on the normalisation
+      const float inv = (DROPOUT ? p.c.keep_scale : 1.0f) / l_run;
       bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)token * p.o_rs + h * HD;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {  // tcgen05.ld is warp-collective: every lane loads, valid rows store
@@ -1148,8 +1150,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
           if (dropout) {
             const uint32_t km = kmw[c];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              ds[i] = pe[c * 32 + i] * (((km >> i) & 1u ? __uint_as_float(dv[i]) * p.c.keep_scale : 0.f) - dl);
+            for (int i = 0; i < 32; ++i)   // dS = P (dP m - delta), m = keep / (1 - p): select, FMA, multiply
+              ds[i] = pe[c * 32 + i] * fmaf(__uint_as_float(dv[i]), (km >> i) & 1u ? p.c.keep_scale : 0.f, -dl);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) ds[i] = pe[c * 32 + i] * (__uint_as_float(dv[i]) - dl);
