@@ -125,6 +125,17 @@ int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_
                            const float* dP, int64_t ld_dp, const float* mean, const float* rstd,
                            float* dgamma, float* dbeta, void* stream);
 
+/* LayerNorm(patch_dim) folded into the Linear(patch_dim, dim) behind it (vit_3d.py:93-94):
+ * Linear(LN(x)) = xhat (W o gamma)^T + (W beta + b). nv_ln_fold writes Wf [D, ld_wf] (bf16 or fp32; columns P..ld_wf-1
+ * zero: K padded to a multiple of 8) and bias_f [D] (b may be NULL); nv_patch_gather_ln with gamma = 1, beta = 0
+ * delivers xhat. nv_ln_fold_grads turns G = de^T xhat [D, ld_g >= P] (one weight-gradient GEMM) and cs = column sums
+ * of de [D] into the gradients of all four parameters, accumulating: dW[D,P] += G o gamma + cs beta^T,
+ * dgamma[P] += sum_k W o G, dbeta[P] += W^T cs, db[D] += cs (db may be NULL). W [D, P] fp32, contiguous. */
+int nv_ln_fold(const float* W, const float* gamma, const float* beta, const float* b, void* Wf, int wf_is_bf16,
+               int64_t ld_wf, float* bias_f, int D, int P, void* stream);
+int nv_ln_fold_grads(const float* G, int64_t ld_g, const float* W, const float* gamma, const float* beta, const float* cs,
+                     float* dW, float* dgamma, float* dbeta, float* db, int D, int P, void* stream);
+
 /* ---- attention --------------------------------------------------------------------------------------
  * replaces: vit_3d.py:51-59. q/k/v are read in place from the QKV projection output
  * [B, N, 3*H*64] (pointers to the q, k, v column blocks; shared batch/row strides), O is written as

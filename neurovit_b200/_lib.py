@@ -41,6 +41,8 @@ SIGNATURES = {
                          _p, _l, _p, _p, _p, _i, _i, _f, _l, _i, _p, _p],
     "nv_cls_row": [_p, _p, _p, _l, _i, _i, _p],
     "nv_patch_gather_ln": [_p, _p, _p, _p, _p, _p, _p, _i, _l, _p, _p, _p, _f, _p],
+    "nv_ln_fold": [_p, _p, _p, _p, _p, _i, _l, _p, _i, _i, _p],
+    "nv_ln_fold_grads": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "nv_patch_ln_param_grad": [_p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p],
     "nv_attention_fwd": [_p, _p, _p, _l, _l, _p, _l, _l, _p, _i, _i, _i, _i, _f, _f, _l, _p, _i, _p],
     "nv_attention_bwd": [_p, _p, _p, _l, _l, _p, _p, _l, _l, _p, _p, _p, _p, _p, _l, _l,

@@ -49,6 +49,11 @@ int nv_cls_row_launch(const float* cls, const float* pos, float* x, int64_t batc
 int nv_patch_gather_ln_launch(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,
                               const float* gamma, const float* beta, void* out, int out_is_bf16, int64_t ld_out,
                               float* raw, float* mean, float* rstd, float eps, cudaStream_t stream);
+int nv_ln_fold_launch(const float* W, const float* gamma, const float* beta, const float* b, void* Wf, int wf_is_bf16,
+                      int64_t ld_wf, float* bias_f, int D, int P, cudaStream_t stream);
+int nv_ln_fold_grads_launch(const float* G, int64_t ld_g, const float* W, const float* gamma, const float* beta,
+                            const float* cs, float* dW, float* dgamma, float* dbeta, float* db, int D, int P,
+                            cudaStream_t stream);
 int nv_patch_ln_param_grad_launch(const float* video, const int64_t* dims, const int64_t* strides,
                                   const int64_t* patch, const float* dP, int64_t ld_dp, const float* mean,
                                   const float* rstd, float* dgamma, float* dbeta, cudaStream_t stream);
@@ -185,6 +190,15 @@ int nv_patch_gather_ln(const float* video, const int64_t* dims, const int64_t* s
                        float* mean, float* rstd, float eps, void* stream) {
   return nv_patch_gather_ln_launch(video, dims, strides, patch, gamma, beta, out, out_is_bf16, ld_out, raw, mean,
                                    rstd, eps, ST(stream));
+}
+
+int nv_ln_fold(const float* W, const float* gamma, const float* beta, const float* b, void* Wf, int wf_is_bf16,
+               int64_t ld_wf, float* bias_f, int D, int P, void* stream) {
+  return nv_ln_fold_launch(W, gamma, beta, b, Wf, wf_is_bf16, ld_wf, bias_f, D, P, ST(stream));
+}
+int nv_ln_fold_grads(const float* G, int64_t ld_g, const float* W, const float* gamma, const float* beta, const float* cs,
+                     float* dW, float* dgamma, float* dbeta, float* db, int D, int P, void* stream) {
+  return nv_ln_fold_grads_launch(G, ld_g, W, gamma, beta, cs, dW, dgamma, dbeta, db, D, P, ST(stream));
 }
 
 int nv_patch_ln_param_grad(const float* video, const int64_t* dims, const int64_t* strides, const int64_t* patch,

@@ -1074,9 +1074,25 @@ class DropoutFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------- autograd: patch embedding
+_UNIT_AFFINE = {}
+
+
+def _unit_affine(P, device):
+    """(ones[P], zeros[P]) fp32, cached: gamma = 1, beta = 0 make the gather kernel write xhat."""
+    key = (int(P), str(device))
+    hit = _UNIT_AFFINE.get(key)
+    if hit is None:
+        hit = _UNIT_AFFINE[key] = (torch.ones(P, device=device, dtype=F32), torch.zeros(P, device=device, dtype=F32))
+    return hit
+
+
 class PatchEmbedFn(torch.autograd.Function):
     """to_patch_embedding + cls token + positional embedding — vit_3d.py:91-96,113-118.
-    Rearrange -> LN(patch_dim) -> Linear(patch_dim, dim) -> LN(dim); x = cat(cls, .) + pos[:, :n+1]."""
+    Rearrange -> LN(patch_dim) -> Linear(patch_dim, dim) -> LN(dim); x = cat(cls, .) + pos[:, :n+1].
+    The first LayerNorm's affine is folded into the Linear: Linear(LN(p)) = xhat (W o gamma)^T + (W beta + b) with
+    xhat = (p - mean) rstd written by the gather kernel. Backward then needs one weight-gradient GEMM G = de^T xhat:
+    dW = G o gamma + cs beta^T, dgamma = sum_k W o G, dbeta = W^T cs, db = cs (cs = column sums of de) — no dP = de W
+    GEMM and no second gather of the volume (csrc/patch_embed.cu, nv_ln_fold / nv_ln_fold_grads)."""
 
     @staticmethod
     def forward(ctx, video, ln1_w, ln1_b, lin_w, lin_b, ln2_w, ln2_b, cls_token, pos_embedding, patch, eps, mode):
@@ -1092,21 +1108,23 @@ class PatchEmbedFn(torch.autograd.Function):
             raise RuntimeError(f"The size of tensor a ({n + 1}) must match the size of tensor b "
                                f"({pos_embedding.shape[1]}) at non-singleton dimension 1")
         dev = video.device
-        Kp = (P + 7) // 8 * 8
-        patches = torch.empty(B * n, Kp, device=dev, dtype=eng.act)
-        mean1 = torch.empty(B * n, device=dev, dtype=F32)
-        rstd1 = torch.empty(B * n, device=dev, dtype=F32)
+        Kp = (P + 7) // 8 * 8 if mode == "bf16" else P   # TMA rows: K padded to 16 bytes (patch 9: 729 -> 736)
+        ones, zeros = _unit_affine(P, dev)
         if "skip_gather" in AB_FLAGS and AB_STATE.get(("gather", B, n, Kp)) is not None:
-            patches, mean1, rstd1 = AB_STATE[("gather", B, n, Kp)]   # measurement only: the first call's real patches again
-        elif "skip_gather" in AB_FLAGS:
-            ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
-            AB_STATE[("gather", B, n, Kp)] = (patches, mean1, rstd1)
+            xhat = AB_STATE[("gather", B, n, Kp)]   # measurement only: the first call's real patches again
         else:
-            ops.patch_gather_ln(video, patch, ln1_w.detach(), ln1_b.detach(), patches, mean=mean1, rstd=rstd1, eps=eps)
+            xhat = torch.empty(B * n, Kp, device=dev, dtype=eng.act)
+            ops.patch_gather_ln(video, patch, ones, zeros, xhat, eps=eps)
+            if "skip_gather" in AB_FLAGS:
+                AB_STATE[("gather", B, n, Kp)] = xhat
+        w_f = torch.empty(D, Kp, device=dev, dtype=eng.act)
+        b_f = torch.empty(D, device=dev, dtype=F32)
+        ops.ln_fold(lin_w.detach(), ln1_w.detach(), ln1_b.detach(), None if lin_b is None else lin_b.detach(), w_f, b_f)
+        e = torch.empty(B * n, D, device=dev, dtype=F32)
         if mode == "bf16":
-            e, _ = eng.linear(patches, lin_w, bias=lin_b, out_dtype=F32, pad_k=Kp)
+            ops.gemm_bf16(xhat, w_f, bias=b_f, out_f32=e)
         else:
-            e, _ = eng.linear(patches[:, :P], lin_w, bias=lin_b, out_dtype=F32)
+            ops.linear_f32(xhat, w_f, bias=b_f, out=e)
         x = torch.empty(B, n + 1, D, device=dev, dtype=F32)
         mean2 = torch.empty(B * n, device=dev, dtype=F32)
         rstd2 = torch.empty(B * n, device=dev, dtype=F32)
@@ -1114,14 +1132,14 @@ class PatchEmbedFn(torch.autograd.Function):
         ops.layernorm_fwd(e, ln2_w.detach(), ln2_b.detach(), x, M=B * n, D=D, ymap=(n, n + 1, 1), add=pos, ld_add=D,
                           add_mod=n, add_off=1, mean=mean2, rstd=rstd2, eps=eps)
         ops.cls_row(cls_token.detach().view(-1), pos, x, (n + 1) * D, B, D)
-        ctx.save_for_backward(video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, ln2_b, lin_w, lin_b)
-        ctx.cfg = (B, n, P, D, patch, mode, pos_embedding.shape, cls_token.shape)
+        ctx.save_for_backward(xhat, e, mean2, rstd2, ln1_w, ln1_b, ln2_w, ln2_b, lin_w, lin_b)
+        ctx.cfg = (B, n, P, D, mode, pos_embedding.shape, cls_token.shape)
         return x
 
     @staticmethod
     def backward(ctx, dx):
-        video, patches, mean1, rstd1, e, mean2, rstd2, ln2_w, ln2_b, lin_w, lin_b = ctx.saved_tensors
-        B, n, P, D, patch, mode, pos_shape, cls_shape = ctx.cfg
+        xhat, e, mean2, rstd2, ln1_w, ln1_b, ln2_w, ln2_b, lin_w, lin_b = ctx.saved_tensors
+        B, n, P, D, mode, pos_shape, cls_shape = ctx.cfg
         eng = engine(mode)
         dev = dx.device
         dx = dx.contiguous()
@@ -1130,28 +1148,23 @@ class PatchEmbedFn(torch.autograd.Function):
         dpos = torch.zeros(pos_shape, device=dev, dtype=F32)
         ops.batch_sum(dx, (n + 1) * D, dpos, B, (n + 1) * D)
         dcls = dpos.view(-1, D)[0].clone().view(cls_shape)
-        # LN(dim) backward on the patch rows only (token offset 1)
+        # LN(dim) backward on the patch rows only (token offset 1); its column sums are the Linear's bias gradient
         de = torch.empty(B * n, D, device=dev, dtype=F32)
         deb = torch.empty(B * n, D, device=dev, dtype=BF16) if mode == "bf16" else None
-        acc_g2, acc_b2, acc_lb = GradAcc(ln2_w, mode), GradAcc(ln2_b, mode), GradAcc(lin_b, mode)
+        acc_g2, acc_b2 = GradAcc(ln2_w, mode), GradAcc(ln2_b, mode)
+        cs = zeros_f32(D, dev)
         ops.layernorm_bwd(dx, e, mean2, rstd2, ln2_w.detach(), M=B * n, D=D, dymap=(n, n + 1, 1), dx=de, dx_bf16=deb,
-                          dgamma=acc_g2.buf, dbeta=acc_b2.buf, colsum=acc_lb.buf)
-        dg2, db2, dlin_b = acc_g2.result(), acc_b2.result(), acc_lb.result()
-        de_act = deb if mode == "bf16" else de
-        Kp = patches.shape[1]
-        if mode == "bf16":
-            dlin_w = eng.wgrad(de_act, patches, k_in=P, acc=GradAcc(lin_w, mode) if Kp == P else None)
-            # dP = de @ W (fp32), only needed for the patch LayerNorm's gamma/beta
-            dP = torch.empty(B * n, Kp, device=dev, dtype=F32)
-            ops.gemm_bf16(de_act, eng.w(lin_w, Kp), b_mn=True, out_f32=dP)
-        else:
-            dlin_w = eng.wgrad(de_act, patches[:, :P])
-            dP = torch.empty(B * n, Kp, device=dev, dtype=F32)
-            ops.linear_f32(de, lin_w.detach(), w_kn=True, out=dP[:, :P])
+                          dgamma=acc_g2.buf, dbeta=acc_b2.buf, colsum=cs)
+        dg2, db2 = acc_g2.result(), acc_b2.result()
+        # G = de^T xhat: the one weight-gradient GEMM of LayerNorm(patch_dim) -> Linear; everything else is closed form
+        G = eng.wgrad(deb if mode == "bf16" else de, xhat)
+        acc_w, acc_lb = GradAcc(lin_w, mode), GradAcc(lin_b, mode) if lin_b is not None else None
         dg1 = zeros_f32(P, dev)
         db1 = zeros_f32(P, dev)
-        ops.patch_ln_param_grad(video, patch, dP, mean1, rstd1, dg1, db1)
-        return None, dg1, db1, dlin_w, dlin_b, dg2, db2, dcls, dpos, None, None, None
+        ops.ln_fold_grads(G, lin_w.detach(), ln1_w.detach(), ln1_b.detach(), cs, acc_w.buf, dg1, db1,
+                          None if acc_lb is None else acc_lb.buf)
+        return (None, dg1, db1, acc_w.result(), None if acc_lb is None else acc_lb.result(), dg2, db2, dcls, dpos,
+                None, None, None)
 
 
 # --------------------------------------------------------------------- autograd: pool + mlp_head

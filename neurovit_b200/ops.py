@@ -287,6 +287,27 @@ def patch_gather_ln(video, patch, gamma, beta, out, *, raw=None, mean=None, rstd
               _ptr(mean), _ptr(rstd), float(eps), _stream())
 
 
+def ln_fold(W, gamma, beta, b, Wf, bias_f):
+    """Fold LayerNorm's affine into the Linear behind it: Wf [D, ld] (bf16 / fp32, pad columns zeroed) = W o gamma,
+    bias_f [D] = b + W beta. W [D, P] fp32 contiguous."""
+    _dev(W)
+    D, P = W.shape
+    assert W.dtype == F32 and W.is_contiguous() and Wf.shape[0] == D and Wf.stride(1) == 1 and Wf.shape[1] >= P
+    assert Wf.stride(0) == Wf.shape[1], "ln_fold zeroes columns P .. row pitch: the pitch must be the padded width"
+    _lib.call("nv_ln_fold", _ptr(W), _ptr(gamma), _ptr(beta), _ptr(b), _ptr(Wf), int(Wf.dtype == BF16), Wf.stride(0),
+              _ptr(bias_f), D, P, _stream())
+
+
+def ln_fold_grads(G, W, gamma, beta, cs, dW, dgamma, dbeta, db=None):
+    """Parameter gradients of LayerNorm -> Linear from G = de^T xhat [D, >= P] and cs = colsum(de) [D]; all outputs +=."""
+    _dev(G)
+    D, P = W.shape
+    assert G.dtype == F32 and G.stride(1) == 1 and G.shape[0] == D and G.shape[1] >= P
+    assert W.dtype == F32 and W.is_contiguous() and dW.dtype == F32 and dW.is_contiguous() and tuple(dW.shape) == (D, P)
+    _lib.call("nv_ln_fold_grads", _ptr(G), G.stride(0), _ptr(W), _ptr(gamma), _ptr(beta), _ptr(cs), _ptr(dW),
+              _ptr(dgamma), _ptr(dbeta), _ptr(db), D, P, _stream())
+
+
 def patch_ln_param_grad(video, patch, dP, mean, rstd, dgamma, dbeta):
     _dev(video)
     assert dP.dtype == F32 and dP.stride(1) == 1

@@ -569,6 +569,40 @@ def test_temporal_head_training_dropout_matches_masked_reference():
     assert 0.85 < (m_attn != 0).double().mean().item() < 0.95 and 0.65 < (m2 != 0).double().mean().item() < 0.75
 
 
+@pytest.mark.parametrize("D,P,Kp", [(1024, 512, 512), (64, 729, 736), (128, 8, 8), (520, 40, 40)])
+def test_layernorm_fold_into_linear_and_its_gradients(D, P, Kp):
+    """nv_ln_fold / nv_ln_fold_grads (patch embedding, vit_3d.py:93-94): Linear(LN(p)) = xhat (W o gamma)^T + (W beta + b),
+    and the gradients of W, b, gamma, beta from G = de^T xhat and cs = colsum(de), against autograd in float64."""
+    torch.manual_seed(3)
+    W = (torch.randn(D, P, device=DEV) * 0.1)
+    g = 1 + 0.3 * torch.randn(P, device=DEV)
+    bt = 0.2 * torch.randn(P, device=DEV)
+    b = torch.randn(D, device=DEV)
+    Wf = torch.full((D, Kp), float("nan"), device=DEV)
+    bias_f = torch.empty(D, device=DEV)
+    ops.ln_fold(W, g, bt, b, Wf, bias_f)
+    assert torch.equal(Wf[:, :P], W * g) and (Wf[:, P:] == 0).all()
+    assert rel_err(bias_f, b.double() + W.double() @ bt.double()) < 1e-6
+    Wfb = torch.full((D, Kp), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.ln_fold(W, g, bt, None, Wfb, bias_f)
+    assert torch.equal(Wfb[:, :P], (W * g).to(torch.bfloat16)) and (Wfb[:, P:] == 0).all()
+    assert rel_err(bias_f, W.double() @ bt.double()) < 1e-6
+    M = 300
+    xhat = torch.randn(M, P, device=DEV, dtype=torch.float64)
+    de = torch.randn(M, D, device=DEV, dtype=torch.float64)
+    Wd, gd, btd, bd = (t.double().requires_grad_(True) for t in (W, g, bt, b))
+    y = (xhat * gd + btd) @ Wd.t() + bd
+    want = torch.autograd.grad((y * de).sum(), (Wd, gd, btd, bd))
+    G = torch.zeros(D, Kp, device=DEV)
+    G[:, :P] = (de.t() @ xhat).float()
+    cs = de.sum(0).float()
+    base = [torch.randn(D, P, device=DEV), torch.randn(P, device=DEV), torch.randn(P, device=DEV), torch.randn(D, device=DEV)]
+    got = [t.clone() for t in base]                    # every output accumulates
+    ops.ln_fold_grads(G, W, g, bt, cs, got[0], got[1], got[2], got[3])
+    for nm, gt, b0, wt in zip(("dW", "dgamma", "dbeta", "db"), got, base, want):
+        assert rel_err(gt - b0, wt) < 2e-5, nm
+
+
 # ---------------------------------------------------------------------------------------- dropout
 def test_dropout_kernel_mask_statistics_and_determinism():
     M, N, p = 1000, 1024, 0.1
