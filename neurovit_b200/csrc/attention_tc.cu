@@ -139,6 +139,7 @@ struct Common {
   int mask_words;     // ceil(N / 32)
   int mask_ready;     // forward: the mask was drawn ahead of time (nv_dropout_bits): read it instead of drawing
   int ntile_ctas;     // B * H * ceil((N-1)/128): CTAs [0, ntile_ctas) run tiles, the rest token 0 (cta_role)
+  int simt_groups;    // (batch, head) pairs served by one token-0 SIMT CTA (1, 2 or 3)
   // raw operands, for the SIMT handling of token 0 (the tiles go through the tensor maps)
   const bf16 *q, *k, *v;
   int64_t qkv_bs, qkv_rs;
@@ -220,25 +221,24 @@ __device__ __forceinline__ void unpack8(const uint4& x, float (&f)[8]) {
 // 64 unpacks). Pairs per CTA, measured (B=64, N=385, dropout 0.1, fwd / bwd us per layer; N=1729, B=16 in brackets):
 // 3 pairs 84.0 / 248.9 (211 / 695), 2 pairs 81.9 / 244.7 (198 / 658), 1 pair 88.1 / 255.0 (186 / 619): with three the
 // SIMT CTAs outlast the tile CTAs they run beside (25-50 k cycles against 16-27 k), with one there are more of them than
-// idle slots at N=385. Two is the default; -DNV_SIMT_GROUPS=n rebuilds with another count.
-#ifndef NV_SIMT_GROUPS
-#define NV_SIMT_GROUPS 2
-#endif
-constexpr int SIMT_GROUPS = NV_SIMT_GROUPS;
-constexpr int SIMT_GTHREADS = NTHREADS / SIMT_GROUPS;   // threads per pair
+// idle slots at N=385. simt_groups_for(N) picks two up to 1000 tokens and one above.
 constexpr int SIMT_LPT = 2;                             // lanes per token
 constexpr int SIMT_DPL = HD / SIMT_LPT;                 // dims per lane (32 = four 16-byte loads)
-constexpr int SIMT_SLOTS = SIMT_GTHREADS / SIMT_LPT;    // tokens processed per pass by one pair's threads
-constexpr int SIMT_GWARPS = SIMT_GTHREADS / 32;
 constexpr int SIMT_WARPS = NTHREADS / 32;
-struct SimtWho { int g, tl, half, slot, b, h; bool valid; };
-__device__ __forceinline__ SimtWho simt_who(int cta_j, int B, int H) {
+// pairs per SIMT CTA, chosen per launch (Common::simt_groups): the measurements above — two at ViT3D's short sequences,
+// one from ~1000 tokens on, where a pair's work is long enough to want the whole CTA
+__host__ __device__ inline int simt_groups_for(int N) { return N > 1000 ? 1 : 2; }
+struct SimtWho { int g, tl, half, slot, b, h; bool valid; int gthreads, slots, gwarps; };
+__device__ __forceinline__ SimtWho simt_who(int cta_j, int B, int H, int groups) {
   SimtWho w;
-  w.g = threadIdx.x / SIMT_GTHREADS;
-  w.tl = threadIdx.x % SIMT_GTHREADS;
+  w.gthreads = NTHREADS / groups;          // threads per pair (192 / 96 / 64: whole warps)
+  w.slots = w.gthreads / SIMT_LPT;         // tokens processed per pass by one pair's threads
+  w.gwarps = w.gthreads / 32;
+  w.g = threadIdx.x / w.gthreads;
+  w.tl = threadIdx.x % w.gthreads;
   w.half = w.tl & 1;
   w.slot = w.tl >> 1;
-  const int pair = cta_j * SIMT_GROUPS + w.g;
+  const int pair = cta_j * groups + w.g;
   w.valid = pair < B * H;
   const int pc = w.valid ? pair : B * H - 1;   // idle groups shadow the last pair (loads only) to keep barriers uniform
   w.h = pc % H;
@@ -389,7 +389,7 @@ __device__ __forceinline__ void store_p_chunk(uint32_t sP_u32, int row, int chun
 template <bool DROPOUT>
 __device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int cta_j) {
   const Common& c = p.c;
-  const SimtWho w = simt_who(cta_j, c.B, c.H);
+  const SimtWho w = simt_who(cta_j, c.B, c.H, c.simt_groups);
   const int t = threadIdx.x, b = w.b, h = w.h;
   const int N = c.N;
   const int64_t bh = (int64_t)b * c.H + h;
@@ -408,7 +408,7 @@ __device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int
   }
   if (DROPOUT) {
     const int64_t mrow = bh * N;  // query token 0
-    for (int wi = w.tl; wi < c.mask_words; wi += SIMT_GTHREADS) {
+    for (int wi = w.tl; wi < c.mask_words; wi += w.gthreads) {
       uint32_t word;
       if (c.mask_ready) {
         word = __ldg(c.mask + mrow * c.mask_words + wi);
@@ -435,11 +435,11 @@ __device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int
     load_row32(kk, kb + roff);
     load_row32(vv, vb + roff);
   }
-  for (int key0 = 0; key0 < N; key0 += SIMT_SLOTS) {   // uniform trip count: the shuffles need whole warps
+  for (int key0 = 0; key0 < N; key0 += w.slots) {   // uniform trip count: the shuffles need whole warps
     const int key = key0 + w.slot;
     Row32 kn, vn;
     {
-      const int64_t roff = (int64_t)min(key + SIMT_SLOTS, N - 1) * c.qkv_rs;
+      const int64_t roff = (int64_t)min(key + w.slots, N - 1) * c.qkv_rs;
       load_row32(kn, kb + roff);
       load_row32(vn, vb + roff);
     }
@@ -470,13 +470,13 @@ __device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int
     kk = kn; vv = vn;
   }
   // merge the pair-group's lane pairs: common reference M, then plain sums
-  const int w0 = w.g * SIMT_GWARPS;  // first warp of this pair-group
+  const int w0 = w.g * w.gwarps;  // first warp of this pair-group
   float mx = warp_max(m_g);
   if ((t & 31) == 0) red[t >> 5][HD + 1] = mx;
   __syncthreads();
   float M = red[w0][HD + 1];
 #pragma unroll
-  for (int i = 1; i < SIMT_GWARPS; ++i) M = fmaxf(M, red[w0 + i][HD + 1]);
+  for (int i = 1; i < w.gwarps; ++i) M = fmaxf(M, red[w0 + i][HD + 1]);
   const float sc_g = ex2(m_g - M);  // 0 for lane pairs without keys
 #pragma unroll
   for (int d = 0; d < 32; ++d) oacc[d] *= sc_g;
@@ -487,7 +487,7 @@ __device__ __forceinline__ void fwd_cls_query(const FwdParams& p, float* sm, int
   if (w.tl < HD && w.valid) {
     float r = 0.f, L = 0.f;
 #pragma unroll
-    for (int i = 0; i < SIMT_GWARPS; ++i) { r += red[w0 + i][w.tl]; L += red[w0 + i][HD]; }
+    for (int i = 0; i < w.gwarps; ++i) { r += red[w0 + i][w.tl]; L += red[w0 + i][HD]; }
     p.o[(int64_t)b * p.o_bs + h * HD + w.tl] = __float2bfloat16(r / L);
     if (w.tl == 0) p.lse[bh * N] = (M + log2f(L)) * LN2;
   }
@@ -796,7 +796,7 @@ struct BwdParams {
 // dQ of query token 0 (and its delta): all N keys, SIMT, two lanes per key.
 __device__ __forceinline__ void bwd_cls_query_dq(const BwdParams& p, float* sm, int cta_j) {
   const Common& c = p.c;
-  const SimtWho w = simt_who(cta_j, c.B, c.H);
+  const SimtWho w = simt_who(cta_j, c.B, c.H, c.simt_groups);
   const int t = threadIdx.x, b = w.b, h = w.h;
   const int N = c.N;
   const int64_t bh = (int64_t)b * c.H + h;
@@ -830,13 +830,13 @@ __device__ __forceinline__ void bwd_cls_query_dq(const BwdParams& p, float* sm, 
     load_row32(kk, kb + roff);
     load_row32(vv, vb + roff);
   }
-  for (int key0 = 0; key0 < N; key0 += SIMT_SLOTS) {
+  for (int key0 = 0; key0 < N; key0 += w.slots) {
     const int key = key0 + w.slot;
     const bool live = key < N;
     const int kc = live ? key : 0;
     Row32 kn, vn;
     {
-      const int64_t roff = (int64_t)min(key + SIMT_SLOTS, N - 1) * c.qkv_rs;
+      const int64_t roff = (int64_t)min(key + w.slots, N - 1) * c.qkv_rs;
       load_row32(kn, kb + roff);
       load_row32(vn, vb + roff);
     }
@@ -862,7 +862,7 @@ __device__ __forceinline__ void bwd_cls_query_dq(const BwdParams& p, float* sm, 
   if (w.tl < HD && w.valid) {
     float r = 0.f;
 #pragma unroll
-    for (int i = 0; i < SIMT_GWARPS; ++i) r += red[w.g * SIMT_GWARPS + i][w.tl];
+    for (int i = 0; i < w.gwarps; ++i) r += red[w.g * w.gwarps + i][w.tl];
     p.dq[(int64_t)b * p.d_bs + h * HD + w.tl] = __float2bfloat16(r * c.scale);
   }
 }
@@ -871,7 +871,7 @@ __device__ __forceinline__ void bwd_cls_query_dq(const BwdParams& p, float* sm, 
 // Reads delta (all queries), so it runs in the dK/dV grid, after the dQ grid has written it.
 __device__ __forceinline__ void bwd_extra_key_dkv(const BwdParams& p, float* sm, int cta_j) {
   const Common& c = p.c;
-  const SimtWho w = simt_who(cta_j, c.B, c.H);
+  const SimtWho w = simt_who(cta_j, c.B, c.H, c.simt_groups);
   const int t = threadIdx.x, b = w.b, h = w.h;
   const int N = c.N;
   const int64_t bh = (int64_t)b * c.H + h;
@@ -899,14 +899,14 @@ __device__ __forceinline__ void bwd_extra_key_dkv(const BwdParams& p, float* sm,
     dl = p.delta[bh * N + ic];   // written by the dQ grid: plain load
     if (dropout) mw = __ldg(c.mask + (bh * N + ic) * c.mask_words + (pos >> 5));
   }
-  for (int i0 = 0; i0 < N; i0 += SIMT_SLOTS) {
+  for (int i0 = 0; i0 < N; i0 += w.slots) {
     const int i = i0 + w.slot;
     const bool live = i < N;
     Row32 qn, dn;
     float l2n, dln;
     uint32_t mwn = 0xFFFFFFFFu;
     {
-      const int ic = min(i + SIMT_SLOTS, N - 1);
+      const int ic = min(i + w.slots, N - 1);
       load_row32(qn, qb + (int64_t)ic * c.qkv_rs);
       load_row32(dn, dob + (int64_t)ic * p.o_rs);
       l2n = __ldg(p.lse + bh * N + ic) * LOG2E;
@@ -948,7 +948,7 @@ __device__ __forceinline__ void bwd_extra_key_dkv(const BwdParams& p, float* sm,
   if (w.tl < HD && w.valid) {
     float rk = 0.f, rv = 0.f;
 #pragma unroll
-    for (int i = 0; i < SIMT_GWARPS; ++i) { rk += red[w.g * SIMT_GWARPS + i][w.tl]; rv += red2[w.g * SIMT_GWARPS + i][w.tl]; }
+    for (int i = 0; i < w.gwarps; ++i) { rk += red[w.g * w.gwarps + i][w.tl]; rv += red2[w.g * w.gwarps + i][w.tl]; }
     p.dk[(int64_t)b * p.d_bs + h * HD + w.tl] = __float2bfloat16(rk * c.scale);
     p.dv[(int64_t)b * p.d_bs + h * HD + w.tl] = __float2bfloat16(rv);
   }
@@ -1639,12 +1639,13 @@ int check_args(const void* p, int64_t bs, int64_t rs, const char* name) {
   return NV_OK;
 }
 
-// 1-D grid of the tile kernels: tiles over tokens 1..N-1 for every (head, batch), then one SIMT CTA per SIMT_GROUPS
+// 1-D grid of the tile kernels: tiles over tokens 1..N-1 for every (head, batch), then one SIMT CTA per simt_groups
 // (head, batch) pairs for token 0. NV_ATTN_X=skipsimt drops the SIMT CTAs (timing experiments only: token 0 is then not computed).
 int tile_grid(Common& c, int B, unsigned* grid) {
   static const char* x = getenv("NV_ATTN_X");
   const int64_t ntile = (int64_t)((c.N - 1 + BQ - 1) / BQ) * c.H * B;
-  const int64_t ncta = ntile + ((x && strstr(x, "skipsimt")) ? 0 : ((int64_t)c.H * B + SIMT_GROUPS - 1) / SIMT_GROUPS);
+  c.simt_groups = simt_groups_for(c.N);
+  const int64_t ncta = ntile + ((x && strstr(x, "skipsimt")) ? 0 : ((int64_t)c.H * B + c.simt_groups - 1) / c.simt_groups);
   c.B = B;
   NV_REQUIRE(ncta < (1ll << 31) && ncta > 0, "attention: bad grid (%lld CTAs)", (long long)ncta);
   c.ntile_ctas = (int)ntile;
@@ -1733,7 +1734,8 @@ int nv_attn_cls_fwd_launch(const bf16* q, const bf16* k, const bf16* v, int64_t 
   if ((s = fwd_attrs_once()) != NV_OK) return s;
   p.c.B = B;
   p.c.ntile_ctas = 0;   // every CTA takes the SIMT role (cta_role)
-  const dim3 grid((unsigned)(((int64_t)H * B + SIMT_GROUPS - 1) / SIMT_GROUPS));
+  p.c.simt_groups = simt_groups_for(N);
+  const dim3 grid((unsigned)(((int64_t)H * B + p.c.simt_groups - 1) / p.c.simt_groups));
   CUtensorMap none;     // the SIMT role returns before any tensor map is touched
   memset(&none, 0, sizeof(none));
   if (p.c.drop_thr != 0) attn_tc_fwd_kernel<true, false><<<grid, NTHREADS, FWD_SMEM, stream>>>(none, none, none, p);
