@@ -237,8 +237,9 @@ head_bwd_kernel(const float* __restrict__ dl, const float* __restrict__ x, int64
 // Keep-bit generator: out[g] = the 8 keep bits of Philox group g (= elements [8g, 8g+8) of a dropout site, or
 // one byte of the attention mask [B*H, N, 4*ceil(N/32)]). The consumers (GEMM epilogues, LayerNorm-backward
 // side-car, attention forward) accept these bytes instead of drawing the bits inline: the Philox arithmetic then
-// runs at full occupancy on a side stream underneath a tensor-core kernel instead of inside that kernel's
-// epilogue or its softmax rows. Bits are identical to the inline draw (same seed, stream, epoch, index).
+// runs on a side stream beside the block's (HBM-bound) LayerNorm instead of inside a GEMM epilogue or the softmax
+// rows. Bits are identical to the inline draw (same seed, stream, epoch, index). Four groups = two Philox calls per
+// word (nv_keep_bits32: pair-shared calls, byte transposes, bit-sliced compare).
 __global__ void dropout_bits_kernel(uint32_t* __restrict__ out, int64_t n_words, uint32_t thr, uint64_t seed_host,
                                     uint32_t stream_id, const uint64_t* epoch) {
   const uint64_t seed = nv_seed(seed_host, epoch);

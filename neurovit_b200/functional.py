@@ -65,11 +65,12 @@ def check_mode(mode: str) -> str:
 
 # ------------------------------------------------------------------------------------ dropout bits
 class MaskGen:
-    """Draws the keep bits of a dropout site AHEAD of the kernel that applies them, on a side stream: the Philox
-    arithmetic then runs at full occupancy underneath the tensor-core kernels of the main stream instead of inside
-    a GEMM epilogue, the LayerNorm-backward loop or the attention softmax rows (where it cost 1.6 ms per step).
-    Bits are identical to the inline draw (same seed / stream / epoch / element index), so consumers may take
-    either; bits of the sites a later Function's backward needs are parked in a small LRU registry."""
+    """Draws the keep bits of a dropout site AHEAD of the kernel that applies them, on a side stream, instead of inside
+    a GEMM epilogue, the LayerNorm-backward loop or the attention softmax rows (where the Philox arithmetic cost 1.6 ms
+    per step). The draws of a block are forked before the block's LayerNorm: an integer-pipe kernel beside an HBM-bound
+    one is the one pairing in the step that really overlaps (profiles/r02_summary.md §7c). Bits are identical to the
+    inline draw (same seed / stream / epoch / element index), so consumers may take either; bits of the sites a later
+    Function's backward needs are parked in a small LRU registry."""
 
     MAX_PARKED = 64
 
