@@ -188,3 +188,27 @@ def test_keep_rate_and_independence_of_lanes():
     assert np.abs(hist / hist.sum() - 1 / 16).max() < 5 * np.sqrt((1 / 16) * (15 / 16) / hist.sum())
     # the epoch moves the seed: same site, next step, different bits
     assert not np.array_equal(bits[:64], R.dropout_bits(64, 0.1, seed=42, stream=1, epoch=1))
+
+
+def test_layernorm_folded_into_linear_algebra():
+    """The identities behind nv_ln_fold / nv_ln_fold_grads (patch embedding, vit_3d.py:93-94), in float64 on the CPU:
+    Linear(LN(p)) = xhat (W o gamma)^T + (W beta + b), and with G = de^T xhat, cs = colsum(de):
+    dW = G o gamma + cs beta^T, dgamma = sum_k W o G, dbeta = W^T cs, db = cs."""
+    torch.manual_seed(9)
+    M, P, D = 37, 24, 16
+    p_in = torch.randn(M, P, dtype=torch.float64) * 3 + 1
+    ln = torch.nn.LayerNorm(P).double()
+    lin = torch.nn.Linear(P, D).double()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.3 * torch.randn(P, dtype=torch.float64))
+        ln.bias.copy_(0.2 * torch.randn(P, dtype=torch.float64))
+    de = torch.randn(M, D, dtype=torch.float64)
+    y = lin(ln(p_in))
+    want = torch.autograd.grad((y * de).sum(), (lin.weight, lin.bias, ln.weight, ln.bias))
+    xhat = (p_in - p_in.mean(1, keepdim=True)) / torch.sqrt(p_in.var(1, unbiased=False, keepdim=True) + ln.eps)
+    W, b, g, bt = lin.weight.detach(), lin.bias.detach(), ln.weight.detach(), ln.bias.detach()
+    assert rel(xhat @ (W * g).t() + (W @ bt + b), y.detach()) < 1e-12
+    G, cs = de.t() @ xhat, de.sum(0)
+    got = (G * g + cs[:, None] * bt[None, :], cs, (W * G).sum(0), W.t() @ cs)
+    for nm, a, w in zip(("dW", "db", "dgamma", "dbeta"), got, want):
+        assert rel(a, w) < 1e-12, nm
